@@ -1,0 +1,341 @@
+"""Spanning-tree initialisation of the global alignment (reference dust3r/cloud_opt_flow/init_im_poses.py).
+
+The reference grows the tree with N-2 *sequential* weighted Procrustes solves on (H,W,3) CPU tensors and
+then runs E more, each followed by host syncs (init_im_poses.py:107-154,219-262).  Here the graph logic
+(scores -> scipy MST -> traversal order, including the reference's stale-variable focal quirk at
+init_im_poses.py:223-224) stays on the host, but every pointmap reduction is one batched kernel launch:
+
+  * world pointmaps are never materialised: pts3d[n] = T_n o X[src_n] is kept symbolically as a
+    similarity T_n (fp64 on the host) and the packed slot src_n it applies to;
+  * similarity-equivariance of the registration (register(x -> T o y) = T o register(x -> y)) turns all
+    E + N-2 solves into slot-to-slot registrations that do not depend on each other
+    -> a3r_procrustes_batched, composed afterwards in tree order;
+  * focals -> a3r_weiszfeld_focal_batched, initial log-depth planes -> a3r_init_depth;
+  * RANSAC-PnP for frames the tree leaves without a pose stays cv2 on the host, as in the reference.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from .. import _lib
+from .commons import edge_str, signed_log1p
+
+
+def _allreduce_np(self, arr: np.ndarray) -> np.ndarray:
+    """Sum a small host array over the frame-window shards (identity on one GPU)."""
+    if self._shard is None or int(self._shard['world']) <= 1:
+        return arr
+    import torch.distributed as dist
+    t = torch.from_numpy(np.ascontiguousarray(arr)).to(self.device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self._shard.get('group'))
+    return t.cpu().numpy()
+
+
+def compute_edge_scores(self):
+    """score(e) = mean(conf_i[e]) * mean(conf_j[e]) (reference commons.py:21-31) from the per-slot
+    confidence sums the pack kernel accumulated."""
+    E = self.n_edges
+    sums = np.zeros(2 * E)
+    local = self._conf_sum.cpu().numpy()
+    for gs, s in self._lslot.items():
+        sums[gs] = local[s]
+    sums = _allreduce_np(self, sums)
+    areas = np.array([h * w for h, w in self.imshapes], dtype=np.float64)
+    scores = {}
+    for e, (i, j) in enumerate(self.edges):
+        mi = np.float32(sums[2 * e] / areas[i])
+        mj = np.float32(sums[2 * e + 1] / areas[j])
+        scores[(i, j)] = float(mi * mj)
+    return scores
+
+
+def dict_to_sparse_graph(dic):
+    """reference init_im_poses.py:438-443."""
+    n_imgs = max(max(e) for e in dic) + 1
+    res = sp.dok_array((n_imgs, n_imgs))
+    for edge, value in dic.items():
+        res[edge] = value
+    return res
+
+
+def _compose(a, b):
+    """Similarity composition a o b for (s, R, t) triples: x -> s_a R_a (s_b R_b x + t_b) + t_a."""
+    sa, Ra, ta = a
+    sb, Rb, tb = b
+    return sa * sb, Ra @ Rb, sa * (Ra @ tb) + ta
+
+
+def _rigid4x4(R, t):
+    M = np.eye(4)
+    M[:3, :3] = R
+    M[:3, 3] = t
+    return M
+
+
+def _run_procrustes(self, pairs):
+    """pairs: list of (x_gslot, y_gslot) living on one frame.  Returns (len, 13) fp64 [s, R(9), t(3)]
+    for every pair (pairs of other shards are filled in by the all-reduce)."""
+    out = np.zeros((len(pairs), 13))
+    mine = [k for k, (x, y) in enumerate(pairs) if x in self._lslot]
+    if mine:
+        dev = self.device
+        xs = torch.tensor([self._lslot[pairs[k][0]] for k in mine], dtype=torch.int32, device=dev)
+        ys = torch.tensor([self._lslot[pairs[k][1]] for k in mine], dtype=torch.int32, device=dev)
+        npx = torch.tensor([self.imshapes[self.edges[pairs[k][0] >> 1][pairs[k][0] & 1]][0]
+                            * self.imshapes[self.edges[pairs[k][0] >> 1][pairs[k][0] & 1]][1] for k in mine],
+                           dtype=torch.int32, device=dev)
+        sums = torch.zeros(len(mine), 20, dtype=torch.float64, device=dev)
+        res = torch.zeros(len(mine), 16, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.a3r_procrustes_batched(_lib.ptr(self._bufs.predw), self._plan.pix_stride, _lib.ptr(xs),
+                                                        _lib.ptr(ys), _lib.ptr(npx), len(mine),
+                                                        _lib.CONF_MODES[self.conf_mode], _lib.ptr(sums), _lib.ptr(res),
+                                                        self._stream()), "a3r_procrustes_batched")
+        out[mine] = res.cpu().numpy()[:, :13]
+    return _allreduce_np(self, out)
+
+
+def _run_focals(self, gslots):
+    """Weiszfeld focal of the pointmaps in the given global slots (reference init_im_poses.py:459-465)."""
+    out = np.zeros(len(gslots))
+    mine = [k for k, g in enumerate(gslots) if g in self._lslot]
+    if mine:
+        dev = self.device
+        sl = torch.tensor([self._lslot[gslots[k]] for k in mine], dtype=torch.int32, device=dev)
+        hw = torch.tensor([self.imshapes[self.edges[gslots[k] >> 1][gslots[k] & 1]] for k in mine], dtype=torch.int32, device=dev)
+        sums = torch.zeros(len(mine), 2, dtype=torch.float64, device=dev)
+        foc = torch.zeros(len(mine), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.a3r_weiszfeld_focal_batched(_lib.ptr(self._bufs.predw), self._plan.pix_stride, _lib.ptr(sl),
+                                                             _lib.ptr(hw), len(mine), _lib.ptr(sums), _lib.ptr(foc),
+                                                             self._stream()), "a3r_weiszfeld_focal_batched")
+        out[mine] = foc.cpu().numpy()
+    return _allreduce_np(self, out)
+
+
+def _pixel_grid(H, W):
+    return np.mgrid[:W, :H].T.astype(np.float32)
+
+
+def fast_pnp(pts3d, focal, msk, pp=None, niter_PnP=10):
+    """RANSAC-PnP on the host, reference init_im_poses.py:473-513.  Returns (focal, cam2world 4x4) or None."""
+    import cv2
+    if msk.sum() < 4:
+        return None
+    H, W, THREE = pts3d.shape
+    assert THREE == 3
+    pixels = _pixel_grid(H, W)
+    if focal is None:
+        S = max(W, H)
+        tentative_focals = np.geomspace(S / 2, S * 3, 21)
+    else:
+        tentative_focals = [focal]
+    if pp is None:
+        pp = (W / 2, H / 2)
+    best = (0,)
+    for f in tentative_focals:
+        K = np.float32([(f, 0, pp[0]), (0, f, pp[1]), (0, 0, 1)])
+        success, R, T, inliers = cv2.solvePnPRansac(pts3d[msk], pixels[msk], K, None, iterationsCount=niter_PnP,
+                                                    reprojectionError=5, flags=cv2.SOLVEPNP_SQPNP)
+        if not success:
+            continue
+        score = len(inliers)
+        if success and score > best[0]:
+            best = score, R, T, f
+    if not best[0]:
+        return None
+    _, R, T, best_focal = best
+    R = cv2.Rodrigues(R)[0]  # world to cam
+    return best_focal, np.linalg.inv(_rigid4x4(R, T.ravel()))  # cam to world
+
+
+@torch.no_grad()
+def init_minimum_spanning_tree(self, save_score_path=None, save_score_only=False, init_priors=None, niter_PnP=10):
+    """Init all camera poses (image-wise and pairwise poses) given an initial set of pairwise
+    estimations - reference init_im_poses.py:88-104,157-284 followed by init_from_pts3d (:107-154)."""
+    if init_priors is not None:
+        raise NotImplementedError("init_priors (hierarchical clip driver, reference init_im_poses.py:173-215) is a "
+                                  "'next' row of the scope table")
+    scores = compute_edge_scores(self)
+    if save_score_only or save_score_path is not None:
+        raise NotImplementedError("save_score_path / save_score_only draw a seaborn heat-map in the reference "
+                                  "(init_im_poses.py:24-42); plotting is out of scope")
+    N, E = self.n_imgs, self.n_edges
+    eid = {ij: e for e, ij in enumerate(self.edges)}
+
+    # ---- spanning tree of the score graph (host) ----
+    sparse_graph = -dict_to_sparse_graph(scores)
+    msp = sp.csgraph.minimum_spanning_tree(sparse_graph).tocoo()
+    todo = sorted(zip(-msp.data, msp.row, msp.col))
+
+    # ---- pass 1: traversal order (pure graph logic) ----
+    score, i, j = todo.pop()
+    if self.verbose:
+        print(f' init edge ({i}*,{j}*) {score=}')
+    k0 = eid[(int(i), int(j))]
+    src = {int(i): 2 * k0, int(j): 2 * k0 + 1}          # frame -> slot its world pointmap is made of
+    done = {int(i), int(j)}
+    first = (int(i), int(j))
+    focal_slot = {int(i): 2 * k0}                        # frame -> slot whose Weiszfeld focal it takes
+    stale_k = k0
+    steps = []                                           # (anchor frame, new frame, x slot, new src slot, pose frame)
+    msp_edges = [first]
+    while todo:
+        score, i, j = todo.pop()
+        i, j = int(i), int(j)
+        if i not in focal_slot:
+            focal_slot[i] = 2 * stale_k                  # the reference's stale ``i_j`` (init_im_poses.py:223-224)
+        if i in done:
+            if self.verbose:
+                print(f' init edge ({i},{j}*) {score=}')
+            assert j not in done
+            k = eid[(i, j)]
+            stale_k = k
+            steps.append((i, j, 2 * k, 2 * k + 1, i))     # register pred_i[k] onto pts3d[i]; pts3d[j] from pred_j[k]
+            src[j] = 2 * k + 1
+            done.add(j)
+            msp_edges.append((i, j))
+        elif j in done:
+            if self.verbose:
+                print(f' init edge ({i}*,{j}) {score=}')
+            assert i not in done
+            k = eid[(i, j)]
+            stale_k = k
+            steps.append((j, i, 2 * k + 1, 2 * k, i))     # register pred_j[k] onto pts3d[j]; pts3d[i] from pred_i[k]
+            src[i] = 2 * k
+            done.add(i)
+            msp_edges.append((i, j))
+        else:
+            todo.insert(0, (score, i, j))
+    # leftover focals, best edge first (init_im_poses.py:266-270)
+    pair_scores = list(sparse_graph.values())
+    edges_from_best_to_worse = np.array(list(sparse_graph.keys()))[np.argsort(pair_scores)]
+    for i, j in edges_from_best_to_worse.tolist():
+        if i not in focal_slot:
+            focal_slot[i] = 2 * eid[(i, j)]
+
+    # ---- pass 2: every pointmap reduction in two batched launches ----
+    pairs = []
+    # tree steps: y = the slot the anchor frame's pointmap is made of *at that time* = src[anchor]
+    for anchor, new, xs, new_src, pose_frame in steps:
+        pairs.append((xs, src[anchor]))
+    for e, (i, j) in enumerate(self.edges):               # init_from_pts3d: pred_i[e] onto pts3d[i]
+        pairs.append((2 * e, src[i]))
+    reg = _run_procrustes(self, pairs)
+    frames_f = sorted(focal_slot)
+    focals = dict(zip(frames_f, _run_focals(self, [focal_slot[n] for n in frames_f]).tolist()))
+
+    def sim(row):
+        return float(row[0]), row[1:10].reshape(3, 3), row[10:13]
+
+    # ---- pass 3: compose in tree order (fp64, host) ----
+    ident = (1.0, np.eye(3), np.zeros(3))
+    T = {first[0]: ident, first[1]: ident}
+    im_poses = [None] * N
+    im_poses[first[0]] = np.eye(4)
+    for t, (anchor, new, xs, new_src, pose_frame) in enumerate(steps):
+        s, R, tt = _compose(T[anchor], sim(reg[t]))
+        T[new] = (s, R, tt)
+        if im_poses[pose_frame] is None:
+            im_poses[pose_frame] = _rigid4x4(R, tt)          # sRT_to_4x4(1, R, T), init_im_poses.py:241-242,258-259
+    im_focals = [focals.get(n) for n in range(N)]
+
+    # ---- frames the tree left without a pose: RANSAC-PnP on the host (init_im_poses.py:272-279) ----
+    pnp = np.zeros((N, 17))
+    for n in range(N):
+        if im_poses[n] is None and n in self._lframe:
+            s, R, tt = T[n]
+            h, w = self.imshapes[n]
+            X = self._bufs.predw[self._lslot[src[n]], :h * w, :3]
+            A = torch.from_numpy((s * R).astype(np.float32)).to(self.device)
+            pts = (X @ A.T + torch.from_numpy(tt.astype(np.float32)).to(self.device)).view(h, w, 3).cpu().numpy()
+            msk = (self.im_conf[self._lframe[n]] > self.min_conf_thr).cpu().numpy()
+            res = fast_pnp(pts, im_focals[n], msk, niter_PnP=niter_PnP)
+            if res:
+                pnp[n, 0] = 1
+                pnp[n, 1:] = res[1].ravel()
+    pnp = _allreduce_np(self, pnp)
+    for n in range(N):
+        if im_poses[n] is None:
+            im_poses[n] = pnp[n, 1:].reshape(4, 4) if pnp[n, 0] > 0 else np.eye(4)
+    im_poses = np.stack(im_poses)
+    return init_from_pts3d(self, T, src, reg[len(steps):], im_focals, im_poses)
+
+
+def init_from_pts3d(self, T, src, edge_reg, im_focals, im_poses):
+    """reference init_im_poses.py:107-154 on symbolic world pointmaps (T_n, src_n)."""
+    from scipy.spatial.transform import Rotation
+    N, E = self.n_imgs, self.n_edges
+    if not self.im_poses.requires_grad:
+        raise NotImplementedError("MST initialisation with preset (frozen) poses: align_multiple_poses branch "
+                                  "(reference init_im_poses.py:109-122) is not built yet")
+
+    # ---- pairwise poses: register(pred_i[e] -> pts3d[i]) = T_i o register(slot 2e -> src_i) ----
+    Rs = np.zeros((E, 3, 3))
+    ts = np.zeros((E, 3))
+    ss = np.zeros(E)
+    for e, (i, j) in enumerate(self.edges):
+        row = edge_reg[e]
+        ss[e], Rs[e], ts[e] = _compose(T[i], (float(row[0]), row[1:10].reshape(3, 3), row[10:13]))
+    pw = np.zeros((E, 8), dtype=np.float32)
+    pw[:, 0:4] = Rotation.from_matrix(Rs).as_quat().astype(np.float32)                  # _set_pose, base_opt.py:221
+    pw[:, 4:7] = signed_log1p(torch.from_numpy((ts / ss[:, None]).astype(np.float32))).numpy()   # :223
+    pw[:, 7] = np.log(ss).astype(np.float32)                                            # :227
+    if self.pw_poses.requires_grad:
+        self.pw_poses.data.copy_(torch.from_numpy(pw).to(self.device))
+
+    # ---- scale normalisation (init_im_poses.py:131-135) ----
+    s_factor = float(self.get_pw_norm_scale_factor()) if self.norm_pw_scale else 1.0
+    im_poses = im_poses.copy()
+    im_poses[:, :3, 3] *= s_factor
+
+    # ---- depth maps: z of inv(cam2world) . (s_factor T_n X) as one launch (init_im_poses.py:138-142) ----
+    plan = self._plan
+    nl = plan.n_local_frames
+    if nl > 0 and self.im_depthmaps.requires_grad:
+        rows = np.zeros((nl, 4))
+        srcs = np.zeros(nl, dtype=np.int32)
+        npix = np.zeros(nl, dtype=np.int32)
+        for k, n in enumerate(plan.lframe_id.tolist()):
+            s, R, tt = T[n]
+            w2c = np.linalg.inv(im_poses[n])
+            rows[k, :3] = s_factor * (w2c[2, :3] @ (s * R))
+            rows[k, 3] = s_factor * (w2c[2, :3] @ tt) + w2c[2, 3]
+            srcs[k] = self._lslot[src[n]]
+            npix[k] = self.imshapes[n][0] * self.imshapes[n][1]
+        dev = self.device
+        d_rows = torch.from_numpy(rows).to(dev)
+        d_src = torch.from_numpy(srcs).to(dev)
+        d_np = torch.from_numpy(npix).to(dev)
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.a3r_init_depth(_lib.ptr(self._bufs.predw), plan.pix_stride, _lib.ptr(d_src), _lib.ptr(d_np),
+                                                _lib.ptr(d_rows), nl, _lib.ptr(self.im_depthmaps.data), self._stream()),
+                       "a3r_init_depth")
+
+    # ---- image poses + focals (init_im_poses.py:143-148) ----
+    po = np.zeros((N, 7), dtype=np.float32)
+    po[:, 0:4] = Rotation.from_matrix(im_poses[:, :3, :3]).as_quat().astype(np.float32)
+    po[:, 4:7] = signed_log1p(torch.from_numpy(im_poses[:, :3, 3].astype(np.float32))).numpy()
+    self.im_poses.data.copy_(torch.from_numpy(po).to(self.device))
+    if self.im_focals.requires_grad:
+        if self.shared_focal:
+            self._set_focal(0, sum(im_focals) / N)
+        else:
+            for n in range(N):
+                if im_focals[n] is not None:
+                    self._set_focal(n, im_focals[n])
+    if N > 2:
+        self._set_init_depthmap()
+    if self.verbose:
+        print(' init loss =', float(self._evaluate(9999)))
+    return None
+
+
+@torch.no_grad()
+def init_from_known_poses(self, niter_PnP=10, min_conf_thr=3):
+    raise NotImplementedError("init='known_poses' (reference init_im_poses.py:44-85) is a secondary entry point "
+                              "(SURVEY.md section 8(a) row E6) and is not built yet")

@@ -1,0 +1,631 @@
+// ga_kernels.cu - hot loop of the global alignment for sm_100a: parameter maps, the fused
+// forward+backward scan over pixel-slots, the small-parameter chain + Adam, the depth Adam.
+// C ABI in include/a3r_ga.h.  No tensor cores on purpose: the scan is HBM/issue bound.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "a3r_ga.h"
+#include "ga_math.cuh"
+#include "a3r_common.cuh"
+
+using namespace a3r;
+
+// ==========================================================================================
+// K0: parameter maps  (reference base_opt.py:195-247, optimizer.py:398-428)
+// ==========================================================================================
+__global__ void __launch_bounds__(256) k_prepare(const A3rProblem p) {
+    __shared__ double s_red[32];
+    __shared__ double s_mean;
+    const int tid = threadIdx.x;
+    const int E = p.n_edges, N = p.n_frames;
+    const bool shared_focal = p.flags & A3R_F_SHARED_FOCAL;
+    const bool norm_scale = p.flags & A3R_F_NORM_PW_SCALE;
+
+    // every CTA recomputes mean_e(log scale) in the same order -> identical on all CTAs
+    double part = 0.0;
+    for (int e = tid; e < E; e += blockDim.x) part += (double)p.pw_poses[8 * e + 7];
+    part = block_sum(part, s_red);
+    if (tid == 0) s_mean = part / (double)E;
+    __syncthreads();
+    const double log_norm = norm_scale ? (log((double)p.base_scale) - s_mean) : 0.0;
+
+    const int gid = blockIdx.x * blockDim.x + tid;
+    const int gstride = gridDim.x * blockDim.x;
+
+    for (int n = gid; n < N; n += gstride) {
+        FrameD F;
+        load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n, shared_focal, (double)p.focal_break, F);
+        derive_frame_par(F, p.frame_par + FP_STRIDE * n);
+    }
+    for (int e = gid; e < E; e += gstride)
+        derive_edge_par(p.pw_poses + 8 * e, p.pw_adaptors + 2 * e, log_norm, norm_scale, (double)p.pw_break, p.edge_par + EP_STRIDE * e);
+    if (p.flags & A3R_F_HAS_FLOW) {
+        for (int gs = gid; gs < 2 * E; gs += gstride) {
+            const int e = gs >> 1, side = gs & 1;
+            const int i = p.edge_ij[2 * e], j = p.edge_ij[2 * e + 1];
+            FrameD S, T;
+            load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, side ? j : i, shared_focal, (double)p.focal_break, S);
+            load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, side ? i : j, shared_focal, (double)p.focal_break, T);
+            derive_slot_par(S, T, p.slot_par + SP_STRIDE * gs);
+        }
+    }
+}
+
+// ==========================================================================================
+// K1 (v1): fused forward + backward over pixel-slots, frame-major, thread-owns-pixels.
+//   CTA = 256 threads, tile = 1024 pixels of one work frame (4 pixels per thread, strided by 256 so
+//   every warp load is 32 consecutive float4 = 512 B).  Per slot: 27 per-thread partial sums ->
+//   warp shuffle reduce -> per-warp fp64 shared accumulators -> fp64 global atomics once per
+//   (CTA, work frame).
+// ==========================================================================================
+constexpr int K1_THREADS = 256;
+constexpr int K1_WARPS = K1_THREADS / 32;
+constexpr int K1_PPT = 4;                       // pixels per thread per tile
+constexpr int K1_TILE = K1_THREADS * K1_PPT;    // 1024
+constexpr int K1_MAXS = 32;                     // slots per work frame
+
+struct K1Shared {
+    SlotConst slot[K1_MAXS];
+    int gslot[K1_MAXS];
+    float fp[FP_STRIDE];
+    double fred[K1_WARPS][FACC_N];
+};
+
+template <bool FLOW, bool L2D>
+__global__ void __launch_bounds__(K1_THREADS, 2) k_accumulate_v1(const A3rProblem p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_wacc = reinterpret_cast<double*>(smem_raw);                      // [K1_WARPS][K1_MAXS][ACC_STRIDE]
+    K1Shared& sh = *reinterpret_cast<K1Shared*>(smem_raw + sizeof(double) * K1_WARPS * K1_MAXS * ACC_STRIDE);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int t0 = p.cta_tile_begin[blockIdx.x], t1 = p.cta_tile_begin[blockIdx.x + 1];
+    if (t0 >= t1) return;
+
+    int wf = 0;
+    while (t0 >= p.wf_tile_begin[wf + 1]) ++wf;
+    int cur_wf = -1, lf = 0, n = 0, P = 0, W = 1, deg = 0, s_begin = 0, accum = 0;
+    float facc[FACC_N];
+#pragma unroll
+    for (int k = 0; k < FACC_N; ++k) facc[k] = 0.f;
+
+    auto flush = [&]() {
+        __syncthreads();
+        for (int idx = tid; idx < deg * ACC_N; idx += K1_THREADS) {
+            const int s = idx / ACC_N, i = idx - s * ACC_N;
+            double sum = 0.0;
+#pragma unroll
+            for (int w = 0; w < K1_WARPS; ++w) sum += s_wacc[(w * K1_MAXS + s) * ACC_STRIDE + i];
+            if (sum != 0.0) atomicAdd(&p.acc_slot[(int64_t)sh.gslot[s] * ACC_STRIDE + i], sum);
+        }
+#pragma unroll
+        for (int k = 0; k < FACC_N; ++k) {
+            const float v = warp_sum(facc[k]);
+            if (lane == 0) sh.fred[warp][k] = (double)v;
+            facc[k] = 0.f;
+        }
+        __syncthreads();
+        if (tid < FACC_N) {
+            double sum = 0.0;
+#pragma unroll
+            for (int w = 0; w < K1_WARPS; ++w) sum += sh.fred[w][tid];
+            atomicAdd(&p.acc_frame[(int64_t)n * FACC_N + tid], sum);
+        }
+    };
+
+    for (int tile = t0; tile < t1; ++tile) {
+        while (tile >= p.wf_tile_begin[wf + 1]) ++wf;
+        if (wf != cur_wf) {
+            if (cur_wf >= 0) flush();
+            cur_wf = wf;
+            lf = p.wf_lframe[wf];
+            n = p.lframe_id[lf];
+            W = p.frame_hw[2 * n + 1];
+            P = p.frame_hw[2 * n] * W;
+            s_begin = p.wf_slot_begin[wf];
+            deg = p.wf_slot_begin[wf + 1] - s_begin;
+            accum = p.wf_accum[wf];
+            __syncthreads();
+            if (tid < FP_STRIDE) sh.fp[tid] = p.frame_par[FP_STRIDE * n + tid];
+            if (tid < deg) {
+                const int gs = p.lslot_gslot[s_begin + tid];
+                sh.gslot[tid] = gs;
+                SlotConst& c = sh.slot[tid];
+                const float* ep = p.edge_par + EP_STRIDE * (gs >> 1);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) c.nM[k] = -ep[EP_M + k];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) c.st[k] = ep[EP_ST + k];
+                if (FLOW) {
+                    const float* sp = p.slot_par + SP_STRIDE * gs;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) c.A[k] = sp[SP_A + k];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) c.b[k] = sp[SP_B + k];
+                }
+                c.wn = (gs & 1) ? p.inv_area_j : p.inv_area_i;
+            }
+            for (int idx = tid; idx < K1_WARPS * K1_MAXS * ACC_STRIDE; idx += K1_THREADS) s_wacc[idx] = 0.0;
+            __syncthreads();
+        }
+        const int p0 = (tile - p.wf_tile_begin[wf]) * K1_TILE;
+        const int64_t pix_base = (int64_t)lf * p.pix_stride;
+
+        // ---- per-pixel state ----
+        float zx[K1_PPT], zy[K1_PPT], zz[K1_PPT], pu[K1_PPT], pv[K1_PPT], disp[K1_PPT];
+        float gsx[K1_PPT], gsy[K1_PPT], gsz[K1_PPT], gfi[K1_PPT], gfj[K1_PPT];
+        bool valid[K1_PPT], stat[K1_PPT];
+#pragma unroll
+        for (int j = 0; j < K1_PPT; ++j) {
+            const int pix = p0 + tid + j * K1_THREADS;
+            valid[j] = pix < P;
+            const float ld = valid[j] ? p.logdepth[pix_base + pix] : 0.f;
+            const int v = pix / W, u = pix - v * W;
+            PixState s;
+            pixel_state(sh.fp, ld, u, v, s);
+            zx[j] = s.zx; zy[j] = s.zy; zz[j] = s.zz; pu[j] = s.u; pv[j] = s.v; disp[j] = s.disp;
+            gsx[j] = gsy[j] = gsz[j] = gfi[j] = gfj[j] = 0.f;
+            stat[j] = false;
+            if (FLOW) stat[j] = valid[j] && (p.static_mask[pix_base + pix] != 0);
+        }
+
+        // ---- slots ----
+        for (int s = 0; s < deg; ++s) {
+            const SlotConst c = sh.slot[s];
+            const bool side_j = sh.gslot[s] & 1;
+            const float4* xw = reinterpret_cast<const float4*>(p.predw) + (int64_t)(s_begin + s) * p.pix_stride + p0 + tid;
+            float4 X[K1_PPT];
+            float2 F[K1_PPT];
+#pragma unroll
+            for (int j = 0; j < K1_PPT; ++j) X[j] = valid[j] ? ld_stream4(xw + j * K1_THREADS) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (FLOW) {
+                const float2* fl = reinterpret_cast<const float2*>(p.flow) + (int64_t)(s_begin + s) * p.pix_stride + p0 + tid;
+#pragma unroll
+                for (int j = 0; j < K1_PPT; ++j) F[j] = stat[j] ? ld_stream2(fl + j * K1_THREADS) : make_float2(0.f, 0.f);
+            }
+            float acc[ACC_N];
+#pragma unroll
+            for (int k = 0; k < ACC_N; ++k) acc[k] = 0.f;
+#pragma unroll
+            for (int j = 0; j < K1_PPT; ++j) {
+                PixState st;
+                st.zx = zx[j]; st.zy = zy[j]; st.zz = zz[j]; st.u = pu[j]; st.v = pv[j]; st.disp = disp[j];
+                align_px<L2D>(c, X[j].x, X[j].y, X[j].z, X[j].w, st, acc, gsx[j], gsy[j], gsz[j]);
+                if (FLOW) {
+                    if (stat[j]) {
+                        const float gd = flow_px(c, st, F[j].x, F[j].y, p.pxl_thre, acc);
+                        if (side_j) gfj[j] += gd; else gfi[j] += gd;
+                    }
+                }
+            }
+            double* wa = s_wacc + (warp * K1_MAXS + s) * ACC_STRIDE;
+#pragma unroll
+            for (int k = 0; k < (FLOW ? ACC_N : ACC_GA); ++k) {
+                const float v = warp_sum(acc[k]);
+                if (lane == 0) wa[k] += (double)v;
+            }
+        }
+
+        // ---- per-pixel gradient planes + per-frame sums ----
+#pragma unroll
+        for (int j = 0; j < K1_PPT; ++j) {
+            if (!valid[j]) continue;
+            const int pix = p0 + tid + j * K1_THREADS;
+            const float ld = p.logdepth[pix_base + pix];
+            const int v = pix / W, u = pix - v * W;
+            PixState s;
+            pixel_state(sh.fp, ld, u, v, s);
+            // d z / d logdepth = R c = z - t
+            const float ga = gsx[j] * (s.zx - sh.fp[FP_T + 0]) + gsy[j] * (s.zy - sh.fp[FP_T + 1]) + gsz[j] * (s.zz - sh.fp[FP_T + 2]);
+            if (accum) {
+                atomicAdd(&p.g_align[pix_base + pix], ga);
+                if (FLOW) {
+                    atomicAdd(&p.g_flow_i[pix_base + pix], gfi[j] * s.dfac);
+                    atomicAdd(&p.g_flow_j[pix_base + pix], gfj[j] * s.dfac);
+                }
+            } else {
+                p.g_align[pix_base + pix] = ga;
+                if (FLOW) {
+                    p.g_flow_i[pix_base + pix] = gfi[j] * s.dfac;
+                    p.g_flow_j[pix_base + pix] = gfj[j] * s.dfac;
+                }
+            }
+            facc[FACC_G + 0] += gsx[j]; facc[FACC_G + 1] += gsy[j]; facc[FACC_G + 2] += gsz[j];
+            facc[FACC_GC + 0] = fmaf(gsx[j], s.cx, facc[FACC_GC + 0]); facc[FACC_GC + 1] = fmaf(gsx[j], s.cy, facc[FACC_GC + 1]); facc[FACC_GC + 2] = fmaf(gsx[j], s.cz, facc[FACC_GC + 2]);
+            facc[FACC_GC + 3] = fmaf(gsy[j], s.cx, facc[FACC_GC + 3]); facc[FACC_GC + 4] = fmaf(gsy[j], s.cy, facc[FACC_GC + 4]); facc[FACC_GC + 5] = fmaf(gsy[j], s.cz, facc[FACC_GC + 5]);
+            facc[FACC_GC + 6] = fmaf(gsz[j], s.cx, facc[FACC_GC + 6]); facc[FACC_GC + 7] = fmaf(gsz[j], s.cy, facc[FACC_GC + 7]); facc[FACC_GC + 8] = fmaf(gsz[j], s.cz, facc[FACC_GC + 8]);
+        }
+    }
+    flush();
+}
+
+// ==========================================================================================
+// K2: loss assembly, gate, temporal term, parameter-chain gradients, Adam on the small parameters.
+//     One CTA (the work is O(E + N) small fp64 blocks).
+// ==========================================================================================
+constexpr int K2_THREADS = 512;
+
+__device__ __forceinline__ void adam_vec(float* prm, float* m, float* v, const float* g, int cnt,
+                                         const A3rProblem& p, const A3rAdamStep& a) {
+    for (int k = 0; k < cnt; ++k)
+        adam_update(prm[k], m[k], v[k], g[k], p.adam_beta1, p.adam_beta2, p.adam_eps, a.step_size, a.bc2_sqrt);
+}
+
+__device__ __forceinline__ void scatter_pair(const PairGrad& g, double* fgS, double* fgT) {
+    for (int k = 0; k < 15; ++k) {
+        if (g.s[k] != 0.0) atomicAdd(&fgS[k], g.s[k]);
+        if (g.t[k] != 0.0) atomicAdd(&fgT[k], g.t[k]);
+    }
+}
+
+__global__ void __launch_bounds__(K2_THREADS, 1) k_update_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam) {
+    __shared__ double s_red[32];
+    __shared__ double s_bc[8];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int N = p.n_frames, E = p.n_edges;
+    const bool shared_focal = p.flags & A3R_F_SHARED_FOCAL;
+    const bool norm_scale = p.flags & A3R_F_NORM_PW_SCALE;
+    const bool flow_active = (mode & A3R_M_FLOW_ACTIVE) && (p.flags & A3R_F_HAS_FLOW) && p.flow_loss_weight > 0.f;
+    const bool apply = mode & A3R_M_APPLY_ADAM;
+    const double fb = (double)p.focal_break;
+    const double tsw = (double)p.temporal_smoothing_weight, tw = (double)p.translation_weight;
+
+    // ---------------- P0: scalars, loss, gate ----------------
+    double l_align = 0, num_i = 0, cnt_i = 0, num_j = 0, cnt_j = 0, l_temp = 0;
+    for (int gs = tid; gs < 2 * E; gs += nt) {
+        const double* a = p.acc_slot + (int64_t)gs * ACC_STRIDE;
+        l_align += a[ACC_LOSS];
+        if (gs & 1) { num_j += a[ACC_FNUM]; cnt_j += a[ACC_FCNT]; }
+        else        { num_i += a[ACC_FNUM]; cnt_i += a[ACC_FCNT]; }
+    }
+    if (tsw > 0) {
+        for (int n = tid; n < N - 1; n += nt) {
+            FrameD T, S;
+            load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n, shared_focal, fb, T);
+            load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n + 1, shared_focal, fb, S);
+            l_temp += temporal_pair(S, T, tsw, tw, nullptr);
+        }
+    }
+    l_align = block_sum(l_align, s_red);
+    num_i = block_sum(num_i, s_red); cnt_i = block_sum(cnt_i, s_red);
+    num_j = block_sum(num_j, s_red); cnt_j = block_sum(cnt_j, s_red);
+    l_temp = block_sum(l_temp, s_red);
+    if (tid == 0) {
+        const LossScalars r = assemble_loss(l_align, l_temp, num_i, cnt_i, num_j, cnt_j, flow_active,
+                                            (double)p.flow_loss_weight, (double)p.flow_loss_thre, tsw);
+        p.scal[A3R_S_LOSS] = r.loss; p.scal[A3R_S_ALIGN] = l_align; p.scal[A3R_S_TEMPORAL] = l_temp;
+        p.scal[A3R_S_FLOW] = r.floss; p.scal[A3R_S_FLOW_DROPPED] = r.dropped;
+        p.scal[A3R_S_SC_I] = r.sc_i; p.scal[A3R_S_SC_J] = r.sc_j;
+        if (r.dropped != 0) p.scal[A3R_S_FLAG_STICKY] = 1.0;
+        if (p.loss_hist && adam.iter >= 0) p.loss_hist[adam.iter] = (float)r.loss;
+        s_bc[0] = r.sc_i; s_bc[1] = r.sc_j;
+    }
+    __syncthreads();
+    const double sc_i = s_bc[0], sc_j = s_bc[1];
+
+    // ---------------- P1: per-frame gradients of the alignment term ----------------
+    for (int n = tid; n < N; n += nt) {
+        FrameD F;
+        load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n, shared_focal, fb, F);
+        frame_align_grad(F, p.acc_frame + (int64_t)n * FACC_N, p.frame_grad + (int64_t)n * FG_STRIDE);
+    }
+    __syncthreads();
+
+    // ---------------- P2: flow + temporal chains (atomics into frame_grad) ----------------
+    if (flow_active && (sc_i != 0 || sc_j != 0)) {
+        for (int gs = tid; gs < 2 * E; gs += nt) {
+            const int e = gs >> 1, side = gs & 1;
+            const int i = p.edge_ij[2 * e], j = p.edge_ij[2 * e + 1];
+            const int sI = side ? j : i, tI = side ? i : j;
+            FrameD S, T;
+            load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, sI, shared_focal, fb, S);
+            load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, tI, shared_focal, fb, T);
+            PairGrad g;
+            slot_flow_chain(S, T, p.acc_slot + (int64_t)gs * ACC_STRIDE, side ? sc_j : sc_i, g);
+            scatter_pair(g, p.frame_grad + (int64_t)sI * FG_STRIDE, p.frame_grad + (int64_t)tI * FG_STRIDE);
+        }
+    }
+    if (tsw > 0) {
+        for (int n = tid; n < N - 1; n += nt) {
+            FrameD T, S;
+            load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n, shared_focal, fb, T);
+            load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n + 1, shared_focal, fb, S);
+            PairGrad g;
+            temporal_pair(S, T, tsw, tw, &g);
+            scatter_pair(g, p.frame_grad + (int64_t)(n + 1) * FG_STRIDE, p.frame_grad + (int64_t)n * FG_STRIDE);
+        }
+    }
+    __syncthreads();
+
+    // ---------------- P3a: d L / d log s_e and its mean (global scale normalisation) ----------------
+    double gsum = 0;
+    for (int e = tid; e < E; e += nt) {
+        const double* a0 = p.acc_slot + (int64_t)(2 * e) * ACC_STRIDE;
+        const double g = edge_logscale_grad(p.edge_par + EP_STRIDE * e, a0, a0 + ACC_STRIDE);
+        p.edge_scratch[e] = g;
+        gsum += g;
+    }
+    gsum = block_sum(gsum, s_red);
+    const double gmean = norm_scale ? gsum / (double)E : 0.0;
+
+    // ---------------- P3b: pairwise poses ----------------
+    for (int e = tid; e < E; e += nt) {
+        const double* a0 = p.acc_slot + (int64_t)(2 * e) * ACC_STRIDE;
+        float g[8], ga[2];
+        edge_pose_grad(p.pw_poses + 8 * e, p.edge_par + EP_STRIDE * e, a0, a0 + ACC_STRIDE, p.edge_scratch[e] - gmean,
+                       p.flags & A3R_F_TRAIN_ADAPTORS, norm_scale, (double)p.pw_break, g, ga);
+        for (int k = 0; k < 8; ++k) p.g_pw_poses[8 * e + k] = g[k];
+        p.g_pw_adaptors[2 * e] = ga[0]; p.g_pw_adaptors[2 * e + 1] = ga[1];
+        if (apply && (p.flags & A3R_F_TRAIN_PW_POSES)) adam_vec(p.pw_poses + 8 * e, p.pw_poses_m + 8 * e, p.pw_poses_v + 8 * e, g, 8, p, adam);
+        if (apply && (p.flags & A3R_F_TRAIN_ADAPTORS)) adam_vec(p.pw_adaptors + 2 * e, p.pw_adaptors_m + 2 * e, p.pw_adaptors_v + 2 * e, ga, 2, p, adam);
+    }
+
+    // ---------------- P3c: image poses, focals, principal points ----------------
+    double gphi_sum = 0;
+    for (int n = tid; n < N; n += nt) {
+        FrameD F;
+        load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n, shared_focal, fb, F);
+        float g[7], gpp[2];
+        double gphi;
+        frame_pose_grad(p.im_poses + 7 * n, F, p.frame_grad + (int64_t)n * FG_STRIDE, fb, p.flags & A3R_F_TRAIN_PP, g, &gphi, gpp);
+        for (int k = 0; k < 7; ++k) p.g_im_poses[7 * n + k] = g[k];
+        p.g_im_pp[2 * n] = gpp[0]; p.g_im_pp[2 * n + 1] = gpp[1];
+        if (shared_focal) gphi_sum += gphi;
+        else {
+            float gf = (float)gphi;
+            p.g_im_focals[n] = gf;
+            if (apply && (p.flags & A3R_F_TRAIN_FOCALS)) adam_vec(p.im_focals + n, p.im_focals_m + n, p.im_focals_v + n, &gf, 1, p, adam);
+        }
+        if (apply && (p.flags & A3R_F_TRAIN_PP)) adam_vec(p.im_pp + 2 * n, p.im_pp_m + 2 * n, p.im_pp_v + 2 * n, gpp, 2, p, adam);
+        if (apply && (p.flags & A3R_F_TRAIN_IM_POSES)) adam_vec(p.im_poses + 7 * n, p.im_poses_m + 7 * n, p.im_poses_v + 7 * n, g, 7, p, adam);
+    }
+    if (shared_focal) {
+        // the shared focal is read by every frame above: update it only after everyone is done
+        gphi_sum = block_sum(gphi_sum, s_red);
+        if (tid == 0) {
+            float gf = (float)gphi_sum;
+            p.g_im_focals[0] = gf;
+            if (apply && (p.flags & A3R_F_TRAIN_FOCALS)) adam_vec(p.im_focals, p.im_focals_m, p.im_focals_v, &gf, 1, p, adam);
+        }
+    }
+}
+
+// ==========================================================================================
+// K3: Adam on the log-depth planes (or, without A3R_M_APPLY_ADAM, total depth gradient -> g_align)
+// ==========================================================================================
+template <bool FLOW>
+__global__ void __launch_bounds__(256) k_update_depth(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam) {
+    const int64_t total4 = (int64_t)p.n_local_frames * p.pix_stride / 4;
+    const float sc_i = (float)p.scal[A3R_S_SC_I], sc_j = (float)p.scal[A3R_S_SC_J];
+    const bool apply = mode & A3R_M_APPLY_ADAM;
+    float4* ld = reinterpret_cast<float4*>(p.logdepth);
+    float4* mm = reinterpret_cast<float4*>(p.logdepth_m);
+    float4* vv = reinterpret_cast<float4*>(p.logdepth_v);
+    float4* ga = reinterpret_cast<float4*>(p.g_align);
+    const float4* gi = reinterpret_cast<const float4*>(p.g_flow_i);
+    const float4* gj = reinterpret_cast<const float4*>(p.g_flow_j);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 g = ga[i];
+        if (FLOW) {
+            const float4 a = gi[i], b = gj[i];
+            g.x += sc_i * a.x + sc_j * b.x; g.y += sc_i * a.y + sc_j * b.y;
+            g.z += sc_i * a.z + sc_j * b.z; g.w += sc_i * a.w + sc_j * b.w;
+        }
+        if (apply) {
+            float4 l = ld[i], m = mm[i], v = vv[i];
+            adam_update(l.x, m.x, v.x, g.x, p.adam_beta1, p.adam_beta2, p.adam_eps, adam.step_size, adam.bc2_sqrt);
+            adam_update(l.y, m.y, v.y, g.y, p.adam_beta1, p.adam_beta2, p.adam_eps, adam.step_size, adam.bc2_sqrt);
+            adam_update(l.z, m.z, v.z, g.z, p.adam_beta1, p.adam_beta2, p.adam_eps, adam.step_size, adam.bc2_sqrt);
+            adam_update(l.w, m.w, v.w, g.w, p.adam_beta1, p.adam_beta2, p.adam_eps, adam.step_size, adam.bc2_sqrt);
+            ld[i] = l; mm[i] = m; vv[i] = v;
+        } else {
+            ga[i] = g;
+        }
+    }
+}
+
+// ==========================================================================================
+// read-out: world pointmaps (reference optimizer.py:468-478)
+// ==========================================================================================
+__global__ void __launch_bounds__(256) k_unproject(const A3rProblem p, float* __restrict__ out) {
+    const int lf = blockIdx.y;
+    const int n = p.lframe_id[lf];
+    const int W = p.frame_hw[2 * n + 1], P = p.frame_hw[2 * n] * W;
+    __shared__ float fp[FP_STRIDE];
+    if (threadIdx.x < FP_STRIDE) fp[threadIdx.x] = p.frame_par[FP_STRIDE * n + threadIdx.x];
+    __syncthreads();
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < P; pix += gridDim.x * blockDim.x) {
+        const int v = pix / W, u = pix - v * W;
+        PixState s;
+        pixel_state(fp, p.logdepth[(int64_t)lf * p.pix_stride + pix], u, v, s);
+        float* o = out + ((int64_t)lf * p.pix_stride + pix) * 3;
+        o[0] = s.zx; o[1] = s.zy; o[2] = s.zz;
+    }
+}
+
+// ==========================================================================================
+// one-off packing
+// ==========================================================================================
+__global__ void __launch_bounds__(256) k_pack_pred(const float* __restrict__ pts, const float* __restrict__ conf, int64_t P,
+                                                   const int32_t* __restrict__ dst_slot, const int32_t* __restrict__ dst_lframe,
+                                                   int64_t pix_stride, int conf_mode, float* __restrict__ predw,
+                                                   float* __restrict__ im_conf, double* __restrict__ conf_sum) {
+    __shared__ double s_red[32];
+    const int k = blockIdx.y;
+    const int slot = dst_slot[k], lf = dst_lframe[k];
+    const float* sp = pts + (int64_t)k * P * 3;
+    const float* sc = conf + (int64_t)k * P;
+    float4* dp = reinterpret_cast<float4*>(predw) + (int64_t)slot * pix_stride;
+    double csum = 0.0;
+    for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < P; pix += (int64_t)gridDim.x * blockDim.x) {
+        const float c = sc[pix];
+        float w;
+        switch (conf_mode) {                   // reference commons.py:53-64
+            case 0: w = logf(c); break;
+            case 1: w = sqrtf(c); break;
+            case 2: w = c - 1.0f; break;
+            default: w = c; break;
+        }
+        dp[pix] = make_float4(sp[3 * pix], sp[3 * pix + 1], sp[3 * pix + 2], w);
+        if (im_conf && c > 0.f) atomicMax(reinterpret_cast<int*>(im_conf + (int64_t)lf * pix_stride + pix), __float_as_int(c));
+        csum += (double)c;
+    }
+    csum = block_sum(csum, s_red);
+    if (threadIdx.x == 0 && conf_sum) atomicAdd(&conf_sum[slot], csum);
+}
+
+__global__ void __launch_bounds__(256) k_pack_flow(const float* __restrict__ src, int64_t P, const int32_t* __restrict__ dst_slot,
+                                                   int64_t pix_stride, float* __restrict__ dst) {
+    const int k = blockIdx.y;
+    const float* fu = src + (int64_t)k * 2 * P;
+    const float* fv = fu + P;
+    float2* d = reinterpret_cast<float2*>(dst) + (int64_t)dst_slot[k] * pix_stride;
+    for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < P; pix += (int64_t)gridDim.x * blockDim.x)
+        d[pix] = make_float2(fu[pix], fv[pix]);
+}
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+static int check_problem(const A3rProblem* p) {
+    if (!p) return a3r_fail(A3R_E_ARG, "problem is NULL");
+    if (p->tile_pixels != K1_TILE) return a3r_fail(A3R_E_ARG, "tile_pixels %d != a3r_tile_pixels() %d", p->tile_pixels, K1_TILE);
+    if (p->n_frames <= 0 || p->n_edges <= 0 || p->n_local_frames < 0 || p->n_ctas <= 0)
+        return a3r_fail(A3R_E_ARG, "bad sizes N=%d E=%d local=%d ctas=%d", p->n_frames, p->n_edges, p->n_local_frames, p->n_ctas);
+    if (p->pix_stride % 4 != 0) return a3r_fail(A3R_E_ARG, "pix_stride must be a multiple of 4");
+    if (p->acc_frame != p->acc_slot + (int64_t)2 * p->n_edges * A3R_SLOT_ACC)
+        return a3r_fail(A3R_E_ARG, "acc_frame must directly follow acc_slot");
+    return A3R_OK;
+}
+
+template <bool FLOW, bool L2D>
+static int launch_accumulate(const A3rProblem* p, cudaStream_t st) {
+    const size_t smem = sizeof(double) * K1_WARPS * K1_MAXS * ACC_STRIDE + sizeof(K1Shared);
+    static bool configured = false;   // per template instantiation
+    if (!configured) {
+        A3R_CUDA(cudaFuncSetAttribute(k_accumulate_v1<FLOW, L2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    k_accumulate_v1<FLOW, L2D><<<p->n_ctas, K1_THREADS, smem, st>>>(*p);
+    A3R_CUDA(cudaGetLastError());
+    return A3R_OK;
+}
+
+extern "C" {
+
+int a3r_abi_version(void) { return A3R_ABI_VERSION; }
+const char* a3r_last_error(void) { return a3r_error_buffer(); }
+int a3r_tile_pixels(void) { return K1_TILE; }
+int a3r_max_slots(void) { return K1_MAXS; }
+
+int a3r_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
+    cudaDeviceProp prop;
+    A3R_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    return A3R_OK;
+}
+
+int a3r_max_ctas(int device) {
+    int sm = 0;
+    if (a3r_device_info(device, &sm, nullptr, nullptr) != A3R_OK) return A3R_E_CUDA;
+    return sm * 2;
+}
+
+int a3r_pack_pred(const float* pts, const float* conf, int32_t n, int64_t P, const int32_t* dst_slot,
+                  const int32_t* dst_lframe, int64_t pix_stride, int32_t conf_mode, float* predw,
+                  float* im_conf, double* conf_sum, void* stream) {
+    if (n <= 0) return A3R_OK;
+    if (!pts || !conf || !dst_slot || !dst_lframe || !predw) return a3r_fail(A3R_E_ARG, "a3r_pack_pred: NULL pointer");
+    dim3 grid((unsigned)((P + 1023) / 1024 < 1 ? 1 : (P + 1023) / 1024), (unsigned)n);
+    if (grid.x > 64) grid.x = 64;
+    k_pack_pred<<<grid, 256, 0, (cudaStream_t)stream>>>(pts, conf, P, dst_slot, dst_lframe, pix_stride, conf_mode, predw, im_conf, conf_sum);
+    A3R_CUDA(cudaGetLastError());
+    return A3R_OK;
+}
+
+int a3r_pack_flow(const float* flow_src, int32_t n, int64_t P, const int32_t* dst_slot, int64_t pix_stride,
+                  float* flow_dst, void* stream) {
+    if (n <= 0) return A3R_OK;
+    if (!flow_src || !dst_slot || !flow_dst) return a3r_fail(A3R_E_ARG, "a3r_pack_flow: NULL pointer");
+    dim3 grid((unsigned)((P + 1023) / 1024 < 1 ? 1 : (P + 1023) / 1024), (unsigned)n);
+    if (grid.x > 64) grid.x = 64;
+    k_pack_flow<<<grid, 256, 0, (cudaStream_t)stream>>>(flow_src, P, dst_slot, pix_stride, flow_dst);
+    A3R_CUDA(cudaGetLastError());
+    return A3R_OK;
+}
+
+int a3r_ga_prepare(const A3rProblem* p, uint32_t mode, void* stream) {
+    (void)mode;
+    if (int rc = check_problem(p)) return rc;
+    int work = 2 * p->n_edges > p->n_frames ? 2 * p->n_edges : p->n_frames;
+    int grid = (work + 255) / 256;
+    if (grid > 148) grid = 148;
+    k_prepare<<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
+    A3R_CUDA(cudaGetLastError());
+    return A3R_OK;
+}
+
+int a3r_ga_accumulate(const A3rProblem* p, uint32_t mode, void* stream) {
+    if (int rc = check_problem(p)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool flow = (mode & A3R_M_FLOW_ACTIVE) && (p->flags & A3R_F_HAS_FLOW) && p->flow_loss_weight > 0.f;
+    if (flow && (!p->flow || !p->static_mask)) return a3r_fail(A3R_E_ARG, "flow active but flow/static_mask planes are NULL");
+    const size_t acc_bytes = sizeof(double) * ((size_t)2 * p->n_edges * A3R_SLOT_ACC + (size_t)p->n_frames * A3R_FRAME_ACC);
+    A3R_CUDA(cudaMemsetAsync(p->acc_slot, 0, acc_bytes, st));
+    if (p->n_work_frames > p->n_local_frames) {     // split frames add their gradients atomically
+        const size_t plane = sizeof(float) * (size_t)p->n_local_frames * p->pix_stride;
+        A3R_CUDA(cudaMemsetAsync(p->g_align, 0, plane, st));
+        if (flow) {
+            A3R_CUDA(cudaMemsetAsync(p->g_flow_i, 0, plane, st));
+            A3R_CUDA(cudaMemsetAsync(p->g_flow_j, 0, plane, st));
+        }
+    }
+    if (p->n_tiles == 0) return A3R_OK;
+    const bool l2 = p->flags & A3R_F_DIST_L2;
+    if (flow) return l2 ? launch_accumulate<true, true>(p, st) : launch_accumulate<true, false>(p, st);
+    return l2 ? launch_accumulate<false, true>(p, st) : launch_accumulate<false, false>(p, st);
+}
+
+int a3r_ga_update(const A3rProblem* p, uint32_t mode, const A3rAdamStep* adam, void* stream) {
+    if (int rc = check_problem(p)) return rc;
+    if (!adam) return a3r_fail(A3R_E_ARG, "adam is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    k_update_small<<<1, K2_THREADS, 0, st>>>(*p, mode, *adam);
+    A3R_CUDA(cudaGetLastError());
+    const bool apply = mode & A3R_M_APPLY_ADAM;
+    if (p->n_local_frames > 0 && (!apply || (p->flags & A3R_F_TRAIN_DEPTH))) {
+        const bool flow = (mode & A3R_M_FLOW_ACTIVE) && (p->flags & A3R_F_HAS_FLOW) && p->flow_loss_weight > 0.f;
+        const int64_t total4 = (int64_t)p->n_local_frames * p->pix_stride / 4;
+        int64_t grid = (total4 + 255) / 256;
+        if (grid > 148 * 8) grid = 148 * 8;
+        if (flow) k_update_depth<true><<<(unsigned)grid, 256, 0, st>>>(*p, mode, *adam);
+        else k_update_depth<false><<<(unsigned)grid, 256, 0, st>>>(*p, mode, *adam);
+        A3R_CUDA(cudaGetLastError());
+    }
+    return A3R_OK;
+}
+
+int a3r_ga_run(const A3rProblem* p, int32_t count, const uint32_t* modes, const A3rAdamStep* steps, void* stream) {
+    if (count < 0 || !modes || !steps) return a3r_fail(A3R_E_ARG, "a3r_ga_run: bad arguments");
+    for (int32_t k = 0; k < count; ++k) {
+        if (int rc = a3r_ga_prepare(p, modes[k], stream)) return rc;
+        if (int rc = a3r_ga_accumulate(p, modes[k], stream)) return rc;
+        if (int rc = a3r_ga_update(p, modes[k], &steps[k], stream)) return rc;
+    }
+    return A3R_OK;
+}
+
+int a3r_ga_unproject(const A3rProblem* p, float* pts3d, void* stream) {
+    if (int rc = check_problem(p)) return rc;
+    if (!pts3d) return a3r_fail(A3R_E_ARG, "pts3d is NULL");
+    if (p->n_local_frames == 0) return A3R_OK;
+    dim3 grid(64, (unsigned)p->n_local_frames);
+    k_unproject<<<grid, 256, 0, (cudaStream_t)stream>>>(*p, pts3d);
+    A3R_CUDA(cudaGetLastError());
+    return A3R_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,252 @@
+// mst_kernels.cu - batched solves of the spanning-tree initialisation for sm_100a:
+//   weighted similarity (Procrustes/Umeyama) registration between two pointmaps of one frame,
+//   Weiszfeld focal estimation, and log-depth initialisation.  C ABI in include/a3r_ga.h.
+// All reductions accumulate in fp64 (one-off work; the B200 fp64 pipe is idle otherwise).
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "a3r_ga.h"
+#include "a3r_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float conf_untrf(float w, int mode) {   // inverse of reference commons.py:53-64
+    switch (mode) {
+        case 0: return expf(w);
+        case 1: return w * w;
+        case 2: return w + 1.0f;
+        default: return w;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Procrustes: per problem 17 weighted moment sums -> sums[k][20]
+//   [0] sum w, [1..3] sum w x, [4..6] sum w y, [7..15] sum w y x^T (row-major y_r x_c), [16] sum w |x|^2
+// ------------------------------------------------------------------------------------------
+constexpr int PR_SUMS = 20;
+constexpr int PR_USED = 17;
+
+__global__ void __launch_bounds__(256) k_procrustes_moments(const float* __restrict__ predw, int64_t pix_stride,
+                                                            const int32_t* __restrict__ xs, const int32_t* __restrict__ ys,
+                                                            const int32_t* __restrict__ npix, int conf_mode,
+                                                            double* __restrict__ sums) {
+    __shared__ double s_red[32];
+    const int k = blockIdx.y;
+    const int P = npix[k];
+    const float4* X = reinterpret_cast<const float4*>(predw) + (int64_t)xs[k] * pix_stride;
+    const float4* Y = reinterpret_cast<const float4*>(predw) + (int64_t)ys[k] * pix_stride;
+    double a[PR_USED];
+#pragma unroll
+    for (int i = 0; i < PR_USED; ++i) a[i] = 0.0;
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < P; pix += gridDim.x * blockDim.x) {
+        const float4 x = ld_stream4(X + pix), y = ld_stream4(Y + pix);
+        const double w = (double)conf_untrf(x.w, conf_mode);
+        const double x0 = x.x, x1 = x.y, x2 = x.z, y0 = y.x, y1 = y.y, y2 = y.z;
+        a[0] += w;
+        a[1] += w * x0; a[2] += w * x1; a[3] += w * x2;
+        a[4] += w * y0; a[5] += w * y1; a[6] += w * y2;
+        const double wy0 = w * y0, wy1 = w * y1, wy2 = w * y2;
+        a[7] += wy0 * x0; a[8] += wy0 * x1; a[9] += wy0 * x2;
+        a[10] += wy1 * x0; a[11] += wy1 * x1; a[12] += wy1 * x2;
+        a[13] += wy2 * x0; a[14] += wy2 * x1; a[15] += wy2 * x2;
+        a[16] += w * (x0 * x0 + x1 * x1 + x2 * x2);
+    }
+#pragma unroll
+    for (int i = 0; i < PR_USED; ++i) {
+        const double v = block_sum(a[i], s_red);
+        if (threadIdx.x == 0) atomicAdd(&sums[(int64_t)k * PR_SUMS + i], v);
+    }
+}
+
+// one-sided Jacobi SVD of a 3x3 matrix: M = U diag(sig) V^T, sig sorted descending
+__device__ void svd3(const double M[9], double U[9], double sig[3], double V[9]) {
+    double A[9];
+    for (int i = 0; i < 9; ++i) { A[i] = M[i]; V[i] = (i % 4 == 0) ? 1.0 : 0.0; }
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0;
+        for (int pq = 0; pq < 3; ++pq) {
+            const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
+            double alpha = 0, beta = 0, gamma = 0;
+            for (int r = 0; r < 3; ++r) {
+                alpha += A[r * 3 + p] * A[r * 3 + p];
+                beta += A[r * 3 + q] * A[r * 3 + q];
+                gamma += A[r * 3 + p] * A[r * 3 + q];
+            }
+            const double lim = 1e-30 + 1e-16 * sqrt(alpha * beta);
+            if (fabs(gamma) <= lim) continue;
+            off = fmax(off, fabs(gamma) / sqrt(alpha * beta + 1e-300));
+            const double zeta = (beta - alpha) / (2.0 * gamma);
+            const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+            for (int r = 0; r < 3; ++r) {
+                const double ap = A[r * 3 + p], aq = A[r * 3 + q];
+                A[r * 3 + p] = c * ap - s * aq;
+                A[r * 3 + q] = s * ap + c * aq;
+                const double vp = V[r * 3 + p], vq = V[r * 3 + q];
+                V[r * 3 + p] = c * vp - s * vq;
+                V[r * 3 + q] = s * vp + c * vq;
+            }
+        }
+        if (off < 1e-15) break;
+    }
+    for (int j = 0; j < 3; ++j) sig[j] = sqrt(A[j] * A[j] + A[3 + j] * A[3 + j] + A[6 + j] * A[6 + j]);
+    // sort columns by descending singular value
+    for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2 - a; ++b)
+            if (sig[b] < sig[b + 1]) {
+                double t = sig[b]; sig[b] = sig[b + 1]; sig[b + 1] = t;
+                for (int r = 0; r < 3; ++r) {
+                    t = A[r * 3 + b]; A[r * 3 + b] = A[r * 3 + b + 1]; A[r * 3 + b + 1] = t;
+                    t = V[r * 3 + b]; V[r * 3 + b] = V[r * 3 + b + 1]; V[r * 3 + b + 1] = t;
+                }
+            }
+    for (int j = 0; j < 3; ++j) {
+        const double inv = sig[j] > 1e-300 ? 1.0 / sig[j] : 0.0;
+        for (int r = 0; r < 3; ++r) U[r * 3 + j] = A[r * 3 + j] * inv;
+    }
+    if (sig[2] <= 1e-14 * sig[0]) {   // rank-deficient: complete U with the cross product of its first two columns
+        U[2] = U[3] * U[7] - U[6] * U[4];
+        U[5] = U[6] * U[1] - U[0] * U[7];
+        U[8] = U[0] * U[4] - U[3] * U[1];
+    }
+}
+
+__device__ __forceinline__ double det3(const double A[9]) {
+    return A[0] * (A[4] * A[8] - A[5] * A[7]) - A[1] * (A[3] * A[8] - A[5] * A[6]) + A[2] * (A[3] * A[7] - A[4] * A[6]);
+}
+
+// weighted Umeyama solve from the moment sums (roma.rigid_points_registration semantics, see
+// oracle/roma_shim.py): out[k] = s, R (9), t (3)
+__global__ void k_procrustes_solve(const double* __restrict__ sums, int count, double* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const double* a = sums + (int64_t)k * PR_SUMS;
+    const double n = a[0];
+    double xm[3], ym[3], M[9];
+    for (int i = 0; i < 3; ++i) { xm[i] = a[1 + i] / n; ym[i] = a[4 + i] / n; }
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) M[r * 3 + c] = a[7 + r * 3 + c] - n * ym[r] * xm[c];
+    const double var = a[16] - n * (xm[0] * xm[0] + xm[1] * xm[1] + xm[2] * xm[2]);
+    double U[9], sig[3], V[9];
+    svd3(M, U, sig, V);
+    const double d = det3(U) * det3(V) < 0 ? -1.0 : 1.0;
+    double R[9];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c)
+            R[r * 3 + c] = U[r * 3] * V[c * 3] + U[r * 3 + 1] * V[c * 3 + 1] + d * U[r * 3 + 2] * V[c * 3 + 2];
+    const double s = (sig[0] + sig[1] + d * sig[2]) / var;
+    double* o = out + (int64_t)k * 16;
+    o[0] = s;
+    for (int i = 0; i < 9; ++i) o[1 + i] = R[i];
+    for (int r = 0; r < 3; ++r) o[10 + r] = ym[r] - s * (R[r * 3] * xm[0] + R[r * 3 + 1] * xm[1] + R[r * 3 + 2] * xm[2]);
+    o[13] = o[14] = o[15] = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Weiszfeld focal (reference post_process.py:36-58): pass 0 = closed-form L2, passes 1..10 = IRLS
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_focal_pass(const float* __restrict__ predw, int64_t pix_stride,
+                                                    const int32_t* __restrict__ sl, const int32_t* __restrict__ hw,
+                                                    const double* __restrict__ focal, int first, double* __restrict__ sums) {
+    __shared__ double s_red[32];
+    const int k = blockIdx.y;
+    const int H = hw[2 * k], W = hw[2 * k + 1], P = H * W;
+    const float4* X = reinterpret_cast<const float4*>(predw) + (int64_t)sl[k] * pix_stride;
+    const float f = first ? 0.f : (float)focal[k];
+    const float ppx = 0.5f * W, ppy = 0.5f * H;
+    double num = 0.0, den = 0.0;
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < P; pix += gridDim.x * blockDim.x) {
+        const float4 x = ld_stream4(X + pix);
+        const int v = pix / W, u = pix - v * W;
+        const float pu = (float)u - ppx, pv = (float)v - ppy;
+        float ax = x.x / x.z, ay = x.y / x.z;
+        if (!isfinite(ax)) ax = 0.f;          // nan_to_num(posinf=0, neginf=0)
+        if (!isfinite(ay)) ay = 0.f;
+        const float dpx = ax * pu + ay * pv;
+        const float dxx = ax * ax + ay * ay;
+        float w = 1.f;
+        if (!first) {
+            const float ex = pu - f * ax, ey = pv - f * ay;
+            w = 1.0f / fmaxf(sqrtf(ex * ex + ey * ey), 1e-8f);
+        }
+        num += (double)(w * dpx);
+        den += (double)(w * dxx);
+    }
+    num = block_sum(num, s_red);
+    den = block_sum(den, s_red);
+    if (threadIdx.x == 0) {
+        atomicAdd(&sums[2 * k], num);
+        atomicAdd(&sums[2 * k + 1], den);
+    }
+}
+
+__global__ void k_focal_finish(const double* __restrict__ sums, int count, double* __restrict__ focal) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < count) focal[k] = sums[2 * k] / sums[2 * k + 1];
+}
+
+// ------------------------------------------------------------------------------------------
+// log-depth planes (reference init_im_poses.py:138-142, optimizer.py:430-436)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_init_depth(const float* __restrict__ predw, int64_t pix_stride,
+                                                    const int32_t* __restrict__ src, const int32_t* __restrict__ npix,
+                                                    const double* __restrict__ rows, float* __restrict__ logdepth) {
+    const int k = blockIdx.y;
+    const int P = npix[k];
+    const float4* X = reinterpret_cast<const float4*>(predw) + (int64_t)src[k] * pix_stride;
+    const float r0 = (float)rows[4 * k], r1 = (float)rows[4 * k + 1], r2 = (float)rows[4 * k + 2], r3 = (float)rows[4 * k + 3];
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < P; pix += gridDim.x * blockDim.x) {
+        const float4 x = ld_stream4(X + pix);
+        const float d = fmaf(r0, x.x, fmaf(r1, x.y, fmaf(r2, x.z, r3)));
+        float l = logf(d);
+        if (isnan(l) || l == -INFINITY) l = 0.f;        // depth.log().nan_to_num(neginf=0)
+        else if (l == INFINITY) l = 3.4028234663852886e38f;
+        logdepth[(int64_t)k * pix_stride + pix] = l;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int a3r_procrustes_batched(const float* predw, int64_t pix_stride, const int32_t* xs, const int32_t* ys,
+                           const int32_t* npix, int32_t count, int32_t conf_mode, double* sums, double* out,
+                           void* stream) {
+    if (count <= 0) return A3R_OK;
+    if (!predw || !xs || !ys || !npix || !sums || !out) return a3r_fail(A3R_E_ARG, "a3r_procrustes_batched: NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    A3R_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * PR_SUMS * (size_t)count, st));
+    const int chunks = count >= 592 ? 8 : (count >= 148 ? 16 : 64);
+    k_procrustes_moments<<<dim3(chunks, count), 256, 0, st>>>(predw, pix_stride, xs, ys, npix, conf_mode, sums);
+    A3R_CUDA(cudaGetLastError());
+    k_procrustes_solve<<<(count + 63) / 64, 64, 0, st>>>(sums, count, out);
+    A3R_CUDA(cudaGetLastError());
+    return A3R_OK;
+}
+
+int a3r_weiszfeld_focal_batched(const float* predw, int64_t pix_stride, const int32_t* sl, const int32_t* hw,
+                                int32_t count, double* sums, double* out_focal, void* stream) {
+    if (count <= 0) return A3R_OK;
+    if (!predw || !sl || !hw || !sums || !out_focal) return a3r_fail(A3R_E_ARG, "a3r_weiszfeld_focal_batched: NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int chunks = count >= 592 ? 8 : (count >= 148 ? 16 : 64);
+    for (int pass = 0; pass <= 10; ++pass) {
+        A3R_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)count, st));
+        k_focal_pass<<<dim3(chunks, count), 256, 0, st>>>(predw, pix_stride, sl, hw, out_focal, pass == 0, sums);
+        A3R_CUDA(cudaGetLastError());
+        k_focal_finish<<<(count + 127) / 128, 128, 0, st>>>(sums, count, out_focal);
+        A3R_CUDA(cudaGetLastError());
+    }
+    return A3R_OK;
+}
+
+int a3r_init_depth(const float* predw, int64_t pix_stride, const int32_t* src, const int32_t* npix,
+                   const double* rows, int32_t n_local_frames, float* logdepth, void* stream) {
+    if (n_local_frames <= 0) return A3R_OK;
+    if (!predw || !src || !npix || !rows || !logdepth) return a3r_fail(A3R_E_ARG, "a3r_init_depth: NULL pointer");
+    k_init_depth<<<dim3(64, n_local_frames), 256, 0, (cudaStream_t)stream>>>(predw, pix_stride, src, npix, rows, logdepth);
+    A3R_CUDA(cudaGetLastError());
+    return A3R_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""Benchmark of the global-alignment hot path (BASELINE.json: GA iterations/s on the 50-frame 288x512
+swin-5 graph with flow + temporal terms; % of the HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2]
+
+A "step" is one GA iteration (parameter maps + fused forward/backward scan + parameter chains + Adam).
+The K timed steps are the K iterations of ``global_alignment_loop(niter=K, schedule='linear', lr=0.01)``
+started from the MST initialisation, so the flow term switches on at iteration 0.1*K exactly as in the
+reference's canonical 300-iteration run.  One JSON line is printed by rank 0.
+
+N > 1 (launched by torchrun): the scene is cut into N contiguous frame windows; a rank owns the slots
+living on its frames; one NCCL all-reduce of the small-parameter accumulators per iteration; total work is
+fixed ("scaling": "strong").
+
+``--impl reference`` times the CPU oracle port of the reference implementation (oracle/ga_oracle.py: same
+torch ops + autograd + torch.optim.Adam as the reference, all host threads) on a bounded sample of the
+same workload and scales by pixel-edges; rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline leg")
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds for the whole --impl reference run")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json (of measured)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s of B200_PROFILING.md (of fallback)"
+
+
+def recorded_traffic():
+    """dram bytes per accumulate launch from the committed ncu capture, if any (profiles/traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(E, N, P, flow):
+    """SURVEY.md section 8(d).  Returns (bytes per whole iteration, bytes of the accumulate kernel alone)."""
+    it = E * P * 32 + N * P * 24 + (E * P * 16 + N * P if flow else 0)
+    k1 = E * P * 32 + N * P * 4 + (E * P * 16 + N * P if flow else 0)
+    return it, k1
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+def oracle_rate(cfg, budget_s, steps, warmup, seed):
+    """Times `steps` iterations (after `warmup`) of the oracle port on a sample of workload cfg sized to the
+    budget.  Returns dict(value = iterations/s scaled to the full workload, sample description, ...)."""
+    import torch
+    from align3r_b200.synth import make_scene, make_edge_list, CANONICAL_KW
+    from oracle import ga_oracle as go
+    n, H, W, graph = cfg
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    full_pe = len(make_edge_list(n, graph)) * H * W
+    # ~1.6e-7 s per pixel-edge per iteration on 8 cores with flow active (measured in the build container)
+    per_pe = 1.6e-7 * 8 / max(cores, 1) ** 0.7
+    ladder = [(10, H, W), (8, H, W), (7, H // 2, W // 2), (6, H // 2, W // 2), (6, H // 4, W // 4), (6, H // 8, W // 8)]
+    total_steps = steps + warmup
+    pick = ladder[-1]
+    for ns, hs, ws in ladder:
+        pe = len(make_edge_list(min(ns, n), graph)) * hs * ws
+        if pe * per_pe * total_steps <= budget_s:
+            pick = (ns, hs, ws)
+            break
+    ns, hs, ws = min(pick[0], n), pick[1], pick[2]
+    scene = make_scene(ns, hs, ws, graph, seed=seed, with_flow=True)
+    kw = dict(CANONICAL_KW, num_total_iter=steps)
+    prob = go.problem_from_output(scene.output, scene.flow_ij, scene.flow_ji, **kw)
+    params, _ = go.mst_init(prob)
+    p = {k: v.detach().clone().requires_grad_(k in go.TRAINABLE) for k, v in params.items()}
+    opt = torch.optim.Adam([p[k] for k in go.TRAINABLE], lr=0.01, betas=(0.9, 0.9))
+
+    def one(it, niter):
+        for g in opt.param_groups:
+            g["lr"] = go.lr_schedule("linear", it / niter, 0.01, 1e-3)
+        opt.zero_grad()
+        loss, _ = go.total_loss(prob, p, it)
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    for w in range(warmup):
+        one(steps - 1, steps)              # warm up with the flow term on
+    t0 = time.perf_counter()
+    for it in range(steps):
+        one(it, steps)
+    dt = time.perf_counter() - t0
+    sample_pe = prob.n_edges * prob.P
+    rate_sample = steps / dt
+    return dict(value=rate_sample * sample_pe / full_pe, unit="iterations/s", cores=cores, kind="port",
+                sample=(f"{steps} iterations (flow on from 0.1*{steps}) of the oracle port on a {ns}-frame {hs}x{ws} {graph} sample "
+                        f"({prob.n_edges} edges, {sample_pe} pixel-edges, {rate_sample:.3f} it/s), scaled by pixel-edges "
+                        f"{sample_pe}/{full_pe} to the full workload"),
+                ms_per_step_sample=1e3 * dt / steps, torch_threads=torch.get_num_threads())
+
+
+def run_reference(args, cfg, name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = oracle_rate(cfg, args.ref_budget, args.steps, args.warmup, args.seed)
+    n, H, W, graph = cfg
+    line = {
+        "impl": "reference", "metric": "ga_iterations_per_sec", "value": r["value"], "unit": "iterations/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / r["value"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{name}: {n}-frame {H}x{W} {graph} PointCloudOptimizer alignment, flow+temporal, linear lr"},
+        "cpu_baseline": {"value": r["value"], "unit": "iterations/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, cfg, name):
+    import torch
+    import torch.distributed as dist
+    from align3r_b200 import _lib
+    from align3r_b200.cloud_opt_flow import GlobalAlignerMode, global_aligner
+    from align3r_b200.cloud_opt_flow.optimizer import global_alignment_loop
+    from align3r_b200.plan import frame_costs, partition_frames
+    from align3r_b200.problem import adam_schedule
+    from align3r_b200.synth import CANONICAL_KW, make_edge_list, make_scene
+    import numpy as np
+    import ctypes as C
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the alignment kernels have no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world != args.gpus:
+        raise SystemExit(f"bench.py --gpus {args.gpus} must be launched with torchrun --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    n, H, W, graph = cfg
+    P = H * W
+    K, Wm = args.steps, args.warmup
+    all_edges = make_edge_list(n, graph)
+    E = len(all_edges)
+    shard, rows = None, None
+    if world > 1:
+        wins = partition_frames(frame_costs(np.asarray(all_edges, dtype=np.int32), np.asarray([(H, W)] * n, dtype=np.int32)), world)
+        lo, hi = wins[rank]
+        rows = [e for e, (i, j) in enumerate(all_edges) if lo <= i < hi or lo <= j < hi]
+        shard = dict(world=world, rank=rank, group=None)
+    scene = make_scene(n, H, W, graph, seed=args.seed, with_flow=True, pin_memory=True,
+                       edges=None if rows is None else [all_edges[e] for e in rows])
+    kw = dict(CANONICAL_KW, num_total_iter=K)
+
+    def output_dict():
+        out = scene.output
+        if rows is not None:          # every rank names the whole graph, rows cover only the edges it touches
+            out = dict(out)
+            out["view1"] = dict(out["view1"], idx=[i for i, _ in all_edges])
+            out["view2"] = dict(out["view2"], idx=[j for _, j in all_edges])
+        return out
+
+    def build():
+        return global_aligner(output_dict(), dev, mode=GlobalAlignerMode.PointCloudOptimizer,
+                              flow=(scene.flow_ij, scene.flow_ji), shard=shard, edge_rows=rows, **kw)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------- end-to-end leg: host buffers -> public API -> host results ----------------
+    h2d = sum(t.numel() * t.element_size() for t in (scene.pred1["pts3d"], scene.pred2["pts3d_in_other_view"], scene.pred1["conf"],
+                                                      scene.pred2["conf"], scene.flow_ij, scene.flow_ji))
+    e2e = None
+    net = None
+    if not args.no_e2e:
+        barrier()
+        t0 = time.perf_counter()
+        net = build()
+        loss_e2e = net.compute_global_alignment(init="mst", niter=K, schedule="linear", lr=0.01)
+        depth_h = [d.detach().cpu() for d in net.get_depthmaps()]
+        poses_h = net.get_im_poses().detach().cpu()
+        foc_h = net.get_focals().detach().cpu()
+        hist_h = net._bufs.loss_hist[:K].cpu()
+        barrier()
+        t_e2e = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_e2e = float(tt)
+            hh = torch.tensor([float(h2d)], device=dev, dtype=torch.float64)
+            dist.all_reduce(hh)
+            h2d_total = float(hh)
+        else:
+            h2d_total = float(h2d)
+        d2h = sum(d.numel() * 4 for d in depth_h) + poses_h.numel() * 4 + foc_h.numel() * 4 + hist_h.numel() * 4
+        e2e = {"value": K / t_e2e, "unit": "iterations/s", "h2d_bytes_per_step": h2d_total / K, "d2h_bytes_per_step": d2h / K,
+               "seconds_total": t_e2e, "final_loss": loss_e2e,
+               "what": "global_aligner(host dict) + compute_global_alignment(init='mst', niter=K) + depth/pose/focal/loss read-back, "
+                       "whole job / K; inputs are uploaded once per job (they are constant across iterations)"}
+        del depth_h
+    if net is None:
+        net = build()
+        net.compute_global_alignment(init="mst", niter=0)
+    else:
+        # restart from the MST initialisation for the device-timed run
+        net.compute_global_alignment(init="mst", niter=0)
+    snap = {k: getattr(net, k).detach().clone() for k in ("pw_poses", "im_depthmaps", "im_poses", "im_focals")}
+
+    # ---------------- warm-up: both kernel variants, then restore the initial state ----------------
+    verbose_was = net.verbose
+    net.verbose = False
+    if Wm > 0:
+        net.num_total_iter = 2 * Wm          # flow on for the second half
+        global_alignment_loop(net, lr=0.01, niter=2 * Wm, schedule="linear")
+        net.num_total_iter = K
+    with torch.no_grad():
+        for k, v in snap.items():
+            getattr(net, k).data.copy_(v)
+    net.flow_loss_flag = False
+
+    # ---------------- timed region: K iterations, device time, max over ranks ----------------
+    sampler = ClockSampler(local).start() if rank == 0 else None
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(torch.cuda.current_stream(dev))
+    final_loss = global_alignment_loop(net, lr=0.01, niter=K, schedule="linear")
+    ev1.record(torch.cuda.current_stream(dev))
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler is not None else None
+    if world > 1:
+        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt)
+    n_flow = sum(1 for it in range(K) if net._flow_active(it))
+
+    # ---------------- roofline of the dominant kernel: the accumulate scan, timed alone ----------------
+    b = net._bufs
+    st = b.struct(net._trainable())
+    stream = net._stream()
+    roof = {}
+    reps = 20
+    for label, mode in (("flow", _lib.M_FLOW_ACTIVE), ("align", 0)):
+        _lib.check(net._lib.a3r_ga_prepare(C.byref(st), mode, stream))
+        for _ in range(3):
+            _lib.check(net._lib.a3r_ga_accumulate(C.byref(st), mode, stream))
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(torch.cuda.current_stream(dev))
+        for _ in range(reps):
+            _lib.check(net._lib.a3r_ga_accumulate(C.byref(st), mode, stream))
+        a1.record(torch.cuda.current_stream(dev))
+        torch.cuda.synchronize(dev)
+        roof[label] = a0.elapsed_time(a1) / reps
+    # per-rank share of the scan (pixel-slots are what a launch processes)
+    local_ps = net._plan.pixel_slots()
+    nl = net._plan.n_local_frames
+    k1_bytes_flow = local_ps * 24 + nl * P * 5
+    k1_bytes_align = local_ps * 16 + nl * P * 4
+    peak, peak_src = measured_peak()
+    ach = k1_bytes_flow / (roof["flow"] * 1e-3) / 1e9
+    traffic = recorded_traffic()
+    it_bytes_flow, _ = algorithmic_bytes(E, n, P, True)
+    it_bytes_align, _ = algorithmic_bytes(E, n, P, False)
+    blended_bytes = (n_flow * it_bytes_flow + (K - n_flow) * it_bytes_align) / K
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": "ga_iterations_per_sec", "value": K / (ms * 1e-3), "unit": "iterations/s", "n_gpus": world,
+            "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{name}: {n}-frame {H}x{W} {graph} PointCloudOptimizer alignment ({E} directed edges, "
+                                   f"{E * P} pixel-edges), shared focal, flow 0.01 + temporal 0.01, linear lr 0.01->1e-3, init=mst",
+                       "iterations_with_flow": n_flow, "parallelism": "single GPU" if world == 1 else f"{world} frame windows, "
+                       "one NCCL all-reduce of the fp64 accumulator block per iteration",
+                       "l2": "inputs exceed L2 (per-iteration scan >> 126 MB)"},
+            "pixel_edges_per_sec": E * P * K / (ms * 1e-3),
+            "final_loss": final_loss,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": (traffic or {}).get("accumulate_flow_bytes_per_launch") if world == 1 else None,
+                         "kernel": "k_accumulate (flow active), timed alone over %d launches" % reps,
+                         "ms_per_launch": roof["flow"], "algorithmic_bytes_per_launch": k1_bytes_flow, "peak_source": peak_src,
+                         "align_only": {"ms_per_launch": roof["align"], "achieved": k1_bytes_align / (roof["align"] * 1e-3) / 1e9,
+                                        "frac": k1_bytes_align / (roof["align"] * 1e-3) / 1e9 / peak}},
+            "roofline_iteration": {"bytes_per_iteration": blended_bytes, "achieved": blended_bytes / world / (ms / K * 1e-3) / 1e9,
+                                   "frac": blended_bytes / (ms / K * 1e-3) / 1e9 / peak / world,
+                                   "note": "whole iteration (all kernels), SURVEY 8(d) bytes, per GPU"},
+            "gpu_launches": 4 * K,
+            "clocks": clocks,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+    # ---------------- CPU baseline beside it (rank 0, N = 1 only) ----------------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        del net
+        torch.cuda.empty_cache()
+        cb = oracle_rate(cfg, args.cpu_budget, 3, 1, args.seed)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    from align3r_b200.synth import CONFIGS
+    cfg = CONFIGS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, cfg, args.workload)
+    else:
+        run_ours(args, cfg, args.workload)
+
+
+if __name__ == "__main__":
+    main()

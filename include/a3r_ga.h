@@ -1,0 +1,210 @@
+/*
+ * a3r_ga.h - C ABI of the B200-native global-alignment kernels (liba3r_ga.so).
+ *
+ * Drop-in boundary.  The reference has no FFI seam on this path: the seam is the Python class
+ * dust3r.cloud_opt_flow.PointCloudOptimizer (reference dust3r/cloud_opt_flow/optimizer.py:30,
+ * base_opt.py:44).  align3r_b200.cloud_opt_flow.PointCloudOptimizer keeps that class API and hands
+ * raw device pointers of PyTorch-owned storage to the entry points below through ctypes.  Each entry
+ * point names the reference code it replaces.
+ *
+ * Contract
+ *  - plain C: no torch / C++ types in any signature; every pointer inside A3rProblem is a DEVICE
+ *    pointer unless its comment says "host"; the caller keeps the memory alive during the call.
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*); no call synchronises
+ *    the device except a3r_device_info.
+ *  - returns 0 on success, a negative A3R_E_* code on failure; a3r_last_error() gives the message of
+ *    the calling thread's last failure.
+ *  - no internal threads, no hidden allocations: all scratch lives in buffers listed in A3rProblem.
+ *  - there is no CPU path.  Without a CUDA device every compute entry point fails with A3R_E_CUDA.
+ *
+ * Index conventions
+ *  N frames, E directed edges e = (i, j).  Every edge has two "slots" (edge-sides): global slot
+ *  gs = 2*e + side, side 0 = the i-side (pred1 pointmap, lives on frame i's pixel grid), side 1 = the
+ *  j-side (pred2 pointmap, lives on frame j's grid).  A device owns a set of "local frames" (all of
+ *  them on one GPU; a contiguous frame window per GPU otherwise) and the slots living on them, stored
+ *  frame-major: the local slots of local frame k are [lframe_slot_begin[k], lframe_slot_begin[k+1]).
+ *  Per-pixel planes are padded to `pix_stride` pixels per frame / per slot, pixel p = v*W + u.
+ */
+#ifndef A3R_GA_H
+#define A3R_GA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define A3R_ABI_VERSION 3
+
+/* error codes */
+#define A3R_OK 0
+#define A3R_E_ARG (-1)
+#define A3R_E_CUDA (-2)
+#define A3R_E_UNSUPPORTED (-3)
+
+/* A3rProblem.flags */
+#define A3R_F_SHARED_FOCAL   (1u << 0)  /* im_focals has one entry used by all frames (optimizer.py:57-59) */
+#define A3R_F_NORM_PW_SCALE  (1u << 1)  /* base_opt.py:230-236 */
+#define A3R_F_DIST_L2        (1u << 2)  /* commons.py:67-68; default is 'l1' = weighted L2 norm (:71-72) */
+#define A3R_F_TRAIN_PW_POSES (1u << 3)
+#define A3R_F_TRAIN_DEPTH    (1u << 4)
+#define A3R_F_TRAIN_IM_POSES (1u << 5)
+#define A3R_F_TRAIN_FOCALS   (1u << 6)
+#define A3R_F_TRAIN_PP       (1u << 7)  /* optimize_pp (optimizer.py:63-64) */
+#define A3R_F_TRAIN_ADAPTORS (1u << 8)  /* allow_pw_adaptors (base_opt.py:113-114) */
+#define A3R_F_HAS_FLOW       (1u << 9)  /* flow planes + dynamic masks are present */
+
+/* a3r_ga_* `mode` argument */
+#define A3R_M_FLOW_ACTIVE (1u << 0)     /* epoch >= num_total_iter*flow_loss_start_epoch (optimizer.py:520) */
+#define A3R_M_APPLY_ADAM  (1u << 1)     /* update parameters; otherwise only loss + gradients are produced */
+
+/* number of fp64 accumulators per slot / per frame produced by a3r_ga_accumulate */
+#define A3R_SLOT_ACC 28
+#define A3R_FRAME_ACC 12
+#define A3R_SCAL 16
+
+/* layout of A3rProblem.scal (fp64[A3R_SCAL]) after a3r_ga_update */
+#define A3R_S_LOSS 0        /* total loss of this evaluation (optimizer.py:554-557) */
+#define A3R_S_ALIGN 1       /* li + lj */
+#define A3R_S_TEMPORAL 2    /* un-weighted temporal term */
+#define A3R_S_FLOW 3        /* un-weighted flow_loss_i + flow_loss_j (NaN when inactive) */
+#define A3R_S_FLOW_DROPPED 4 /* 1 when the gate dropped the flow term in this evaluation (optimizer.py:540-542) */
+#define A3R_S_SC_I 5        /* flow_loss_weight / sum(per_pixel_mask_i), 0 when inactive or dropped */
+#define A3R_S_SC_J 6
+#define A3R_S_FLAG_STICKY 7 /* flow_loss_flag: set once the gate has tripped at least once */
+
+typedef struct A3rProblem {
+    /* ---- sizes ---- */
+    int32_t n_frames;        /* N (global) */
+    int32_t n_edges;         /* E (global, directed) */
+    int32_t n_local_frames;  /* frames whose pixel planes live on this device */
+    int32_t n_local_slots;   /* slots living on those frames */
+    int32_t n_work_frames;   /* >= n_local_frames: a frame with more than a3r_max_slots() slots is split */
+    int32_t n_tiles;         /* sum over work frames of ceil(P / tile_pixels) */
+    int32_t n_ctas;          /* persistent CTAs of the accumulate kernel (multiple of the SM count) */
+    int32_t tile_pixels;     /* must equal a3r_tile_pixels() */
+    uint32_t flags;          /* A3R_F_* */
+    int64_t pix_stride;      /* padded pixels per frame plane and per slot plane (max area) */
+
+    /* ---- hyper-parameters (reference optimizer.py:36-38, base_opt.py:61-71) ---- */
+    float focal_break, pw_break, base_scale;
+    float flow_loss_weight, flow_loss_thre, pxl_thre;
+    float temporal_smoothing_weight, translation_weight;
+    float inv_area_i, inv_area_j;     /* 1/total_area_i, 1/total_area_j (optimizer.py:91-92, GLOBAL sums) */
+    float adam_beta1, adam_beta2, adam_eps, _pad0;
+
+    /* ---- global graph, replicated on every device ---- */
+    const int32_t *edge_ij;           /* [E][2] */
+    const int32_t *frame_hw;          /* [N][2] (H, W) */
+
+    /* ---- small parameters + Adam moments (fp32, replicated) ---- */
+    float *pw_poses, *pw_poses_m, *pw_poses_v;          /* [E][8]  qx qy qz qw tx~ ty~ tz~ log-scale */
+    float *pw_adaptors, *pw_adaptors_m, *pw_adaptors_v; /* [E][2] */
+    float *im_poses, *im_poses_m, *im_poses_v;          /* [N][7] */
+    float *im_focals, *im_focals_m, *im_focals_v;       /* [1] if shared else [N]: focal_break*log f */
+    float *im_pp, *im_pp_m, *im_pp_v;                   /* [N][2] */
+    /* gradients of the last evaluation (always written by a3r_ga_update) */
+    float *g_pw_poses, *g_pw_adaptors, *g_im_poses, *g_im_focals, *g_im_pp;
+
+    /* ---- derived per-iteration blocks written by a3r_ga_prepare (fp32) ---- */
+    float *frame_par;                 /* [N][16]  R(9) t(3) f cx cy - */
+    float *edge_par;                  /* [E][16]  s*R*diag(a) (9), s*t (3), s, a(3) */
+    float *slot_par;                  /* [2E][16] flow homography A (9), b (3), - */
+
+    /* ---- local shard description ---- */
+    const int32_t *lframe_id;         /* [n_local_frames] global frame index */
+    const int32_t *wf_lframe;         /* [n_work_frames] local frame a work frame belongs to */
+    const int32_t *wf_slot_begin;     /* [n_work_frames+1] local slots of a work frame (<= a3r_max_slots()) */
+    const int32_t *wf_tile_begin;     /* [n_work_frames+1] */
+    const int32_t *wf_accum;          /* [n_work_frames] 0: store per-pixel gradients, 1: atomically add them
+                                         (frames split over several work frames; planes are zeroed first) */
+    const int32_t *lslot_gslot;       /* [n_local_slots] global slot id 2*e+side */
+    const int32_t *cta_tile_begin;    /* [n_ctas+1] balanced contiguous tile ranges */
+
+    /* ---- local constant inputs ---- */
+    const float *predw;               /* [n_local_slots][pix_stride][4]  X Y Z weight(=conf_trf(conf)) */
+    const float *flow;                /* [n_local_slots][pix_stride][2]  or NULL */
+    const uint8_t *static_mask;       /* [n_local_frames][pix_stride]  1 = ~dynamic_mask, or NULL */
+
+    /* ---- local per-pixel state ---- */
+    float *logdepth, *logdepth_m, *logdepth_v;   /* [n_local_frames][pix_stride] */
+    float *g_align, *g_flow_i, *g_flow_j;        /* [n_local_frames][pix_stride] per-pixel gradient planes */
+
+    /* ---- reduction buffers (fp64).  Multi-GPU: all-reduce(sum) acc_slot..acc_frame between
+     *      a3r_ga_accumulate and a3r_ga_update; they are contiguous: acc_frame = acc_slot + 2E*28 ---- */
+    double *acc_slot;                 /* [2E][A3R_SLOT_ACC] */
+    double *acc_frame;                /* [N][A3R_FRAME_ACC] */
+    double *frame_grad;               /* [N][16] scratch of a3r_ga_update */
+    double *edge_scratch;             /* [E] scratch of a3r_ga_update */
+    double *scal;                     /* [A3R_SCAL] */
+    float *loss_hist;                 /* [>= niter] loss of every iteration, or NULL */
+} A3rProblem;
+
+/* Adam scalars of one step, computed on the host in double like torch/optim/adam.py:457-547 */
+typedef struct A3rAdamStep {
+    float step_size;        /* lr / (1 - beta1^t) */
+    float bc2_sqrt;         /* sqrt(1 - beta2^t) */
+    int32_t iter;           /* index into loss_hist */
+    int32_t _pad;
+} A3rAdamStep;
+
+/* ---- library ---- */
+int a3r_abi_version(void);
+const char *a3r_last_error(void);
+int a3r_tile_pixels(void);              /* pixels per tile the accumulate kernel was built for */
+int a3r_max_slots(void);                /* most slots one work frame may hold */
+int a3r_max_ctas(int device);           /* recommended n_ctas = SM count * resident CTAs per SM */
+int a3r_device_info(int device, int *sm_count, int *cc_major, int *cc_minor);
+
+/* ---- one-off packing (replaces the ParameterStack buffers of reference optimizer.py:80-92,
+ *      _compute_img_conf base_opt.py:187-193 and compute_edge_scores commons.py:21-31) ----
+ * pts [n][P][3], conf [n][P] raw network outputs of n edge-sides (device, fp32); dst_slot[n] (host)
+ * local slot index of each; conf_mode 0=log 1=sqrt 2=m1 3=id.  Writes predw, max-merges raw conf into
+ * im_conf[lframe][pix_stride] (frame index per slot in dst_lframe, host) and adds sum(conf) into
+ * conf_sum[dst_slot] (fp64, device). */
+int a3r_pack_pred(const float *pts, const float *conf, int32_t n, int64_t P, const int32_t *dst_slot,
+                  const int32_t *dst_lframe, int64_t pix_stride, int32_t conf_mode, float *predw,
+                  float *im_conf, double *conf_sum, void *stream);
+/* flow [n][2][P] (reference get_flow layout, optimizer.py:118-154) -> flow plane [slot][pix_stride][2] */
+int a3r_pack_flow(const float *flow_src, int32_t n, int64_t P, const int32_t *dst_slot, int64_t pix_stride,
+                  float *flow_dst, void *stream);
+
+/* ---- hot loop ---- */
+/* parameter maps: reference base_opt.py:195-247, optimizer.py:398-428 -> frame_par/edge_par/slot_par */
+int a3r_ga_prepare(const A3rProblem *p, uint32_t mode, void *stream);
+/* fused forward + backward over all local pixel-slots: reference optimizer.py:500-544 and its autograd
+ * backward.  Zeroes then fills acc_slot/acc_frame, writes g_align/g_flow_i/g_flow_j. */
+int a3r_ga_accumulate(const A3rProblem *p, uint32_t mode, void *stream);
+/* loss assembly + gate (optimizer.py:538-557), temporal term (:559-572), parameter-chain gradients,
+ * torch.optim.Adam step (base_opt.py:524,581) on the small parameters and on the depth planes. */
+int a3r_ga_update(const A3rProblem *p, uint32_t mode, const A3rAdamStep *adam, void *stream);
+/* prepare + accumulate + update, `count` consecutive iterations (single-device loop of
+ * global_alignment_loop, base_opt.py:513-547).  steps/modes are host arrays of length count. */
+int a3r_ga_run(const A3rProblem *p, int32_t count, const uint32_t *modes, const A3rAdamStep *steps, void *stream);
+
+/* ---- read-out (reference optimizer.py:468-478 depth_to_pts3d) ----
+ * world points [n_local_frames][pix_stride][3] from logdepth + frame_par (call a3r_ga_prepare first) */
+int a3r_ga_unproject(const A3rProblem *p, float *pts3d, void *stream);
+
+/* ---- MST initialisation solves (reference init_im_poses.py:446-465, post_process.py:36-58) ---- */
+/* count weighted similarity registrations y ~ s R x + t between two slots living on the same frame:
+ * x = slot xs[k] (weights = raw conf = conf_untrf(w)), y = slot ys[k]; P[k] valid pixels.
+ * out [count][16] fp64: s, R(9 row-major), t(3), -.  xs/ys/P are device int32 arrays.
+ * sums [count][20] fp64 scratch. */
+int a3r_procrustes_batched(const float *predw, int64_t pix_stride, const int32_t *xs, const int32_t *ys,
+                           const int32_t *npix, int32_t count, int32_t conf_mode, double *sums, double *out,
+                           void *stream);
+/* count Weiszfeld focal estimates (closed-form L2 start + 10 IRLS steps) of slots sl[k] with image size
+ * hw[k] = (H, W) and principal point (W/2, H/2).  out_focal [count] fp64; sums [count][2] fp64 scratch. */
+int a3r_weiszfeld_focal_batched(const float *predw, int64_t pix_stride, const int32_t *sl, const int32_t *hw,
+                                int32_t count, double *sums, double *out_focal, void *stream);
+/* log-depth planes from transformed source slots (reference init_im_poses.py:138-142,
+ * optimizer.py:430-436): for local frame k, depth = row[k] . (X_src, 1) with row [k][4] fp64 and the
+ * source slot src[k]; writes logdepth (log, nan/-inf -> 0). */
+int a3r_init_depth(const float *predw, int64_t pix_stride, const int32_t *src, const int32_t *npix,
+                   const double *rows, int32_t n_local_frames, float *logdepth, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* A3R_GA_H */

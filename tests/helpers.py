@@ -1,0 +1,142 @@
+"""Shared test utilities: oracle import, CPU emulation harness of the kernel math, comparisons."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import ga_oracle as go          # noqa: E402
+from align3r_b200 import _lib               # noqa: E402
+from align3r_b200.plan import build_plan    # noqa: E402
+from align3r_b200.problem import ProblemBuffers, adam_schedule   # noqa: E402
+from align3r_b200.synth import make_scene, CANONICAL_KW          # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+TRAIN_ALL = dict(pw_poses=True, im_depthmaps=True, im_poses=True, im_focals=True, im_pp=False, pw_adaptors=False)
+
+
+def load_golden(name):
+    return torch.load(os.path.join(GOLDEN, f"{name}.pt"), weights_only=False)
+
+
+def scene_checksum(scene):
+    acc = 0.0
+    for t in (scene.pred1["pts3d"], scene.pred2["pts3d_in_other_view"], scene.pred1["conf"], scene.pred2["conf"]):
+        acc += float(t.double().sum())
+    if scene.flow_ij is not None:
+        acc += float(scene.flow_ij.double().sum()) + float(scene.flow_ji.double().sum())
+    return acc
+
+
+def golden_case(name):
+    """(fixture dict, regenerated scene, oracle problem)."""
+    fx = load_golden(name)
+    scene = make_scene(**fx["recipe"])
+    assert scene.edges == [tuple(e) for e in fx["edges"]]
+    assert abs(scene_checksum(scene) - fx["checksum"]) <= 1e-9 * abs(fx["checksum"]), "synthetic generator drifted"
+    prob = go.problem_from_output(scene.output, scene.flow_ij, scene.flow_ji, **fx["kw"])
+    return fx, scene, prob
+
+
+def rel_err(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-300))
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU emulation harness (tests/native/ga_emul.cpp): same per-element math as the CUDA kernels
+# ---------------------------------------------------------------------------------------------
+_EMUL = None
+
+
+def emul_lib():
+    global _EMUL
+    if _EMUL is not None:
+        return _EMUL
+    src = os.path.join(ROOT, "tests", "native", "ga_emul.cpp")
+    out_dir = os.path.join(ROOT, "tests", "native", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libga_emul.so")
+    deps = [src, os.path.join(ROOT, "align3r_b200", "csrc", "ga_math.cuh"), os.path.join(ROOT, "include", "a3r_ga.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off",
+               "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "align3r_b200", "csrc"), "-o", so, src]
+        subprocess.run(cmd, check=True)
+    lib = C.CDLL(so)
+    lib.emul_prepare.argtypes = [C.POINTER(_lib.A3rProblem)]
+    lib.emul_accumulate.argtypes = [C.POINTER(_lib.A3rProblem), C.c_uint32]
+    lib.emul_update.argtypes = [C.POINTER(_lib.A3rProblem), C.c_uint32, C.POINTER(_lib.A3rAdamStep)]
+    _EMUL = lib
+    return lib
+
+
+def hyper_from_problem(prob: go.OracleProblem):
+    return dict(shared_focal=prob.shared_focal, norm_pw_scale=prob.norm_pw_scale, dist=prob.dist,
+                focal_break=prob.focal_break, pw_break=prob.pw_break, base_scale=prob.base_scale,
+                flow_loss_weight=prob.flow_loss_weight, flow_loss_thre=prob.flow_loss_thre, pxl_thre=prob.pxl_thre,
+                temporal_smoothing_weight=prob.temporal_smoothing_weight, translation_weight=prob.translation_weight)
+
+
+def pack_on_host(bufs: ProblemBuffers, prob: go.OracleProblem):
+    """torch-CPU packing of the oracle problem into the kernel layout (the CUDA pack kernels' job)."""
+    plan = bufs.plan
+    wi, wj = prob.weights()
+    P = prob.P
+    lslot = plan.local_slot_of()
+    for e in range(prob.n_edges):
+        for side, (pts, w, fl) in enumerate(((prob.pred_i, wi, prob.flow_ij), (prob.pred_j, wj, prob.flow_ji))):
+            gs = 2 * e + side
+            if gs not in lslot:
+                continue
+            s = lslot[gs]
+            bufs.predw[s, :P, :3] = pts[e]
+            bufs.predw[s, :P, 3] = w[e]
+            if bufs.has_flow:
+                bufs.flow[s, :P, 0] = fl[e, 0].reshape(-1)
+                bufs.flow[s, :P, 1] = fl[e, 1].reshape(-1)
+    if bufs.has_flow:
+        for k, n in enumerate(plan.lframe_id.tolist()):
+            bufs.static_mask[k, :P] = (~prob.dynamic_masks[n]).reshape(-1).to(torch.uint8)
+
+
+def cpu_problem(prob: go.OracleProblem, params: dict, trainable=None, n_ctas=3, frame_range=None,
+                tile_pixels=1024, max_slots=32):
+    """ProblemBuffers on the CPU for the emulator.  params are copied (fp32)."""
+    H, W = prob.H, prob.W
+    plan = build_plan(prob.edges, [(H, W)] * prob.n_imgs, tile_pixels, max_slots, n_ctas, frame_range)
+    has_flow = prob.flow_ij is not None and prob.flow_loss_weight > 0
+    p = {k: v.detach().clone().float().contiguous() for k, v in params.items()}
+    depth = torch.zeros(plan.n_local_frames, plan.pix_stride)
+    depth[:, :prob.P] = p["im_depthmaps"][plan.lframe_id.tolist()]
+    p["im_depthmaps"] = depth
+    p["im_focals"] = p["im_focals"].reshape(-1).contiguous()
+    bufs = ProblemBuffers(plan, "cpu", p, hyper_from_problem(prob), has_flow)
+    pack_on_host(bufs, prob)
+    return bufs
+
+
+def emul_eval(bufs: ProblemBuffers, flow_active: bool, apply=False, lr=0.01, step=0, trainable=None):
+    """One evaluation through the emulator.  Returns (loss, grads dict, scal tensor)."""
+    lib = emul_lib()
+    trainable = trainable or TRAIN_ALL
+    st = bufs.struct(trainable)
+    mode = (_lib.M_FLOW_ACTIVE if flow_active else 0) | (_lib.M_APPLY_ADAM if apply else 0)
+    adam = adam_schedule([lr], start_step=step)
+    assert lib.emul_prepare(C.byref(st)) == 0
+    assert lib.emul_accumulate(C.byref(st), mode) == 0
+    assert lib.emul_update(C.byref(st), mode, adam) == 0
+    grads = {k: v.clone() for k, v in bufs.grads.items()}
+    grads["im_depthmaps"] = bufs.g_align.clone()
+    return float(bufs.scal[_lib.S_LOSS]), grads, bufs.scal.clone()
+
+
+def gather_depth(bufs: ProblemBuffers, t, P):
+    return t[:, :P]

@@ -1,0 +1,294 @@
+"""Parity of the CUDA path (through the drop-in Python class and the C ABI) against the reference fixtures
+and the CPU oracle.  Run on the B200 box:  python -m pytest tests -m gpu"""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import CANONICAL_KW, go, golden_case, make_scene, rel_err
+from align3r_b200 import _lib
+from align3r_b200.cloud_opt_flow import GlobalAlignerMode, global_aligner
+from align3r_b200.cloud_opt_flow import init_im_poses as init_fun
+from align3r_b200.problem import adam_schedule
+
+pytestmark = pytest.mark.gpu
+CASES = ["small_flow", "small_perframe_focal", "small_gate_trips"]
+FLOOR = 5e-5        # see tests/test_math_emulation.py: gradients are judged against the fp64 arbiter
+
+
+def build(scene, kw, **extra):
+    kw = dict(kw)
+    kw.update(extra)
+    flow = (scene.flow_ij, scene.flow_ji) if kw.get("flow_loss_weight", 0) > 0 else None
+    return global_aligner(scene.output, "cuda", mode=GlobalAlignerMode.PointCloudOptimizer, flow=flow, **kw)
+
+
+def set_params(net, params):
+    P = params["im_depthmaps"].shape[1]
+    with torch.no_grad():
+        for k, v in params.items():
+            if k == "im_depthmaps":
+                net.im_depthmaps.data[:, :P] = v[net._plan.lframe_id.tolist()].to(net.device)
+            else:
+                getattr(net, k).data.copy_(v.to(net.device).view_as(getattr(net, k)))
+
+
+def grads_of(net, P):
+    out = {}
+    for k in ("pw_poses", "im_depthmaps", "im_poses", "im_focals"):
+        g = getattr(net, k).grad
+        out[k] = (g[:, :P] if k == "im_depthmaps" else g).detach().cpu()
+    return out
+
+
+def test_native_library_is_the_one_running(cuda_device):
+    lib = _lib.load()
+    sm, major, minor = C.c_int(), C.c_int(), C.c_int()
+    assert lib.a3r_device_info(0, C.byref(sm), C.byref(major), C.byref(minor)) == 0
+    assert major.value >= 10, f"expected a Blackwell GPU, got sm_{major.value}{minor.value}"
+    assert "liba3r_ga.so" in open("/proc/self/maps").read()
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("tag", ["pre_flow", "flow"])
+def test_teacher_forced_loss_and_gradients(cuda_device, name, tag):
+    fx, scene, prob = golden_case(name)
+    g32, g64 = fx[f"tf32_{tag}"], fx[f"tf64_{tag}"]
+    net = build(scene, fx["kw"])
+    set_params(net, fx["init_params"])
+    loss = net(epoch=g32["epoch"])
+    loss.backward()
+    assert abs(float(loss) - float(g64["loss"])) <= 2e-6 * abs(float(g64["loss"]))
+    assert net.flow_loss_flag == g32["flow_dropped"]
+    mine = grads_of(net, prob.P)
+    for k in mine:
+        err, ref_err = rel_err(mine[k].reshape(g64["grads"][k].shape), g64["grads"][k]), rel_err(g32["grads"][k], g64["grads"][k])
+        assert err <= max(2 * ref_err, FLOOR), (k, err, ref_err)
+    # frozen parameters get no gradient
+    assert net.pw_adaptors.grad is None and net.im_pp.grad is None
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_adam_step(cuda_device, name):
+    fx, scene, prob = golden_case(name)
+    st = fx["adam_step"]
+    net = build(scene, fx["kw"])
+    set_params(net, fx["init_params"])
+    b = net._bufs
+    b.reset_adam()
+    mode = _lib.M_FLOW_ACTIVE | _lib.M_APPLY_ADAM
+    net._phase_accumulate(mode)
+    net._phase_update(mode, adam_schedule([st["lr"]], start_step=0, first_iter=0))
+    assert abs(float(b.loss_hist[0]) - st["loss"]) <= 2e-6 * abs(st["loss"])
+    lr = st["lr"]
+    for k in go.TRAINABLE:
+        mine = getattr(net, k).detach().cpu()
+        mine = mine[:, :prob.P] if k == "im_depthmaps" else mine.reshape(st["params"][k].shape)
+        d = (mine - st["params"][k]).abs()
+        assert float(d.max()) <= 2.0 * lr + 1e-6, k
+        assert float((d > 1e-5).float().mean()) < 0.02, (k, float((d > 1e-5).float().mean()))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_mst_initialisation(cuda_device, name):
+    fx, scene, prob = golden_case(name)
+    net = build(scene, fx["kw"])
+    init_fun.init_minimum_spanning_tree(net, niter_PnP=10)
+    ref = fx["init_params"]
+    # pairwise poses: compare the transforms they encode (quaternion sign is free)
+    T_ref = go.pw_pose_matrices(prob, ref["pw_poses"])
+    T = net.get_pw_poses().detach().cpu()
+    assert float((T - T_ref).abs().max()) < 5e-5
+    # image poses, focal, depth: frames initialised by RANSAC-PnP inherit its sensitivity to fp32 rounding
+    P_ref = go.poses_to_matrices(ref["im_poses"])
+    Pm = net.get_im_poses().detach().cpu()
+    assert float((Pm - P_ref).abs().max()) < 2e-3
+    f_ref = go.focals(prob, ref["im_focals"])
+    assert rel_err(net.get_focals().detach().cpu(), f_ref) < 1e-5
+    d = (net.im_depthmaps.detach().cpu()[:, :prob.P] - ref["im_depthmaps"]).abs()
+    assert float(d.median()) < 1e-5 and float(d.max()) < 2e-3
+    # and the loss right after the init is the reference's
+    loss0 = float(net(epoch=0))
+    assert abs(loss0 - float(fx["tf32_pre_flow"]["loss"])) <= 5e-4 * abs(float(fx["tf32_pre_flow"]["loss"]))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_free_running_alignment(cuda_device, name):
+    """The canonical call (init='mst', linear schedule) ends where the reference ends.
+    Tolerances: final loss 5e-4 relative, median |log-depth| difference 5e-4, camera matrices 5e-3."""
+    fx, scene, prob = golden_case(name)
+    net = build(scene, fx["kw"])
+    loss = net.compute_global_alignment(init='mst', niter=fx["niter"], schedule='linear', lr=0.01)
+    ref = fx["free_run"]
+    assert net.flow_loss_flag == ref["flow_dropped"]
+    assert abs(loss - ref["loss"]) <= 5e-4 * abs(ref["loss"])
+    d = (net.im_depthmaps.detach().cpu()[:, :prob.P] - ref["params"]["im_depthmaps"]).abs()
+    assert float(d.median()) < 5e-4
+    assert float((net.get_im_poses().detach().cpu() - ref["im_poses_4x4"]).abs().max()) < 5e-3
+    assert rel_err(net.get_focals().detach().cpu(), ref["focals"]) < 1e-3
+    # getters keep the reference's shapes
+    assert len(net.get_depthmaps()) == prob.n_imgs and net.get_depthmaps()[0].shape == (prob.H, prob.W)
+    assert net.get_pts3d()[0].shape == (prob.H, prob.W, 3) and net.get_intrinsics().shape == (prob.n_imgs, 3, 3)
+    tum, tt = net.get_tum_poses()
+    assert tum.shape == (prob.n_imgs, 7) and len(tt) == prob.n_imgs
+
+
+def test_pointmaps_and_getters_against_oracle(cuda_device):
+    fx, scene, prob = golden_case("small_flow")
+    net = build(scene, fx["kw"])
+    set_params(net, fx["init_params"])
+    world = go.unproject(prob, fx["init_params"])
+    mine = torch.stack([p.reshape(-1, 3) for p in net.get_pts3d()]).cpu()
+    assert float((mine - world).abs().max()) < 2e-5
+    K = go.intrinsics(prob, fx["init_params"]["im_focals"], fx["init_params"]["im_pp"])
+    assert torch.allclose(net.get_intrinsics().cpu(), K, rtol=1e-6, atol=1e-4)
+    assert torch.allclose(net.get_pw_scale().detach().cpu(), go.pw_scale(prob, fx["init_params"]["pw_poses"]), rtol=1e-5)
+    assert torch.allclose(torch.stack(net.get_depthmaps()).detach().cpu().reshape(prob.n_imgs, -1),
+                          fx["init_params"]["im_depthmaps"].exp(), rtol=1e-6)
+    # im_conf = max over incident edges of the raw confidences (reference base_opt.py:187-193)
+    conf = torch.zeros(prob.n_imgs, prob.P)
+    for e, (i, j) in enumerate(prob.edges):
+        conf[i] = torch.maximum(conf[i], prob.conf_i[e])
+        conf[j] = torch.maximum(conf[j], prob.conf_j[e])
+    assert torch.equal(torch.stack([c.reshape(-1) for c in net.im_conf]).cpu(), conf)
+    assert torch.equal(torch.stack(net.get_masks()).cpu().reshape(prob.n_imgs, -1), conf > 3)
+    assert torch.allclose(net.pred_i[net.str_edges[2]].cpu(), scene.pred1["pts3d"][2])
+    assert torch.allclose(net.conf_j[net.str_edges[1]].cpu(), scene.pred2["conf"][1], rtol=1e-6)
+
+
+@pytest.mark.parametrize("variant", ["l2", "adaptors_pp", "no_flow_masks_absent"])
+def test_medium_scene_against_live_oracle(cuda_device, variant):
+    """96x128, 8 frames, swin-3: several tiles per frame, every frame class of the sliding window."""
+    scene = make_scene(8, 96, 128, "swin-3-noncyclic", seed=21, with_flow=True)
+    kw = dict(CANONICAL_KW, num_total_iter=10, flow_loss_thre=0)
+    extra = {}
+    if variant == "l2":
+        kw["dist"] = "l2"
+    if variant == "adaptors_pp":
+        extra = dict(allow_pw_adaptors=True, optimize_pp=True)
+    if variant == "no_flow_masks_absent":
+        kw["flow_loss_weight"] = 0.0
+    prob = go.problem_from_output(scene.output, scene.flow_ij, scene.flow_ji, **kw)
+    params, _ = go.mst_init(prob)
+    g = torch.Generator().manual_seed(1)
+    names = list(go.TRAINABLE)
+    if variant == "adaptors_pp":
+        params["pw_adaptors"] = 0.3 * torch.randn(prob.n_edges, 2, generator=g)
+        params["im_pp"] = 0.2 * torch.randn(prob.n_imgs, 2, generator=g)
+        names += ["pw_adaptors", "im_pp"]
+    p64 = {k: v.double() for k, v in params.items()}
+    loss64, g64, _ = go.loss_and_grads(prob.to(torch.float64), p64, 9999, trainable=names)
+    _, g32, _ = go.loss_and_grads(prob, params, 9999, trainable=names)
+    net = build(scene, kw, **extra)
+    set_params(net, params)
+    loss = net(epoch=9999)
+    loss.backward()
+    assert abs(float(loss) - float(loss64)) <= 2e-6 * abs(float(loss64))
+    for k in names:
+        m = getattr(net, k).grad.detach().cpu()
+        m = m[:, :prob.P] if k == "im_depthmaps" else m.reshape(g64[k].shape)
+        err, ref_err = rel_err(m, g64[k]), rel_err(g32[k], g64[k])
+        assert err <= max(2 * ref_err, FLOOR), (k, err, ref_err)
+
+
+def test_split_work_frames_complete_graph(cuda_device):
+    """A complete graph over 18 frames puts 34 slots on every frame (> a3r_max_slots() = 32): frames are split
+    into work frames whose per-pixel gradients are added atomically."""
+    scene = make_scene(18, 16, 24, "complete", seed=4, with_flow=False)
+    kw = dict(CANONICAL_KW, flow_loss_weight=0.0)
+    prob = go.problem_from_output(scene.output, None, None, **kw)
+    g = torch.Generator().manual_seed(0)
+    E, N = prob.n_edges, prob.n_imgs
+    params = dict(pw_poses=0.3 * torch.randn(E, 8, generator=g), pw_adaptors=torch.zeros(E, 2),
+                  im_depthmaps=0.7 + 0.1 * torch.randn(N, prob.P, generator=g), im_poses=0.3 * torch.randn(N, 7, generator=g),
+                  im_focals=torch.tensor([[20 * math.log(20.0)]]), im_pp=torch.zeros(N, 2))
+    params["pw_poses"][:, 3] += 2
+    params["im_poses"][:, 3] += 2
+    net = build(scene, kw)
+    assert net._plan.n_work_frames == 2 * N
+    set_params(net, params)
+    loss = net(epoch=0)
+    loss.backward()
+    p64 = {k: v.double() for k, v in params.items()}
+    loss64, g64, _ = go.loss_and_grads(prob.to(torch.float64), p64, 0)
+    assert abs(float(loss) - float(loss64)) <= 2e-6 * abs(float(loss64))
+    mine = grads_of(net, prob.P)
+    for k in mine:
+        assert rel_err(mine[k].reshape(g64[k].shape), g64[k]) < 5e-4, k
+
+
+def test_rank_emulated_frame_window_sharding(cuda_device):
+    """Two frame-window shards driven from one process on one GPU (their accumulator blocks summed in-process
+    instead of by NCCL) take exactly the steps of the unsharded problem."""
+    fx, scene, prob = golden_case("small_flow")
+    kw = fx["kw"]
+    full = build(scene, kw)
+    shards = [build(scene, kw, shard=dict(world=2, rank=r, group=None)) for r in range(2)]
+    for net in [full] + shards:
+        set_params(net, fx["init_params"])
+        net._bufs.reset_adam()
+        net._reduce_accumulators = lambda: None
+    assert shards[0]._plan.n_local_frames + shards[1]._plan.n_local_frames == prob.n_imgs
+    mode = _lib.M_FLOW_ACTIVE | _lib.M_APPLY_ADAM
+    for it in range(3):
+        adam = adam_schedule([0.01], start_step=it, first_iter=it)
+        full._phase_accumulate(mode)
+        full._phase_update(mode, adam)
+        for net in shards:
+            net._phase_accumulate(mode)
+        total = shards[0]._bufs.acc + shards[1]._bufs.acc
+        for net in shards:
+            net._bufs.acc.copy_(total)
+            net._phase_update(mode, adam)
+    for it in range(3):
+        a, b0, b1 = (float(n._bufs.loss_hist[it]) for n in [full] + shards)
+        assert b0 == b1 and abs(a - b0) <= 1e-6 * abs(a)
+    for k in ("pw_poses", "im_poses", "im_focals"):
+        assert torch.equal(getattr(shards[0], k), getattr(shards[1], k)), k
+        assert torch.allclose(getattr(full, k), getattr(shards[0], k), rtol=0, atol=5e-6), k
+    depth = torch.cat([s.im_depthmaps.detach() for s in shards])
+    assert torch.allclose(depth, full.im_depthmaps.detach(), rtol=0, atol=5e-6)
+
+
+def test_full_size_properties_c2(cuda_device):
+    """BASELINE config C2 (50 frames, 288x512, swin-5, flow + temporal): size-independent properties."""
+    from align3r_b200.synth import CONFIGS
+    n, H, W, graph = CONFIGS["c2"]
+    scene = make_scene(n, H, W, graph, seed=0, with_flow=True)
+    kw = dict(CANONICAL_KW)
+    net = build(scene, kw)
+    assert net.n_edges == 470 and net._plan.pixel_slots() == 2 * 470 * H * W
+    net.compute_global_alignment(init='mst', niter=0)
+    l0 = float(net(epoch=0))
+    l0b = float(net(epoch=0))
+    assert abs(l0 - l0b) <= 1e-6 * abs(l0)                        # only the order of fp64 atomics may differ
+    lf = float(net(epoch=300))
+    assert math.isfinite(lf) and lf > l0 and not net.flow_loss_flag   # flow term adds a positive amount, gate stays open
+    # edge-order invariance: the same scene with its pair list reversed gives the same loss
+    perm = list(range(net.n_edges))[::-1]
+    out = scene.output
+    v1 = {k: ([v[p] for p in perm] if isinstance(v, list) else v[perm]) for k, v in out["view1"].items()}
+    v2 = {k: ([v[p] for p in perm] if isinstance(v, list) else v[perm]) for k, v in out["view2"].items()}
+    p1 = {k: v[perm] for k, v in out["pred1"].items()}
+    p2 = {k: v[perm] for k, v in out["pred2"].items()}
+    net2 = global_aligner(dict(view1=v1, view2=v2, pred1=p1, pred2=p2), "cuda", flow=(scene.flow_ij[perm], scene.flow_ji[perm]), **kw)
+    with torch.no_grad():
+        net2.pw_poses.data.copy_(net.pw_poses.data[perm])
+        for k in ("im_depthmaps", "im_poses", "im_focals"):
+            getattr(net2, k).data.copy_(getattr(net, k).data)
+    assert abs(float(net2(epoch=300)) - lf) <= 1e-6 * abs(lf)
+    del net2
+    # the optimisation makes progress and ends with sane geometry
+    final = net.compute_global_alignment(init=None, niter=60, schedule='linear', lr=0.01)
+    hist = net._bufs.loss_hist[:60].cpu()
+    assert math.isfinite(final) and float(hist[5]) < float(hist[0]) and float(hist[:6].max()) < 1.01 * float(hist[0])
+    depth = torch.stack(net.get_depthmaps()).detach()
+    assert bool(torch.isfinite(depth).all()) and float(depth.min()) > 0
+    gt_depth = torch.stack([scene.gt.depth(k) for k in range(n)]).float()
+    dm = go.depth_metrics(depth.cpu().numpy()[::5], gt_depth.numpy()[::5])
+    assert dm["abs_rel"] < 0.05 and dm["d1"] > 0.97, dm
+    pm = go.pose_metrics(net.get_im_poses().detach().cpu().numpy(), scene.gt.cam2world)
+    assert pm["ate"] < 0.05 and pm["rpe_rot"] < 1.0, pm

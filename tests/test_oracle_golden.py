@@ -1,0 +1,81 @@
+"""The CPU oracle (oracle/ga_oracle.py) against fixtures produced by the REAL reference
+(oracle/make_golden.py -> tests/golden/*.pt).  This is what pins the oracle."""
+import pytest
+import torch
+
+from tests.helpers import go, golden_case, rel_err
+
+CASES = ["small_flow", "small_perframe_focal", "small_gate_trips"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_mst_init_matches_reference(name):
+    fx, scene, prob = golden_case(name)
+    params, info = go.mst_init(prob)
+    for k, ref in fx["init_params"].items():
+        assert params[k].shape == ref.shape, k
+        # same algorithm, same op order on the same machine class -> tight
+        assert torch.allclose(params[k], ref, rtol=1e-5, atol=1e-6), (k, float((params[k] - ref).abs().max()))
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("tag", ["pre_flow", "flow"])
+def test_teacher_forced_loss_and_grads(name, tag):
+    fx, scene, prob = golden_case(name)
+    g32, g64 = fx[f"tf32_{tag}"], fx[f"tf64_{tag}"]
+    loss, grads, info = go.loss_and_grads(prob, fx["init_params"], g32["epoch"])
+    assert info["flow_dropped"] == g32["flow_dropped"]
+    assert abs(float(loss) - float(g32["loss"])) <= 1e-6 * abs(float(g32["loss"]))
+    for k, ref in g32["grads"].items():
+        # fp32 vs fp32 with a different op order: bounded by the reference's own fp32 noise floor
+        noise = rel_err(ref, g64["grads"][k])
+        assert rel_err(grads[k], ref) <= max(2 * noise, 1e-5), k
+    # fp64 arbiter
+    p64 = {k: v.double() for k, v in fx["init_params"].items()}
+    loss64, grads64, _ = go.loss_and_grads(prob.to(torch.float64), p64, g64["epoch"])
+    assert abs(float(loss64) - float(g64["loss"])) <= 1e-10 * abs(float(g64["loss"]))
+    for k, ref in g64["grads"].items():
+        assert rel_err(grads64[k], ref) <= 1e-9, k
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_adam_step_matches_reference(name):
+    fx, scene, prob = golden_case(name)
+    st = fx["adam_step"]
+    p = {k: v.clone().requires_grad_(k in go.TRAINABLE) for k, v in fx["init_params"].items()}
+    opt = torch.optim.Adam([p[k] for k in go.TRAINABLE], lr=0.01, betas=(0.9, 0.9))
+    lr = go.lr_schedule("linear", st["epoch"] / fx["niter"], 0.01, 1e-3)
+    assert abs(lr - st["lr"]) < 1e-15
+    for g in opt.param_groups:
+        g["lr"] = lr
+    loss, _ = go.total_loss(prob, p, st["epoch"])
+    loss.backward()
+    opt.step()
+    assert abs(float(loss) - st["loss"]) <= 1e-6 * abs(st["loss"])
+    for k in go.TRAINABLE:
+        # Adam's first step moves every entry by ~lr*sign(g): entries whose gradient is fp32 noise may flip
+        d = (p[k].detach() - st["params"][k]).abs()
+        assert float(d.max()) <= 2.0 * lr + 1e-6, k
+        assert float((d > 1e-5).float().mean()) < 0.02, (k, float((d > 1e-5).float().mean()))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_free_run_matches_reference(name):
+    fx, scene, prob = golden_case(name)
+    params, _ = go.mst_init(prob)
+    final, losses, dropped = go.run_alignment(prob, params, niter=fx["niter"], schedule="linear", lr=0.01)
+    ref = fx["free_run"]
+    assert dropped == ref["flow_dropped"]
+    assert abs(losses[-1] - ref["loss"]) <= 1e-4 * abs(ref["loss"])
+    assert float((final["im_depthmaps"] - ref["params"]["im_depthmaps"]).abs().median()) < 1e-4
+    T = go.poses_to_matrices(final["im_poses"])
+    assert float((T - ref["im_poses_4x4"]).abs().max()) < 1e-3
+
+
+def test_schedules():
+    assert go.lr_schedule("linear", 0.0, 0.01, 1e-3) == 0.01
+    assert abs(go.lr_schedule("linear", 1.0, 0.01, 1e-3) - 1e-3) < 1e-18
+    assert abs(go.lr_schedule("cosine", 0.5, 0.01, 1e-3) - (1e-3 + 0.009 * 0.5)) < 1e-12
+    assert abs(go.lr_schedule("cycle2", 0.25, 0.01, 1e-3) - go.lr_schedule("linear", 0.5, 0.01, 1e-3)) < 1e-15
+    with pytest.raises(ValueError):
+        go.lr_schedule("nope", 0.1, 0.01, 1e-3)
