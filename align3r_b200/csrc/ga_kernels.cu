@@ -216,8 +216,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k_accumulate_v1(const A3rProble
             const int v = pix / W, u = pix - v * W;
             PixState s;
             pixel_state(sh.fp, ld, u, v, s);
-            // d z / d logdepth = R c = z - t
-            const float ga = gsx[j] * (s.zx - sh.fp[FP_T + 0]) + gsy[j] * (s.zy - sh.fp[FP_T + 1]) + gsz[j] * (s.zz - sh.fp[FP_T + 2]);
+            const float ga = pixel_epilogue(sh.fp, s, gsx[j], gsy[j], gsz[j], facc);
             if (accum) {
                 atomicAdd(&p.g_align[pix_base + pix], ga);
                 if (FLOW) {
@@ -231,10 +230,6 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k_accumulate_v1(const A3rProble
                     p.g_flow_j[pix_base + pix] = gfj[j] * s.dfac;
                 }
             }
-            facc[FACC_G + 0] += gsx[j]; facc[FACC_G + 1] += gsy[j]; facc[FACC_G + 2] += gsz[j];
-            facc[FACC_GC + 0] = fmaf(gsx[j], s.cx, facc[FACC_GC + 0]); facc[FACC_GC + 1] = fmaf(gsx[j], s.cy, facc[FACC_GC + 1]); facc[FACC_GC + 2] = fmaf(gsx[j], s.cz, facc[FACC_GC + 2]);
-            facc[FACC_GC + 3] = fmaf(gsy[j], s.cx, facc[FACC_GC + 3]); facc[FACC_GC + 4] = fmaf(gsy[j], s.cy, facc[FACC_GC + 4]); facc[FACC_GC + 5] = fmaf(gsy[j], s.cz, facc[FACC_GC + 5]);
-            facc[FACC_GC + 6] = fmaf(gsz[j], s.cx, facc[FACC_GC + 6]); facc[FACC_GC + 7] = fmaf(gsz[j], s.cy, facc[FACC_GC + 7]); facc[FACC_GC + 8] = fmaf(gsz[j], s.cz, facc[FACC_GC + 8]);
         }
     }
     flush();

@@ -29,7 +29,9 @@ enum : int {
     ACC_N = 27,
     ACC_STRIDE = 28
 };
-// per-frame accumulators (A3R_FRAME_ACC = 12): sum gsum (3), sum gsum c^T (9)
+// per-frame accumulators (A3R_FRAME_ACC = 12), in the CAMERA frame: with h = R^T gsum (gsum = sum over the
+// pixel's slots of dL/dz): sum h (3), sum h c^T (9).  The focal / principal-point gradients are single entries
+// of sum h c^T (no cancellation between separately rounded sums).
 enum : int { FACC_G = 0, FACC_GC = 3, FACC_N = 12 };
 // frame_grad scratch rows (16 doubles): dL/dR (9), dL/dt (3), dL/df, dL/dcx, dL/dcy
 enum : int { FG_R = 0, FG_T = 9, FG_F = 12, FG_CX = 13, FG_CY = 14, FG_STRIDE = 16 };
@@ -213,17 +215,16 @@ A3R_HD void rel_chain(const FrameD& S, const FrameD& T, const double GrelR[9], c
     }
 }
 
-// per-frame gradient of the alignment term from the frame accumulators (sum gsum, sum gsum c^T)
+// per-frame gradient of the alignment term from the frame accumulators (sum h, sum h c^T; h = R^T gsum):
+// z = R c + t  =>  dL/dR = R (sum h c^T), dL/dt = R sum h;  c = d ((u-cx)/f, (v-cy)/f, 1)  =>
+// dL/df = -(H00 + H11)/f, dL/dcx = -H02/f, dL/dcy = -H12/f
 A3R_HD void frame_align_grad(const FrameD& F, const double* a, double* fg) {
-    for (int k = 0; k < 9; ++k) fg[FG_R + k] = a[FACC_GC + k];
-    for (int k = 0; k < 3; ++k) fg[FG_T + k] = a[FACC_G + k];
-    double gf = 0, gcx = 0, gcy = 0;
+    const double* H = a + FACC_GC;
     for (int m = 0; m < 3; ++m) {
-        gf += F.R[m * 3] * a[FACC_GC + m * 3] + F.R[m * 3 + 1] * a[FACC_GC + m * 3 + 1];
-        gcx += F.R[m * 3] * a[FACC_GC + m * 3 + 2];
-        gcy += F.R[m * 3 + 1] * a[FACC_GC + m * 3 + 2];
+        for (int k = 0; k < 3; ++k) fg[FG_R + m * 3 + k] = F.R[m * 3] * H[k] + F.R[m * 3 + 1] * H[3 + k] + F.R[m * 3 + 2] * H[6 + k];
+        fg[FG_T + m] = F.R[m * 3] * a[FACC_G] + F.R[m * 3 + 1] * a[FACC_G + 1] + F.R[m * 3 + 2] * a[FACC_G + 2];
     }
-    fg[FG_F] = -gf / F.f; fg[FG_CX] = -gcx / F.f; fg[FG_CY] = -gcy / F.f; fg[15] = 0;
+    fg[FG_F] = -(H[0] + H[4]) / F.f; fg[FG_CX] = -H[2] / F.f; fg[FG_CY] = -H[5] / F.f; fg[15] = 0;
 }
 
 // flow chain of one slot (src S -> tgt T): G_A, G_b (already scaled by flow_weight / count) ->
@@ -370,6 +371,18 @@ A3R_HD void pixel_state(const float* fp, float logd, int u, int v, PixState& s) 
     const float de = d + 1e-6f;
     s.disp = 1.0f / de;
     s.dfac = -d * s.disp * s.disp;
+}
+
+// per-pixel epilogue of the scan: h = R^T gsum; d L_align / d logdepth = gsum . (R c) = h . c; frame sums
+A3R_HD float pixel_epilogue(const float* fp, const PixState& s, float gsx, float gsy, float gsz, float* facc) {
+    const float hx = fp[FP_R + 0] * gsx + fp[FP_R + 3] * gsy + fp[FP_R + 6] * gsz;
+    const float hy = fp[FP_R + 1] * gsx + fp[FP_R + 4] * gsy + fp[FP_R + 7] * gsz;
+    const float hz = fp[FP_R + 2] * gsx + fp[FP_R + 5] * gsy + fp[FP_R + 8] * gsz;
+    facc[FACC_G + 0] += hx; facc[FACC_G + 1] += hy; facc[FACC_G + 2] += hz;
+    facc[FACC_GC + 0] = fmaf(hx, s.cx, facc[FACC_GC + 0]); facc[FACC_GC + 1] = fmaf(hx, s.cy, facc[FACC_GC + 1]); facc[FACC_GC + 2] = fmaf(hx, s.cz, facc[FACC_GC + 2]);
+    facc[FACC_GC + 3] = fmaf(hy, s.cx, facc[FACC_GC + 3]); facc[FACC_GC + 4] = fmaf(hy, s.cy, facc[FACC_GC + 4]); facc[FACC_GC + 5] = fmaf(hy, s.cz, facc[FACC_GC + 5]);
+    facc[FACC_GC + 6] = fmaf(hz, s.cx, facc[FACC_GC + 6]); facc[FACC_GC + 7] = fmaf(hz, s.cy, facc[FACC_GC + 7]); facc[FACC_GC + 8] = fmaf(hz, s.cz, facc[FACC_GC + 8]);
+    return hx * s.cx + hy * s.cy + hz * s.cz;
 }
 
 // constants of one slot as the accumulate kernel wants them

@@ -140,3 +140,25 @@ def emul_eval(bufs: ProblemBuffers, flow_active: bool, apply=False, lr=0.01, ste
 
 def gather_depth(bufs: ProblemBuffers, t, P):
     return t[:, :P]
+
+
+# ---------------------------------------------------------------------------------------------
+# gradient parity criterion (hard part 1)
+# ---------------------------------------------------------------------------------------------
+GRAD_FLOOR = 5e-5
+FOCAL_ABS_FLOOR = 3e-8
+
+
+def grad_close(name, mine, g32, g64):
+    """Gradients are judged against the reference's fp64 gradients (the arbiter).  The reference's own fp32
+    gradients sit 2e-5 (depth) ... 8e-4 (focal) away from them, so a bare "1e-5 relative to the fp32 reference"
+    is below the reference's rounding noise.  Accepted: relative L2 error no worse than 3x the reference's own
+    fp32 error, or 5e-5.  The focal gradient is one scalar made of large cancelling sums (the target-side and
+    source-side parts of the flow homography cancel to the rotation angle): both implementations carry an
+    absolute fp32 forward-noise floor of ~1e-8 there, so it additionally passes on |err| <= 3e-8."""
+    mine, g32, g64 = mine.double().reshape(-1), g32.double().reshape(-1), g64.double().reshape(-1)
+    err, ref = rel_err(mine, g64), rel_err(g32, g64)
+    ok = err <= max(3 * ref, GRAD_FLOOR)
+    if not ok and name == "im_focals":
+        ok = float((mine - g64).abs().max()) <= max(4 * float((g32 - g64).abs().max()), FOCAL_ABS_FLOOR)
+    return ok, err, ref

@@ -90,17 +90,15 @@ extern "C" int emul_accumulate(const A3rProblem* p, uint32_t mode) {
                 double* a = p->acc_slot + (int64_t)gs * ACC_STRIDE;
                 for (int k = 0; k < ACC_N; ++k) a[k] += (double)acc[k];
             }
-            p->g_align[base + pix] += gsx * (st.zx - fp[FP_T]) + gsy * (st.zy - fp[FP_T + 1]) + gsz * (st.zz - fp[FP_T + 2]);
+            float fa32[FACC_N];
+            for (int k = 0; k < FACC_N; ++k) fa32[k] = 0.f;
+            p->g_align[base + pix] += pixel_epilogue(fp, st, gsx, gsy, gsz, fa32);
             if (flow) {
                 p->g_flow_i[base + pix] += gfi * st.dfac;
                 p->g_flow_j[base + pix] += gfj * st.dfac;
             }
             double* fa = p->acc_frame + (int64_t)n * FACC_N;
-            const float g[3] = {gsx, gsy, gsz}, cc[3] = {st.cx, st.cy, st.cz};
-            for (int r = 0; r < 3; ++r) {
-                fa[FACC_G + r] += (double)g[r];
-                for (int c = 0; c < 3; ++c) fa[FACC_GC + r * 3 + c] += (double)(g[r] * cc[c]);
-            }
+            for (int k = 0; k < FACC_N; ++k) fa[k] += (double)fa32[k];
         }
     }
     return 0;

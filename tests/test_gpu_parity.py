@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.helpers import CANONICAL_KW, go, golden_case, make_scene, rel_err
+from tests.helpers import CANONICAL_KW, go, golden_case, grad_close, make_scene, rel_err
 from align3r_b200 import _lib
 from align3r_b200.cloud_opt_flow import GlobalAlignerMode, global_aligner
 from align3r_b200.cloud_opt_flow import init_im_poses as init_fun
@@ -16,7 +16,6 @@ from align3r_b200.problem import adam_schedule
 
 pytestmark = pytest.mark.gpu
 CASES = ["small_flow", "small_perframe_focal", "small_gate_trips"]
-FLOOR = 5e-5        # see tests/test_math_emulation.py: gradients are judged against the fp64 arbiter
 
 
 def build(scene, kw, **extra):
@@ -61,12 +60,12 @@ def test_teacher_forced_loss_and_gradients(cuda_device, name, tag):
     set_params(net, fx["init_params"])
     loss = net(epoch=g32["epoch"])
     loss.backward()
-    assert abs(float(loss) - float(g64["loss"])) <= 2e-6 * abs(float(g64["loss"]))
+    assert abs(float(loss.detach()) - float(g64["loss"])) <= 2e-6 * abs(float(g64["loss"]))
     assert net.flow_loss_flag == g32["flow_dropped"]
     mine = grads_of(net, prob.P)
     for k in mine:
-        err, ref_err = rel_err(mine[k].reshape(g64["grads"][k].shape), g64["grads"][k]), rel_err(g32["grads"][k], g64["grads"][k])
-        assert err <= max(2 * ref_err, FLOOR), (k, err, ref_err)
+        ok, err, ref_err = grad_close(k, mine[k], g32["grads"][k], g64["grads"][k])
+        assert ok, (k, err, ref_err)
     # frozen parameters get no gradient
     assert net.pw_adaptors.grad is None and net.im_pp.grad is None
 
@@ -116,19 +115,38 @@ def test_mst_initialisation(cuda_device, name):
 
 
 @pytest.mark.parametrize("name", CASES)
+def test_free_running_loop_from_reference_init(cuda_device, name):
+    """From the reference's own MST initialisation the loop (niter iterations of K0-K3) ends where the reference
+    ends: final loss 2e-5 relative, median |log-depth| difference 2e-6, camera matrices 2e-5."""
+    fx, scene, prob = golden_case(name)
+    net = build(scene, fx["kw"])
+    set_params(net, fx["init_params"])
+    loss = net.compute_global_alignment(init=None, niter=fx["niter"], schedule='linear', lr=0.01)
+    ref = fx["free_run"]
+    assert net.flow_loss_flag == ref["flow_dropped"]
+    assert abs(loss - ref["loss"]) <= 2e-5 * abs(ref["loss"])
+    d = (net.im_depthmaps.detach().cpu()[:, :prob.P] - ref["params"]["im_depthmaps"]).abs()
+    assert float(d.median()) < 2e-6
+    assert float((net.get_im_poses().detach().cpu() - ref["im_poses_4x4"]).abs().max()) < 2e-5
+    assert rel_err(net.get_focals().detach().cpu(), ref["focals"]) < 2e-5
+
+
+@pytest.mark.parametrize("name", CASES)
 def test_free_running_alignment(cuda_device, name):
-    """The canonical call (init='mst', linear schedule) ends where the reference ends.
-    Tolerances: final loss 5e-4 relative, median |log-depth| difference 5e-4, camera matrices 5e-3."""
+    """The canonical call (init='mst', linear schedule).  Our MST initialisation differs from the reference's by
+    fp32 rounding (~5e-7, different summation order); Adam's sign-like first steps amplify that on parameters
+    whose gradient starts near zero (hard part 3), so the end state is compared with the
+    stated end-state tolerances: final loss 2e-3 relative, median |log-depth| difference 2e-3, cameras 1e-2."""
     fx, scene, prob = golden_case(name)
     net = build(scene, fx["kw"])
     loss = net.compute_global_alignment(init='mst', niter=fx["niter"], schedule='linear', lr=0.01)
     ref = fx["free_run"]
     assert net.flow_loss_flag == ref["flow_dropped"]
-    assert abs(loss - ref["loss"]) <= 5e-4 * abs(ref["loss"])
+    assert abs(loss - ref["loss"]) <= 2e-3 * abs(ref["loss"])
     d = (net.im_depthmaps.detach().cpu()[:, :prob.P] - ref["params"]["im_depthmaps"]).abs()
-    assert float(d.median()) < 5e-4
-    assert float((net.get_im_poses().detach().cpu() - ref["im_poses_4x4"]).abs().max()) < 5e-3
-    assert rel_err(net.get_focals().detach().cpu(), ref["focals"]) < 1e-3
+    assert float(d.median()) < 2e-3
+    assert float((net.get_im_poses().detach().cpu() - ref["im_poses_4x4"]).abs().max()) < 1e-2
+    assert rel_err(net.get_focals().detach().cpu(), ref["focals"]) < 5e-3
     # getters keep the reference's shapes
     assert len(net.get_depthmaps()) == prob.n_imgs and net.get_depthmaps()[0].shape == (prob.H, prob.W)
     assert net.get_pts3d()[0].shape == (prob.H, prob.W, 3) and net.get_intrinsics().shape == (prob.n_imgs, 3, 3)
@@ -186,12 +204,12 @@ def test_medium_scene_against_live_oracle(cuda_device, variant):
     set_params(net, params)
     loss = net(epoch=9999)
     loss.backward()
-    assert abs(float(loss) - float(loss64)) <= 2e-6 * abs(float(loss64))
+    assert abs(float(loss.detach()) - float(loss64)) <= 2e-6 * abs(float(loss64))
     for k in names:
         m = getattr(net, k).grad.detach().cpu()
         m = m[:, :prob.P] if k == "im_depthmaps" else m.reshape(g64[k].shape)
-        err, ref_err = rel_err(m, g64[k]), rel_err(g32[k], g64[k])
-        assert err <= max(2 * ref_err, FLOOR), (k, err, ref_err)
+        ok, err, ref_err = grad_close(k, m, g32[k], g64[k])
+        assert ok, (k, err, ref_err)
 
 
 def test_split_work_frames_complete_graph(cuda_device):
@@ -214,7 +232,7 @@ def test_split_work_frames_complete_graph(cuda_device):
     loss.backward()
     p64 = {k: v.double() for k, v in params.items()}
     loss64, g64, _ = go.loss_and_grads(prob.to(torch.float64), p64, 0)
-    assert abs(float(loss) - float(loss64)) <= 2e-6 * abs(float(loss64))
+    assert abs(float(loss.detach()) - float(loss64)) <= 2e-6 * abs(float(loss64))
     mine = grads_of(net, prob.P)
     for k in mine:
         assert rel_err(mine[k].reshape(g64[k].shape), g64[k]) < 5e-4, k
