@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SOURCES = ["a3r_common.cu", "ga_kernels.cu", "mst_kernels.cu"]
-HEADERS = ["a3r_common.cuh", "ga_math.cuh"]
+HEADERS = ["a3r_common.cuh", "ga_math.cuh", "ga_scan_v2.cuh"]
 
 
 def lib_path():

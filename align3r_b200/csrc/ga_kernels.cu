@@ -9,6 +9,8 @@
 #include "a3r_ga.h"
 #include "ga_math.cuh"
 #include "a3r_common.cuh"
+#include "ga_scan_v2.cuh"
+#include <stdlib.h>
 
 using namespace a3r;
 
@@ -483,9 +485,22 @@ __global__ void __launch_bounds__(256) k_pack_flow(const float* __restrict__ src
 // ==========================================================================================
 // C ABI
 // ==========================================================================================
+// Scan kernel variant: v2 (TMA-fed, warp-owns-slot) is the product path; A3R_SCAN=v1 selects the simple
+// thread-owns-pixels kernel, kept as an on-device cross-check of v2.
+static int scan_variant() {
+    static int v = [] {
+        const char* e = getenv("A3R_SCAN");
+        return (e && e[0] == 'v' && e[1] == '1') ? 1 : 2;
+    }();
+    return v;
+}
+static int scan_tile() { return scan_variant() == 1 ? K1_TILE : V2_T; }
+static int scan_slots() { return scan_variant() == 1 ? K1_MAXS : V2_SLOTS; }
+
 static int check_problem(const A3rProblem* p) {
     if (!p) return a3r_fail(A3R_E_ARG, "problem is NULL");
-    if (p->tile_pixels != K1_TILE) return a3r_fail(A3R_E_ARG, "tile_pixels %d != a3r_tile_pixels() %d", p->tile_pixels, K1_TILE);
+    if (p->tile_pixels != scan_tile()) return a3r_fail(A3R_E_ARG, "tile_pixels %d != a3r_tile_pixels() %d", p->tile_pixels, scan_tile());
+    if (p->pix_stride % scan_tile() != 0) return a3r_fail(A3R_E_ARG, "pix_stride must be a multiple of a3r_tile_pixels()");
     if (p->n_frames <= 0 || p->n_edges <= 0 || p->n_local_frames < 0 || p->n_ctas <= 0)
         return a3r_fail(A3R_E_ARG, "bad sizes N=%d E=%d local=%d ctas=%d", p->n_frames, p->n_edges, p->n_local_frames, p->n_ctas);
     if (p->pix_stride % 4 != 0) return a3r_fail(A3R_E_ARG, "pix_stride must be a multiple of 4");
@@ -496,13 +511,23 @@ static int check_problem(const A3rProblem* p) {
 
 template <bool FLOW, bool L2D>
 static int launch_accumulate(const A3rProblem* p, cudaStream_t st) {
-    const size_t smem = sizeof(double) * K1_WARPS * K1_MAXS * ACC_STRIDE + sizeof(K1Shared);
-    static bool configured = false;   // per template instantiation
-    if (!configured) {
-        A3R_CUDA(cudaFuncSetAttribute(k_accumulate_v1<FLOW, L2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+    if (scan_variant() == 1) {
+        const size_t smem = sizeof(double) * K1_WARPS * K1_MAXS * ACC_STRIDE + sizeof(K1Shared);
+        static bool configured = false;   // per template instantiation
+        if (!configured) {
+            A3R_CUDA(cudaFuncSetAttribute(k_accumulate_v1<FLOW, L2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = true;
+        }
+        k_accumulate_v1<FLOW, L2D><<<p->n_ctas, K1_THREADS, smem, st>>>(*p);
+    } else {
+        const size_t smem = sizeof(V2Smem);
+        static bool configured = false;
+        if (!configured) {
+            A3R_CUDA(cudaFuncSetAttribute(k_accumulate_v2<FLOW, L2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = true;
+        }
+        k_accumulate_v2<FLOW, L2D><<<p->n_ctas, V2_THREADS, smem, st>>>(*p);
     }
-    k_accumulate_v1<FLOW, L2D><<<p->n_ctas, K1_THREADS, smem, st>>>(*p);
     A3R_CUDA(cudaGetLastError());
     return A3R_OK;
 }
@@ -511,8 +536,8 @@ extern "C" {
 
 int a3r_abi_version(void) { return A3R_ABI_VERSION; }
 const char* a3r_last_error(void) { return a3r_error_buffer(); }
-int a3r_tile_pixels(void) { return K1_TILE; }
-int a3r_max_slots(void) { return K1_MAXS; }
+int a3r_tile_pixels(void) { return scan_tile(); }
+int a3r_max_slots(void) { return scan_slots(); }
 
 int a3r_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
     cudaDeviceProp prop;
@@ -526,7 +551,7 @@ int a3r_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
 int a3r_max_ctas(int device) {
     int sm = 0;
     if (a3r_device_info(device, &sm, nullptr, nullptr) != A3R_OK) return A3R_E_CUDA;
-    return sm * 2;
+    return scan_variant() == 1 ? sm * 2 : sm;      // v1: 2 resident CTAs per SM; v2: one persistent CTA per SM
 }
 
 int a3r_pack_pred(const float* pts, const float* conf, int32_t n, int64_t P, const int32_t* dst_slot,

@@ -52,8 +52,8 @@ def test_high_degree_frames_are_split_into_work_frames():
 
 
 def test_ragged_and_tiny_inputs():
-    pl = build_plan([(0, 1), (1, 0)], [(3, 5), (4, 4)], 1024, 32, 4)
-    assert pl.pix_stride == 16 and pl.n_tiles == 2
+    pl = build_plan([(0, 1), (1, 0)], [(3, 5), (4, 4)], 8, 32, 4)
+    assert pl.pix_stride == 16 and pl.n_tiles == 4          # planes are padded to whole tiles
     assert pl.total_area_i == 15 + 16 and pl.total_area_j == 16 + 15
     with pytest.raises(AssertionError):
         check_edges([(0, 2)])                      # reference base_opt.py:184: indices must be contiguous
