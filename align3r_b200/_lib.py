@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "liba3r_ga.so")
+LIB_PATH = os.environ.get("A3R_LIB") or os.path.join(HERE, "lib", "liba3r_ga.so")   # A3R_LIB: tuning builds
 ABI_VERSION = 3
 
 # A3rProblem.flags

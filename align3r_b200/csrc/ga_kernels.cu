@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k_accumulate_v1(const A3rProble
 
     int wf = 0;
     while (t0 >= p.wf_tile_begin[wf + 1]) ++wf;
+    const float thre_eff = flow_thre_eff(p.pxl_thre);
     int cur_wf = -1, lf = 0, n = 0, P = 0, W = 1, deg = 0, s_begin = 0, accum = 0;
     float facc[FACC_N];
 #pragma unroll
@@ -193,10 +194,12 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k_accumulate_v1(const A3rProble
             for (int j = 0; j < K1_PPT; ++j) {
                 PixState st;
                 st.zx = zx[j]; st.zy = zy[j]; st.zz = zz[j]; st.u = pu[j]; st.v = pv[j]; st.disp = disp[j];
-                align_px<L2D>(c, X[j].x, X[j].y, X[j].z, X[j].w, st, acc, gsx[j], gsy[j], gsz[j]);
+                float gx, gy, gz;
+                align_px<L2D>(c, X[j].x, X[j].y, X[j].z, X[j].w, st, acc, gx, gy, gz);
+                gsx[j] += gx; gsy[j] += gy; gsz[j] += gz;
                 if (FLOW) {
                     if (stat[j]) {
-                        const float gd = flow_px(c, st, F[j].x, F[j].y, p.pxl_thre, acc);
+                        const float gd = flow_px(c, st, F[j].x, F[j].y, thre_eff, true, acc);
                         if (side_j) gfj[j] += gd; else gfi[j] += gd;
                     }
                 }

@@ -42,16 +42,22 @@ enum : int { EP_M = 0, EP_ST = 9, EP_S = 12, EP_A = 13, EP_STRIDE = 16 };
 // slot_par rows (16 floats): A (9), b (3)
 enum : int { SP_A = 0, SP_B = 9, SP_STRIDE = 16 };
 
+// single-MUFU reciprocal square root / reciprocal (flush-to-zero, ~1 ulp): the scan is issue-bound, the
+// IEEE-denormal fix-up sequences of rsqrtf()/__fdividef() cost 4-5 extra instructions per call
 A3R_HD float fast_rsqrt(float x) {
 #if defined(__CUDA_ARCH__)
-    return rsqrtf(x);
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 #else
     return 1.0f / sqrtf(x);
 #endif
 }
 A3R_HD float fast_rcp(float x) {
 #if defined(__CUDA_ARCH__)
-    return __fdividef(1.0f, x);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 #else
     return 1.0f / x;
 #endif
@@ -394,10 +400,10 @@ struct SlotConst {
     float wn;        // 1 / total_area of this side's class
 };
 
-// alignment residual of one pixel-slot: updates acc[ACC_SG..ACC_LOSS] and the pixel's gsum
+// alignment residual of one pixel-slot: updates acc[ACC_SG..ACC_LOSS], returns the pixel-slot's g = dL/dz
 template <bool L2DIST>
 A3R_HD void align_px(const SlotConst& c, float X0, float X1, float X2, float w, const PixState& s,
-                     float* acc, float& gsx, float& gsy, float& gsz) {
+                     float* acc, float& gx, float& gy, float& gz) {
     const float w2 = w * c.wn;
     float rx = s.zx - c.st[0], ry = s.zy - c.st[1], rz = s.zz - c.st[2];
     rx = fmaf(c.nM[0], X0, fmaf(c.nM[1], X1, fmaf(c.nM[2], X2, rx)));
@@ -413,17 +419,21 @@ A3R_HD void align_px(const SlotConst& c, float X0, float X1, float X2, float w, 
         acc[ACC_LOSS] = fmaf(w2, r2 * inv, acc[ACC_LOSS]);
         k = w2 * inv;
     }
-    const float gx = k * rx, gy = k * ry, gz = k * rz;
+    gx = k * rx; gy = k * ry; gz = k * rz;
     acc[ACC_SG + 0] += gx; acc[ACC_SG + 1] += gy; acc[ACC_SG + 2] += gz;
     acc[ACC_SGX + 0] = fmaf(gx, X0, acc[ACC_SGX + 0]); acc[ACC_SGX + 1] = fmaf(gx, X1, acc[ACC_SGX + 1]); acc[ACC_SGX + 2] = fmaf(gx, X2, acc[ACC_SGX + 2]);
     acc[ACC_SGX + 3] = fmaf(gy, X0, acc[ACC_SGX + 3]); acc[ACC_SGX + 4] = fmaf(gy, X1, acc[ACC_SGX + 4]); acc[ACC_SGX + 5] = fmaf(gy, X2, acc[ACC_SGX + 5]);
     acc[ACC_SGX + 6] = fmaf(gz, X0, acc[ACC_SGX + 6]); acc[ACC_SGX + 7] = fmaf(gz, X1, acc[ACC_SGX + 7]); acc[ACC_SGX + 8] = fmaf(gz, X2, acc[ACC_SGX + 8]);
-    gsx += gx; gsy += gy; gsz += gz;
 }
 
-// flow-projection residual of one (static) pixel-slot: updates acc[ACC_GA..ACC_FCNT], returns g_q . b
-// (the un-scaled d loss / d disp).  Reference optimizer.py:18-24,531-537, goem_opt.py:221-236.
-A3R_HD float flow_px(const SlotConst& c, const PixState& s, float fu, float fv, float pxl_thre, float* acc) {
+// flow-projection residual of one pixel-slot: updates acc[ACC_GA..ACC_FCNT], returns g_q . b (the un-scaled
+// d loss / d disp).  Reference optimizer.py:18-24,531-537, goem_opt.py:221-236.
+//   stat      false for dynamic / out-of-frame pixels: they are evaluated but contribute exactly nothing
+//             (branch-free: the mask enters through the per-pixel-mask select)
+//   thre_eff  pxl_thre, or +inf when pxl_thre <= 0 (per_pixel_mask = mask, optimizer.py:20-23)
+A3R_HD float flow_thre_eff(float pxl_thre) { return pxl_thre > 0.0f ? pxl_thre : INFINITY; }
+
+A3R_HD float flow_px(const SlotConst& c, const PixState& s, float fu, float fv, float thre_eff, bool stat, float* acc) {
     const float qx = fmaf(c.A[0], s.u, fmaf(c.A[1], s.v, c.A[2])) + s.disp * c.b[0];
     const float qy = fmaf(c.A[3], s.u, fmaf(c.A[4], s.v, c.A[5])) + s.disp * c.b[1];
     const float qz = fmaf(c.A[6], s.u, fmaf(c.A[7], s.v, c.A[8])) + s.disp * c.b[2];
@@ -433,12 +443,12 @@ A3R_HD float flow_px(const SlotConst& c, const PixState& s, float fu, float fv, 
     const float au = fabsf(eu), av = fabsf(ev);
     const float ru = au < 1.0f ? 0.5f * eu * eu : au - 0.5f;          // smooth L1, beta = 1
     const float rv = av < 1.0f ? 0.5f * ev * ev : av - 0.5f;
-    const float pu = (pxl_thre > 0.0f && !(ru < pxl_thre)) ? 0.0f : 1.0f;   // per_pixel_mask
-    const float pv = (pxl_thre > 0.0f && !(rv < pxl_thre)) ? 0.0f : 1.0f;
-    acc[ACC_FNUM] += ru * pu + rv * pv;
+    const float pu = (stat && ru < thre_eff) ? 1.0f : 0.0f;           // per_pixel_mask (NaN residuals are out)
+    const float pv = (stat && rv < thre_eff) ? 1.0f : 0.0f;
+    acc[ACC_FNUM] += (pu != 0.0f ? ru : 0.0f) + (pv != 0.0f ? rv : 0.0f);
     acc[ACC_FCNT] += pu + pv;
-    const float geu = fminf(fmaxf(eu, -1.0f), 1.0f) * pu;
-    const float gev = fminf(fmaxf(ev, -1.0f), 1.0f) * pv;
+    const float geu = pu != 0.0f ? fminf(fmaxf(eu, -1.0f), 1.0f) : 0.0f;
+    const float gev = pv != 0.0f ? fminf(fmaxf(ev, -1.0f), 1.0f) : 0.0f;
     const float gqx = geu * inv, gqy = gev * inv;
     const float gqz = -(gqx * up + gqy * vp);
     acc[ACC_GA + 0] = fmaf(gqx, s.u, acc[ACC_GA + 0]); acc[ACC_GA + 1] = fmaf(gqx, s.v, acc[ACC_GA + 1]); acc[ACC_GA + 2] += gqx;

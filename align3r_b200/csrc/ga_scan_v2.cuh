@@ -21,12 +21,21 @@
 #pragma once
 #include "ga_math.cuh"
 #include "a3r_common.cuh"
+#include <stddef.h>
 
 namespace a3r {
 
-constexpr int V2_T = 128;                      // pixels per tile
+#ifndef A3R_V2_T
+#define A3R_V2_T 128
+#endif
+#ifndef A3R_V2_STAGES
+#define A3R_V2_STAGES 3
+#endif
+constexpr int V2_T = A3R_V2_T;                 // pixels per tile (multiple of 32)
 constexpr int V2_SLOTS = 20;                   // slot warps == max slots per work frame
-constexpr int V2_STAGES = 3;                   // ring depth (tiles)
+constexpr int V2_STAGES = A3R_V2_STAGES;       // ring depth (tiles): one being computed, one held by the lagging
+                                               // phase C, V2_STAGES - 2 in flight from HBM
+constexpr int V2_AHEAD = V2_STAGES - 2;        // prefetch distance in tiles
 constexpr int V2_PIXW = V2_T / 32;             // pixel warps
 constexpr int V2_THREADS = (V2_SLOTS + V2_PIXW) * 32;   // 768
 constexpr int V2_DRAIN = 32;                   // tiles between fp32 -> fp64 drains (128 pixels per lane)
@@ -34,11 +43,12 @@ constexpr int V2_DRAIN = 32;                   // tiles between fp32 -> fp64 dra
 struct V2Smem {
     float4 xw[V2_STAGES][V2_SLOTS][V2_T];      // 122880 B  TMA destination, overwritten in place by (g, g_q.b)
     float2 fl[V2_STAGES][V2_SLOTS][V2_T];      //  61440 B
-    float4 pixA[2][V2_T];                      // zx zy zz disp (disp < 0: pixel is dynamic / outside the frame)
+    float4 pixA[2][V2_T];                      // zx zy zz +-disp (negative: pixel is dynamic / outside the frame)
     float2 pixB[2][V2_T];                      // u v
     double dacc[V2_SLOTS][ACC_STRIDE];         // fp64 accumulators of the slot warps
     unsigned long long full[V2_STAGES][V2_SLOTS];
     unsigned long long slots_done[V2_STAGES];
+    unsigned long long stage_free[V2_STAGES];
     unsigned long long pix_ready[2];
     unsigned long long pix_free[2];
     float fp[2][FP_STRIDE];                    // frame blocks of the two work frames phases A and C may straddle
@@ -75,15 +85,63 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// raw shared-memory accesses: one base register per tile + compile-time immediates per pixel
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t a) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t a, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t a, uint32_t parity) {
+    uint32_t ok, spins = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (!ok && ++spins > (1u << 24)) __trap();     // a lost arrival must fail loudly, never hang the GPU
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_1d_a(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void pixel_warps_sync() { asm volatile("bar.sync 1, %0;" ::"n"(V2_PIXW * 32) : "memory"); }
 
-// walks the work-frame table: position of a tile
+// optional per-phase timestamps of CTA 0 (tuning builds only: -DA3R_V2_TRACE): edge_scratch[(tile*12)+k]
+#ifdef A3R_V2_TRACE
+#define A3R_TRACE(WHO, I, K)                                                                         \
+    do {                                                                                             \
+        if (blockIdx.x == A3R_V2_TRACE && (WHO) && (I) >= 100 && (I) < 136)                                      \
+            p.edge_scratch[((I) - 100) * 12 + (K)] = __longlong_as_double(clock64() - trace_t0);                 \
+    } while (0)
+#else
+#define A3R_TRACE(WHO, I, K) do { } while (0)
+#endif
+
+// walks the work-frame table: position of a tile.  The boundary of the current work frame is cached in a
+// register so the steady state costs one compare per tile.
 struct WfCursor {
-    int wf = 0;
-    __device__ __forceinline__ void seek(const A3rProblem& p, int tile) {
+    int wf = 0, end = -1;
+    __device__ __forceinline__ bool seek(const A3rProblem& p, int tile) {     // true when the work frame changed
+        if (tile < end) return false;
         while (tile >= p.wf_tile_begin[wf + 1]) ++wf;
+        end = p.wf_tile_begin[wf + 1];
+        return true;
     }
 };
 
@@ -95,11 +153,15 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_accumulate_v2(const A3rProble
     const int t0 = p.cta_tile_begin[blockIdx.x], t1 = p.cta_tile_begin[blockIdx.x + 1];
     const int nt = t1 - t0;
     if (nt <= 0) return;
+#ifdef A3R_V2_TRACE
+    const long long trace_t0 = clock64();
+#endif
 
     if (tid == 0) {
         for (int b = 0; b < V2_STAGES; ++b) {
             for (int s = 0; s < V2_SLOTS; ++s) mbar_init(&sm.full[b][s], 1);
             mbar_init(&sm.slots_done[b], V2_SLOTS);
+            mbar_init(&sm.stage_free[b], V2_PIXW);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&sm.pix_ready[b], V2_PIXW);
@@ -112,41 +174,41 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_accumulate_v2(const A3rProble
 
     if (warp >= V2_SLOTS) {
         // =====================================================================================
-        // pixel warps (+ producer)
+        // pixel warps: phase A of tile i, then phase C of tile i-1
         // =====================================================================================
         const int ptid = tid - V2_SLOTS * 32;            // pixel of the tile owned by this thread
-        const bool is_producer = (ptid == 0);
-        const float4* xw_g = reinterpret_cast<const float4*>(p.predw);
-        const float2* fl_g = reinterpret_cast<const float2*>(p.flow);
-        const uint32_t bytes = V2_T * 16 + (FLOW ? V2_T * 8 : 0);
-        WfCursor cur_load;
-        auto issue_tile = [&](int i) {                    // producer: all chunks of local tile i -> stage i % 3
-            const int tile = t0 + i, stage = i % V2_STAGES;
-            cur_load.seek(p, tile);
-            const int s_begin = p.wf_slot_begin[cur_load.wf], deg = p.wf_slot_begin[cur_load.wf + 1] - s_begin;
-            const int64_t p0 = (int64_t)(tile - p.wf_tile_begin[cur_load.wf]) * V2_T;
-            for (int s = 0; s < deg; ++s) {
-                const int64_t off = (int64_t)(s_begin + s) * p.pix_stride + p0;
-                mbar_arrive_expect_tx(&sm.full[stage][s], bytes);
-                tma_load_1d(&sm.xw[stage][s][0], xw_g + off, V2_T * 16, &sm.full[stage][s]);
-                if (FLOW) tma_load_1d(&sm.fl[stage][s][0], fl_g + off, V2_T * 8, &sm.full[stage][s]);
-            }
-        };
-        if (is_producer)
-            for (int i = 0; i < V2_STAGES && i < nt; ++i) issue_tile(i);
-
         float facc[FACC_N];
 #pragma unroll
         for (int k = 0; k < FACC_N; ++k) facc[k] = 0.f;
         WfCursor cur_a;
         int wf_a = -1, wfpar_a = 1;          // phase A's work frame and which fp[]/side_j[] copy holds it
-        int lf_a = 0, n_a = 0, P_a = 0, W_a = 1;
-        // phase C state (lags one tile): the values phase A had for the previous tile
+        int lf_a = 0, n_a = 0, P_a = 0, W_a = 1, deg_a = 0, accum_a = 0, tile0_a = 0;
+        // phase C state (lags one tile): what phase A had for the previous tile
         PixState ps_c;
         bool valid_c = false;
         int wfpar_c = 0, deg_c = 0, accum_c = 0, n_c = 0;
         int64_t out_c = 0;
-
+        // software prefetch of the next tile's log-depth / mask (global latency off the critical path).  Within a
+        // work frame the next tile is V2_T pixels on; only a work-frame change walks the tables.
+        float ld_next = 0.f;
+        unsigned char mk_next = 0;
+        int pf_wf = 0, pf_end = -1, pf_pix = 0, pf_P = 0;
+        int64_t pf_base = 0;
+        auto prefetch = [&](int i) {
+            if (i >= nt) return;
+            const int tile = t0 + i;
+            if (tile >= pf_end) {
+                while (tile >= p.wf_tile_begin[pf_wf + 1]) ++pf_wf;
+                pf_end = p.wf_tile_begin[pf_wf + 1];
+                const int lf = p.wf_lframe[pf_wf], n = p.lframe_id[lf];
+                pf_P = p.frame_hw[2 * n] * p.frame_hw[2 * n + 1];
+                pf_pix = (tile - p.wf_tile_begin[pf_wf]) * V2_T + ptid;
+                pf_base = (int64_t)lf * p.pix_stride;
+            }
+            ld_next = pf_pix < pf_P ? p.logdepth[pf_base + pf_pix] : 0.f;
+            if (FLOW) mk_next = pf_pix < pf_P ? p.static_mask[pf_base + pf_pix] : 0;
+            pf_pix += V2_T;
+        };
         auto flush_frame = [&](int n) {
 #pragma unroll
             for (int k = 0; k < FACC_N; ++k) {
@@ -155,51 +217,54 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_accumulate_v2(const A3rProble
                 facc[k] = 0.f;
             }
         };
+        prefetch(0);
 
         for (int i = 0; i <= nt; ++i) {
             PixState ps_a;
             bool valid_a = false;
-            int deg_a = 0, accum_a = 0;
             int64_t out_a = 0;
             if (i < nt) {
                 // ---------------- phase A of tile i ----------------
                 const int tile = t0 + i, pb = i & 1;
-                cur_a.seek(p, tile);
-                if (cur_a.wf != wf_a) {
+                A3R_TRACE(ptid == 0, i, 6);
+                const float ld = ld_next;
+                const unsigned char mk = mk_next;
+                if (cur_a.seek(p, tile)) {
                     wf_a = cur_a.wf;
                     wfpar_a ^= 1;
                     lf_a = p.wf_lframe[wf_a];
                     n_a = p.lframe_id[lf_a];
                     W_a = p.frame_hw[2 * n_a + 1];
                     P_a = p.frame_hw[2 * n_a] * W_a;
-                    // fp[wfpar_a] was last read by phase C of a tile two work frames ago: all pixel warps are past it
+                    const int s_begin = p.wf_slot_begin[wf_a];
+                    deg_a = p.wf_slot_begin[wf_a + 1] - s_begin;
+                    accum_a = p.wf_accum[wf_a];
+                    tile0_a = p.wf_tile_begin[wf_a];
+                    // fp[wfpar_a] was last read by phase C two work frames ago: every pixel warp is past it
                     pixel_warps_sync();
-                    const int s_begin = p.wf_slot_begin[wf_a], deg = p.wf_slot_begin[wf_a + 1] - s_begin;
                     if (ptid < FP_STRIDE) sm.fp[wfpar_a][ptid] = p.frame_par[FP_STRIDE * n_a + ptid];
-                    if (ptid < deg) sm.side_j[wfpar_a][ptid] = (p.lslot_gslot[s_begin + ptid] & 1) ? 1.f : 0.f;
+                    if (ptid < deg_a) sm.side_j[wfpar_a][ptid] = (p.lslot_gslot[s_begin + ptid] & 1) ? 1.f : 0.f;
                     pixel_warps_sync();
                 }
-                deg_a = p.wf_slot_begin[wf_a + 1] - p.wf_slot_begin[wf_a];
-                accum_a = p.wf_accum[wf_a];
-                const int p0 = (tile - p.wf_tile_begin[wf_a]) * V2_T;
-                const int pix = p0 + ptid;
+                prefetch(i + 1);
+                const int pix = (tile - tile0_a) * V2_T + ptid;
                 valid_a = pix < P_a;
                 out_a = (int64_t)lf_a * p.pix_stride + pix;
-                const float ld = valid_a ? p.logdepth[out_a] : 0.f;
                 const int v = pix / W_a, u = pix - v * W_a;
                 pixel_state(sm.fp[wfpar_a], ld, u, v, ps_a);
-                bool stat = false;
-                if (FLOW) stat = valid_a && (p.static_mask[out_a] != 0);
+                const bool stat = FLOW && valid_a && mk != 0;
                 if (i >= 2) mbar_wait(&sm.pix_free[pb], ((i >> 1) - 1) & 1);      // slot warps are done with tile i-2's state
-                sm.pixA[pb][ptid] = make_float4(ps_a.zx, ps_a.zy, ps_a.zz, stat ? ps_a.disp : -1.f);
+                sm.pixA[pb][ptid] = make_float4(ps_a.zx, ps_a.zy, ps_a.zz, stat ? ps_a.disp : -ps_a.disp);
                 sm.pixB[pb][ptid] = make_float2(ps_a.u, ps_a.v);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.pix_ready[pb]);
+                A3R_TRACE(ptid == 0, i, 7);
             }
             if (i >= 1) {
                 // ---------------- phase C of tile i-1 ----------------
                 const int j = i - 1, stage = j % V2_STAGES;
                 mbar_wait(&sm.slots_done[stage], (j / V2_STAGES) & 1);
+                A3R_TRACE(ptid == 0, j, 8);
                 float gsx = 0.f, gsy = 0.f, gsz = 0.f, gfi = 0.f, gfj = 0.f;
 #pragma unroll 4
                 for (int s = 0; s < deg_c; ++s) {
@@ -211,6 +276,10 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_accumulate_v2(const A3rProble
                         gfi = fmaf(g.w, 1.f - sj, gfi);
                     }
                 }
+                // the stage may be refilled (by the slot warps' own TMA loads) once all pixel warps have read it
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.stage_free[stage]);
+                A3R_TRACE(ptid == 0, j, 9);
                 const float ga = pixel_epilogue(sm.fp[wfpar_c], ps_c, gsx, gsy, gsz, facc);
                 if (valid_c) {
                     if (accum_c) {
@@ -221,12 +290,9 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_accumulate_v2(const A3rProble
                         if (FLOW) { p.g_flow_i[out_c] = gfi * ps_c.dfac; p.g_flow_j[out_c] = gfj * ps_c.dfac; }
                     }
                 }
-                // the stage is free once all pixel warps have read it; then the producer refills it
-                fence_proxy_async();
-                pixel_warps_sync();
-                if (is_producer && j + V2_STAGES < nt) issue_tile(j + V2_STAGES);
                 // end of this CTA's share of a frame: hand the per-frame sums over
                 if (i == nt || n_a != n_c) flush_frame(n_c);
+                A3R_TRACE(ptid == 0, j, 10);
             }
             // what phase A just computed becomes phase C's tile in the next iteration
             ps_c = ps_a; valid_c = valid_a; wfpar_c = wfpar_a; deg_c = deg_a; accum_c = accum_a; n_c = n_a; out_c = out_a;
@@ -235,46 +301,96 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_accumulate_v2(const A3rProble
     }
 
     // =========================================================================================
-    // slot warps
+    // slot warps: own TMA loads + phase B
     // =========================================================================================
     float acc[ACC_N];
 #pragma unroll
     for (int k = 0; k < ACC_N; ++k) acc[k] = 0.f;
     SlotConst c;
-    int my_gs = -1, cur_wf = -1, deg = 0, since_drain = 0;
-    uint32_t full_phase = 0;                       // one parity bit per stage, for this warp's own full[] barriers
-    WfCursor cur;
+    int my_gs = -1;
+    const float4* xw_g = reinterpret_cast<const float4*>(p.predw);
+    const float2* fl_g = reinterpret_cast<const float2*>(p.flow);
+    constexpr uint32_t kBytes = V2_T * 16 + (FLOW ? V2_T * 8 : 0);
+    constexpr int kAcc = FLOW ? ACC_N : ACC_GA;
+    const float thre_eff = flow_thre_eff(p.pxl_thre);
 
-    auto drain = [&]() {            // fp32 register partial sums -> this warp's fp64 shared accumulators
-        if (my_gs >= 0) {
+    // shared-memory addresses (32-bit, shared state space): everything is base + stage/parity stride + immediates
+    // (re-derived from one base register per tile: a handful of integer ops, no persistent registers)
+    const uint32_t sm0 = smem_u32(&sm);
+#define xw_w (sm0 + (uint32_t)offsetof(V2Smem, xw) + warp * (V2_T * 16))        /* this warp's chunk in stage 0 */
+#define fl_w (sm0 + (uint32_t)offsetof(V2Smem, fl) + warp * (V2_T * 8))
+#define full_w (sm0 + (uint32_t)offsetof(V2Smem, full) + warp * 8)
+#define pixA_l (sm0 + (uint32_t)offsetof(V2Smem, pixA) + lane * 16)
+#define pixB_l (sm0 + (uint32_t)offsetof(V2Smem, pixB) + lane * 8)
+#define bar_done (sm0 + (uint32_t)offsetof(V2Smem, slots_done))
+#define bar_free (sm0 + (uint32_t)offsetof(V2Smem, stage_free))
+#define bar_ready (sm0 + (uint32_t)offsetof(V2Smem, pix_ready))
+#define bar_pfree (sm0 + (uint32_t)offsetof(V2Smem, pix_free))
+    constexpr uint32_t kXwStage = V2_SLOTS * V2_T * 16, kFlStage = V2_SLOTS * V2_T * 8, kFullStage = V2_SLOTS * 8;
+
+    // running state: stage = i % 3, its successor, parities as bits that flip when their ring wraps
+    int cw = 0, cw_end = -1;                       // work frame of the tile being computed
+    uint32_t stage = 0, nstage = V2_AHEAD % V2_STAGES;   // stage of tile i and of tile i + V2_AHEAD
+    uint32_t full_phase = 0;                       // parity bit per stage of this warp's own full[] barriers
+    uint32_t free_phase = 0;                       // parity bit per stage of stage_free[] (consumed by lane 0)
+
+    // the tile being loaded is at most a few work frames ahead of the one being computed: the issuing lane
+    // re-derives its position from the tables (cached loads, one lane, off the other lanes' critical path)
+#define A3R_V2_ISSUE(I, ST)                                                                                      \
+    do {                                                                                                         \
+        const int tile_l = t0 + (I);                                                                             \
+        int lw = cw;                                                                                             \
+        while (tile_l >= p.wf_tile_begin[lw + 1]) ++lw;                                                          \
+        const int lw_begin = p.wf_tile_begin[lw], lw_sbegin = p.wf_slot_begin[lw];                               \
+        const int lw_deg = p.wf_slot_begin[lw + 1] - lw_sbegin;                                                  \
+        if (warp < lw_deg) {                                                                                     \
+            const int64_t off = (int64_t)(lw_sbegin + warp) * p.pix_stride + (int64_t)(tile_l - lw_begin) * V2_T; \
+            const uint32_t bar_l = full_w + (ST) * kFullStage;                                                   \
+            mbar_expect_tx_a(bar_l, kBytes);                                                                     \
+            tma_load_1d_a(xw_w + (ST) * kXwStage, xw_g + off, V2_T * 16, bar_l);                                 \
+            if (FLOW) tma_load_1d_a(fl_w + (ST) * kFlStage, fl_g + off, V2_T * 8, bar_l);                        \
+        }                                                                                                        \
+    } while (0)
+
+#define A3R_V2_DRAIN()                                                                                           \
+    do {                                                                                                         \
+        if (my_gs >= 0) {                                                                                        \
+            _Pragma("unroll") for (int k = 0; k < kAcc; ++k) {                                                   \
+                const float v = warp_sum(acc[k]);                                                                \
+                if (lane == k) sm.dacc[warp][k] += (double)v;                                                    \
+                acc[k] = 0.f;                                                                                    \
+            }                                                                                                    \
+        }                                                                                                        \
+    } while (0)
+
+#define A3R_V2_FLUSH()                                                                                           \
+    do {                                                                                                         \
+        A3R_V2_DRAIN();                                                                                          \
+        __syncwarp();                                                                                            \
+        if (my_gs >= 0 && lane < kAcc) {                                                                         \
+            const double v = sm.dacc[warp][lane];                                                                \
+            if (v != 0.0) atomicAdd(&p.acc_slot[(int64_t)my_gs * ACC_STRIDE + lane], v);                         \
+            sm.dacc[warp][lane] = 0.0;                                                                           \
+        }                                                                                                        \
+        __syncwarp();                                                                                            \
+    } while (0)
+
+    if (lane == 0) {
 #pragma unroll
-            for (int k = 0; k < (FLOW ? ACC_N : ACC_GA); ++k) {
-                const float v = warp_sum(acc[k]);
-                if (lane == k) sm.dacc[warp][k] += (double)v;
-                acc[k] = 0.f;
-            }
-        }
-        since_drain = 0;
-    };
-    auto flush = [&]() {            // end of this CTA's share of a work frame
-        drain();
-        __syncwarp();
-        if (my_gs >= 0 && lane < (FLOW ? ACC_N : ACC_GA)) {
-            const double v = sm.dacc[warp][lane];
-            if (v != 0.0) atomicAdd(&p.acc_slot[(int64_t)my_gs * ACC_STRIDE + lane], v);
-            sm.dacc[warp][lane] = 0.0;
-        }
-        __syncwarp();
-    };
+        for (int k = 0; k < V2_AHEAD; ++k)
+            if (k < nt) A3R_V2_ISSUE(k, (uint32_t)k);
+    }
 
     for (int i = 0; i < nt; ++i) {
-        const int tile = t0 + i, stage = i % V2_STAGES, pb = i & 1;
-        cur.seek(p, tile);
-        if (cur.wf != cur_wf) {
-            if (cur_wf >= 0) flush();
-            cur_wf = cur.wf;
-            const int s_begin = p.wf_slot_begin[cur_wf];
-            deg = p.wf_slot_begin[cur_wf + 1] - s_begin;
+        const int tile = t0 + i;
+        const uint32_t pb = i & 1;
+        A3R_TRACE(tid == 0, i, 0);
+        if (tile >= cw_end) {
+            if (cw_end >= 0) A3R_V2_FLUSH();
+            while (tile >= p.wf_tile_begin[cw + 1]) ++cw;
+            cw_end = p.wf_tile_begin[cw + 1];
+            const int s_begin = p.wf_slot_begin[cw];
+            const int deg = p.wf_slot_begin[cw + 1] - s_begin;
             my_gs = -1;
             if (warp < deg) {
                 my_gs = p.lslot_gslot[s_begin + warp];
@@ -293,39 +409,75 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_accumulate_v2(const A3rProble
                 c.wn = (my_gs & 1) ? p.inv_area_j : p.inv_area_i;
             }
         }
-        mbar_wait(&sm.pix_ready[pb], (i >> 1) & 1);
-        if (my_gs >= 0) {
-            mbar_wait(&sm.full[stage][warp], (full_phase >> stage) & 1);
-            full_phase ^= 1u << stage;
-#pragma unroll
-            for (int j = 0; j < V2_T / 32; ++j) {
-                const int pix = j * 32 + lane;
-                const float4 X = sm.xw[stage][warp][pix];
-                const float4 A = sm.pixA[pb][pix];
-                PixState st;
-                st.zx = A.x; st.zy = A.y; st.zz = A.z; st.disp = A.w;
-                float gx = 0.f, gy = 0.f, gz = 0.f, gd = 0.f;
-                align_px<L2D>(c, X.x, X.y, X.z, X.w, st, acc, gx, gy, gz);
-                if (FLOW) {
-                    if (A.w > 0.f) {
-                        const float2 B = sm.pixB[pb][pix];
-                        const float2 F = sm.fl[stage][warp][pix];
-                        st.u = B.x; st.v = B.y;
-                        gd = flow_px(c, st, F.x, F.y, p.pxl_thre, acc);
-                    }
-                }
-                sm.xw[stage][warp][pix] = make_float4(gx, gy, gz, gd);
+        // prefetch: tile i+AHEAD goes into the stage tile i-2 used; phase C of tile i-2 ran during B(i-1), so this
+        // wait is already satisfied in steady state.  (B(i) and the lagging phase C(i-1) hold two other stages.)
+        // The proxy fence orders this warp's earlier generic-proxy writes to that stage before the TMA write.
+        if (lane == 0 && i + V2_AHEAD < nt) {
+            if (i >= 2) {
+                mbar_wait_a(bar_free + nstage * 8, (free_phase >> nstage) & 1);
+                free_phase ^= 1u << nstage;
             }
-            fence_proxy_async();          // these generic-proxy writes precede the next TMA write of this stage
+            fence_proxy_async();
+            A3R_V2_ISSUE(i + V2_AHEAD, nstage);
         }
         __syncwarp();
-        if (lane == 0) {
-            mbar_arrive(&sm.slots_done[stage]);
-            mbar_arrive(&sm.pix_free[pb]);
+        A3R_TRACE(tid == 0, i, 1);
+        mbar_wait_a(bar_ready + pb * 8, (i >> 1) & 1);
+        A3R_TRACE(tid == 0, i, 2);
+        if (my_gs >= 0) {
+            mbar_wait_a(full_w + stage * kFullStage, (full_phase >> stage) & 1);
+            A3R_TRACE(tid == 0, i, 3);
+            full_phase ^= 1u << stage;
+            const uint32_t xa = xw_w + stage * kXwStage + lane * 16;
+            const uint32_t fa = fl_w + stage * kFlStage + lane * 8;
+            const uint32_t pa = pixA_l + pb * (V2_T * 16);
+            const uint32_t pq = pixB_l + pb * (V2_T * 8);
+#ifdef A3R_EXP_CHEAP_B
+#pragma unroll
+            for (int j = 0; j < 1; ++j) {
+#else
+#pragma unroll
+            for (int j = 0; j < V2_T / 32; ++j) {
+#endif
+                const float4 X = lds128(xa + j * 512);
+                const float4 A = lds128(pa + j * 512);
+                PixState st;
+                st.zx = A.x; st.zy = A.y; st.zz = A.z; st.disp = fabsf(A.w);
+                float gx, gy, gz, gd = 0.f;
+                align_px<L2D>(c, X.x, X.y, X.z, X.w, st, acc, gx, gy, gz);
+                if (FLOW) {
+                    const float2 B = lds64(pq + j * 256);
+                    const float2 F = lds64(fa + j * 256);
+                    st.u = B.x; st.v = B.y;
+                    gd = flow_px(c, st, F.x, F.y, thre_eff, A.w > 0.f, acc);
+                }
+                sts128(xa + j * 512, gx, gy, gz, gd);
+            }
         }
-        if (++since_drain >= V2_DRAIN) drain();
+        __syncwarp();
+        A3R_TRACE(tid == 0, i, 4);
+        if (lane == 0) {
+            mbar_arrive_a(bar_done + stage * 8);
+            mbar_arrive_a(bar_pfree + pb * 8);
+        }
+        A3R_TRACE(tid == 0, i, 5);
+        if ((i & (V2_DRAIN - 1)) == V2_DRAIN - 1) A3R_V2_DRAIN();
+        stage = stage == V2_STAGES - 1 ? 0u : stage + 1;
+        nstage = nstage == V2_STAGES - 1 ? 0u : nstage + 1;
     }
-    flush();
+    A3R_V2_FLUSH();
+#undef A3R_V2_ISSUE
+#undef A3R_V2_DRAIN
+#undef A3R_V2_FLUSH
+#undef xw_w
+#undef fl_w
+#undef full_w
+#undef pixA_l
+#undef pixB_l
+#undef bar_done
+#undef bar_free
+#undef bar_ready
+#undef bar_pfree
 }
 
 }  // namespace a3r

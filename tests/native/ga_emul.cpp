@@ -80,11 +80,13 @@ extern "C" int emul_accumulate(const A3rProblem* p, uint32_t mode) {
                 const float* x = p->predw + ((int64_t)s * p->pix_stride + pix) * 4;
                 float acc[ACC_STRIDE];
                 for (int k = 0; k < ACC_STRIDE; ++k) acc[k] = 0.f;
-                if (l2) align_px<true>(c, x[0], x[1], x[2], x[3], st, acc, gsx, gsy, gsz);
-                else align_px<false>(c, x[0], x[1], x[2], x[3], st, acc, gsx, gsy, gsz);
-                if (stat) {
+                float gx, gy, gz;
+                if (l2) align_px<true>(c, x[0], x[1], x[2], x[3], st, acc, gx, gy, gz);
+                else align_px<false>(c, x[0], x[1], x[2], x[3], st, acc, gx, gy, gz);
+                gsx += gx; gsy += gy; gsz += gz;
+                if (flow) {         // evaluated for every pixel, masked branch-free like the kernels
                     const float* f = p->flow + ((int64_t)s * p->pix_stride + pix) * 2;
-                    const float gd = flow_px(c, st, f[0], f[1], p->pxl_thre, acc);
+                    const float gd = flow_px(c, st, f[0], f[1], flow_thre_eff(p->pxl_thre), stat, acc);
                     if (gs & 1) gfj += gd; else gfi += gd;
                 }
                 double* a = p->acc_slot + (int64_t)gs * ACC_STRIDE;
