@@ -10,6 +10,7 @@
 #include "ga_math.cuh"
 #include "a3r_common.cuh"
 #include "ga_scan_v2.cuh"
+#include "ga_scan_v3.cuh"
 #include <stdlib.h>
 
 using namespace a3r;
@@ -488,17 +489,20 @@ __global__ void __launch_bounds__(256) k_pack_flow(const float* __restrict__ src
 // ==========================================================================================
 // C ABI
 // ==========================================================================================
-// Scan kernel variant: v2 (TMA-fed, warp-owns-slot) is the product path; A3R_SCAN=v1 selects the simple
-// thread-owns-pixels kernel, kept as an on-device cross-check of v2.
+// Scan kernel variant.  v3 (independent warps, private TMA rings, transposing butterfly reduction) is the product
+// path.  A3R_SCAN=v1 selects the simple thread-owns-pixels kernel (on-device cross-check in the GPU tests);
+// A3R_SCAN=v2 the warp-owns-slot / pixel-warp pipeline (kept for the record: fewer instructions per pixel-slot,
+// but its per-tile hand-offs leave the slot warps idle half of the time - see DESIGN.md section 8).
 static int scan_variant() {
     static int v = [] {
         const char* e = getenv("A3R_SCAN");
-        return (e && e[0] == 'v' && e[1] == '1') ? 1 : 2;
+        if (e && e[0] == 'v' && e[1] >= '1' && e[1] <= '3') return e[1] - '0';
+        return 3;
     }();
     return v;
 }
-static int scan_tile() { return scan_variant() == 1 ? K1_TILE : V2_T; }
-static int scan_slots() { return scan_variant() == 1 ? K1_MAXS : V2_SLOTS; }
+static int scan_tile() { const int v = scan_variant(); return v == 1 ? K1_TILE : (v == 2 ? V2_T : V3_T); }
+static int scan_slots() { const int v = scan_variant(); return v == 1 ? K1_MAXS : (v == 2 ? V2_SLOTS : V3_SLOTS); }
 
 static int check_problem(const A3rProblem* p) {
     if (!p) return a3r_fail(A3R_E_ARG, "problem is NULL");
@@ -522,7 +526,7 @@ static int launch_accumulate(const A3rProblem* p, cudaStream_t st) {
             configured = true;
         }
         k_accumulate_v1<FLOW, L2D><<<p->n_ctas, K1_THREADS, smem, st>>>(*p);
-    } else {
+    } else if (scan_variant() == 2) {
         const size_t smem = sizeof(V2Smem);
         static bool configured = false;
         if (!configured) {
@@ -530,6 +534,15 @@ static int launch_accumulate(const A3rProblem* p, cudaStream_t st) {
             configured = true;
         }
         k_accumulate_v2<FLOW, L2D><<<p->n_ctas, V2_THREADS, smem, st>>>(*p);
+    } else {
+        if (p->n_ctas % V3_WARPS != 0) return a3r_fail(A3R_E_ARG, "n_ctas must be a multiple of %d for the v3 scan", V3_WARPS);
+        const size_t smem = sizeof(V3Smem);
+        static bool configured = false;
+        if (!configured) {
+            A3R_CUDA(cudaFuncSetAttribute(k_accumulate_v3<FLOW, L2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = true;
+        }
+        k_accumulate_v3<FLOW, L2D><<<p->n_ctas / V3_WARPS, V3_THREADS, smem, st>>>(*p);
     }
     A3R_CUDA(cudaGetLastError());
     return A3R_OK;
@@ -554,7 +567,9 @@ int a3r_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
 int a3r_max_ctas(int device) {
     int sm = 0;
     if (a3r_device_info(device, &sm, nullptr, nullptr) != A3R_OK) return A3R_E_CUDA;
-    return scan_variant() == 1 ? sm * 2 : sm;      // v1: 2 resident CTAs per SM; v2: one persistent CTA per SM
+    // v1: 2 resident CTAs per SM; v2: one persistent CTA per SM; v3: every warp has its own range of the plan
+    const int v = scan_variant();
+    return v == 1 ? sm * 2 : (v == 2 ? sm : sm * V3_WARPS);
 }
 
 int a3r_pack_pred(const float* pts, const float* conf, int32_t n, int64_t P, const int32_t* dst_slot,
