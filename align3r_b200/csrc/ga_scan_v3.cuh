@@ -27,11 +27,14 @@ constexpr int V3_THREADS = V3_WARPS * 32;
 #endif
 constexpr int V3_STAGES = A3R_V3_STAGES;
 constexpr int V3_SLOTS = 24;                  // max slots per work frame
+constexpr int V3_TR = 28;                     // row stride (floats) of the transpose buffer: 28/4 odd -> float4 rows of
+                                              // 8 consecutive lanes fall into distinct 16-byte bank groups
 
 struct V3Smem {
     float4 xw[V3_WARPS][V3_STAGES][V3_T];     // 98304 B
     float2 fl[V3_WARPS][V3_STAGES][V3_T];     // 49152 B
-    float wacc[V3_WARPS][V3_SLOTS][32];       // 49152 B  per-warp running sums (column l = sum l)
+    float wacc[V3_WARPS][V3_SLOTS][32];       // per-warp running sums (column l = sum l)
+    float tr[V3_WARPS][32 * V3_TR + 4];       // per-warp transpose buffer of the cross-lane reduction
     unsigned long long full[V3_WARPS][V3_STAGES];
 };
 
@@ -74,6 +77,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) k_accumulate_v3(const A3rProble
     const uint32_t xw_s = smem_u32(&sm.xw[warp][0][0]);
     const uint32_t fl_s = smem_u32(&sm.fl[warp][0][0]);
     const uint32_t bar_s = smem_u32(&sm.full[warp][0]);
+    const uint32_t tr_s = smem_u32(&sm.tr[warp][0]);
     float* wacc = &sm.wacc[warp][0][0];
 
     if (lane == 0) {
@@ -186,8 +190,8 @@ __global__ void __launch_bounds__(V3_THREADS, 1) k_accumulate_v3(const A3rProble
             {
                 const float4* ep = reinterpret_cast<const float4*>(p.edge_par + EP_STRIDE * (gs >> 1));
                 const float4 e0 = __ldg(ep), e1 = __ldg(ep + 1), e2 = __ldg(ep + 2);
-                c.nM[0] = -e0.x; c.nM[1] = -e0.y; c.nM[2] = -e0.z; c.nM[3] = -e0.w;
-                c.nM[4] = -e1.x; c.nM[5] = -e1.y; c.nM[6] = -e1.z; c.nM[7] = -e1.w;
+                c.nM[0] = -e0.x; c.nM[1] = -e0.y; c.nM[2] = -e0.z; c.nM[3] = -e0.w;      // (negations fold into
+                c.nM[4] = -e1.x; c.nM[5] = -e1.y; c.nM[6] = -e1.z; c.nM[7] = -e1.w;      //  the FFMA operand modifiers)
                 c.nM[8] = -e2.x; c.st[0] = e2.y; c.st[1] = e2.z; c.st[2] = e2.w;
                 if (FLOW) {
                     const float4* sp = reinterpret_cast<const float4*>(p.slot_par + SP_STRIDE * gs);
@@ -225,9 +229,25 @@ __global__ void __launch_bounds__(V3_THREADS, 1) k_accumulate_v3(const A3rProble
             __syncwarp();
             if (lane == 0) A3R_V3_ISSUE();
             stage = stage == V3_STAGES - 1 ? 0u : stage + 1;
-            // 27 (13) per-lane partial sums -> warp totals, lane l gets sum l, added to the warp's running sums
-            const float tot = warp_transpose_sum<NV>(acc, lane);
-            wacc[s * 32 + lane] += tot;
+            // 27 (13) per-lane partial sums -> warp totals through a shared-memory transpose: every lane stores its
+            // row as float4, then lane l adds up column l (4 independent chains) into the warp's running sums
+            {
+                const uint32_t row = tr_s + lane * (V3_TR * 4);
+#pragma unroll
+                for (int q = 0; q < (NV + 3) / 4; ++q) sts128(row + q * 16, acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+                __syncwarp();
+                const uint32_t col = tr_s + lane * 4;
+                float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+#pragma unroll
+                for (int r = 0; r < 32; r += 4) {
+                    t0 += lds32(col + (r + 0) * (V3_TR * 4));
+                    t1 += lds32(col + (r + 1) * (V3_TR * 4));
+                    t2 += lds32(col + (r + 2) * (V3_TR * 4));
+                    t3 += lds32(col + (r + 3) * (V3_TR * 4));
+                }
+                wacc[s * 32 + lane] += (t0 + t1) + (t2 + t3);
+                __syncwarp();
+            }
         }
 
         // ---- per-pixel gradient planes + per-frame sums ----
