@@ -244,20 +244,32 @@ def init_minimum_spanning_tree(self, save_score_path=None, save_score_only=False
             im_poses[pose_frame] = _rigid4x4(R, tt)          # sRT_to_4x4(1, R, T), init_im_poses.py:241-242,258-259
     im_focals = [focals.get(n) for n in range(N)]
 
-    # ---- frames the tree left without a pose: RANSAC-PnP on the host (init_im_poses.py:272-279) ----
+    # ---- frames the tree left without a pose: RANSAC-PnP on the host (init_im_poses.py:272-279).  The calls are
+    # independent (cv2 seeds its RANSAC generator per call) and release the GIL: run them on a thread pool.
     pnp = np.zeros((N, 17))
+    jobs = []
     for n in range(N):
         if im_poses[n] is None and n in self._lframe:
             s, R, tt = T[n]
             h, w = self.imshapes[n]
             X = self._bufs.predw[self._lslot[src[n]], :h * w, :3]
             A = torch.from_numpy((s * R).astype(np.float32)).to(self.device)
-            pts = (X @ A.T + torch.from_numpy(tt.astype(np.float32)).to(self.device)).view(h, w, 3).cpu().numpy()
-            msk = (self.im_conf[self._lframe[n]] > self.min_conf_thr).cpu().numpy()
-            res = fast_pnp(pts, im_focals[n], msk, niter_PnP=niter_PnP)
-            if res:
-                pnp[n, 0] = 1
-                pnp[n, 1:] = res[1].ravel()
+            pts = (X @ A.T + torch.from_numpy(tt.astype(np.float32)).to(self.device)).view(h, w, 3)
+            msk = self.im_conf[self._lframe[n]] > self.min_conf_thr
+            jobs.append((n, pts.cpu(), msk.cpu()))
+    if jobs:
+        from concurrent.futures import ThreadPoolExecutor
+        import os as _os
+
+        def _solve(job):
+            n, pts, msk = job
+            return n, fast_pnp(pts.numpy(), im_focals[n], msk.numpy(), niter_PnP=niter_PnP)
+
+        with ThreadPoolExecutor(max_workers=min(len(jobs), _os.cpu_count() or 1)) as pool:
+            for n, res in pool.map(_solve, jobs):
+                if res:
+                    pnp[n, 0] = 1
+                    pnp[n, 1:] = res[1].ravel()
     pnp = _allreduce_np(self, pnp)
     for n in range(N):
         if im_poses[n] is None:

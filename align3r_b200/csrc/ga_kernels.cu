@@ -243,16 +243,9 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k_accumulate_v1(const A3rProble
 
 // ==========================================================================================
 // K2: loss assembly, gate, temporal term, parameter-chain gradients, Adam on the small parameters.
-//     One CTA (the work is O(E + N) small fp64 blocks).
+//     O(E + N) small fp64 blocks, split at its two global dependencies into four tiny launches:
+//     scalars/gate -> camera chains (atomics) -> gradients + Adam -> shared focal.
 // ==========================================================================================
-constexpr int K2_THREADS = 512;
-
-__device__ __forceinline__ void adam_vec(float* prm, float* m, float* v, const float* g, int cnt,
-                                         const A3rProblem& p, const A3rAdamStep& a) {
-    for (int k = 0; k < cnt; ++k)
-        adam_update(prm[k], m[k], v[k], g[k], p.adam_beta1, p.adam_beta2, p.adam_eps, a.step_size, a.bc2_sqrt);
-}
-
 __device__ __forceinline__ void scatter_pair(const PairGrad& g, double* fgS, double* fgT) {
     for (int k = 0; k < 15; ++k) {
         if (g.s[k] != 0.0) atomicAdd(&fgS[k], g.s[k]);
@@ -260,19 +253,19 @@ __device__ __forceinline__ void scatter_pair(const PairGrad& g, double* fgS, dou
     }
 }
 
-__global__ void __launch_bounds__(K2_THREADS, 1) k_update_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam) {
+// extra scratch scalars of the update step (A3rProblem.scal)
+constexpr int S_GSUM = 8;      // sum_e dL/dlog s_e  (mean coupling of the pair scales)
+constexpr int S_GPHI = 9;      // sum_n dL/dphi_n    (shared focal)
+
+// K2a: loss assembly + gate (one small CTA: 3 sums over 2E slots, N-1 temporal pairs)
+__global__ void __launch_bounds__(512, 1) k_loss_scalars(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam) {
     __shared__ double s_red[32];
-    __shared__ double s_bc[8];
     const int tid = threadIdx.x, nt = blockDim.x;
     const int N = p.n_frames, E = p.n_edges;
     const bool shared_focal = p.flags & A3R_F_SHARED_FOCAL;
-    const bool norm_scale = p.flags & A3R_F_NORM_PW_SCALE;
     const bool flow_active = (mode & A3R_M_FLOW_ACTIVE) && (p.flags & A3R_F_HAS_FLOW) && p.flow_loss_weight > 0.f;
-    const bool apply = mode & A3R_M_APPLY_ADAM;
     const double fb = (double)p.focal_break;
     const double tsw = (double)p.temporal_smoothing_weight, tw = (double)p.translation_weight;
-
-    // ---------------- P0: scalars, loss, gate ----------------
     double l_align = 0, num_i = 0, cnt_i = 0, num_j = 0, cnt_j = 0, l_temp = 0;
     for (int gs = tid; gs < 2 * E; gs += nt) {
         const double* a = p.acc_slot + (int64_t)gs * ACC_STRIDE;
@@ -299,24 +292,33 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k_update_small(const A3rProblem
         p.scal[A3R_S_FLOW] = r.floss; p.scal[A3R_S_FLOW_DROPPED] = r.dropped;
         p.scal[A3R_S_SC_I] = r.sc_i; p.scal[A3R_S_SC_J] = r.sc_j;
         if (r.dropped != 0) p.scal[A3R_S_FLAG_STICKY] = 1.0;
+        p.scal[S_GSUM] = 0.0; p.scal[S_GPHI] = 0.0;
         if (p.loss_hist && adam.iter >= 0) p.loss_hist[adam.iter] = (float)r.loss;
-        s_bc[0] = r.sc_i; s_bc[1] = r.sc_j;
     }
-    __syncthreads();
-    const double sc_i = s_bc[0], sc_j = s_bc[1];
+}
 
-    // ---------------- P1: per-frame gradients of the alignment term ----------------
-    for (int n = tid; n < N; n += nt) {
-        FrameD F;
-        load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n, shared_focal, fb, F);
-        frame_align_grad(F, p.acc_frame + (int64_t)n * FACC_N, p.frame_grad + (int64_t)n * FG_STRIDE);
-    }
-    __syncthreads();
-
-    // ---------------- P2: flow + temporal chains (atomics into frame_grad) ----------------
-    if (flow_active && (sc_i != 0 || sc_j != 0)) {
-        for (int gs = tid; gs < 2 * E; gs += nt) {
-            const int e = gs >> 1, side = gs & 1;
+// K2b: every chain that ends in a camera (frame_grad, zeroed beforehand; fp64 atomics) + dL/dlog s_e
+//   items: [0,N) alignment part of frame n | [N, N+2E) flow chain of a slot | [.., +N-1) temporal pair | [.., +E) edge
+__global__ void __launch_bounds__(128) k_chain(const A3rProblem p, const uint32_t mode) {
+    const int N = p.n_frames, E = p.n_edges;
+    const bool shared_focal = p.flags & A3R_F_SHARED_FOCAL;
+    const bool flow_active = (mode & A3R_M_FLOW_ACTIVE) && (p.flags & A3R_F_HAS_FLOW) && p.flow_loss_weight > 0.f;
+    const double fb = (double)p.focal_break;
+    const double tsw = (double)p.temporal_smoothing_weight, tw = (double)p.translation_weight;
+    const double sc_i = p.scal[A3R_S_SC_I], sc_j = p.scal[A3R_S_SC_J];
+    const int total = N + 2 * E + (N - 1) + E;
+    for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < total; it += gridDim.x * blockDim.x) {
+        if (it < N) {
+            const int n = it;
+            FrameD F;
+            load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n, shared_focal, fb, F);
+            double fg[FG_STRIDE];
+            frame_align_grad(F, p.acc_frame + (int64_t)n * FACC_N, fg);
+            double* dst = p.frame_grad + (int64_t)n * FG_STRIDE;
+            for (int k = 0; k < 15; ++k) atomicAdd(&dst[k], fg[k]);
+        } else if (it < N + 2 * E) {
+            if (!(flow_active && (sc_i != 0 || sc_j != 0))) continue;
+            const int gs = it - N, e = gs >> 1, side = gs & 1;
             const int i = p.edge_ij[2 * e], j = p.edge_ij[2 * e + 1];
             const int sI = side ? j : i, tI = side ? i : j;
             FrameD S, T;
@@ -325,70 +327,77 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k_update_small(const A3rProblem
             PairGrad g;
             slot_flow_chain(S, T, p.acc_slot + (int64_t)gs * ACC_STRIDE, side ? sc_j : sc_i, g);
             scatter_pair(g, p.frame_grad + (int64_t)sI * FG_STRIDE, p.frame_grad + (int64_t)tI * FG_STRIDE);
-        }
-    }
-    if (tsw > 0) {
-        for (int n = tid; n < N - 1; n += nt) {
+        } else if (it < N + 2 * E + N - 1) {
+            if (!(tsw > 0)) continue;
+            const int n = it - N - 2 * E;
             FrameD T, S;
             load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n, shared_focal, fb, T);
             load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n + 1, shared_focal, fb, S);
             PairGrad g;
             temporal_pair(S, T, tsw, tw, &g);
             scatter_pair(g, p.frame_grad + (int64_t)(n + 1) * FG_STRIDE, p.frame_grad + (int64_t)n * FG_STRIDE);
+        } else {
+            const int e = it - N - 2 * E - (N - 1);
+            const double* a0 = p.acc_slot + (int64_t)(2 * e) * ACC_STRIDE;
+            const double g = edge_logscale_grad(p.edge_par + EP_STRIDE * e, a0, a0 + ACC_STRIDE);
+            p.edge_scratch[e] = g;
+            atomicAdd(&p.scal[S_GSUM], g);
         }
     }
-    __syncthreads();
+}
 
-    // ---------------- P3a: d L / d log s_e and its mean (global scale normalisation) ----------------
-    double gsum = 0;
-    for (int e = tid; e < E; e += nt) {
-        const double* a0 = p.acc_slot + (int64_t)(2 * e) * ACC_STRIDE;
-        const double g = edge_logscale_grad(p.edge_par + EP_STRIDE * e, a0, a0 + ACC_STRIDE);
-        p.edge_scratch[e] = g;
-        gsum += g;
-    }
-    gsum = block_sum(gsum, s_red);
-    const double gmean = norm_scale ? gsum / (double)E : 0.0;
+__device__ __forceinline__ void adam_vec(float* prm, float* m, float* v, const float* g, int cnt,
+                                         const A3rProblem& p, const A3rAdamStep& a) {
+    for (int k = 0; k < cnt; ++k)
+        adam_update(prm[k], m[k], v[k], g[k], p.adam_beta1, p.adam_beta2, p.adam_eps, a.step_size, a.bc2_sqrt);
+}
 
-    // ---------------- P3b: pairwise poses ----------------
-    for (int e = tid; e < E; e += nt) {
-        const double* a0 = p.acc_slot + (int64_t)(2 * e) * ACC_STRIDE;
-        float g[8], ga[2];
-        edge_pose_grad(p.pw_poses + 8 * e, p.edge_par + EP_STRIDE * e, a0, a0 + ACC_STRIDE, p.edge_scratch[e] - gmean,
-                       p.flags & A3R_F_TRAIN_ADAPTORS, norm_scale, (double)p.pw_break, g, ga);
-        for (int k = 0; k < 8; ++k) p.g_pw_poses[8 * e + k] = g[k];
-        p.g_pw_adaptors[2 * e] = ga[0]; p.g_pw_adaptors[2 * e + 1] = ga[1];
-        if (apply && (p.flags & A3R_F_TRAIN_PW_POSES)) adam_vec(p.pw_poses + 8 * e, p.pw_poses_m + 8 * e, p.pw_poses_v + 8 * e, g, 8, p, adam);
-        if (apply && (p.flags & A3R_F_TRAIN_ADAPTORS)) adam_vec(p.pw_adaptors + 2 * e, p.pw_adaptors_m + 2 * e, p.pw_adaptors_v + 2 * e, ga, 2, p, adam);
-    }
-
-    // ---------------- P3c: image poses, focals, principal points ----------------
-    double gphi_sum = 0;
-    for (int n = tid; n < N; n += nt) {
-        FrameD F;
-        load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n, shared_focal, fb, F);
-        float g[7], gpp[2];
-        double gphi;
-        frame_pose_grad(p.im_poses + 7 * n, F, p.frame_grad + (int64_t)n * FG_STRIDE, fb, p.flags & A3R_F_TRAIN_PP, g, &gphi, gpp);
-        for (int k = 0; k < 7; ++k) p.g_im_poses[7 * n + k] = g[k];
-        p.g_im_pp[2 * n] = gpp[0]; p.g_im_pp[2 * n + 1] = gpp[1];
-        if (shared_focal) gphi_sum += gphi;
-        else {
-            float gf = (float)gphi;
-            p.g_im_focals[n] = gf;
-            if (apply && (p.flags & A3R_F_TRAIN_FOCALS)) adam_vec(p.im_focals + n, p.im_focals_m + n, p.im_focals_v + n, &gf, 1, p, adam);
+// K2c: gradients of the small parameters + torch.optim.Adam.  items: [0,E) pairwise pose | [E, E+N) image pose
+__global__ void __launch_bounds__(128) k_adam_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam) {
+    const int N = p.n_frames, E = p.n_edges;
+    const bool shared_focal = p.flags & A3R_F_SHARED_FOCAL;
+    const bool norm_scale = p.flags & A3R_F_NORM_PW_SCALE;
+    const bool apply = mode & A3R_M_APPLY_ADAM;
+    const double fb = (double)p.focal_break;
+    const double gmean = norm_scale ? p.scal[S_GSUM] / (double)E : 0.0;
+    for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < E + N; it += gridDim.x * blockDim.x) {
+        if (it < E) {
+            const int e = it;
+            const double* a0 = p.acc_slot + (int64_t)(2 * e) * ACC_STRIDE;
+            float g[8], ga[2];
+            edge_pose_grad(p.pw_poses + 8 * e, p.edge_par + EP_STRIDE * e, a0, a0 + ACC_STRIDE, p.edge_scratch[e] - gmean,
+                           p.flags & A3R_F_TRAIN_ADAPTORS, norm_scale, (double)p.pw_break, g, ga);
+            for (int k = 0; k < 8; ++k) p.g_pw_poses[8 * e + k] = g[k];
+            p.g_pw_adaptors[2 * e] = ga[0]; p.g_pw_adaptors[2 * e + 1] = ga[1];
+            if (apply && (p.flags & A3R_F_TRAIN_PW_POSES)) adam_vec(p.pw_poses + 8 * e, p.pw_poses_m + 8 * e, p.pw_poses_v + 8 * e, g, 8, p, adam);
+            if (apply && (p.flags & A3R_F_TRAIN_ADAPTORS)) adam_vec(p.pw_adaptors + 2 * e, p.pw_adaptors_m + 2 * e, p.pw_adaptors_v + 2 * e, ga, 2, p, adam);
+        } else {
+            const int n = it - E;
+            FrameD F;
+            load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n, shared_focal, fb, F);
+            float g[7], gpp[2];
+            double gphi;
+            frame_pose_grad(p.im_poses + 7 * n, F, p.frame_grad + (int64_t)n * FG_STRIDE, fb, p.flags & A3R_F_TRAIN_PP, g, &gphi, gpp);
+            for (int k = 0; k < 7; ++k) p.g_im_poses[7 * n + k] = g[k];
+            p.g_im_pp[2 * n] = gpp[0]; p.g_im_pp[2 * n + 1] = gpp[1];
+            if (shared_focal) atomicAdd(&p.scal[S_GPHI], gphi);     // applied by k_adam_focal once every frame has read f
+            else {
+                float gf = (float)gphi;
+                p.g_im_focals[n] = gf;
+                if (apply && (p.flags & A3R_F_TRAIN_FOCALS)) adam_vec(p.im_focals + n, p.im_focals_m + n, p.im_focals_v + n, &gf, 1, p, adam);
+            }
+            if (apply && (p.flags & A3R_F_TRAIN_PP)) adam_vec(p.im_pp + 2 * n, p.im_pp_m + 2 * n, p.im_pp_v + 2 * n, gpp, 2, p, adam);
+            if (apply && (p.flags & A3R_F_TRAIN_IM_POSES)) adam_vec(p.im_poses + 7 * n, p.im_poses_m + 7 * n, p.im_poses_v + 7 * n, g, 7, p, adam);
         }
-        if (apply && (p.flags & A3R_F_TRAIN_PP)) adam_vec(p.im_pp + 2 * n, p.im_pp_m + 2 * n, p.im_pp_v + 2 * n, gpp, 2, p, adam);
-        if (apply && (p.flags & A3R_F_TRAIN_IM_POSES)) adam_vec(p.im_poses + 7 * n, p.im_poses_m + 7 * n, p.im_poses_v + 7 * n, g, 7, p, adam);
     }
-    if (shared_focal) {
-        // the shared focal is read by every frame above: update it only after everyone is done
-        gphi_sum = block_sum(gphi_sum, s_red);
-        if (tid == 0) {
-            float gf = (float)gphi_sum;
-            p.g_im_focals[0] = gf;
-            if (apply && (p.flags & A3R_F_TRAIN_FOCALS)) adam_vec(p.im_focals, p.im_focals_m, p.im_focals_v, &gf, 1, p, adam);
-        }
+}
+
+// K2d: the shared focal (one scalar that every frame reads)
+__global__ void k_adam_focal(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        float gf = (float)p.scal[S_GPHI];
+        p.g_im_focals[0] = gf;
+        if ((mode & A3R_M_APPLY_ADAM) && (p.flags & A3R_F_TRAIN_FOCALS)) adam_vec(p.im_focals, p.im_focals_m, p.im_focals_v, &gf, 1, p, adam);
     }
 }
 
@@ -631,7 +640,14 @@ int a3r_ga_update(const A3rProblem* p, uint32_t mode, const A3rAdamStep* adam, v
     if (int rc = check_problem(p)) return rc;
     if (!adam) return a3r_fail(A3R_E_ARG, "adam is NULL");
     cudaStream_t st = (cudaStream_t)stream;
-    k_update_small<<<1, K2_THREADS, 0, st>>>(*p, mode, *adam);
+    A3R_CUDA(cudaMemsetAsync(p->frame_grad, 0, sizeof(double) * FG_STRIDE * (size_t)p->n_frames, st));
+    k_loss_scalars<<<1, 512, 0, st>>>(*p, mode, *adam);
+    {
+        const int items = p->n_frames + 2 * p->n_edges + (p->n_frames - 1) + p->n_edges;
+        k_chain<<<(items + 127) / 128, 128, 0, st>>>(*p, mode);
+        k_adam_small<<<(p->n_edges + p->n_frames + 127) / 128, 128, 0, st>>>(*p, mode, *adam);
+        if (p->flags & A3R_F_SHARED_FOCAL) k_adam_focal<<<1, 32, 0, st>>>(*p, mode, *adam);
+    }
     A3R_CUDA(cudaGetLastError());
     const bool apply = mode & A3R_M_APPLY_ADAM;
     if (p->n_local_frames > 0 && (!apply || (p->flags & A3R_F_TRAIN_DEPTH))) {
