@@ -546,12 +546,21 @@ static int launch_accumulate(const A3rProblem* p, cudaStream_t st) {
     } else {
         if (p->n_ctas % V3_WARPS != 0) return a3r_fail(A3R_E_ARG, "n_ctas must be a multiple of %d for the v3 scan", V3_WARPS);
         const size_t smem = sizeof(V3Smem);
+        // copy engine of the private rings: TMA bulk copies for the flow-active scan, per-lane cp.async otherwise
+        // (measured, see ga_scan_v3.cuh); A3R_V3_COPY=tma|ldgsts forces one
+        static const int forced = [] {
+            const char* e = getenv("A3R_V3_COPY");
+            return !e ? 0 : (e[0] == 't' ? 1 : 2);
+        }();
+        const bool tma = forced ? forced == 1 : FLOW;
         static bool configured = false;
         if (!configured) {
-            A3R_CUDA(cudaFuncSetAttribute(k_accumulate_v3<FLOW, L2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            A3R_CUDA(cudaFuncSetAttribute(k_accumulate_v3<FLOW, L2D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            A3R_CUDA(cudaFuncSetAttribute(k_accumulate_v3<FLOW, L2D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             configured = true;
         }
-        k_accumulate_v3<FLOW, L2D><<<p->n_ctas / V3_WARPS, V3_THREADS, smem, st>>>(*p);
+        if (tma) k_accumulate_v3<FLOW, L2D, true><<<p->n_ctas / V3_WARPS, V3_THREADS, smem, st>>>(*p);
+        else k_accumulate_v3<FLOW, L2D, false><<<p->n_ctas / V3_WARPS, V3_THREADS, smem, st>>>(*p);
     }
     A3R_CUDA(cudaGetLastError());
     return A3R_OK;

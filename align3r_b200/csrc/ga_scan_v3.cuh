@@ -2,8 +2,14 @@
 //
 // Every warp is an independent stream: it owns a contiguous range of 128-pixel tiles (4 pixels per lane, state
 // in registers), and for each tile walks the slots living on that frame.  The (X,Y,Z,w) + flow chunk of every
-// (tile, slot) - 3 KB - is fetched by the warp's own cp.async.bulk (TMA bulk copy) into a private 3-stage
-// shared-memory ring, two chunks ahead of the one being computed; completion on the warp's own mbarriers.
+// (tile, slot) - 3 KB - lands in a private 3-stage shared-memory ring, three chunks ahead of the one being
+// computed, through one of two copy engines (template parameter TMA):
+//   TMA  = true : lane 0 issues cp.async.bulk (TMA bulk copies, 2 KB + 1 KB), completion on the warp's own mbarrier;
+//   TMA  = false: every lane issues cp.async (LDGSTS) for exactly the pixels it will read - completion is per lane
+//                 (cp.async.wait_group): no mbarrier, no elected issuer, no cross-lane hand-off at all.
+// Measured on C2 (B200): flow-active scan 0.957 ms (TMA) vs 0.963 ms (LDGSTS); align-only 0.609 vs 0.550 ms - the
+// TMA elect / uniform-register issue sequence + try_wait loop is ~80 warp instructions per chunk, which matters when a
+// chunk is only ~330 instructions of work.  The launcher picks TMA for the flow-active scan, LDGSTS otherwise.
 // Per (tile, slot) the 27 per-lane partial sums are combined with a transposing butterfly (31 shuffles: lane l
 // ends up holding the warp total of sum l) and added to the warp's private shared accumulators; fp64 global
 // atomics happen once per (warp, work frame).  16 independent warps per SM hide each other's latencies; there
@@ -35,8 +41,18 @@ struct V3Smem {
     float2 fl[V3_WARPS][V3_STAGES][V3_T];     // 49152 B
     float wacc[V3_WARPS][V3_SLOTS][32];       // per-warp running sums (column l = sum l)
     float tr[V3_WARPS][32 * V3_TR + 4];       // per-warp transpose buffer of the cross-lane reduction
-    unsigned long long full[V3_WARPS][V3_STAGES];
+    unsigned long long full[V3_WARPS][V3_STAGES];   // TMA completion barriers (TMA = true only)
 };
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Transposing butterfly: in: a[0..31] per lane (entries >= NV are structurally zero); out: the warp-wide total of
 // entry `lane`.  log2(32) exchange steps, the vector halves at every step: 16+8+4+2+1 = 31 shuffles.
@@ -60,7 +76,7 @@ __device__ __forceinline__ float warp_transpose_sum(float (&a)[32], int lane) {
     return a[0];
 }
 
-template <bool FLOW, bool L2D>
+template <bool FLOW, bool L2D, bool TMA>
 __global__ void __launch_bounds__(V3_THREADS, 1) k_accumulate_v3(const A3rProblem p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     V3Smem& sm = *reinterpret_cast<V3Smem*>(smem_raw);
@@ -69,18 +85,18 @@ __global__ void __launch_bounds__(V3_THREADS, 1) k_accumulate_v3(const A3rProble
     const int t0 = p.cta_tile_begin[gw], t1 = p.cta_tile_begin[gw + 1];
     if (t0 >= t1) return;
     constexpr int NV = FLOW ? ACC_N : ACC_GA;
-    constexpr uint32_t kBytes = V3_T * 16 + (FLOW ? V3_T * 8 : 0);
     const float thre_eff = flow_thre_eff(p.pxl_thre);
     const float4* xw_g = reinterpret_cast<const float4*>(p.predw);
     const float2* fl_g = reinterpret_cast<const float2*>(p.flow);
 
     const uint32_t xw_s = smem_u32(&sm.xw[warp][0][0]);
     const uint32_t fl_s = smem_u32(&sm.fl[warp][0][0]);
-    const uint32_t bar_s = smem_u32(&sm.full[warp][0]);
     const uint32_t tr_s = smem_u32(&sm.tr[warp][0]);
+    const uint32_t bar_s = smem_u32(&sm.full[warp][0]);
+    constexpr uint32_t kBytes = V3_T * 16 + (FLOW ? V3_T * 8 : 0);
     float* wacc = &sm.wacc[warp][0][0];
 
-    if (lane == 0) {
+    if (TMA && lane == 0) {
 #pragma unroll
         for (int s = 0; s < V3_STAGES; ++s) mbar_init(&sm.full[warp][s], 1);
         fence_mbar_init();
@@ -102,23 +118,33 @@ __global__ void __launch_bounds__(V3_THREADS, 1) k_accumulate_v3(const A3rProble
                 l_deg = p.wf_slot_begin[l_wf + 1] - l_sbegin;                                                    \
             }                                                                                                    \
             const int64_t off = (int64_t)(l_sbegin + l_s) * p.pix_stride + (int64_t)(l_tile - l_tile0) * V3_T;   \
-            const uint32_t bar_l = bar_s + l_stage * 8;                                                          \
-            mbar_expect_tx_a(bar_l, kBytes);                                                                     \
-            tma_load_1d_a(xw_s + l_stage * (V3_T * 16), xw_g + off, V3_T * 16, bar_l);                           \
-            if (FLOW) tma_load_1d_a(fl_s + l_stage * (V3_T * 8), fl_g + off, V3_T * 8, bar_l);                   \
+            if (TMA) {                                                                                           \
+                const uint32_t bar_l = bar_s + l_stage * 8;                                                      \
+                mbar_expect_tx_a(bar_l, kBytes);                                                                 \
+                tma_load_1d_a(xw_s + l_stage * (V3_T * 16), xw_g + off, V3_T * 16, bar_l);                       \
+                if (FLOW) tma_load_1d_a(fl_s + l_stage * (V3_T * 8), fl_g + off, V3_T * 8, bar_l);               \
+            } else {                                                                                             \
+                const uint32_t xd = xw_s + l_stage * (V3_T * 16) + lane * 16;                                    \
+                const uint32_t fd = fl_s + l_stage * (V3_T * 8) + lane * 8;                                      \
+                _Pragma("unroll") for (int j = 0; j < V3_PPL; ++j) {                                             \
+                    cp_async16(xd + j * 512, xw_g + off + lane + j * 32);                                        \
+                    if (FLOW) cp_async8(fd + j * 256, fl_g + off + lane + j * 32);                               \
+                }                                                                                                \
+            }                                                                                                    \
             l_stage = l_stage == V3_STAGES - 1 ? 0u : l_stage + 1;                                               \
             if (++l_s >= l_deg) { l_s = 0; ++l_tile; }                                                           \
         }                                                                                                        \
+        if (!TMA) cp_async_commit();   /* one group per chunk slot, empty past the end: uniform wait_group accounting */ \
     } while (0)
 
-    if (lane == 0) {
+    if (!TMA || lane == 0) {          // TMA: one elected issuer; LDGSTS: every lane copies its own pixels
 #pragma unroll
         for (int k = 0; k < V3_STAGES; ++k) A3R_V3_ISSUE();
     }
 
     // ---- compute cursor ----
     int cw = 0, cw_end = -1, lf = 0, n = 0, P = 0, W = 1, deg = 0, s_begin = 0, accum = 0, tile0 = 0;
-    uint32_t stage = 0, phase = 0;              // ring position of the chunk being consumed; parity bit per stage
+    uint32_t stage = 0, phase = 0;              // ring position of the chunk being consumed; TMA: parity bit per stage
     float facc[FACC_N];
 #pragma unroll
     for (int k = 0; k < FACC_N; ++k) facc[k] = 0.f;
@@ -207,8 +233,12 @@ __global__ void __launch_bounds__(V3_THREADS, 1) k_accumulate_v3(const A3rProble
 #pragma unroll
             for (int k = 0; k < 32; ++k) acc[k] = 0.f;
 
-            mbar_wait_a(bar_s + stage * 8, (phase >> stage) & 1);
-            phase ^= 1u << stage;
+            if (TMA) {
+                mbar_wait_a(bar_s + stage * 8, (phase >> stage) & 1);
+                phase ^= 1u << stage;
+            } else {
+                cp_async_wait<V3_STAGES - 1>();       // this lane's copies of the oldest chunk have landed
+            }
             const uint32_t xa = xw_s + stage * (V3_T * 16) + lane * 16;
             const uint32_t fa = fl_s + stage * (V3_T * 8) + lane * 8;
 #pragma unroll
@@ -225,9 +255,13 @@ __global__ void __launch_bounds__(V3_THREADS, 1) k_accumulate_v3(const A3rProble
                     if (side_j) gfj[j] += gd; else gfi[j] += gd;
                 }
             }
-            // the chunk is consumed: refill its stage with the chunk three ahead
-            __syncwarp();
-            if (lane == 0) A3R_V3_ISSUE();
+            // the chunk is consumed: refill its stage (LDGSTS: a lane only ever reads what it copied itself)
+            if (TMA) {
+                __syncwarp();
+                if (lane == 0) A3R_V3_ISSUE();
+            } else {
+                A3R_V3_ISSUE();
+            }
             stage = stage == V3_STAGES - 1 ? 0u : stage + 1;
             // 27 (13) per-lane partial sums -> warp totals through a shared-memory transpose: every lane stores its
             // row as float4, then lane l adds up column l (4 independent chains) into the warp's running sums

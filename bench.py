@@ -280,7 +280,7 @@ def run_ours(args, cfg, name):
         loss_e2e = net.compute_global_alignment(init=None, niter=K, schedule="linear", lr=0.01)
         torch.cuda.synchronize(dev)
         t_l = time.perf_counter()
-        depth_h = [d.detach().cpu() for d in net.get_depthmaps()]
+        depth_h = [net.get_depthmaps(raw=True).detach().cpu()]         # (frames, pix_stride) in one copy
         poses_h = net.get_im_poses().detach().cpu()
         foc_h = net.get_focals().detach().cpu()
         hist_h = net._bufs.loss_hist[:K].cpu()
