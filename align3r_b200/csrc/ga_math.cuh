@@ -35,8 +35,8 @@ enum : int {
 enum : int { FACC_G = 0, FACC_GC = 3, FACC_N = 12 };
 // frame_grad scratch rows (16 doubles): dL/dR (9), dL/dt (3), dL/df, dL/dcx, dL/dcy
 enum : int { FG_R = 0, FG_T = 9, FG_F = 12, FG_CX = 13, FG_CY = 14, FG_STRIDE = 16 };
-// frame_par rows (16 floats)
-enum : int { FP_R = 0, FP_T = 9, FP_F = 12, FP_CX = 13, FP_CY = 14, FP_STRIDE = 16 };
+// frame_par rows (16 floats): R (9), t (3), f, cx, cy, 1/f
+enum : int { FP_R = 0, FP_T = 9, FP_F = 12, FP_CX = 13, FP_CY = 14, FP_INVF = 15, FP_STRIDE = 16 };
 // edge_par rows (16 floats): M = s R diag(a) (9), s t (3), s, a (3)
 enum : int { EP_M = 0, EP_ST = 9, EP_S = 12, EP_A = 13, EP_STRIDE = 16 };
 // slot_par rows (16 floats): A (9), b (3)
@@ -165,7 +165,7 @@ A3R_HD void flow_homography(const FrameD& S, const FrameD& T, double A[9], doubl
 A3R_HD void derive_frame_par(const FrameD& F, float* o) {
     for (int k = 0; k < 9; ++k) o[FP_R + k] = (float)F.R[k];
     for (int k = 0; k < 3; ++k) o[FP_T + k] = (float)F.t[k];
-    o[FP_F] = (float)F.f; o[FP_CX] = (float)F.cx; o[FP_CY] = (float)F.cy; o[15] = 0.f;
+    o[FP_F] = (float)F.f; o[FP_CX] = (float)F.cx; o[FP_CY] = (float)F.cy; o[FP_INVF] = (float)(1.0 / F.f);
 }
 
 // pairwise pose block: M = s R diag(a), s t, s, a with s = exp(s~ + log_norm)
@@ -368,14 +368,15 @@ A3R_HD void pixel_state(const float* fp, float logd, int u, int v, PixState& s) 
     const float d = expf(logd);                                        // optimizer.py:462-466
     s.u = (float)u;
     s.v = (float)v;
-    s.cx = d * (s.u - fp[FP_CX]) / fp[FP_F];                            // optimizer.py:574-581
-    s.cy = d * (s.v - fp[FP_CY]) / fp[FP_F];
+    // optimizer.py:574-581 computes d (u - cx) / f; here the division is a multiplication by the fp64-rounded 1/f
+    // of the prepare kernel (<= 1 ulp apart), and 1/(d + 1e-6) is a single-MUFU reciprocal on the device
+    s.cx = d * (s.u - fp[FP_CX]) * fp[FP_INVF];
+    s.cy = d * (s.v - fp[FP_CY]) * fp[FP_INVF];
     s.cz = d;
     s.zx = fp[FP_R + 0] * s.cx + fp[FP_R + 1] * s.cy + fp[FP_R + 2] * s.cz + fp[FP_T + 0];
     s.zy = fp[FP_R + 3] * s.cx + fp[FP_R + 4] * s.cy + fp[FP_R + 5] * s.cz + fp[FP_T + 1];
     s.zz = fp[FP_R + 6] * s.cx + fp[FP_R + 7] * s.cy + fp[FP_R + 8] * s.cz + fp[FP_T + 2];
-    const float de = d + 1e-6f;
-    s.disp = 1.0f / de;
+    s.disp = fast_rcp(d + 1e-6f);
     s.dfac = -d * s.disp * s.disp;
 }
 
@@ -416,8 +417,8 @@ A3R_HD void align_px(const SlotConst& c, float X0, float X1, float X2, float w, 
         k = 2.0f * w2;
     } else {                          // reference commons.py:71-72 ('l1' = un-squared L2 norm)
         const float inv = fast_rsqrt(fmaxf(r2, 1e-30f));      // rho = 0 -> zero (sub)gradient, as torch.norm
-        acc[ACC_LOSS] = fmaf(w2, r2 * inv, acc[ACC_LOSS]);
         k = w2 * inv;
+        acc[ACC_LOSS] = fmaf(k, r2, acc[ACC_LOSS]);             // w rho = (w / rho) rho^2
     }
     gx = k * rx; gy = k * ry; gz = k * rz;
     acc[ACC_SG + 0] += gx; acc[ACC_SG + 1] += gy; acc[ACC_SG + 2] += gz;
@@ -433,31 +434,35 @@ A3R_HD void align_px(const SlotConst& c, float X0, float X1, float X2, float w, 
 //   thre_eff  pxl_thre, or +inf when pxl_thre <= 0 (per_pixel_mask = mask, optimizer.py:20-23)
 A3R_HD float flow_thre_eff(float pxl_thre) { return pxl_thre > 0.0f ? pxl_thre : INFINITY; }
 
-A3R_HD float flow_px(const SlotConst& c, const PixState& s, float fu, float fv, float thre_eff, bool stat, float* acc) {
-    const float qx = fmaf(c.A[0], s.u, fmaf(c.A[1], s.v, c.A[2])) + s.disp * c.b[0];
-    const float qy = fmaf(c.A[3], s.u, fmaf(c.A[4], s.v, c.A[5])) + s.disp * c.b[1];
-    const float qz = fmaf(c.A[6], s.u, fmaf(c.A[7], s.v, c.A[8])) + s.disp * c.b[2];
+// Returns gf0 + g_q . b (gf0: the running d loss / d disp of this pixel, so that the dot product folds into FMAs).
+A3R_HD float flow_px(const SlotConst& c, const PixState& s, float fu, float fv, float thre_eff, bool stat, float* acc,
+                     float gf0 = 0.0f) {
+    const float qx = fmaf(c.A[0], s.u, fmaf(c.A[1], s.v, fmaf(s.disp, c.b[0], c.A[2])));
+    const float qy = fmaf(c.A[3], s.u, fmaf(c.A[4], s.v, fmaf(s.disp, c.b[1], c.A[5])));
+    const float qz = fmaf(c.A[6], s.u, fmaf(c.A[7], s.v, fmaf(s.disp, c.b[2], c.A[8])));
     const float inv = fast_rcp(qz + 1e-6f);
     const float up = qx * inv, vp = qy * inv;
     const float eu = (up - s.u) - fu, ev = (vp - s.v) - fv;
+    // smooth L1, beta = 1, in min form: m = min(|e|, 1); loss = m (|e| - m/2); d loss / d e = sign(e) m
     const float au = fabsf(eu), av = fabsf(ev);
-    const float ru = au < 1.0f ? 0.5f * eu * eu : au - 0.5f;          // smooth L1, beta = 1
-    const float rv = av < 1.0f ? 0.5f * ev * ev : av - 0.5f;
-    const float pu = (stat && ru < thre_eff) ? 1.0f : 0.0f;           // per_pixel_mask (NaN residuals are out)
-    const float pv = (stat && rv < thre_eff) ? 1.0f : 0.0f;
-    acc[ACC_FNUM] += (pu != 0.0f ? ru : 0.0f) + (pv != 0.0f ? rv : 0.0f);
-    acc[ACC_FCNT] += pu + pv;
-    const float geu = pu != 0.0f ? fminf(fmaxf(eu, -1.0f), 1.0f) : 0.0f;
-    const float gev = pv != 0.0f ? fminf(fmaxf(ev, -1.0f), 1.0f) : 0.0f;
+    const float mu = fminf(au, 1.0f), mv = fminf(av, 1.0f);
+    const float ru = mu * fmaf(-0.5f, mu, au);
+    const float rv = mv * fmaf(-0.5f, mv, av);
+    const bool pu = stat && ru < thre_eff;                            // per_pixel_mask (NaN residuals are out)
+    const bool pv = stat && rv < thre_eff;
+    if (pu) { acc[ACC_FNUM] += ru; acc[ACC_FCNT] += 1.0f; }
+    if (pv) { acc[ACC_FNUM] += rv; acc[ACC_FCNT] += 1.0f; }
+    const float geu = pu ? copysignf(mu, eu) : 0.0f;
+    const float gev = pv ? copysignf(mv, ev) : 0.0f;
     const float gqx = geu * inv, gqy = gev * inv;
-    const float gqz = -(gqx * up + gqy * vp);
+    const float gqz = -fmaf(gqx, up, gqy * vp);
     acc[ACC_GA + 0] = fmaf(gqx, s.u, acc[ACC_GA + 0]); acc[ACC_GA + 1] = fmaf(gqx, s.v, acc[ACC_GA + 1]); acc[ACC_GA + 2] += gqx;
     acc[ACC_GA + 3] = fmaf(gqy, s.u, acc[ACC_GA + 3]); acc[ACC_GA + 4] = fmaf(gqy, s.v, acc[ACC_GA + 4]); acc[ACC_GA + 5] += gqy;
     acc[ACC_GA + 6] = fmaf(gqz, s.u, acc[ACC_GA + 6]); acc[ACC_GA + 7] = fmaf(gqz, s.v, acc[ACC_GA + 7]); acc[ACC_GA + 8] += gqz;
     acc[ACC_GB + 0] = fmaf(s.disp, gqx, acc[ACC_GB + 0]);
     acc[ACC_GB + 1] = fmaf(s.disp, gqy, acc[ACC_GB + 1]);
     acc[ACC_GB + 2] = fmaf(s.disp, gqz, acc[ACC_GB + 2]);
-    return gqx * c.b[0] + gqy * c.b[1] + gqz * c.b[2];
+    return fmaf(gqx, c.b[0], fmaf(gqy, c.b[1], fmaf(gqz, c.b[2], gf0)));
 }
 
 // ------------------------------------------------------------------------------------------

@@ -21,7 +21,10 @@
 
 namespace a3r {
 
-constexpr int V3_T = 128;                     // pixels per tile (4 per lane)
+#ifndef A3R_V3_T
+#define A3R_V3_T 128
+#endif
+constexpr int V3_T = A3R_V3_T;                // pixels per tile (V3_T / 32 per lane)
 constexpr int V3_PPL = V3_T / 32;
 #ifndef A3R_V3_WARPS
 #define A3R_V3_WARPS 12

@@ -1,0 +1,357 @@
+// ga_scan_v4.cuh - K1 (v4): the fused forward+backward scan, v3's organisation with the per-chunk overhead cut.
+//
+// As in v3 every warp is an independent stream: it owns a contiguous range of 128-pixel tiles (4 pixels per lane,
+// per-pixel state in registers) and walks, per tile, the slots living on that frame; the (X,Y,Z,w) + flow chunk of
+// every (tile, slot) - 3 KB - lands in the warp's private 3-stage shared-memory ring three chunks ahead of the one
+// being computed (TMA bulk copies issued by an elected lane, or per-lane cp.async).  No cross-warp hand-off exists.
+//
+// v3 spent 630 warp instructions per chunk (4 pixel-slots per lane) of which ~210 were not arithmetic
+// (profiles/r01_scan_v3c_*): re-materialised addresses, a dependent global-load chain for the slot constants, the
+// copy-issue sequence and the cross-lane reduction.  v4 removes most of that:
+//   * everything a warp owns lives in ONE contiguous shared-memory block (ring, slot table, running sums, transpose
+//     buffer, barriers): a single base register + compile-time offsets;
+//   * the constants of the frame's slots (-M, s t, flow homography, 1/area, global slot) are staged once per
+//     (warp, work frame) into a shared-memory slot table: 7 LDS.128 per chunk instead of an index load, 64-bit
+//     address arithmetic and 7 dependent LDG.128;
+//   * the copy cursor is a running 64-bit pixel offset (one add per chunk);
+//   * the 27 per-lane partial sums are reduced through the transpose buffer by half-warps: lane (h, c) adds rows
+//     16h..16h+15 of column pair c with LDS.64 (16 loads instead of 32), two shuffles join the halves;
+//   * the 12 per-frame sums go through the same transpose once per tile instead of living in registers;
+//   * leaner per-pixel-slot arithmetic (ga_math.cuh: min-form smooth L1, predicated mask sums, folded dot products).
+#pragma once
+#include "ga_math.cuh"
+#include "a3r_common.cuh"
+#include "ga_scan_v2.cuh"     // PTX helpers (mbarrier, bulk copy, raw shared-memory accesses)
+#include "ga_scan_v3.cuh"     // cp.async helpers
+
+namespace a3r {
+
+constexpr int V4_T = 128;                     // pixels per tile
+constexpr int V4_PPL = V4_T / 32;             // 4 per lane
+#ifndef A3R_V4_WARPS
+#define A3R_V4_WARPS 12
+#endif
+constexpr int V4_WARPS = A3R_V4_WARPS;
+constexpr int V4_THREADS = V4_WARPS * 32;
+constexpr int V4_STAGES = 3;
+constexpr int V4_SLOTS = 24;                  // max slots per work frame
+constexpr int V4_ROW = 28;                    // floats per row of the slot table / running sums / transpose buffer
+
+// byte offsets inside a warp's private block
+constexpr uint32_t V4_XW = 0;                                             // [STAGES][T] float4
+constexpr uint32_t V4_FL = V4_XW + V4_STAGES * V4_T * 16;                 // [STAGES][T] float2
+constexpr uint32_t V4_STAB = V4_FL + V4_STAGES * V4_T * 8;                // [SLOTS][28] slot table
+constexpr uint32_t V4_WACC = V4_STAB + V4_SLOTS * V4_ROW * 4;             // [SLOTS + 1][28] running sums (+ frame row)
+constexpr uint32_t V4_TR = V4_WACC + (V4_SLOTS + 1) * V4_ROW * 4;         // [32][28] + 4 transpose buffer
+constexpr uint32_t V4_FP = V4_TR + (32 * V4_ROW + 4) * 4;                 // [16] frame block
+constexpr uint32_t V4_BAR = V4_FP + 16 * 4;                               // [STAGES] mbarriers
+constexpr uint32_t V4_WARP_BYTES = ((V4_BAR + V4_STAGES * 8 + 127) / 128) * 128;
+constexpr size_t V4_SMEM = (size_t)V4_WARP_BYTES * V4_WARPS;
+
+// slot table row: q0..q2 = -M (9), s t (3); q3..q5 = A (9), b (3); q6 = 1/area, side, global slot, -
+__device__ __forceinline__ void sts64(uint32_t a, float x, float y) {
+    asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, float x) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory"); }
+
+// exact pix -> (u, v) for pix < 2^24 without an integer division: the float quotient is off by at most one
+__device__ __forceinline__ void pix_to_uv(int pix, int W, float invW, int& u, int& v) {
+    v = __float2int_rz(__int2float_rn(pix) * invW);
+    u = pix - v * W;
+    if (u < 0) { u += W; --v; }
+    else if (u >= W) { u -= W; ++v; }
+}
+
+// Reduce the per-lane rows (NQ float4 each) through the warp's transpose buffer; returns in lanes 0..13 the warp
+// totals of columns (2 lane, 2 lane + 1) (all lanes of both halves hold them; lanes & 15 >= 14 hold garbage).
+template <int NQ>
+__device__ __forceinline__ float2 transpose_reduce(uint32_t tr_s, int lane, const float* a) {
+    const uint32_t row = tr_s + lane * (V4_ROW * 4);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) sts128(row + q * 16, a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+    __syncwarp();
+    const uint32_t col = tr_s + (lane >> 4) * (16 * V4_ROW * 4) + (lane & 15) * 8;
+    float2 t0 = make_float2(0.f, 0.f), t1 = t0;
+#pragma unroll
+    for (int r = 0; r < 16; r += 2) {
+        const float2 x0 = lds64(col + r * (V4_ROW * 4));
+        const float2 x1 = lds64(col + (r + 1) * (V4_ROW * 4));
+        t0.x += x0.x; t0.y += x0.y;
+        t1.x += x1.x; t1.y += x1.y;
+    }
+    t0.x += t1.x; t0.y += t1.y;
+    t0.x += __shfl_xor_sync(0xffffffffu, t0.x, 16);
+    t0.y += __shfl_xor_sync(0xffffffffu, t0.y, 16);
+    return t0;
+}
+
+template <bool FLOW, bool L2D, bool TMA>
+__global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProblem p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gw = blockIdx.x * V4_WARPS + warp;                 // this warp's range in the plan ("CTA" = warp here)
+    const int t0 = p.cta_tile_begin[gw], t1 = p.cta_tile_begin[gw + 1];
+    if (t0 >= t1) return;
+    constexpr int NV = FLOW ? ACC_N : ACC_GA;
+    constexpr int NQ = (NV + 3) / 4;
+    const float thre_eff = flow_thre_eff(p.pxl_thre);
+    const float4* xw_g = reinterpret_cast<const float4*>(p.predw);
+    const float2* fl_g = reinterpret_cast<const float2*>(p.flow);
+    const int64_t stride = p.pix_stride;
+
+    const uint32_t wb = smem_u32(smem_raw) + warp * V4_WARP_BYTES;         // the warp's private block
+    constexpr uint32_t kBytes = V4_T * 16 + (FLOW ? V4_T * 8 : 0);
+
+    if (TMA && lane == 0) {
+#pragma unroll
+        for (int s = 0; s < V4_STAGES; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(wb + V4_BAR + s * 8), "r"(1) : "memory");
+        fence_mbar_init();
+    }
+    for (int k = lane; k < (V4_SLOTS + 1) * V4_ROW; k += 32) sts32(wb + V4_WACC + k * 4, 0.f);
+    __syncwarp();
+
+    // ---- copy cursor: next chunk = (l_tile, l_s) at pixel offset l_off of the slot-major planes ----
+    int l_tile = t0, l_wf = 0, l_wf_end = -1, l_s = 0, l_deg = 1;
+    int64_t l_off = 0;
+    auto issue = [&](uint32_t stage_off) {      // stage_off = stage * (V4_T * 16)
+        if (l_tile < t1) {
+            if (l_tile >= l_wf_end) {
+                while (l_tile >= p.wf_tile_begin[l_wf + 1]) ++l_wf;
+                l_wf_end = p.wf_tile_begin[l_wf + 1];
+                const int sb = p.wf_slot_begin[l_wf];
+                l_deg = p.wf_slot_begin[l_wf + 1] - sb;
+                l_off = (int64_t)sb * stride + (int64_t)(l_tile - p.wf_tile_begin[l_wf]) * V4_T;
+                l_s = 0;
+            }
+            if (TMA) {
+                if (lane == 0) {
+                    const uint32_t bar = wb + V4_BAR + (stage_off >> 8);
+                    mbar_expect_tx_a(bar, kBytes);
+                    tma_load_1d_a(wb + V4_XW + stage_off, xw_g + l_off, V4_T * 16, bar);
+                    if (FLOW) tma_load_1d_a(wb + V4_FL + (stage_off >> 1), fl_g + l_off, V4_T * 8, bar);
+                }
+            } else {
+                const uint32_t xd = wb + V4_XW + stage_off + lane * 16;
+                const uint32_t fd = wb + V4_FL + (stage_off >> 1) + lane * 8;
+#pragma unroll
+                for (int j = 0; j < V4_PPL; ++j) {
+                    cp_async16(xd + j * 512, xw_g + l_off + lane + j * 32);
+                    if (FLOW) cp_async8(fd + j * 256, fl_g + l_off + lane + j * 32);
+                }
+            }
+            if (++l_s >= l_deg) { l_s = 0; ++l_tile; l_off += V4_T - (int64_t)(l_deg - 1) * stride; }
+            else l_off += stride;
+        }
+        if (!TMA) cp_async_commit();   // one group per chunk slot, empty past the end: uniform wait_group accounting
+    };
+#pragma unroll
+    for (int k = 0; k < V4_STAGES; ++k) issue(k * (V4_T * 16));
+
+    // ---- compute cursor ----
+    int cw = 0, cw_end = -1, lf = 0, n = 0, P = 0, W = 1, deg = 0, s_begin = 0, accum = 0, tile0 = 0;
+    float invW = 1.f;
+    uint32_t stage_off = 0, phase = 0;          // ring position of the chunk being consumed; TMA: parity bit per stage
+
+    auto flush = [&]() {                        // this warp's share of a work frame is complete
+        __syncwarp();
+        for (int s = 0; s < deg; ++s) {
+            const uint32_t a = wb + V4_WACC + (s * V4_ROW + lane) * 4;
+            if (lane < NV) {
+                const float v = lds32(a);
+                sts32(a, 0.f);
+                if (v != 0.f) atomicAdd(&p.acc_slot[(int64_t)p.lslot_gslot[s_begin + s] * ACC_STRIDE + lane], (double)v);
+            }
+        }
+        if (lane < FACC_N) {
+            const uint32_t a = wb + V4_WACC + (V4_SLOTS * V4_ROW + lane) * 4;
+            const float v = lds32(a);
+            sts32(a, 0.f);
+            atomicAdd(&p.acc_frame[(int64_t)n * FACC_N + lane], (double)v);
+        }
+        __syncwarp();
+    };
+
+    for (int tile = t0; tile < t1; ++tile) {
+        if (tile >= cw_end) {
+            if (cw_end >= 0) flush();
+            while (tile >= p.wf_tile_begin[cw + 1]) ++cw;
+            cw_end = p.wf_tile_begin[cw + 1];
+            tile0 = p.wf_tile_begin[cw];
+            lf = p.wf_lframe[cw];
+            n = p.lframe_id[lf];
+            W = p.frame_hw[2 * n + 1];
+            P = p.frame_hw[2 * n] * W;
+            invW = 1.0f / (float)W;
+            s_begin = p.wf_slot_begin[cw];
+            deg = p.wf_slot_begin[cw + 1] - s_begin;
+            accum = p.wf_accum[cw];
+            // stage the frame block and the slot table of this work frame
+            if (lane < 4) {
+                const float4 v4 = __ldg(reinterpret_cast<const float4*>(p.frame_par + FP_STRIDE * n) + lane);
+                sts128(wb + V4_FP + lane * 16, v4.x, v4.y, v4.z, v4.w);
+            }
+            for (int k = lane; k < deg * 7; k += 32) {
+                const int s = k / 7, q = k - s * 7;
+                const int gs = p.lslot_gslot[s_begin + s];
+                float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (q < 3) {
+                    v4 = __ldg(reinterpret_cast<const float4*>(p.edge_par + EP_STRIDE * (gs >> 1)) + q);
+                    v4.x = -v4.x;                                     // -M (9 entries), s t (3) stay positive
+                    if (q < 2) { v4.y = -v4.y; v4.z = -v4.z; v4.w = -v4.w; }
+                } else if (q < 6) {
+                    if (FLOW) v4 = __ldg(reinterpret_cast<const float4*>(p.slot_par + SP_STRIDE * gs) + (q - 3));
+                } else {
+                    v4.x = (gs & 1) ? p.inv_area_j : p.inv_area_i;
+                    v4.y = (gs & 1) ? 1.0f : 0.0f;
+                }
+                sts128(wb + V4_STAB + (s * V4_ROW + q * 4) * 4, v4.x, v4.y, v4.z, v4.w);
+            }
+            __syncwarp();
+        }
+        const int p0 = (tile - tile0) * V4_T;
+        const int64_t pix_base = (int64_t)lf * stride + p0;
+
+        // ---- per-pixel state (4 pixels per lane) ----
+        float zx[V4_PPL], zy[V4_PPL], zz[V4_PPL], pu[V4_PPL], pv[V4_PPL], sdisp[V4_PPL], dep[V4_PPL];
+        float gsx[V4_PPL], gsy[V4_PPL], gsz[V4_PPL];
+        float gfc[V4_PPL], gfo[V4_PPL];          // d loss / d disp of the current side's flow class (i or j) / of the other one
+        bool cur_j = false;                      // the plan orders a frame's slots side i first: one swap per tile
+        {
+            float fpr[FP_STRIDE];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float4 v4 = lds128(wb + V4_FP + k * 16);
+                fpr[4 * k] = v4.x; fpr[4 * k + 1] = v4.y; fpr[4 * k + 2] = v4.z; fpr[4 * k + 3] = v4.w;
+            }
+#pragma unroll
+            for (int j = 0; j < V4_PPL; ++j) {
+                const int pl = j * 32 + lane, pix = p0 + pl;
+                const bool valid = pix < P;
+                const float ld = valid ? p.logdepth[pix_base + pl] : 0.f;
+                bool stat = false;
+                if (FLOW) stat = valid && p.static_mask[pix_base + pl] != 0;
+                int u, v;
+                pix_to_uv(pix, W, invW, u, v);
+                PixState s;
+                pixel_state(fpr, ld, u, v, s);
+                zx[j] = s.zx; zy[j] = s.zy; zz[j] = s.zz; pu[j] = s.u; pv[j] = s.v; dep[j] = s.cz;
+                sdisp[j] = stat ? s.disp : -s.disp;
+                gsx[j] = gsy[j] = gsz[j] = gfc[j] = gfo[j] = 0.f;
+            }
+        }
+
+        // ---- slots ----
+        for (int s = 0; s < deg; ++s) {
+            const uint32_t tab = wb + V4_STAB + s * (V4_ROW * 4);
+            if (TMA) {
+                mbar_wait_a(wb + V4_BAR + (stage_off >> 8), (phase >> (stage_off >> 11)) & 1);
+                phase ^= 1u << (stage_off >> 11);
+            } else {
+                cp_async_wait<V4_STAGES - 1>();       // this lane's copies of the oldest chunk have landed
+            }
+            float acc[4 * NQ];
+#pragma unroll
+            for (int k = 0; k < 4 * NQ; ++k) acc[k] = 0.f;
+            const uint32_t xa = wb + V4_XW + stage_off + lane * 16;
+            const uint32_t fa = wb + V4_FL + (stage_off >> 1) + lane * 8;
+            const float4 q6 = lds128(tab + 96);
+            {
+                SlotConst c;
+                const float4 q0 = lds128(tab), q1 = lds128(tab + 16), q2 = lds128(tab + 32);
+                c.nM[0] = q0.x; c.nM[1] = q0.y; c.nM[2] = q0.z; c.nM[3] = q0.w;
+                c.nM[4] = q1.x; c.nM[5] = q1.y; c.nM[6] = q1.z; c.nM[7] = q1.w;
+                c.nM[8] = q2.x; c.st[0] = q2.y; c.st[1] = q2.z; c.st[2] = q2.w;
+                c.wn = q6.x;
+#pragma unroll
+                for (int j = 0; j < V4_PPL; ++j) {
+                    const float4 X = lds128(xa + j * 512);
+                    PixState st;
+                    st.zx = zx[j]; st.zy = zy[j]; st.zz = zz[j];
+                    float gx, gy, gz;
+                    align_px<L2D>(c, X.x, X.y, X.z, X.w, st, acc, gx, gy, gz);
+                    gsx[j] += gx; gsy[j] += gy; gsz[j] += gz;
+                }
+            }
+            if (FLOW) {
+                SlotConst c;
+                const float4 q3 = lds128(tab + 48), q4 = lds128(tab + 64), q5 = lds128(tab + 80);
+                c.A[0] = q3.x; c.A[1] = q3.y; c.A[2] = q3.z; c.A[3] = q3.w;
+                c.A[4] = q4.x; c.A[5] = q4.y; c.A[6] = q4.z; c.A[7] = q4.w;
+                c.A[8] = q5.x; c.b[0] = q5.y; c.b[1] = q5.z; c.b[2] = q5.w;
+                const bool side_j = q6.y != 0.f;
+                if (side_j != cur_j) {               // warp-uniform; correct for any slot order, cheap for the sorted one
+                    cur_j = side_j;
+#pragma unroll
+                    for (int j = 0; j < V4_PPL; ++j) { const float t = gfc[j]; gfc[j] = gfo[j]; gfo[j] = t; }
+                }
+#pragma unroll
+                for (int j = 0; j < V4_PPL; ++j) {
+                    const float2 F = lds64(fa + j * 256);
+                    PixState st;
+                    st.u = pu[j]; st.v = pv[j]; st.disp = fabsf(sdisp[j]);
+                    gfc[j] = flow_px(c, st, F.x, F.y, thre_eff, sdisp[j] > 0.f, acc, gfc[j]);
+                }
+            }
+            // the chunk is consumed: refill its stage (LDGSTS: a lane only ever reads what it copied itself)
+            if (TMA) __syncwarp();
+            issue(stage_off);
+            stage_off = stage_off == (V4_STAGES - 1) * (V4_T * 16) ? 0u : stage_off + V4_T * 16;
+            // 27 (13) per-lane partial sums -> warp totals -> the warp's running sums of this slot
+            {
+                const float2 t = transpose_reduce<NQ>(wb + V4_TR, lane, acc);
+                if (lane < (NV + 1) / 2) {
+                    const uint32_t a = wb + V4_WACC + s * (V4_ROW * 4) + lane * 8;
+                    const float2 o = lds64(a);
+                    sts64(a, o.x + t.x, o.y + t.y);
+                }
+                __syncwarp();
+            }
+        }
+
+        // ---- per-pixel gradient planes + per-frame sums ----
+        {
+            float fpr[FP_STRIDE];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float4 v4 = lds128(wb + V4_FP + k * 16);
+                fpr[4 * k] = v4.x; fpr[4 * k + 1] = v4.y; fpr[4 * k + 2] = v4.z; fpr[4 * k + 3] = v4.w;
+            }
+            float facc[FACC_N];
+#pragma unroll
+            for (int k = 0; k < FACC_N; ++k) facc[k] = 0.f;
+#pragma unroll
+            for (int j = 0; j < V4_PPL; ++j) {
+                const int pl = j * 32 + lane, pix = p0 + pl;
+                if (pix >= P) continue;
+                PixState s;
+                const float d = dep[j];
+                s.cx = d * (pu[j] - fpr[FP_CX]) * fpr[FP_INVF];
+                s.cy = d * (pv[j] - fpr[FP_CY]) * fpr[FP_INVF];
+                s.cz = d;
+                const float disp = fabsf(sdisp[j]);
+                const float dfac = -d * disp * disp;
+                const float ga = pixel_epilogue(fpr, s, gsx[j], gsy[j], gsz[j], facc);
+                const float gfi = cur_j ? gfo[j] : gfc[j], gfj = cur_j ? gfc[j] : gfo[j];
+                const int64_t o = pix_base + pl;
+                if (accum) {
+                    atomicAdd(&p.g_align[o], ga);
+                    if (FLOW) { atomicAdd(&p.g_flow_i[o], gfi * dfac); atomicAdd(&p.g_flow_j[o], gfj * dfac); }
+                } else {
+                    p.g_align[o] = ga;
+                    if (FLOW) { p.g_flow_i[o] = gfi * dfac; p.g_flow_j[o] = gfj * dfac; }
+                }
+            }
+            const float2 t = transpose_reduce<FACC_N / 4>(wb + V4_TR, lane, facc);
+            if (lane < FACC_N / 2) {
+                const uint32_t a = wb + V4_WACC + V4_SLOTS * (V4_ROW * 4) + lane * 8;
+                const float2 o = lds64(a);
+                sts64(a, o.x + t.x, o.y + t.y);
+            }
+            __syncwarp();
+        }
+    }
+    flush();
+}
+
+}  // namespace a3r

@@ -133,7 +133,7 @@ def build_plan(edges, frame_hw, tile_pixels: int, max_slots: int, n_ctas: int, f
     slot_begin, lslots = [0], []
     wf_lframe, wf_slot_begin, wf_tile_begin, wf_accum = [], [0], [0], []
     for k, n in enumerate(lframe_id.tolist()):
-        sl = sorted(per_frame[n])
+        sl = sorted(per_frame[n], key=lambda g: (g & 1, g))     # side-i slots first (the v4 scan swaps its flow-gradient class once per tile)
         base = len(lslots)
         lslots.extend(sl)
         slot_begin.append(len(lslots))
