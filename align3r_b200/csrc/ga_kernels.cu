@@ -564,12 +564,12 @@ static int launch_accumulate(const A3rProblem* p, cudaStream_t st) {
         else k_accumulate_v3<FLOW, L2D, false><<<p->n_ctas / V3_WARPS, V3_THREADS, smem, st>>>(*p);
     } else {
         if (p->n_ctas % V4_WARPS != 0) return a3r_fail(A3R_E_ARG, "n_ctas must be a multiple of %d for the v4 scan", V4_WARPS);
-        // copy engine of the private rings (A3R_V4_COPY=tma|ldgsts forces one; default: see scan_v4_default_tma)
+        // copy engine of the private rings (A3R_V4_COPY=tma|ldgsts forces one; default: per-lane cp.async)
         static const int forced = [] {
             const char* e = getenv("A3R_V4_COPY");
             return (!e || !e[0]) ? 0 : (e[0] == 't' ? 1 : 2);
         }();
-        const bool tma = forced ? forced == 1 : FLOW;
+        const bool tma = forced == 1;      // measured on C2: per-lane cp.async 0.760 / 0.474 ms (flow / align), TMA 0.843 / 0.533 ms
         static bool configured = false;
         if (!configured) {
             A3R_CUDA(cudaFuncSetAttribute(k_accumulate_v4<FLOW, L2D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V4_SMEM));

@@ -2,8 +2,15 @@
 //
 // As in v3 every warp is an independent stream: it owns a contiguous range of 128-pixel tiles (4 pixels per lane,
 // per-pixel state in registers) and walks, per tile, the slots living on that frame; the (X,Y,Z,w) + flow chunk of
-// every (tile, slot) - 3 KB - lands in the warp's private 3-stage shared-memory ring three chunks ahead of the one
-// being computed (TMA bulk copies issued by an elected lane, or per-lane cp.async).  No cross-warp hand-off exists.
+// every (tile, slot) - 3 KB - lands in the warp's private shared-memory ring STAGES chunks ahead of the one being
+// computed (per-lane cp.async - a lane only ever reads what it copied itself, completion is cp.async.wait_group; or TMA
+// bulk copies issued by an elected lane, completion on the warp's own mbarriers).  No cross-warp hand-off exists.
+//
+// Measured on C2 (B200, profiles/): 16 warps x 2 stages x 127 registers: 0.721 ms flow-active (71 % of the measured
+// HBM peak), 0.424 ms align-only (81 %); 12 warps x 3 stages x 149 registers: 0.766 / 0.473 ms; 13 and 14 warps are
+// slower than 12 (uneven warps per scheduler); TMA copies 0.843 / 0.533 ms (elect + uniform-register issue sequence
+// and try_wait loop per chunk).  The kernel is bound by instruction issue, not by HBM: warps per scheduler matter
+// more than prefetch depth.
 //
 // v3 spent 630 warp instructions per chunk (4 pixel-slots per lane) of which ~210 were not arithmetic
 // (profiles/r01_scan_v3c_*): re-materialised addresses, a dependent global-load chain for the slot constants, the
@@ -17,6 +24,8 @@
 //   * the 27 per-lane partial sums are reduced through the transpose buffer by half-warps: lane (h, c) adds rows
 //     16h..16h+15 of column pair c with LDS.64 (16 loads instead of 32), two shuffles join the halves;
 //   * the 12 per-frame sums go through the same transpose once per tile instead of living in registers;
+//   * a frame's side-i slots are walked before its side-j slots (plan order): one running flow-gradient register
+//     per pixel, parked in its plane when the class is complete;
 //   * leaner per-pixel-slot arithmetic (ga_math.cuh: min-form smooth L1, predicated mask sums, folded dot products).
 #pragma once
 #include "ga_math.cuh"
@@ -29,12 +38,18 @@ namespace a3r {
 constexpr int V4_T = 128;                     // pixels per tile
 constexpr int V4_PPL = V4_T / 32;             // 4 per lane
 #ifndef A3R_V4_WARPS
-#define A3R_V4_WARPS 12
+#define A3R_V4_WARPS 16
 #endif
 constexpr int V4_WARPS = A3R_V4_WARPS;
 constexpr int V4_THREADS = V4_WARPS * 32;
-constexpr int V4_STAGES = 3;
-constexpr int V4_SLOTS = 24;                  // max slots per work frame
+#ifndef A3R_V4_STAGES
+#define A3R_V4_STAGES 2
+#endif
+constexpr int V4_STAGES = A3R_V4_STAGES;
+#ifndef A3R_V4_SLOTS
+#define A3R_V4_SLOTS 20
+#endif
+constexpr int V4_SLOTS = A3R_V4_SLOTS;        // max slots per work frame
 constexpr int V4_ROW = 28;                    // floats per row of the slot table / running sums / transpose buffer
 
 // byte offsets inside a warp's private block
@@ -47,6 +62,7 @@ constexpr uint32_t V4_FP = V4_TR + (32 * V4_ROW + 4) * 4;                 // [16
 constexpr uint32_t V4_BAR = V4_FP + 16 * 4;                               // [STAGES] mbarriers
 constexpr uint32_t V4_WARP_BYTES = ((V4_BAR + V4_STAGES * 8 + 127) / 128) * 128;
 constexpr size_t V4_SMEM = (size_t)V4_WARP_BYTES * V4_WARPS;
+static_assert(V4_SMEM <= 232448, "v4 scan: shared memory of one CTA exceeds the 227 KB opt-in limit");
 
 // slot table row: q0..q2 = -M (9), s t (3); q3..q5 = A (9), b (3); q6 = 1/area, side, global slot, -
 __device__ __forceinline__ void sts64(uint32_t a, float x, float y) {
@@ -149,7 +165,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
     for (int k = 0; k < V4_STAGES; ++k) issue(k * (V4_T * 16));
 
     // ---- compute cursor ----
-    int cw = 0, cw_end = -1, lf = 0, n = 0, P = 0, W = 1, deg = 0, s_begin = 0, accum = 0, tile0 = 0;
+    int cw = 0, cw_end = -1, lf = 0, n = 0, P = 0, W = 1, deg = 0, n_i = 0, s_begin = 0, accum = 0, tile0 = 0;
     float invW = 1.f;
     uint32_t stage_off = 0, phase = 0;          // ring position of the chunk being consumed; TMA: parity bit per stage
 
@@ -207,6 +223,12 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
                 }
                 sts128(wb + V4_STAB + (s * V4_ROW + q * 4) * 4, v4.x, v4.y, v4.z, v4.w);
             }
+            {
+                const bool is_i = lane < deg && (p.lslot_gslot[s_begin + (lane < deg ? lane : 0)] & 1) == 0;
+                const unsigned mi = __ballot_sync(0xffffffffu, is_i);
+                n_i = __popc(mi);
+                if (FLOW && mi != (n_i >= 32 ? 0xffffffffu : (1u << n_i) - 1u)) __trap();   // plan contract: side-i slots first
+            }
             __syncwarp();
         }
         const int p0 = (tile - tile0) * V4_T;
@@ -215,8 +237,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
         // ---- per-pixel state (4 pixels per lane) ----
         float zx[V4_PPL], zy[V4_PPL], zz[V4_PPL], pu[V4_PPL], pv[V4_PPL], sdisp[V4_PPL], dep[V4_PPL];
         float gsx[V4_PPL], gsy[V4_PPL], gsz[V4_PPL];
-        float gfc[V4_PPL], gfo[V4_PPL];          // d loss / d disp of the current side's flow class (i or j) / of the other one
-        bool cur_j = false;                      // the plan orders a frame's slots side i first: one swap per tile
+        float gf[V4_PPL];                        // d loss / d disp of the flow class (side i, then side j) being walked
         {
             float fpr[FP_STRIDE];
 #pragma unroll
@@ -237,12 +258,18 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
                 pixel_state(fpr, ld, u, v, s);
                 zx[j] = s.zx; zy[j] = s.zy; zz[j] = s.zz; pu[j] = s.u; pv[j] = s.v; dep[j] = s.cz;
                 sdisp[j] = stat ? s.disp : -s.disp;
-                gsx[j] = gsy[j] = gsz[j] = gfc[j] = gfo[j] = 0.f;
+                gsx[j] = gsy[j] = gsz[j] = gf[j] = 0.f;
             }
         }
 
-        // ---- slots ----
-        for (int s = 0; s < deg; ++s) {
+        // ---- slots: the side-i slots of the frame, then its side-j slots (the plan orders them so; checked when the
+        //      slot table is staged).  The two flow classes are normalised by different global counts that are only
+        //      known after the scan, so each class parks its own per-pixel plane as soon as it is complete. ----
+#pragma unroll 1
+        for (int cls = 0; cls < (FLOW ? 2 : 1); ++cls) {
+        const int s_lo = (FLOW && cls) ? n_i : 0, s_hi = (FLOW && !cls) ? n_i : deg;
+#pragma unroll 1
+        for (int s = s_lo; s < s_hi; ++s) {
             const uint32_t tab = wb + V4_STAB + s * (V4_ROW * 4);
             if (TMA) {
                 mbar_wait_a(wb + V4_BAR + (stage_off >> 8), (phase >> (stage_off >> 11)) & 1);
@@ -279,18 +306,12 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
                 c.A[0] = q3.x; c.A[1] = q3.y; c.A[2] = q3.z; c.A[3] = q3.w;
                 c.A[4] = q4.x; c.A[5] = q4.y; c.A[6] = q4.z; c.A[7] = q4.w;
                 c.A[8] = q5.x; c.b[0] = q5.y; c.b[1] = q5.z; c.b[2] = q5.w;
-                const bool side_j = q6.y != 0.f;
-                if (side_j != cur_j) {               // warp-uniform; correct for any slot order, cheap for the sorted one
-                    cur_j = side_j;
-#pragma unroll
-                    for (int j = 0; j < V4_PPL; ++j) { const float t = gfc[j]; gfc[j] = gfo[j]; gfo[j] = t; }
-                }
 #pragma unroll
                 for (int j = 0; j < V4_PPL; ++j) {
                     const float2 F = lds64(fa + j * 256);
                     PixState st;
                     st.u = pu[j]; st.v = pv[j]; st.disp = fabsf(sdisp[j]);
-                    gfc[j] = flow_px(c, st, F.x, F.y, thre_eff, sdisp[j] > 0.f, acc, gfc[j]);
+                    gf[j] = flow_px(c, st, F.x, F.y, thre_eff, sdisp[j] > 0.f, acc, gf[j]);
                 }
             }
             // the chunk is consumed: refill its stage (LDGSTS: a lane only ever reads what it copied itself)
@@ -308,8 +329,22 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
                 __syncwarp();
             }
         }
+        if (FLOW) {                                   // this class's d loss / d logdepth plane (un-normalised)
+            float* plane = cls ? p.g_flow_j : p.g_flow_i;
+#pragma unroll
+            for (int j = 0; j < V4_PPL; ++j) {
+                const int pl = j * 32 + lane;
+                if (p0 + pl < P) {
+                    const float disp = fabsf(sdisp[j]);
+                    const float v = gf[j] * (-dep[j] * disp * disp);
+                    if (accum) atomicAdd(&plane[pix_base + pl], v); else plane[pix_base + pl] = v;
+                }
+                gf[j] = 0.f;
+            }
+        }
+        }
 
-        // ---- per-pixel gradient planes + per-frame sums ----
+        // ---- alignment gradient plane + per-frame sums ----
         {
             float fpr[FP_STRIDE];
 #pragma unroll
@@ -329,18 +364,9 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
                 s.cx = d * (pu[j] - fpr[FP_CX]) * fpr[FP_INVF];
                 s.cy = d * (pv[j] - fpr[FP_CY]) * fpr[FP_INVF];
                 s.cz = d;
-                const float disp = fabsf(sdisp[j]);
-                const float dfac = -d * disp * disp;
                 const float ga = pixel_epilogue(fpr, s, gsx[j], gsy[j], gsz[j], facc);
-                const float gfi = cur_j ? gfo[j] : gfc[j], gfj = cur_j ? gfc[j] : gfo[j];
                 const int64_t o = pix_base + pl;
-                if (accum) {
-                    atomicAdd(&p.g_align[o], ga);
-                    if (FLOW) { atomicAdd(&p.g_flow_i[o], gfi * dfac); atomicAdd(&p.g_flow_j[o], gfj * dfac); }
-                } else {
-                    p.g_align[o] = ga;
-                    if (FLOW) { p.g_flow_i[o] = gfi * dfac; p.g_flow_j[o] = gfj * dfac; }
-                }
+                if (accum) atomicAdd(&p.g_align[o], ga); else p.g_align[o] = ga;
             }
             const float2 t = transpose_reduce<FACC_N / 4>(wb + V4_TR, lane, facc);
             if (lane < FACC_N / 2) {

@@ -1,0 +1,41 @@
+"""Diagnostic (not a test): the accumulate scan of workload C2 alone - a cheap target for timing and ncu captures.
+
+    python tools/scan_only.py [--reps 20] [--mode flow|align|both] [--workload c2]
+    ncu --set full --clock-control none --import-source on -k regex:k_accumulate --launch-skip 3 -c 1 \
+        -o gpurun_out/prof python tools/scan_only.py --reps 2 --mode flow
+"""
+import argparse, ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from align3r_b200 import _lib
+from align3r_b200.cloud_opt_flow import global_aligner
+from align3r_b200.synth import CANONICAL_KW, CONFIGS, make_scene
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--reps", type=int, default=20)
+ap.add_argument("--mode", default="both")
+ap.add_argument("--workload", default="c2")
+a = ap.parse_args()
+n, H, W, graph = CONFIGS[a.workload]
+sc = make_scene(n, H, W, graph, seed=0, with_flow=True)
+net = global_aligner(sc.output, "cuda", flow=(sc.flow_ij, sc.flow_ji), **dict(CANONICAL_KW))
+net.verbose = False
+net.compute_global_alignment(init="mst", niter=0)
+st = net._bufs.struct(net._trainable())
+stream = net._stream()
+ps, nl, P = net._plan.pixel_slots(), net._plan.n_local_frames, H * W
+for label, mode, nbytes in (("flow", _lib.M_FLOW_ACTIVE, ps * 24 + nl * P * 5), ("align", 0, ps * 16 + nl * P * 4)):
+    if a.mode not in ("both", label):
+        continue
+    _lib.check(net._lib.a3r_ga_prepare(C.byref(st), mode, stream))
+    for _ in range(3):
+        _lib.check(net._lib.a3r_ga_accumulate(C.byref(st), mode, stream))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.reps):
+        _lib.check(net._lib.a3r_ga_accumulate(C.byref(st), mode, stream))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.reps
+    print(f"scan[{label}] {ms:.4f} ms/launch  {nbytes / ms / 1e6:.1f} GB/s algorithmic  ({nbytes / ms / 1e6 / 6549.4:.3f} of 6549.4 GB/s measured peak)", flush=True)
