@@ -662,12 +662,47 @@ int a3r_ga_accumulate(const A3rProblem* p, uint32_t mode, void* stream) {
     return l2 ? launch_accumulate<false, true>(p, st) : launch_accumulate<false, false>(p, st);
 }
 
-int a3r_ga_update(const A3rProblem* p, uint32_t mode, const A3rAdamStep* adam, void* stream) {
-    if (int rc = check_problem(p)) return rc;
-    if (!adam) return a3r_fail(A3R_E_ARG, "adam is NULL");
-    cudaStream_t st = (cudaStream_t)stream;
+// The depth-plane Adam step (K3, HBM-bound, ~38 us on C2) only needs the flow normalisers of k_loss_scalars; the chain /
+// small-parameter Adam / next prepare kernels (latency-bound, ~40 us together) never touch the depth planes.  They run
+// side by side: K3 on a library-owned auxiliary stream, forked after k_loss_scalars and joined before the next scan.
+struct AuxLane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static int aux_lane(AuxLane** out) {
+    static AuxLane lanes[64];
+    int dev = 0;
+    A3R_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return a3r_fail(A3R_E_ARG, "device index %d out of range", dev);
+    AuxLane& l = lanes[dev];
+    if (!l.stream) {
+        A3R_CUDA(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+        A3R_CUDA(cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming));
+        A3R_CUDA(cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming));
+    }
+    *out = &l;
+    return A3R_OK;
+}
+
+// update without the final join: *pending_join is set when K3 is still running on the auxiliary stream
+static int update_forked(const A3rProblem* p, uint32_t mode, const A3rAdamStep* adam, cudaStream_t st, AuxLane* lane, bool* pending_join) {
+    *pending_join = false;
     A3R_CUDA(cudaMemsetAsync(p->frame_grad, 0, sizeof(double) * FG_STRIDE * (size_t)p->n_frames, st));
     k_loss_scalars<<<1, 512, 0, st>>>(*p, mode, *adam);
+    const bool apply = mode & A3R_M_APPLY_ADAM;
+    if (p->n_local_frames > 0 && (!apply || (p->flags & A3R_F_TRAIN_DEPTH))) {
+        A3R_CUDA(cudaEventRecord(lane->fork, st));
+        A3R_CUDA(cudaStreamWaitEvent(lane->stream, lane->fork, 0));
+        const bool flow = (mode & A3R_M_FLOW_ACTIVE) && (p->flags & A3R_F_HAS_FLOW) && p->flow_loss_weight > 0.f;
+        const int64_t total4 = (int64_t)p->n_local_frames * p->pix_stride / 4;
+        int64_t grid = (total4 + 255) / 256;
+        if (grid > 148 * 8) grid = 148 * 8;
+        if (flow) k_update_depth<true><<<(unsigned)grid, 256, 0, lane->stream>>>(*p, mode, *adam);
+        else k_update_depth<false><<<(unsigned)grid, 256, 0, lane->stream>>>(*p, mode, *adam);
+        A3R_CUDA(cudaGetLastError());
+        A3R_CUDA(cudaEventRecord(lane->join, lane->stream));
+        *pending_join = true;
+    }
     {
         const int items = p->n_frames + 2 * p->n_edges + (p->n_frames - 1) + p->n_edges;
         k_chain<<<(items + 127) / 128, 128, 0, st>>>(*p, mode);
@@ -675,26 +710,36 @@ int a3r_ga_update(const A3rProblem* p, uint32_t mode, const A3rAdamStep* adam, v
         if (p->flags & A3R_F_SHARED_FOCAL) k_adam_focal<<<1, 32, 0, st>>>(*p, mode, *adam);
     }
     A3R_CUDA(cudaGetLastError());
-    const bool apply = mode & A3R_M_APPLY_ADAM;
-    if (p->n_local_frames > 0 && (!apply || (p->flags & A3R_F_TRAIN_DEPTH))) {
-        const bool flow = (mode & A3R_M_FLOW_ACTIVE) && (p->flags & A3R_F_HAS_FLOW) && p->flow_loss_weight > 0.f;
-        const int64_t total4 = (int64_t)p->n_local_frames * p->pix_stride / 4;
-        int64_t grid = (total4 + 255) / 256;
-        if (grid > 148 * 8) grid = 148 * 8;
-        if (flow) k_update_depth<true><<<(unsigned)grid, 256, 0, st>>>(*p, mode, *adam);
-        else k_update_depth<false><<<(unsigned)grid, 256, 0, st>>>(*p, mode, *adam);
-        A3R_CUDA(cudaGetLastError());
-    }
+    return A3R_OK;
+}
+
+int a3r_ga_update(const A3rProblem* p, uint32_t mode, const A3rAdamStep* adam, void* stream) {
+    if (int rc = check_problem(p)) return rc;
+    if (!adam) return a3r_fail(A3R_E_ARG, "adam is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    AuxLane* lane = nullptr;
+    if (int rc = aux_lane(&lane)) return rc;
+    bool pending = false;
+    if (int rc = update_forked(p, mode, adam, st, lane, &pending)) return rc;
+    if (pending) A3R_CUDA(cudaStreamWaitEvent(st, lane->join, 0));      // everything is ordered in the caller's stream on return
     return A3R_OK;
 }
 
 int a3r_ga_run(const A3rProblem* p, int32_t count, const uint32_t* modes, const A3rAdamStep* steps, void* stream) {
     if (count < 0 || !modes || !steps) return a3r_fail(A3R_E_ARG, "a3r_ga_run: bad arguments");
+    if (int rc = check_problem(p)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    AuxLane* lane = nullptr;
+    if (int rc = aux_lane(&lane)) return rc;
+    bool pending = false;
     for (int32_t k = 0; k < count; ++k) {
-        if (int rc = a3r_ga_prepare(p, modes[k], stream)) return rc;
+        if (int rc = a3r_ga_prepare(p, modes[k], stream)) return rc;                 // overlaps the previous iteration's K3
+        if (pending) A3R_CUDA(cudaStreamWaitEvent(st, lane->join, 0));               // the scan reads the depth planes
         if (int rc = a3r_ga_accumulate(p, modes[k], stream)) return rc;
-        if (int rc = a3r_ga_update(p, modes[k], &steps[k], stream)) return rc;
+        if (!steps) return a3r_fail(A3R_E_ARG, "steps is NULL");
+        if (int rc = update_forked(p, modes[k], &steps[k], st, lane, &pending)) return rc;
     }
+    if (pending) A3R_CUDA(cudaStreamWaitEvent(st, lane->join, 0));
     return A3R_OK;
 }
 
