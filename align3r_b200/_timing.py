@@ -1,0 +1,28 @@
+"""A3R_TIMING=1: wall-clock of the phases of a host-side call on stderr (diagnostic; off by default)."""
+import os
+import sys
+import time
+
+import torch
+
+
+class Phases:
+    def __init__(self, name, device=None, sync=False):
+        self.on = bool(os.environ.get("A3R_TIMING"))
+        self.name, self.dev, self.sync, self.rows = name, device, sync, []
+        if self.on:
+            if self.sync:
+                torch.cuda.synchronize(self.dev)
+            self.t = time.perf_counter()
+
+    def mark(self, label):
+        if self.on:
+            if self.sync:
+                torch.cuda.synchronize(self.dev)
+            now = time.perf_counter()
+            self.rows.append(f"{label} {1e3 * (now - self.t):.1f}")
+            self.t = now
+
+    def done(self):
+        if self.on:
+            print(f"[a3r {self.name} ms] " + "  ".join(self.rows), file=sys.stderr, flush=True)

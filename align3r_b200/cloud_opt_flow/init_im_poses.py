@@ -22,6 +22,7 @@ import scipy.sparse as sp
 import torch
 
 from .. import _lib
+from .._timing import Phases
 from .commons import edge_str, signed_log1p
 
 
@@ -160,7 +161,9 @@ def init_minimum_spanning_tree(self, save_score_path=None, save_score_only=False
     if init_priors is not None:
         raise NotImplementedError("init_priors (hierarchical clip driver, reference init_im_poses.py:173-215) is a "
                                   "'next' row of the scope table")
+    ph = Phases('mst-init', self.device)
     scores = compute_edge_scores(self)
+    ph.mark('scores')
     if save_score_only or save_score_path is not None:
         raise NotImplementedError("save_score_path / save_score_only draw a seaborn heat-map in the reference "
                                   "(init_im_poses.py:24-42); plotting is out of scope")
@@ -218,6 +221,7 @@ def init_minimum_spanning_tree(self, save_score_path=None, save_score_only=False
         if i not in focal_slot:
             focal_slot[i] = 2 * eid[(i, j)]
 
+    ph.mark('tree')
     # ---- pass 2: every pointmap reduction in two batched launches ----
     pairs = []
     # tree steps: y = the slot the anchor frame's pointmap is made of *at that time* = src[anchor]
@@ -226,8 +230,11 @@ def init_minimum_spanning_tree(self, save_score_path=None, save_score_only=False
     for e, (i, j) in enumerate(self.edges):               # init_from_pts3d: pred_i[e] onto pts3d[i]
         pairs.append((2 * e, src[i]))
     reg = _run_procrustes(self, pairs)
+    ph.mark('procrustes')
     frames_f = sorted(focal_slot)
     focals = dict(zip(frames_f, _run_focals(self, [focal_slot[n] for n in frames_f]).tolist()))
+
+    ph.mark('focals')
 
     def sim(row):
         return float(row[0]), row[1:10].reshape(3, 3), row[10:13]
@@ -250,32 +257,39 @@ def init_minimum_spanning_tree(self, save_score_path=None, save_score_only=False
     jobs = []
     for n in range(N):
         if im_poses[n] is None and n in self._lframe:
-            s, R, tt = T[n]
             h, w = self.imshapes[n]
-            X = self._bufs.predw[self._lslot[src[n]], :h * w, :3]
-            A = torch.from_numpy((s * R).astype(np.float32)).to(self.device)
-            pts = (X @ A.T + torch.from_numpy(tt.astype(np.float32)).to(self.device)).view(h, w, 3)
-            msk = self.im_conf[self._lframe[n]] > self.min_conf_thr
-            jobs.append((n, pts.cpu(), msk.cpu()))
+            # the raw slot plane and the confidence map go to the host as they are; the similarity that makes the
+            # world pointmap of frame n is applied by the worker (numpy), next to the cv2 call that consumes it
+            X = self._bufs.predw[self._lslot[src[n]], :h * w].to('cpu', non_blocking=False)
+            msk = (self.im_conf[self._lframe[n]] > self.min_conf_thr).cpu()
+            jobs.append((n, X, msk, T[n], (h, w)))
+    ph.mark(f'pnp-prep({len(jobs)})')
     if jobs:
         from concurrent.futures import ThreadPoolExecutor
         import os as _os
 
         def _solve(job):
-            n, pts, msk = job
-            return n, fast_pnp(pts.numpy(), im_focals[n], msk.numpy(), niter_PnP=niter_PnP)
+            n, X, msk, (s, R, tt), (h, w) = job
+            A, t32, Xn = (s * R).astype(np.float32), tt.astype(np.float32), X.numpy()
+            # plain ufuncs (no BLAS: a threaded GEMM inside every worker would oversubscribe the host)
+            pts = (Xn[:, 0:1] * A[:, 0] + Xn[:, 1:2] * A[:, 1] + Xn[:, 2:3] * A[:, 2] + t32).reshape(h, w, 3)
+            return n, fast_pnp(pts, im_focals[n], msk.numpy(), niter_PnP=niter_PnP)
 
         with ThreadPoolExecutor(max_workers=min(len(jobs), _os.cpu_count() or 1)) as pool:
             for n, res in pool.map(_solve, jobs):
                 if res:
                     pnp[n, 0] = 1
                     pnp[n, 1:] = res[1].ravel()
+    ph.mark('pnp-solve')
     pnp = _allreduce_np(self, pnp)
     for n in range(N):
         if im_poses[n] is None:
             im_poses[n] = pnp[n, 1:].reshape(4, 4) if pnp[n, 0] > 0 else np.eye(4)
     im_poses = np.stack(im_poses)
-    return init_from_pts3d(self, T, src, reg[len(steps):], im_focals, im_poses)
+    res = init_from_pts3d(self, T, src, reg[len(steps):], im_focals, im_poses)
+    ph.mark('init_from_pts3d')
+    ph.done()
+    return res
 
 
 def init_from_pts3d(self, T, src, edge_reg, im_focals, im_poses):

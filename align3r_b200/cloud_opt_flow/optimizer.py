@@ -22,6 +22,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
+from .._timing import Phases
 from ..plan import build_plan, check_edges, frame_costs, partition_frames
 from ..problem import ProblemBuffers, adam_schedule, modes_array
 from .commons import (edge_str, get_conf_trf, get_conf_untrf, signed_expm1, signed_log1p, schedule_lr,
@@ -176,6 +177,7 @@ class PointCloudOptimizer(nn.Module):
         self.total_area_i = sum(im_areas[i] for i, j in self.edges)
         self.total_area_j = sum(im_areas[j] for i, j in self.edges)
 
+        ph = Phases('construct')
         # ---------------- plan + shard ----------------
         self._shard = shard
         frame_range = None
@@ -195,8 +197,33 @@ class PointCloudOptimizer(nn.Module):
         self._lslot = plan.local_slot_of()
         self._lframe = plan.local_frame_of()
 
+        ph.mark('plan')
+        # ---------------- device buffers; the big host->device uploads start first ----------------
+        want_flow = flow_loss_weight > 0
+        hyper = self._hyper()
+        self._bufs = ProblemBuffers(plan, device, None, hyper, want_flow, loss_hist_len=max(1024, num_total_iter))
+        self._conf_sum = torch.zeros(max(plan.n_local_slots, 1), dtype=torch.float64, device=device)
+        self._im_conf_plane = torch.zeros(max(plan.n_local_frames, 1), plan.pix_stride, device=device)
+        ph.mark('alloc')
+        self._dest = None
+        self._pack_predictions(pred1_pts, pred2_pts, pred1_conf, pred2_conf, pack_chunk)
+        ph.mark('enqueue-pred')
+        self._injected_flow = flow
+        self._uploads_ready = None
+        if want_flow:
+            self.flow_ij, self.flow_ji, self.flow_valid_mask_i, self.flow_valid_mask_j = self.get_flow(sintel_ckpt)
+            # on a side stream: the initialisation does not read the flow planes, its kernels need not queue behind
+            # these copies; the hot loop joins (self._join_uploads)
+            self._upload_stream = torch.cuda.Stream(device)
+            self._upload_stream.wait_stream(torch.cuda.current_stream(device))
+            self._bufs.arena.record_stream(self._upload_stream)
+            with torch.cuda.stream(self._upload_stream):
+                self._pack_flow(masks=False)      # asynchronous from pinned host memory; the masks follow below
+
+        ph.mark('enqueue-flow')
         # ---------------- parameters (reference base_opt.py:112-114, optimizer.py:54-75) ----------------
-        # drawn on the CPU in the reference's order so that a seeded run starts from the same values
+        # drawn on the CPU in the reference's order so that a seeded run starts from the same values (the copies above
+        # are in flight meanwhile)
         pw_poses = rand_pose((self.n_edges, 1 + self.POSE_DIM))
         depth0 = [torch.randn(H, W) / 10 - 3 for H, W in self.imshapes]
         im_poses = torch.stack([rand_pose(self.POSE_DIM) for _ in range(self.n_imgs)])
@@ -209,7 +236,9 @@ class PointCloudOptimizer(nn.Module):
         self.pw_poses = nn.Parameter(pw_poses.float().to(device).contiguous())
         self.pw_adaptors = nn.Parameter(torch.zeros((self.n_edges, 2), device=device))
         self.pw_adaptors.requires_grad_(allow_pw_adaptors)
+        ph.mark('rand-params')
         self.im_depthmaps = nn.Parameter(depth_local.to(device))          # (local frames, pix_stride) log-depth
+        ph.mark('depth-upload')
         self.im_poses = nn.Parameter(im_poses.float().to(device).contiguous())
         self.im_focals = nn.Parameter(im_focals.to(device))
         self.im_pp = nn.Parameter(torch.zeros((self.n_imgs, 2), device=device))
@@ -217,21 +246,16 @@ class PointCloudOptimizer(nn.Module):
         self.register_buffer('_pp', torch.tensor([(w / 2, h / 2) for h, w in self.imshapes], device=device))
         self.register_buffer('_ei', torch.tensor([i for i, j in self.edges], device=device))
         self.register_buffer('_ej', torch.tensor([j for i, j in self.edges], device=device))
-
-        # ---------------- device buffers ----------------
-        want_flow = flow_loss_weight > 0
-        hyper = self._hyper()
-        params = dict(pw_poses=self.pw_poses.data, pw_adaptors=self.pw_adaptors.data, im_depthmaps=self.im_depthmaps.data,
-                      im_poses=self.im_poses.data, im_focals=self.im_focals.data.view(-1), im_pp=self.im_pp.data)
-        self._bufs = ProblemBuffers(plan, device, params, hyper, want_flow, loss_hist_len=max(1024, num_total_iter))
-        self._conf_sum = torch.zeros(max(plan.n_local_slots, 1), dtype=torch.float64, device=device)
-        self._im_conf_plane = torch.zeros(max(plan.n_local_frames, 1), plan.pix_stride, device=device)
-        self._pack_predictions(pred1_pts, pred2_pts, pred1_conf, pred2_conf, pack_chunk)
+        self._bufs.attach_params(dict(pw_poses=self.pw_poses.data, pw_adaptors=self.pw_adaptors.data,
+                                      im_depthmaps=self.im_depthmaps.data, im_poses=self.im_poses.data,
+                                      im_focals=self.im_focals.data.view(-1), im_pp=self.im_pp.data))
         self.im_conf = [self._im_conf_plane[k, :im_areas[n]].view(self.imshapes[n]) for k, n in enumerate(plan.lframe_id.tolist())]
-        self.init_conf_maps = [c.clone() for c in self.im_conf]
+        init_plane = self._im_conf_plane.clone()
+        self.init_conf_maps = [init_plane[k, :im_areas[n]].view(self.imshapes[n]) for k, n in enumerate(plan.lframe_id.tolist())]
         self.pred_i, self.pred_j = _SlotDict(self, 0, "pts"), _SlotDict(self, 1, "pts")
         self.conf_i, self.conf_j = _SlotDict(self, 0, "conf"), _SlotDict(self, 1, "conf")
 
+        ph.mark('attach')
         # ---------------- optional per-frame extras (reference base_opt.py:118-157) ----------------
         self.imgs = None
         if 'img' in view1 and 'img' in view2:
@@ -267,10 +291,8 @@ class PointCloudOptimizer(nn.Module):
             self.img_pathes = img_pathes
 
         # ---------------- flow term inputs (reference optimizer.py:104-116) ----------------
-        self._injected_flow = flow
         self.sam2_dynamic_masks = None
         if want_flow:
-            self.flow_ij, self.flow_ji, self.flow_valid_mask_i, self.flow_valid_mask_j = self.get_flow(sintel_ckpt)
             if use_self_mask:
                 raise NotImplementedError("use_self_mask=True (get_motion_mask_from_pairs, reference optimizer.py:156-235) "
                                           "is a 'next' row of the scope table; pass dynamic_mask in the views instead")
@@ -278,7 +300,11 @@ class PointCloudOptimizer(nn.Module):
                 raise ValueError("the flow term needs dynamic masks: put 'dynamic_mask' into view1/view2 "
                                  "(the reference fails with torch.stack(None) here, optimizer.py:533)")
             assert len(set(self.imshapes)) == 1, "the flow term requires uniform image shapes (reference optimizer.py:528)"
-            self._pack_flow()
+            with torch.cuda.stream(self._upload_stream):
+                self._upload_masks()
+                self._uploads_ready = self._upload_stream.record_event()
+        ph.mark('extras+masks')
+        ph.done()
         self._adam_step = 0
         self._eval_version = 0
         self._forward_param_names = ()
@@ -314,13 +340,34 @@ class PointCloudOptimizer(nn.Module):
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self._device).cuda_stream)
 
+    def _join_uploads(self):
+        """The flow planes / static masks were uploaded on a side stream: order the current stream after them."""
+        if self._uploads_ready is not None:
+            torch.cuda.current_stream(self._device).wait_event(self._uploads_ready)
+            self._uploads_ready = None
+
+    def _dest_tables(self, side):
+        """(local slot, local frame) of every row this device packs, per side - uploaded once, before the first big copy is
+        queued (a pageable upload is synchronous: issued later it would wait for all the copies ahead of it)."""
+        if self._dest is None:
+            rows = [[(e, r) for e, r in sorted(self._row_of_edge.items()) if (2 * e + sd) in self._lslot] for sd in (0, 1)]
+            flat = []
+            for sd in (0, 1):
+                flat += [self._lslot[2 * e + sd] for e, _ in rows[sd]] + [self._lframe[self.edges[e][sd]] for e, _ in rows[sd]]
+            t = torch.tensor(flat, dtype=torch.int32).to(self._device)
+            n0, n1 = len(rows[0]), len(rows[1])
+            self._dest = ((t[:n0], t[n0:2 * n0]), (t[2 * n0:2 * n0 + n1], t[2 * n0 + n1:]))
+        return self._dest[side]
+
     def _pack_predictions(self, pts1, pts2, conf1, conf2, chunk):
+        chunk = max(1, min(int(chunk), self._bufs.stage_rows))
         """Upload the raw pair predictions chunk by chunk and pack them into the slot planes."""
         plan, dev, b = self._plan, self._device, self._bufs
         mode = _lib.CONF_MODES[self.conf_mode]
         with torch.cuda.device(dev):
             for side, (pts, conf) in enumerate(((pts1, conf1), (pts2, conf2))):
                 todo = [(e, r) for e, r in sorted(self._row_of_edge.items()) if (2 * e + side) in self._lslot]
+                slots_all, lfr_all = self._dest_tables(side)
                 # group consecutive rows of equal shape into one upload
                 k = 0
                 while k < len(todo):
@@ -331,29 +378,30 @@ class PointCloudOptimizer(nn.Module):
                            and tuple(pts[r0 + m].shape[0:2]) == shp):
                         m += 1
                     P = shp[0] * shp[1]
+                    # staged through the problem's one staging area: copy(k+1) queues behind pack(k) on this stream
+                    dp = b.stage[:m * P * 3].view(m, P, 3)
+                    dc = b.stage[m * P * 3:m * P * 4].view(m, P)
                     if isinstance(pts, torch.Tensor):
-                        dp = pts[r0:r0 + m].to(dev, dtype=torch.float32, non_blocking=True).reshape(m, P, 3).contiguous()
-                        dc = conf[r0:r0 + m].to(dev, dtype=torch.float32, non_blocking=True).reshape(m, P).contiguous()
+                        dp.copy_(pts[r0:r0 + m].reshape(m, P, 3), non_blocking=True)
+                        dc.copy_(conf[r0:r0 + m].reshape(m, P), non_blocking=True)
                     else:
-                        dp = torch.stack([pts[r0 + q].reshape(P, 3) for q in range(m)]).to(dev, dtype=torch.float32)
-                        dc = torch.stack([conf[r0 + q].reshape(P) for q in range(m)]).to(dev, dtype=torch.float32)
-                    es = [todo[k + q][0] for q in range(m)]
-                    slots = torch.tensor([self._lslot[2 * e + side] for e in es], dtype=torch.int32, device=dev)
-                    lfr = torch.tensor([self._lframe[self.edges[e][side]] for e in es], dtype=torch.int32, device=dev)
+                        dp.copy_(torch.stack([torch.as_tensor(pts[r0 + q]).reshape(P, 3) for q in range(m)]), non_blocking=True)
+                        dc.copy_(torch.stack([torch.as_tensor(conf[r0 + q]).reshape(P) for q in range(m)]), non_blocking=True)
+                    slots, lfr = slots_all[k:k + m], lfr_all[k:k + m]
                     _lib.check(self._lib.a3r_pack_pred(_lib.ptr(dp), _lib.ptr(dc), m, P, _lib.ptr(slots), _lib.ptr(lfr),
                                                        plan.pix_stride, mode, _lib.ptr(b.predw), _lib.ptr(self._im_conf_plane),
                                                        _lib.ptr(self._conf_sum), self._stream()), "a3r_pack_pred")
-                    dp.record_stream(torch.cuda.current_stream(dev))
-                    dc.record_stream(torch.cuda.current_stream(dev))
                     k += m
 
-    def _pack_flow(self, chunk=32):
+    def _pack_flow(self, chunk=32, masks=True):
+        chunk = max(1, min(int(chunk), self._bufs.stage_rows))
         plan, dev, b = self._plan, self._device, self._bufs
         H, W = self.imshape
         P = H * W
         with torch.cuda.device(dev):
             for side, fl in enumerate((self.flow_ij, self.flow_ji)):
                 todo = [(e, r) for e, r in sorted(self._row_of_edge.items()) if (2 * e + side) in self._lslot]
+                slots_all, _ = self._dest_tables(side)
                 for k in range(0, len(todo), chunk):
                     part = todo[k:k + chunk]
                     rows = [r for _, r in part]
@@ -361,18 +409,24 @@ class PointCloudOptimizer(nn.Module):
                         src = fl[rows[0]:rows[0] + len(rows)]
                     else:
                         src = fl[rows]
-                    d = src.to(dev, dtype=torch.float32, non_blocking=True).reshape(len(rows), 2, P).contiguous()
-                    slots = torch.tensor([self._lslot[2 * e + side] for e, _ in part], dtype=torch.int32, device=dev)
+                    d = b.stage[:len(rows) * 2 * P].view(len(rows), 2, P)
+                    d.copy_(src.reshape(len(rows), 2, P), non_blocking=True)
+                    slots = slots_all[k:k + len(part)]
                     _lib.check(self._lib.a3r_pack_flow(_lib.ptr(d), len(rows), P, _lib.ptr(slots), plan.pix_stride,
                                                        _lib.ptr(b.flow), self._stream()), "a3r_pack_flow")
-                    d.record_stream(torch.cuda.current_stream(dev))
-            self._upload_masks()
+            if masks:
+                self._upload_masks()
 
     def _upload_masks(self):
         """static_mask = ~dynamic_mask per local frame (reference optimizer.py:533-537)."""
         b, plan = self._bufs, self._plan
         masks = self.sam2_dynamic_masks if self.sam2_dynamic_masks is not None else self.dynamic_masks
-        for k, n in enumerate(plan.lframe_id.tolist()):
+        lfr = plan.lframe_id.tolist()
+        if len(lfr) and len({tuple(torch.as_tensor(masks[n]).shape) for n in lfr}) == 1:      # one upload for all frames
+            m = torch.stack([torch.as_tensor(masks[n]).bool().reshape(-1) for n in lfr])
+            b.static_mask[:, :m.shape[1]] = (~m).to(torch.uint8).to(self._device)
+            return
+        for k, n in enumerate(lfr):
             m = torch.as_tensor(masks[n]).to(self._device).bool().reshape(-1)
             b.static_mask[k, :m.numel()] = (~m).to(torch.uint8)
 
@@ -386,8 +440,9 @@ class PointCloudOptimizer(nn.Module):
         flow_ij, flow_ji = self._injected_flow[:2]
         n = flow_ij.shape[0]
         H, W = flow_ij.shape[-2:]
-        ones = torch.ones((n, 1, H, W), dtype=torch.bool)
-        return flow_ij, flow_ji, ones, ones.clone()
+        # the reference stores OccMask validity maps it never reads (optimizer.py:105-111): all-true, broadcast views
+        ones = torch.ones((1, 1, 1, 1), dtype=torch.bool).expand(n, 1, H, W)
+        return flow_ij, flow_ji, ones, ones
 
     # =====================================================================================
     # properties (reference base_opt.py:159-173)
@@ -694,6 +749,7 @@ class PointCloudOptimizer(nn.Module):
     def _phase_accumulate(self, mode):
         """parameter maps + fused forward/backward scan over this device's pixel-slots."""
         with torch.cuda.device(self._device):
+            self._join_uploads()
             st = self._bufs.struct(self._trainable())
             s = self._stream()
             _lib.check(self._lib.a3r_ga_prepare(C.byref(st), mode, s), "a3r_ga_prepare")
@@ -820,6 +876,7 @@ def global_alignment_loop(net, lr=0.01, niter=300, schedule='cosine', lr_min=1e-
         import tqdm
         bar = tqdm.tqdm(total=niter)
     with torch.cuda.device(net._device):
+        net._join_uploads()
         st = b.struct(trainable)
         s = net._stream()
         it = 0

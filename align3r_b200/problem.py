@@ -48,33 +48,45 @@ class ProblemBuffers:
         self.lslot_gslot = i32(plan.lslot_gslot)
         self.cta_tile_begin = i32(plan.cta_tile_begin)
 
-        # parameters (owned by the caller, e.g. nn.Parameters) + Adam moments + gradients
-        self.params = params
-        for k in PARAM_NAMES:
-            t = params[k]
-            assert t.device == dev and t.dtype == torch.float32 and t.is_contiguous(), k
-        assert tuple(params["pw_poses"].shape) == (E, 8)
-        assert tuple(params["pw_adaptors"].shape) == (E, 2)
-        assert tuple(params["im_poses"].shape) == (N, 7)
-        assert tuple(params["im_pp"].shape) == (N, 2)
-        assert tuple(params["im_depthmaps"].shape) == (nl, stride), (params["im_depthmaps"].shape, nl, stride)
-        assert params["im_focals"].numel() == (1 if hyper["shared_focal"] else N)
-        self.moments = {k: (torch.zeros_like(params[k]), torch.zeros_like(params[k])) for k in PARAM_NAMES}
-        self.grads = {k: torch.zeros_like(params[k]) for k in PARAM_NAMES if k != "im_depthmaps"}
+        # parameters (owned by the caller, e.g. nn.Parameters) + Adam moments + gradients: attach_params()
+        self.params, self.moments, self.grads = None, None, None
+        if params is not None:
+            self.attach_params(params)
 
         self.frame_par = zeros(N, 16)
         self.edge_par = zeros(E, 16)
         self.slot_par = zeros(2 * E, 16)
 
-        # packed constant inputs
-        self.predw = zeros(max(nls, 1), stride, 4)
-        self.flow = zeros(max(nls, 1), stride, 2) if has_flow else None
-        self.static_mask = zeros(max(nl, 1), stride, dtype=torch.uint8) if has_flow else None
+        # packed constant inputs, per-pixel gradient planes and the upload staging area: ONE device allocation carved
+        # into views (a cudaMalloc costs milliseconds on a B200 box; a job would otherwise pay a dozen of them)
+        nls1, nl1 = max(nls, 1), max(nl, 1)
+        self.stage_rows = 32                                    # rows (edge-sides) per staged upload chunk
+        parts = [("predw", nls1 * stride * 4, torch.float32), ("flow", nls1 * stride * 2 if has_flow else 0, torch.float32),
+                 ("g_align", nl1 * stride, torch.float32), ("g_flow_i", nl1 * stride if has_flow else 0, torch.float32),
+                 ("g_flow_j", nl1 * stride if has_flow else 0, torch.float32),
+                 ("stage", self.stage_rows * stride * 4, torch.float32),
+                 ("static_mask", nl1 * stride if has_flow else 0, torch.uint8)]
+        offs, total = {}, 0
+        for name, numel, dt in parts:
+            offs[name] = total
+            total += (numel * torch.empty((), dtype=dt).element_size() + 255) // 256 * 256
+        self.arena = torch.empty(total, dtype=torch.uint8, device=dev)
+        zero_to = offs["stage"]                                 # the staging area and what follows need no fill ...
+        self.arena[:zero_to].zero_()
 
-        # per-pixel gradient planes
-        self.g_align = zeros(max(nl, 1), stride)
-        self.g_flow_i = zeros(max(nl, 1), stride) if has_flow else self.g_align
-        self.g_flow_j = zeros(max(nl, 1), stride) if has_flow else self.g_align
+        def carve(name, dt, *shape):
+            n = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+            return self.arena[offs[name]:offs[name] + n].view(dt).view(*shape)
+
+        self.predw = carve("predw", torch.float32, nls1, stride, 4)
+        self.flow = carve("flow", torch.float32, nls1, stride, 2) if has_flow else None
+        self.static_mask = carve("static_mask", torch.uint8, nl1, stride) if has_flow else None
+        if has_flow:
+            self.static_mask.zero_()                            # ... except the masks behind it
+        self.g_align = carve("g_align", torch.float32, nl1, stride)
+        self.g_flow_i = carve("g_flow_i", torch.float32, nl1, stride) if has_flow else self.g_align
+        self.g_flow_j = carve("g_flow_j", torch.float32, nl1, stride) if has_flow else self.g_align
+        self.stage = carve("stage", torch.float32, self.stage_rows * stride * 4)
 
         # fp64 reduction buffers: acc_slot and acc_frame are one contiguous allocation
         self.acc = zeros(2 * E * _lib.SLOT_ACC + N * _lib.FRAME_ACC, dtype=torch.float64)
@@ -84,6 +96,26 @@ class ProblemBuffers:
         self.edge_scratch = zeros(E, dtype=torch.float64)
         self.scal = zeros(_lib.SCAL, dtype=torch.float64)
         self.loss_hist = zeros(loss_hist_len)
+        self._struct = None
+
+    # -----------------------------------------------------------------------------------
+    def attach_params(self, params: dict):
+        """Parameter tensors may arrive after the input planes were allocated (the constructor of the optimiser starts the
+        big host->device uploads first and draws the random initial parameters on the CPU while they run)."""
+        plan, dev = self.plan, self.device
+        N, E, nl, stride = plan.n_frames, plan.n_edges, plan.n_local_frames, plan.pix_stride
+        self.params = params
+        for k in PARAM_NAMES:
+            t = params[k]
+            assert t.device == dev and t.dtype == torch.float32 and t.is_contiguous(), k
+        assert tuple(params["pw_poses"].shape) == (E, 8)
+        assert tuple(params["pw_adaptors"].shape) == (E, 2)
+        assert tuple(params["im_poses"].shape) == (N, 7)
+        assert tuple(params["im_pp"].shape) == (N, 2)
+        assert tuple(params["im_depthmaps"].shape) == (nl, stride), (params["im_depthmaps"].shape, nl, stride)
+        assert params["im_focals"].numel() == (1 if self.hyper["shared_focal"] else N)
+        self.moments = {k: (torch.zeros_like(params[k]), torch.zeros_like(params[k])) for k in PARAM_NAMES}
+        self.grads = {k: torch.zeros_like(params[k]) for k in PARAM_NAMES if k != "im_depthmaps"}
         self._struct = None
 
     # -----------------------------------------------------------------------------------
