@@ -70,6 +70,28 @@ def _compose(a, b):
     return sa * sb, Ra @ Rb, sa * (Ra @ tb) + ta
 
 
+def _umeyama(x, y):
+    """Unweighted similarity registration y ~ s R x + t (roma.rigid_points_registration(compute_scaling=True)), fp64."""
+    xm, ym = x.mean(0), y.mean(0)
+    xc, yc = x - xm, y - ym
+    U, D, Vt = np.linalg.svd(yc.T @ xc)
+    d = np.sign(np.linalg.det(U @ Vt))
+    R = U @ np.diag([1.0, 1.0, d]) @ Vt
+    s = (D[0] + D[1] + d * D[2]) / (xc ** 2).sum()
+    return float(s), R, ym - s * (R @ xm)
+
+
+def align_multiple_poses(src_poses, target_poses):
+    """reference init_im_poses.py:534-542 on (N,4,4) numpy cam-to-world poses -> (s, R, t)."""
+    from scipy.spatial.distance import pdist
+
+    def center_and_z(P):
+        eps = float(np.median(pdist(P[:, :3, 3]))) / 100          # utils/geometry.py:370-372
+        return np.concatenate((P[:, :3, 3], P[:, :3, 3] + eps * P[:, :3, 2]))
+
+    return _umeyama(center_and_z(np.asarray(src_poses, dtype=np.float64)), center_and_z(np.asarray(target_poses, dtype=np.float64)))
+
+
 def _rigid4x4(R, t):
     M = np.eye(4)
     M[:3, :3] = R
@@ -297,8 +319,17 @@ def init_from_pts3d(self, T, src, edge_reg, im_focals, im_poses):
     from scipy.spatial.transform import Rotation
     N, E = self.n_imgs, self.n_edges
     if not self.im_poses.requires_grad:
-        raise NotImplementedError("MST initialisation with preset (frozen) poses: align_multiple_poses branch "
-                                  "(reference init_im_poses.py:109-122) is not built yet")
+        # every pose was preset and frozen (preset_pose): global Sim(3) alignment of the tree onto the known poses
+        # (reference init_im_poses.py:109-122); world pointmaps are symbolic, so "rotate everything" = compose T_n
+        if N == 1:
+            raise NotImplementedError("Would be simpler to just align everything afterwards on the single known pose")
+        known = self.get_im_poses().detach().cpu().double().numpy()
+        s, R, t = align_multiple_poses(im_poses, known)
+        trf = np.eye(4)
+        trf[:3, :3], trf[:3, 3] = s * R, t
+        im_poses = trf @ im_poses
+        im_poses[:, :3, :3] /= s
+        T = {n: _compose((s, R, t), Tn) for n, Tn in T.items()}
 
     # ---- pairwise poses: register(pred_i[e] -> pts3d[i]) = T_i o register(slot 2e -> src_i) ----
     Rs = np.zeros((E, 3, 3))
@@ -346,7 +377,8 @@ def init_from_pts3d(self, T, src, edge_reg, im_focals, im_poses):
     po = np.zeros((N, 7), dtype=np.float32)
     po[:, 0:4] = Rotation.from_matrix(im_poses[:, :3, :3]).as_quat().astype(np.float32)
     po[:, 4:7] = signed_log1p(torch.from_numpy(im_poses[:, :3, 3].astype(np.float32))).numpy()
-    self.im_poses.data.copy_(torch.from_numpy(po).to(self.device))
+    if self.im_poses.requires_grad:                       # _set_pose only writes parameters that are not preset
+        self.im_poses.data.copy_(torch.from_numpy(po).to(self.device))
     if self.im_focals.requires_grad:
         if self.shared_focal:
             self._set_focal(0, sum(im_focals) / N)
@@ -363,5 +395,48 @@ def init_from_pts3d(self, T, src, edge_reg, im_focals, im_poses):
 
 @torch.no_grad()
 def init_from_known_poses(self, niter_PnP=10, min_conf_thr=3):
-    raise NotImplementedError("init='known_poses' (reference init_im_poses.py:44-85) is a secondary entry point "
-                              "(SURVEY.md section 8(a) row E6) and is not built yet")
+    """init='known_poses' - reference init_im_poses.py:44-85.  Pairwise poses: RANSAC-PnP pose of the second view of
+    every pair (on the host, as in the reference) aligned with the two known cameras; depth maps: the best-scoring
+    pred_i of every frame, rescaled.  Single-device only (an edge's two sides may live on different frame windows)."""
+    if self._shard is not None and int(self._shard['world']) > 1:
+        raise NotImplementedError("init='known_poses' on a frame-window sharded problem")
+    from concurrent.futures import ThreadPoolExecutor
+    import os as _os
+    from scipy.spatial.transform import Rotation
+    E = self.n_edges
+    known = self.get_im_poses().detach().cpu().double().numpy()
+    focals = self.get_focals().detach().cpu().numpy().reshape(self.n_imgs, -1).mean(axis=1)
+    pps = self.get_principal_points().detach().cpu().numpy()
+    jobs = []
+    for e, (i, j) in enumerate(self.edges):
+        i_j = edge_str(i, j)
+        conf = self.conf_i[i_j].cpu()
+        msk = conf > min(min_conf_thr, float(conf.min()) - 0.1)
+        jobs.append((e, self.pred_j[i_j].cpu().numpy(), msk.numpy(), float(focals[i]), tuple(pps[i]), float(conf.mean())))
+
+    def _solve(job):
+        e, pts, msk, f, pp, _ = job
+        return e, fast_pnp(pts, f, msk, pp=pp, niter_PnP=niter_PnP)
+
+    pw = np.zeros((E, 8), dtype=np.float32)
+    best = {}
+    with ThreadPoolExecutor(max_workers=min(len(jobs), _os.cpu_count() or 1)) as pool:
+        results = dict(pool.map(_solve, jobs))
+    for e, (i, j) in enumerate(self.edges):
+        res = results[e]
+        if res is None:
+            raise RuntimeError(f"init='known_poses': PnP failed on pair {edge_str(i, j)} (the reference fails here too)")
+        s, R, t = align_multiple_poses(np.stack((np.eye(4), res[1])), known[[i, j]])
+        pw[e, 0:4] = Rotation.from_matrix(R).as_quat().astype(np.float32)                       # _set_pose, base_opt.py:221
+        pw[e, 4:7] = signed_log1p(torch.from_numpy((t / s).astype(np.float32))).numpy()
+        pw[e, 7] = np.float32(np.log(s))
+        score = jobs[e][5]
+        if score > best.get(i, (0,))[0]:
+            best[i] = (score, e, s)
+    if self.pw_poses.requires_grad:
+        self.pw_poses.data.copy_(torch.from_numpy(pw).to(self.device))
+    for n in range(self.n_imgs):
+        if n in best:
+            _, e, scale = best[n]
+            i, j = self.edges[e]
+            self._set_depthmap(n, self.pred_i[edge_str(i, j)][:, :, 2] * float(scale))

@@ -313,3 +313,41 @@ def test_full_size_properties_c2(cuda_device):
     print("C2 after 60 iterations:", dm, pm)
     assert dm["abs_rel"] < 0.1 and dm["d1"] > 0.9, dm
     assert pm["ate"] < 0.2 and pm["rpe_rot"] < 2.0, pm
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# preset camera poses against the fixture the real reference produced
+# ---------------------------------------------------------------------------------------------------------------
+def test_mst_initialisation_with_frozen_known_poses(cuda_device):
+    fx, scene, prob = golden_case("small_known_poses")
+    ref = fx["mst_frozen"]["params"]
+    net = build(scene, fx["kw"])
+    net.preset_pose(fx["known_c2w"])
+    assert not net.im_poses.requires_grad and net.norm_pw_scale is False
+    init_fun.init_minimum_spanning_tree(net, niter_PnP=10)
+    assert float((net.get_im_poses().detach().cpu() - fx["known_c2w"]).abs().max()) < 1e-5
+    prob.norm_pw_scale = False                                 # preset_pose switches the pair-scale normalisation off
+    T_ref = go.pw_pose_matrices(prob, ref["pw_poses"])
+    assert float((net.get_pw_poses().detach().cpu() - T_ref).abs().max()) < 2e-3      # PnP-initialised frames: fp32 sensitivity
+    d = (net.im_depthmaps.detach().cpu()[:, :prob.P] - ref["im_depthmaps"]).abs()
+    assert float(d.median()) < 1e-4 and float(d.max()) < 5e-3
+    assert rel_err(net.get_focals().detach().cpu(), go.focals(prob, ref["im_focals"])) < 1e-5
+    # the loop then runs with the poses frozen and ends on a finite loss
+    loss = net.compute_global_alignment(init=None, niter=10, schedule="linear", lr=0.01)
+    assert loss == loss and loss < 1e3
+    assert float((net.get_im_poses().detach().cpu() - fx["known_c2w"]).abs().max()) < 1e-5
+
+
+def test_known_poses_initialisation(cuda_device):
+    fx, scene, prob = golden_case("small_known_poses")
+    ref = fx["known_poses"]["params"]
+    net = build(scene, fx["kw"])
+    net.camera_poses = [p for p in fx["known_c2w"]]
+    loss = net.compute_global_alignment(init="known_poses", niter=0)
+    assert net.im_poses.requires_grad
+    assert float((net.get_im_poses().detach().cpu() - fx["known_c2w"]).abs().max()) < 1e-5
+    prob.norm_pw_scale = False
+    T_ref = go.pw_pose_matrices(prob, ref["pw_poses"])
+    assert float((net.get_pw_poses().detach().cpu() - T_ref).abs().max()) < 2e-3
+    d = (net.im_depthmaps.detach().cpu()[:, :prob.P] - ref["im_depthmaps"]).abs()
+    assert float(d.median()) < 1e-5

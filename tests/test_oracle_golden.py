@@ -79,3 +79,30 @@ def test_schedules():
     assert abs(go.lr_schedule("cycle2", 0.25, 0.01, 1e-3) - go.lr_schedule("linear", 0.5, 0.01, 1e-3)) < 1e-15
     with pytest.raises(ValueError):
         go.lr_schedule("nope", 0.1, 0.01, 1e-3)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# preset camera poses: fixture from the real reference, oracle/make_golden_known_poses.py
+# ---------------------------------------------------------------------------------------------------------------
+def test_mst_init_with_frozen_known_poses_matches_reference():
+    fx, scene, prob = golden_case("small_known_poses")
+    ref = fx["mst_frozen"]
+    assert ref["im_poses_requires_grad"] is False and ref["norm_pw_scale"] is False
+    params, info = go.mst_init(prob, known_poses=fx["known_c2w"])
+    assert info["s_factor"] == 1.0
+    T_ref, T = go.poses_to_matrices(ref["params"]["im_poses"]), go.poses_to_matrices(params["im_poses"])
+    assert float((T - T_ref).abs().max()) < 1e-5               # the preset values, untouched by the init
+    assert float((T - fx["known_c2w"]).abs().max()) < 1e-5
+    for k in ("pw_poses", "im_depthmaps", "im_focals"):
+        assert torch.allclose(params[k], ref["params"][k], rtol=1e-4, atol=2e-5), (k, float((params[k] - ref["params"][k]).abs().max()))
+
+
+def test_known_poses_init_matches_reference():
+    fx, scene, prob = golden_case("small_known_poses")
+    ref = fx["known_poses"]
+    pw, depth = go.known_poses_init(prob, fx["known_c2w"], ref["focals"].reshape(-1), niter_PnP=10, min_conf_thr=prob.min_conf_thr)
+    Tp, Tr = go.pw_pose_matrices(prob, pw), go.pw_pose_matrices(prob, ref["params"]["pw_poses"])
+    assert float((Tp - Tr).abs().max()) < 1e-4
+    assert len(depth) > 0
+    for n, d in depth.items():
+        assert torch.allclose(d, ref["params"]["im_depthmaps"][n], rtol=1e-5, atol=1e-5), n
