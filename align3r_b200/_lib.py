@@ -7,7 +7,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("A3R_LIB") or os.path.join(HERE, "lib", "liba3r_ga.so")   # A3R_LIB: tuning builds
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # A3rProblem.flags
 F_SHARED_FOCAL, F_NORM_PW_SCALE, F_DIST_L2 = 1 << 0, 1 << 1, 1 << 2
@@ -15,8 +15,9 @@ F_TRAIN_PW_POSES, F_TRAIN_DEPTH, F_TRAIN_IM_POSES, F_TRAIN_FOCALS = 1 << 3, 1 <<
 F_TRAIN_PP, F_TRAIN_ADAPTORS, F_HAS_FLOW = 1 << 7, 1 << 8, 1 << 9
 # mode bits
 M_FLOW_ACTIVE, M_APPLY_ADAM = 1 << 0, 1 << 1
-SLOT_ACC, FRAME_ACC, SCAL = 28, 12, 16
+SLOT_ACC, FRAME_ACC, PRIOR_ACC, SCAL = 28, 12, 4, 16
 S_LOSS, S_ALIGN, S_TEMPORAL, S_FLOW, S_FLOW_DROPPED, S_SC_I, S_SC_J, S_FLAG_STICKY = range(8)
+S_PRIOR = 10
 CONF_MODES = {"log": 0, "sqrt": 1, "m1": 2, "id": 3, "none": 3}
 
 _i32, _u32, _i64, _f32, _vp = C.c_int32, C.c_uint32, C.c_int64, C.c_float, C.c_void_p
@@ -32,6 +33,7 @@ _POINTER_FIELDS = [
     "predw", "flow", "static_mask",
     "logdepth", "logdepth_m", "logdepth_v", "g_align", "g_flow_i", "g_flow_j",
     "acc_slot", "acc_frame", "frame_grad", "edge_scratch", "scal", "loss_hist",
+    "logdepth_init", "prior_acc",
 ]
 
 
@@ -42,7 +44,7 @@ class A3rProblem(C.Structure):
         + [("flags", _u32), ("pix_stride", _i64)]
         + [(n, _f32) for n in ("focal_break", "pw_break", "base_scale", "flow_loss_weight", "flow_loss_thre",
                                "pxl_thre", "temporal_smoothing_weight", "translation_weight", "inv_area_i",
-                               "inv_area_j", "adam_beta1", "adam_beta2", "adam_eps", "_pad0")]
+                               "inv_area_j", "adam_beta1", "adam_beta2", "adam_eps", "depth_regularize_weight")]
         + [(n, _vp) for n in _POINTER_FIELDS]
     )
 

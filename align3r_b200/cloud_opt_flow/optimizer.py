@@ -118,9 +118,6 @@ class PointCloudOptimizer(nn.Module):
             device = torch.device('cuda', torch.cuda.current_device())
         self._lib = _lib.load()
         self._device = device
-        if depth_regularize_weight:
-            raise NotImplementedError("depth_regularize_weight > 0 (reference optimizer.py:546-552) is not built yet; "
-                                      "every caller of the reference leaves it at 0")
         if sam2_mask_refine:
             raise NotImplementedError("sam2_mask_refine is out of scope (SAM-2 pre-step, SURVEY.md section 2 #23)")
         if flow_loss_fn != 'smooth_l1':
@@ -201,7 +198,9 @@ class PointCloudOptimizer(nn.Module):
         # ---------------- device buffers; the big host->device uploads start first ----------------
         want_flow = flow_loss_weight > 0
         hyper = self._hyper()
-        self._bufs = ProblemBuffers(plan, device, None, hyper, want_flow, loss_hist_len=max(1024, num_total_iter))
+        want_prior = depth_regularize_weight > 0
+        self._bufs = ProblemBuffers(plan, device, None, hyper, want_flow, loss_hist_len=max(1024, num_total_iter),
+                                    has_prior=want_prior)
         self._conf_sum = torch.zeros(max(plan.n_local_slots, 1), dtype=torch.float64, device=device)
         self._im_conf_plane = torch.zeros(max(plan.n_local_frames, 1), plan.pix_stride, device=device)
         ph.mark('alloc')
@@ -210,6 +209,7 @@ class PointCloudOptimizer(nn.Module):
         ph.mark('enqueue-pred')
         self._injected_flow = flow
         self._uploads_ready = None
+        self._prior_ready = False
         if want_flow:
             self.flow_ij, self.flow_ji, self.flow_valid_mask_i, self.flow_valid_mask_j = self.get_flow(sintel_ckpt)
             # on a side stream: the initialisation does not read the flow planes, its kernels need not queue behind
@@ -303,6 +303,11 @@ class PointCloudOptimizer(nn.Module):
             with torch.cuda.stream(self._upload_stream):
                 self._upload_masks()
                 self._uploads_ready = self._upload_stream.record_event()
+        if want_prior and not want_flow:
+            if self.dynamic_masks is None:
+                raise ValueError("depth_regularize_weight > 0 weighs pixels by 1 + dynamic_mask: put 'dynamic_mask' into "
+                                 "view1/view2 (the reference fails with torch.stack(None) here, optimizer.py:549)")
+            self._upload_masks()
         ph.mark('extras+masks')
         ph.done()
         self._adam_step = 0
@@ -318,7 +323,8 @@ class PointCloudOptimizer(nn.Module):
                     focal_break=float(self.focal_break), pw_break=float(self.pw_break), base_scale=float(self.base_scale),
                     flow_loss_weight=float(self.flow_loss_weight), flow_loss_thre=float(self.flow_loss_thre),
                     pxl_thre=float(self.pxl_thre), temporal_smoothing_weight=float(self.temporal_smoothing_weight),
-                    translation_weight=float(self.translation_weight))
+                    translation_weight=float(self.translation_weight),
+                    depth_regularize_weight=float(self.depth_regularize_weight))
 
     def _check_edges(self):
         return check_edges(self.edges)
@@ -339,6 +345,11 @@ class PointCloudOptimizer(nn.Module):
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self._device).cuda_stream)
+
+    def _check_prior(self):
+        if self._bufs.has_prior and not self._prior_ready:
+            raise RuntimeError("depth_regularize_weight > 0 needs the initial depth maps: run an initialisation first "
+                               "(the reference fails in get_init_depthmaps here, optimizer.py:547)")
 
     def _join_uploads(self):
         """The flow planes / static masks were uploaded on a side stream: order the current stream after them."""
@@ -611,6 +622,9 @@ class PointCloudOptimizer(nn.Module):
     def _set_init_depthmap(self):
         depth_maps = self.get_depthmaps(raw=True)
         self.init_depthmap = [dm.detach().clone() for dm in depth_maps]
+        if self._bufs.has_prior:        # what the depth prior compares with: log(clamp(init depth, 1e-6)), goem_opt.py:17-20
+            self._bufs.logdepth_init.copy_(torch.stack(self.init_depthmap).clamp(min=1e-6).log())
+            self._prior_ready = True
 
     def get_init_depthmaps(self, raw=False):
         res = self.init_depthmap
@@ -750,6 +764,7 @@ class PointCloudOptimizer(nn.Module):
         """parameter maps + fused forward/backward scan over this device's pixel-slots."""
         with torch.cuda.device(self._device):
             self._join_uploads()
+            self._check_prior()
             st = self._bufs.struct(self._trainable())
             s = self._stream()
             _lib.check(self._lib.a3r_ga_prepare(C.byref(st), mode, s), "a3r_ga_prepare")
@@ -877,6 +892,7 @@ def global_alignment_loop(net, lr=0.01, niter=300, schedule='cosine', lr_min=1e-
         bar = tqdm.tqdm(total=niter)
     with torch.cuda.device(net._device):
         net._join_uploads()
+        net._check_prior()
         st = b.struct(trainable)
         s = net._stream()
         it = 0

@@ -258,6 +258,24 @@ __device__ __forceinline__ void scatter_pair(const PairGrad& g, double* fgS, dou
 constexpr int S_GSUM = 8;      // sum_e dL/dlog s_e  (mean coupling of the pair scales)
 constexpr int S_GPHI = 9;      // sum_n dL/dphi_n    (shared focal)
 
+// depth prior: 4 sums per local frame (grid: chunks x local frames), fp64 atomics into prior_acc
+__global__ void __launch_bounds__(256) k_depth_prior(const A3rProblem p) {
+    __shared__ double s_red[32];
+    const int lf = blockIdx.y, n = p.lframe_id[lf];
+    const int P = p.frame_hw[2 * n] * p.frame_hw[2 * n + 1];
+    const int64_t base = (int64_t)lf * p.pix_stride;
+    double a[PR_N] = {0, 0, 0, 0};
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < P; q += gridDim.x * blockDim.x) {
+        const float d = prior_delta(p.logdepth[base + q], p.logdepth_init[base + q]);
+        const float w = p.static_mask[base + q] ? 1.0f : 2.0f;          // 1 + dynamic_mask
+        a[PR_D] += d; a[PR_W] += w; a[PR_WD] += w * d; a[PR_WDD] += w * d * d;
+    }
+    for (int k = 0; k < PR_N; ++k) {
+        const double v = block_sum(a[k], s_red);
+        if (threadIdx.x == 0) atomicAdd(&p.prior_acc[(int64_t)n * PR_N + k], v);
+    }
+}
+
 // K2a: loss assembly + gate (one small CTA: 3 sums over 2E slots, N-1 temporal pairs)
 __global__ void __launch_bounds__(512, 1) k_loss_scalars(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam) {
     __shared__ double s_red[32];
@@ -267,7 +285,10 @@ __global__ void __launch_bounds__(512, 1) k_loss_scalars(const A3rProblem p, con
     const bool flow_active = (mode & A3R_M_FLOW_ACTIVE) && (p.flags & A3R_F_HAS_FLOW) && p.flow_loss_weight > 0.f;
     const double fb = (double)p.focal_break;
     const double tsw = (double)p.temporal_smoothing_weight, tw = (double)p.translation_weight;
-    double l_align = 0, num_i = 0, cnt_i = 0, num_j = 0, cnt_j = 0, l_temp = 0;
+    double l_align = 0, num_i = 0, cnt_i = 0, num_j = 0, cnt_j = 0, l_temp = 0, l_prior = 0;
+    if (p.depth_regularize_weight > 0.f)
+        for (int n = tid; n < N; n += nt)
+            l_prior += prior_frame(p.prior_acc + (int64_t)n * PR_N, (double)p.frame_hw[2 * n] * p.frame_hw[2 * n + 1]).loss;
     for (int gs = tid; gs < 2 * E; gs += nt) {
         const double* a = p.acc_slot + (int64_t)gs * ACC_STRIDE;
         l_align += a[ACC_LOSS];
@@ -286,9 +307,12 @@ __global__ void __launch_bounds__(512, 1) k_loss_scalars(const A3rProblem p, con
     num_i = block_sum(num_i, s_red); cnt_i = block_sum(cnt_i, s_red);
     num_j = block_sum(num_j, s_red); cnt_j = block_sum(cnt_j, s_red);
     l_temp = block_sum(l_temp, s_red);
+    l_prior = block_sum(l_prior, s_red) / (double)N;
     if (tid == 0) {
-        const LossScalars r = assemble_loss(l_align, l_temp, num_i, cnt_i, num_j, cnt_j, flow_active,
+        LossScalars r = assemble_loss(l_align, l_temp, num_i, cnt_i, num_j, cnt_j, flow_active,
                                             (double)p.flow_loss_weight, (double)p.flow_loss_thre, tsw);
+        r.loss += (double)p.depth_regularize_weight * l_prior;           // optimizer.py:554-557
+        p.scal[A3R_S_PRIOR] = l_prior;
         p.scal[A3R_S_LOSS] = r.loss; p.scal[A3R_S_ALIGN] = l_align; p.scal[A3R_S_TEMPORAL] = l_temp;
         p.scal[A3R_S_FLOW] = r.floss; p.scal[A3R_S_FLOW_DROPPED] = r.dropped;
         p.scal[A3R_S_SC_I] = r.sc_i; p.scal[A3R_S_SC_J] = r.sc_j;
@@ -408,6 +432,7 @@ __global__ void k_adam_focal(const A3rProblem p, const uint32_t mode, const A3rA
 template <bool FLOW>
 __global__ void __launch_bounds__(256) k_update_depth(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam) {
     const int64_t total4 = (int64_t)p.n_local_frames * p.pix_stride / 4;
+    const bool prior = p.depth_regularize_weight > 0.f;
     const float sc_i = (float)p.scal[A3R_S_SC_I], sc_j = (float)p.scal[A3R_S_SC_J];
     const bool apply = mode & A3R_M_APPLY_ADAM;
     float4* ld = reinterpret_cast<float4*>(p.logdepth);
@@ -422,6 +447,25 @@ __global__ void __launch_bounds__(256) k_update_depth(const A3rProblem p, const 
             const float4 a = gi[i], b = gj[i];
             g.x += sc_i * a.x + sc_j * b.x; g.y += sc_i * a.y + sc_j * b.y;
             g.z += sc_i * a.z + sc_j * b.z; g.w += sc_i * a.w + sc_j * b.w;
+        }
+        if (prior) {               // d (weight * prior) / d logdepth: per-frame scalars from the 4 sums, then per pixel
+            const int64_t e0 = i * 4;
+            const int lf = (int)(e0 / p.pix_stride);
+            const int q0 = (int)(e0 - (int64_t)lf * p.pix_stride);
+            const int n = p.lframe_id[lf];
+            const int P = p.frame_hw[2 * n] * p.frame_hw[2 * n + 1];
+            if (q0 < P) {
+                const PriorFrame pf = prior_frame(p.prior_acc + (int64_t)n * PR_N, (double)P);
+                const float coef = (float)(2.0 * (double)p.depth_regularize_weight / ((double)p.n_frames * (double)P));
+                const float4 l = ld[i];
+                const float4 l0 = reinterpret_cast<const float4*>(p.logdepth_init)[i];
+                const uchar4 sm = reinterpret_cast<const uchar4*>(p.static_mask)[i];
+                const float s = (float)pf.s, mb = (float)pf.mean_b;
+                g.x += prior_grad(l.x, l0.x, sm.x ? 1.f : 2.f, s, mb, coef);
+                if (q0 + 1 < P) g.y += prior_grad(l.y, l0.y, sm.y ? 1.f : 2.f, s, mb, coef);
+                if (q0 + 2 < P) g.z += prior_grad(l.z, l0.z, sm.z ? 1.f : 2.f, s, mb, coef);
+                if (q0 + 3 < P) g.w += prior_grad(l.w, l0.w, sm.w ? 1.f : 2.f, s, mb, coef);
+            }
         }
         if (apply) {
             float4 l = ld[i], m = mm[i], v = vv[i];
@@ -646,8 +690,17 @@ int a3r_ga_accumulate(const A3rProblem* p, uint32_t mode, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const bool flow = (mode & A3R_M_FLOW_ACTIVE) && (p->flags & A3R_F_HAS_FLOW) && p->flow_loss_weight > 0.f;
     if (flow && (!p->flow || !p->static_mask)) return a3r_fail(A3R_E_ARG, "flow active but flow/static_mask planes are NULL");
-    const size_t acc_bytes = sizeof(double) * ((size_t)2 * p->n_edges * A3R_SLOT_ACC + (size_t)p->n_frames * A3R_FRAME_ACC);
+    const bool prior = p->depth_regularize_weight > 0.f;
+    if (prior && (!p->logdepth_init || !p->static_mask || !p->prior_acc))
+        return a3r_fail(A3R_E_ARG, "depth_regularize_weight > 0 needs logdepth_init, static_mask and prior_acc");
+    if (prior && p->prior_acc != p->acc_frame + (int64_t)p->n_frames * A3R_FRAME_ACC)
+        return a3r_fail(A3R_E_ARG, "prior_acc must directly follow acc_frame");
+    const size_t acc_bytes = sizeof(double) * ((size_t)2 * p->n_edges * A3R_SLOT_ACC + (size_t)p->n_frames * (A3R_FRAME_ACC + (prior ? A3R_PRIOR_ACC : 0)));
     A3R_CUDA(cudaMemsetAsync(p->acc_slot, 0, acc_bytes, st));
+    if (prior && p->n_local_frames > 0) {
+        k_depth_prior<<<dim3(16, (unsigned)p->n_local_frames), 256, 0, st>>>(*p);
+        A3R_CUDA(cudaGetLastError());
+    }
     if (p->n_work_frames > p->n_local_frames) {     // split frames add their gradients atomically
         const size_t plane = sizeof(float) * (size_t)p->n_local_frames * p->pix_stride;
         A3R_CUDA(cudaMemsetAsync(p->g_align, 0, plane, st));

@@ -466,6 +466,29 @@ A3R_HD float flow_px(const SlotConst& c, const PixState& s, float fu, float fv, 
 }
 
 // ------------------------------------------------------------------------------------------
+// depth prior (reference optimizer.py:546-552, goem_opt.py:15-36): scale-invariant deviation of the log-depth from its
+// initial value, pixel weight 1 + dynamic_mask.  Per frame with d_p = l_p - l0_p (both clamped at log 1e-6),
+// s = -mean d:  loss_n = (1/P) sum w (d + s)^2 = (S_wdd + 2 s S_wd + s^2 S_w) / P;  the total is the mean over frames.
+// d loss / d l_q = (2 / (N P)) [ w_q (d_q + s) - (S_wd + s S_w) / P ]   (0 where l_q sits on the clamp)
+// ------------------------------------------------------------------------------------------
+enum : int { PR_D = 0, PR_W = 1, PR_WD = 2, PR_WDD = 3, PR_N = 4 };
+#define A3R_LOG_EPS (-13.815510557964274f)      /* log(1e-6): goem_opt.py clamps both depths at eps = 1e-6 */
+
+A3R_HD float prior_delta(float logd, float logd_init) { return fmaxf(logd, A3R_LOG_EPS) - logd_init; }
+
+struct PriorFrame { double s, mean_b, loss; };
+A3R_HD PriorFrame prior_frame(const double* a, double P) {
+    PriorFrame r;
+    r.s = -a[PR_D] / P;
+    r.mean_b = (a[PR_WD] + r.s * a[PR_W]) / P;
+    r.loss = (a[PR_WDD] + 2.0 * r.s * a[PR_WD] + r.s * r.s * a[PR_W]) / P;
+    return r;
+}
+A3R_HD float prior_grad(float logd, float logd_init, float w, float s, float mean_b, float coef) {
+    return logd > A3R_LOG_EPS ? coef * (w * (prior_delta(logd, logd_init) + s) - mean_b) : 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------
 // torch.optim.Adam, single-tensor math (torch/optim/adam.py:457-547), fp32
 // ------------------------------------------------------------------------------------------
 A3R_HD void adam_update(float& p, float& m, float& v, float g, float beta1, float beta2, float eps,

@@ -23,7 +23,8 @@ class ProblemBuffers:
     in place; the depth parameter holds only the local frames' rows.
     """
 
-    def __init__(self, plan: ShardPlan, device, params: dict, hyper: dict, has_flow: bool, loss_hist_len: int = 4096):
+    def __init__(self, plan: ShardPlan, device, params: dict, hyper: dict, has_flow: bool, loss_hist_len: int = 4096,
+                 has_prior: bool = False):
         self.plan = plan
         self.device = torch.device(device)
         dev = self.device
@@ -31,6 +32,7 @@ class ProblemBuffers:
         nl, nls, stride = plan.n_local_frames, plan.n_local_slots, plan.pix_stride
         self.hyper = dict(hyper)
         self.has_flow = bool(has_flow)
+        self.has_prior = bool(has_prior)          # depth prior: masks, initial log-depth and 4 more sums per frame
 
         def i32(a):
             return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
@@ -65,7 +67,8 @@ class ProblemBuffers:
                  ("g_align", nl1 * stride, torch.float32), ("g_flow_i", nl1 * stride if has_flow else 0, torch.float32),
                  ("g_flow_j", nl1 * stride if has_flow else 0, torch.float32),
                  ("stage", self.stage_rows * stride * 4, torch.float32),
-                 ("static_mask", nl1 * stride if has_flow else 0, torch.uint8)]
+                 ("logdepth_init", nl1 * stride if has_prior else 0, torch.float32),
+                 ("static_mask", nl1 * stride if (has_flow or has_prior) else 0, torch.uint8)]
         offs, total = {}, 0
         for name, numel, dt in parts:
             offs[name] = total
@@ -80,18 +83,23 @@ class ProblemBuffers:
 
         self.predw = carve("predw", torch.float32, nls1, stride, 4)
         self.flow = carve("flow", torch.float32, nls1, stride, 2) if has_flow else None
-        self.static_mask = carve("static_mask", torch.uint8, nl1, stride) if has_flow else None
-        if has_flow:
+        self.static_mask = carve("static_mask", torch.uint8, nl1, stride) if (has_flow or has_prior) else None
+        if self.static_mask is not None:
             self.static_mask.zero_()                            # ... except the masks behind it
+        self.logdepth_init = carve("logdepth_init", torch.float32, nl1, stride) if has_prior else None
+        if has_prior:
+            self.logdepth_init.zero_()
         self.g_align = carve("g_align", torch.float32, nl1, stride)
         self.g_flow_i = carve("g_flow_i", torch.float32, nl1, stride) if has_flow else self.g_align
         self.g_flow_j = carve("g_flow_j", torch.float32, nl1, stride) if has_flow else self.g_align
         self.stage = carve("stage", torch.float32, self.stage_rows * stride * 4)
 
         # fp64 reduction buffers: acc_slot and acc_frame are one contiguous allocation
-        self.acc = zeros(2 * E * _lib.SLOT_ACC + N * _lib.FRAME_ACC, dtype=torch.float64)
+        n_acc = 2 * E * _lib.SLOT_ACC + N * _lib.FRAME_ACC
+        self.acc = zeros(n_acc + (N * _lib.PRIOR_ACC if has_prior else 0), dtype=torch.float64)    # what multi-GPU runs all-reduce
         self.acc_slot = self.acc[: 2 * E * _lib.SLOT_ACC].view(2 * E, _lib.SLOT_ACC)
-        self.acc_frame = self.acc[2 * E * _lib.SLOT_ACC:].view(N, _lib.FRAME_ACC)
+        self.acc_frame = self.acc[2 * E * _lib.SLOT_ACC:n_acc].view(N, _lib.FRAME_ACC)
+        self.prior_acc = self.acc[n_acc:].view(N, _lib.PRIOR_ACC) if has_prior else None
         self.frame_grad = zeros(N, 16, dtype=torch.float64)
         self.edge_scratch = zeros(E, dtype=torch.float64)
         self.scal = zeros(_lib.SCAL, dtype=torch.float64)
@@ -152,6 +160,7 @@ class ProblemBuffers:
         p.temporal_smoothing_weight, p.translation_weight = h["temporal_smoothing_weight"], h["translation_weight"]
         p.inv_area_i, p.inv_area_j = 1.0 / pl.total_area_i, 1.0 / pl.total_area_j
         p.adam_beta1, p.adam_beta2, p.adam_eps = h.get("adam_betas", (0.9, 0.9)) + (h.get("adam_eps", 1e-8),)
+        p.depth_regularize_weight = float(h.get("depth_regularize_weight", 0.0)) if self.has_prior else 0.0
         P = _lib.ptr
         p.edge_ij, p.frame_hw = P(self.edge_ij), P(self.frame_hw)
         for cname, pname in (("pw_poses", "pw_poses"), ("pw_adaptors", "pw_adaptors"), ("im_poses", "im_poses"),
@@ -171,6 +180,7 @@ class ProblemBuffers:
         p.acc_slot, p.acc_frame = P(self.acc_slot), P(self.acc_frame)
         p.frame_grad, p.edge_scratch, p.scal = P(self.frame_grad), P(self.edge_scratch), P(self.scal)
         p.loss_hist = P(self.loss_hist)
+        p.logdepth_init, p.prior_acc = P(self.logdepth_init), P(self.prior_acc)
         self._struct = p
         return p
 

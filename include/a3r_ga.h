@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define A3R_ABI_VERSION 3
+#define A3R_ABI_VERSION 4
 
 /* error codes */
 #define A3R_OK 0
@@ -61,6 +61,7 @@ extern "C" {
 /* number of fp64 accumulators per slot / per frame produced by a3r_ga_accumulate */
 #define A3R_SLOT_ACC 28
 #define A3R_FRAME_ACC 12
+#define A3R_PRIOR_ACC 4      /* per frame: sum d, sum w, sum w d, sum w d^2 of the depth prior (d = log-depth - its initial value) */
 #define A3R_SCAL 16
 
 /* layout of A3rProblem.scal (fp64[A3R_SCAL]) after a3r_ga_update */
@@ -72,6 +73,7 @@ extern "C" {
 #define A3R_S_SC_I 5        /* flow_loss_weight / sum(per_pixel_mask_i), 0 when inactive or dropped */
 #define A3R_S_SC_J 6
 #define A3R_S_FLAG_STICKY 7 /* flow_loss_flag: set once the gate has tripped at least once */
+#define A3R_S_PRIOR 10       /* un-weighted depth prior loss (0 when off) */
 
 typedef struct A3rProblem {
     /* ---- sizes ---- */
@@ -91,7 +93,8 @@ typedef struct A3rProblem {
     float flow_loss_weight, flow_loss_thre, pxl_thre;
     float temporal_smoothing_weight, translation_weight;
     float inv_area_i, inv_area_j;     /* 1/total_area_i, 1/total_area_j (optimizer.py:91-92, GLOBAL sums) */
-    float adam_beta1, adam_beta2, adam_eps, _pad0;
+    float adam_beta1, adam_beta2, adam_eps;
+    float depth_regularize_weight;    /* optimizer.py:546-552; needs logdepth_init + static_mask + prior_acc when > 0 */
 
     /* ---- global graph, replicated on every device ---- */
     const int32_t *edge_ij;           /* [E][2] */
@@ -138,6 +141,10 @@ typedef struct A3rProblem {
     double *edge_scratch;             /* [E] scratch of a3r_ga_update */
     double *scal;                     /* [A3R_SCAL] */
     float *loss_hist;                 /* [>= niter] loss of every iteration, or NULL */
+
+    /* ---- depth prior (reference optimizer.py:546-552, goem_opt.py:15-36), only read when depth_regularize_weight > 0 ---- */
+    const float *logdepth_init;       /* [n_local_frames][pix_stride] log(clamp(initial depth, 1e-6)) */
+    double *prior_acc;                /* [N][A3R_PRIOR_ACC], directly after acc_frame (rides on the same all-reduce) */
 } A3rProblem;
 
 /* Adam scalars of one step, computed on the host in double like torch/optim/adam.py:457-547 */

@@ -351,3 +351,33 @@ def test_known_poses_initialisation(cuda_device):
     assert float((net.get_pw_poses().detach().cpu() - T_ref).abs().max()) < 2e-3
     d = (net.im_depthmaps.detach().cpu()[:, :prob.P] - ref["im_depthmaps"]).abs()
     assert float(d.median()) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# depth prior against the fixture the real reference produced
+# ---------------------------------------------------------------------------------------------------------------
+def test_depth_prior_teacher_forced_and_free_run(cuda_device):
+    fx, scene, prob = golden_case("small_depth_prior")
+    fr, g32, g64 = fx["free_run"], fx["tf32_final"], fx["tf64_final"]
+    net = build(scene, fx["kw"])
+    with pytest.raises(RuntimeError, match="initial depth"):
+        net(epoch=0)                                            # no initialisation yet: nothing to regularise towards
+    set_params(net, fr["params"])
+    P = prob.P
+    with torch.no_grad():                                        # the reference's initial depth maps
+        net._bufs.logdepth_init[:, :P] = fr["init_depth"][net._plan.lframe_id.tolist(), :P].clamp(min=1e-6).log().to(net.device)
+    net._prior_ready = True
+    loss = net(epoch=g32["epoch"])
+    loss.backward()
+    assert abs(float(loss.detach()) - float(g64["loss"])) <= 2e-6 * abs(float(g64["loss"]))
+    assert float(net._bufs.scal[_lib.S_PRIOR]) > 0
+    mine = grads_of(net, P)
+    for k in mine:
+        ok, err, ref_err = grad_close(k, mine[k], g32["grads"][k], g64["grads"][k])
+        assert ok, (k, err, ref_err)
+    # free run through our own initialisation ends where the reference ends
+    net2 = build(scene, fx["kw"])
+    final = net2.compute_global_alignment(init="mst", niter=fx["niter"], schedule="linear", lr=0.01)
+    assert abs(final - fr["loss"]) <= 2e-3 * abs(fr["loss"])
+    d = (net2.im_depthmaps.detach().cpu()[:, :P] - fr["params"]["im_depthmaps"]).abs()
+    assert float(d.median()) < 2e-3

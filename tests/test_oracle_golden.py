@@ -106,3 +106,23 @@ def test_known_poses_init_matches_reference():
     assert len(depth) > 0
     for n, d in depth.items():
         assert torch.allclose(d, ref["params"]["im_depthmaps"][n], rtol=1e-5, atol=1e-5), n
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# depth prior: fixture from the real reference, oracle/make_golden_depth_prior.py
+# ---------------------------------------------------------------------------------------------------------------
+def test_depth_prior_loss_and_grads_match_reference():
+    fx, scene, prob = golden_case("small_depth_prior")
+    assert prob.depth_regularize_weight == 0.5
+    fr, g32, g64 = fx["free_run"], fx["tf32_final"], fx["tf64_final"]
+    loss, grads, info = go.loss_and_grads(prob, fr["params"], g32["epoch"], init_depth=fr["init_depth"])
+    assert abs(float(loss) - float(g32["loss"])) <= 2e-6 * abs(float(g32["loss"]))
+    without, _, _ = go.loss_and_grads(prob, fr["params"], g32["epoch"], init_depth=fr["init_depth"].clone().fill_(1.0))
+    assert abs(float(loss) - float(without)) > 1e-4 * abs(float(loss)), "the fixture must exercise the prior"
+    for k, ref in g32["grads"].items():
+        assert rel_err(grads[k], ref) <= max(2 * rel_err(ref, g64["grads"][k]), 1e-5), k
+    p64 = {k: v.double() for k, v in fr["params"].items()}
+    loss64, grads64, _ = go.loss_and_grads(prob.to(torch.float64), p64, g64["epoch"], init_depth=fr["init_depth"].double())
+    assert abs(float(loss64) - float(g64["loss"])) <= 1e-10 * abs(float(g64["loss"]))
+    for k, ref in g64["grads"].items():
+        assert rel_err(grads64[k], ref) <= 1e-9, k
