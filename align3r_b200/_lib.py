@@ -49,6 +49,13 @@ class A3rProblem(C.Structure):
     )
 
 
+MAX_PEERS = 8
+
+
+class A3rPeers(C.Structure):
+    _fields_ = [("world", _i32), ("rank", _i32), ("n_acc", _i64), ("base", _vp * MAX_PEERS)]
+
+
 class A3rAdamStep(C.Structure):
     _fields_ = [("step_size", _f32), ("bc2_sqrt", _f32), ("iter", _i32), ("_pad", _i32)]
 
@@ -67,6 +74,12 @@ _SIGNATURES = {
     "a3r_ga_update": (C.c_int, [C.POINTER(A3rProblem), _u32, C.POINTER(A3rAdamStep), _vp]),
     "a3r_ga_run": (C.c_int, [C.POINTER(A3rProblem), _i32, C.POINTER(_u32), C.POINTER(A3rAdamStep), _vp]),
     "a3r_ga_unproject": (C.c_int, [C.POINTER(A3rProblem), _vp, _vp]),
+    "a3r_peer_region_bytes": (C.c_size_t, [_i64]),
+    "a3r_peer_alloc": (C.c_int, [_i64, C.POINTER(_vp), C.c_char_p]),
+    "a3r_peer_open": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
+    "a3r_peer_close": (C.c_int, [_vp]),
+    "a3r_peer_free": (C.c_int, [_vp]),
+    "a3r_ga_run_peers": (C.c_int, [C.POINTER(A3rProblem), C.POINTER(A3rPeers), _u32, _i32, C.POINTER(_u32), C.POINTER(A3rAdamStep), _vp]),
     "a3r_procrustes_batched": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "a3r_weiszfeld_focal_batched": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp]),
     "a3r_init_depth": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, _vp, _vp]),

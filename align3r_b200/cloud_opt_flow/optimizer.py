@@ -209,6 +209,7 @@ class PointCloudOptimizer(nn.Module):
         ph.mark('enqueue-pred')
         self._injected_flow = flow
         self._uploads_ready = None
+        self._peers, self._peers_tried = None, False
         self._prior_ready = False
         if want_flow:
             self.flow_ij, self.flow_ji, self.flow_valid_mask_i, self.flow_valid_mask_j = self.get_flow(sintel_ckpt)
@@ -760,6 +761,53 @@ class PointCloudOptimizer(nn.Module):
             import torch.distributed as dist
             dist.all_reduce(self._bufs.acc, op=dist.ReduceOp.SUM, group=self._shard.get('group'))
 
+    def _setup_peers(self):
+        """Frame-window sharded runs on one node: map every rank's partial-sum region (CUDA IPC over NVLink) so that the
+        per-iteration exchange is one kernel of ours (a3r_ga_run_peers) instead of a library all-reduce between launches.
+        Returns the A3rPeers descriptor, or None when the NCCL path is to be used (A3R_EXCHANGE=nccl, more ranks than
+        A3R_MAX_PEERS, or peer mapping unavailable on some rank - all ranks take the same decision)."""
+        if self._peers is not None or self._peers_tried:
+            return self._peers
+        self._peers_tried = True
+        import os
+        import torch.distributed as dist
+        world, rank, group = int(self._shard['world']), int(self._shard['rank']), self._shard.get('group')
+        if not (dist.is_available() and dist.is_initialized()):
+            return None
+        want = os.environ.get("A3R_EXCHANGE", "peer") != "nccl" and world <= _lib.MAX_PEERS
+        n_acc = int(self._bufs.acc.numel())
+        region, handle, ok = C.c_void_p(), C.create_string_buffer(64), want
+        with torch.cuda.device(self._device):
+            if want and self._lib.a3r_peer_alloc(n_acc, C.byref(region), handle) != 0:
+                ok = False
+            handles = [None] * world
+            dist.all_gather_object(handles, (bool(ok), bytes(handle.raw)), group=group)
+            ok = all(h[0] for h in handles)
+            peers = _lib.A3rPeers()
+            peers.world, peers.rank, peers.n_acc = world, rank, n_acc
+            opened = []
+            if ok:
+                for r in range(world):
+                    if r == rank:
+                        peers.base[r] = region.value
+                        continue
+                    ptr = C.c_void_p()
+                    if self._lib.a3r_peer_open(handles[r][1], C.byref(ptr)) != 0:
+                        ok = False
+                        break
+                    opened.append(ptr)
+                    peers.base[r] = ptr.value
+            flag = torch.tensor([1 if ok else 0], device=self._device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 0:                       # some rank cannot map its peers: everybody uses NCCL
+                for ptr in opened:
+                    self._lib.a3r_peer_close(ptr)
+                if region.value:
+                    self._lib.a3r_peer_free(region)
+                return None
+        self._peers, self._peer_region, self._peer_opened, self._peer_tag = peers, region, opened, 0
+        return peers
+
     def _phase_accumulate(self, mode):
         """parameter maps + fused forward/backward scan over this device's pixel-slots."""
         with torch.cuda.device(self._device):
@@ -884,7 +932,8 @@ def global_alignment_loop(net, lr=0.01, niter=300, schedule='cosine', lr_min=1e-
     steps = adam_schedule(lrs, start_step=0, betas=(0.9, 0.9), first_iter=0)
     marr = modes_array(modes)
     sharded = net._shard is not None and int(net._shard['world']) > 1
-    chunk = niter if not (net.verbose or sharded) else (1 if sharded else max(1, min(50, niter // 10 or 1)))
+    peers = net._setup_peers() if sharded else None
+    chunk = niter if not (net.verbose or (sharded and peers is None)) else (1 if sharded and peers is None else max(1, min(50, niter // 10 or 1)))
 
     bar = None
     if net.verbose:
@@ -898,7 +947,12 @@ def global_alignment_loop(net, lr=0.01, niter=300, schedule='cosine', lr_min=1e-
         it = 0
         while it < niter:
             n = min(chunk, niter - it)
-            if sharded:
+            if sharded and peers is not None:
+                sub_m = (C.c_uint32 * n).from_buffer(marr, 4 * it)
+                sub_s = (_lib.A3rAdamStep * n).from_buffer(steps, C.sizeof(_lib.A3rAdamStep) * it)
+                _lib.check(net._lib.a3r_ga_run_peers(C.byref(st), C.byref(peers), net._peer_tag, n, sub_m, sub_s, s), "a3r_ga_run_peers")
+                net._peer_tag += n
+            elif sharded:
                 for k in range(it, it + n):
                     _lib.check(net._lib.a3r_ga_prepare(C.byref(st), marr[k], s), "a3r_ga_prepare")
                     _lib.check(net._lib.a3r_ga_accumulate(C.byref(st), marr[k], s), "a3r_ga_accumulate")

@@ -796,6 +796,115 @@ int a3r_ga_run(const A3rProblem* p, int32_t count, const uint32_t* modes, const 
     return A3R_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// multi-GPU exchange over peer memory
+// ------------------------------------------------------------------------------------------------------------
+constexpr size_t PEER_FLAG_STRIDE = 128;
+constexpr size_t PEER_HEADER = A3R_MAX_PEERS * PEER_FLAG_STRIDE;
+
+size_t a3r_peer_region_bytes(int64_t n_acc) { return PEER_HEADER + 2 * sizeof(double) * (size_t)n_acc; }
+
+int a3r_peer_alloc(int64_t n_acc, void** region, unsigned char handle[64]) {
+    if (n_acc <= 0 || !region || !handle) return a3r_fail(A3R_E_ARG, "a3r_peer_alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    void* ptr = nullptr;
+    const size_t bytes = a3r_peer_region_bytes(n_acc);
+    A3R_CUDA(cudaMalloc(&ptr, bytes));
+    A3R_CUDA(cudaMemset(ptr, 0, bytes));
+    cudaIpcMemHandle_t h;
+    A3R_CUDA(cudaIpcGetMemHandle(&h, ptr));
+    memcpy(handle, &h, 64);
+    *region = ptr;
+    return A3R_OK;
+}
+int a3r_peer_open(const unsigned char handle[64], void** region) {
+    if (!handle || !region) return a3r_fail(A3R_E_ARG, "a3r_peer_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    A3R_CUDA(cudaIpcOpenMemHandle(region, h, cudaIpcMemLazyEnablePeerAccess));
+    return A3R_OK;
+}
+int a3r_peer_close(void* region) { if (region) A3R_CUDA(cudaIpcCloseMemHandle(region)); return A3R_OK; }
+int a3r_peer_free(void* region) { if (region) A3R_CUDA(cudaFree(region)); return A3R_OK; }
+
+}  // extern "C"
+
+__device__ __forceinline__ void st_release_sys(uint32_t* q, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(q), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* q) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(q) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_peer_f64(const double* q) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(q) : "memory");
+    return v;
+}
+
+// signal + wait + reduce in one launch (every CTA is resident: grid <= SM count)
+__global__ void __launch_bounds__(256) k_exchange(const A3rPeers peers, const uint32_t tag, double* __restrict__ out) {
+    const int W = peers.world, me = peers.rank;
+    if (blockIdx.x == 0 && threadIdx.x < W && (int)threadIdx.x != me) {
+        // the scan of this iteration completed before this kernel started (stream order): publish its sums
+        __threadfence_system();
+        uint32_t* flag = reinterpret_cast<uint32_t*>(static_cast<char*>(peers.base[threadIdx.x]) + (size_t)me * PEER_FLAG_STRIDE);
+        st_release_sys(flag, tag);
+    }
+    if (threadIdx.x < W && (int)threadIdx.x != me) {
+        const uint32_t* flag = reinterpret_cast<const uint32_t*>(static_cast<const char*>(peers.base[me]) + (size_t)threadIdx.x * PEER_FLAG_STRIDE);
+        uint32_t spins = 0;
+        while ((int32_t)(ld_acquire_sys(flag) - tag) < 0) {
+            if (++spins > (1u << 26)) __trap();          // a peer that never arrives must fail loudly, not hang the GPU
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    const size_t off = PEER_HEADER + (size_t)(tag & 1u) * sizeof(double) * (size_t)peers.n_acc;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < peers.n_acc; i += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < W; ++r)                       // rank order: the same sum, bit for bit, on every rank
+            s += ld_peer_f64(reinterpret_cast<const double*>(static_cast<const char*>(peers.base[r]) + off) + i);
+        out[i] = s;
+    }
+}
+
+extern "C" {
+
+int a3r_ga_run_peers(const A3rProblem* p, const A3rPeers* peers, uint32_t tag0, int32_t count, const uint32_t* modes,
+                     const A3rAdamStep* steps, void* stream) {
+    if (count < 0 || !modes || !steps || !peers) return a3r_fail(A3R_E_ARG, "a3r_ga_run_peers: bad arguments");
+    if (int rc = check_problem(p)) return rc;
+    if (peers->world < 1 || peers->world > A3R_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world)
+        return a3r_fail(A3R_E_ARG, "a3r_ga_run_peers: world %d rank %d", peers->world, peers->rank);
+    const bool prior = p->depth_regularize_weight > 0.f;
+    const int64_t n_acc = (int64_t)2 * p->n_edges * A3R_SLOT_ACC + (int64_t)p->n_frames * (A3R_FRAME_ACC + (prior ? A3R_PRIOR_ACC : 0));
+    if (peers->n_acc != n_acc) return a3r_fail(A3R_E_ARG, "a3r_ga_run_peers: n_acc %lld != %lld", (long long)peers->n_acc, (long long)n_acc);
+    cudaStream_t st = (cudaStream_t)stream;
+    AuxLane* lane = nullptr;
+    if (int rc = aux_lane(&lane)) return rc;
+    int sm = 148;
+    { int dev = 0; A3R_CUDA(cudaGetDevice(&dev)); A3R_CUDA(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev)); }
+    int grid = (int)((n_acc + 255) / 256);
+    if (grid > sm) grid = sm;
+    bool pending = false;
+    for (int32_t k = 0; k < count; ++k) {
+        const uint32_t tag = tag0 + 1u + (uint32_t)k;
+        A3rProblem q = *p;                               // the scan adds into this rank's shared partial-sum buffer
+        double* part = reinterpret_cast<double*>(static_cast<char*>(peers->base[peers->rank]) + PEER_HEADER) + (size_t)(tag & 1u) * (size_t)n_acc;
+        q.acc_slot = part;
+        q.acc_frame = part + (int64_t)2 * p->n_edges * A3R_SLOT_ACC;
+        if (prior) q.prior_acc = q.acc_frame + (int64_t)p->n_frames * A3R_FRAME_ACC;
+        if (int rc = a3r_ga_prepare(p, modes[k], stream)) return rc;
+        if (pending) A3R_CUDA(cudaStreamWaitEvent(st, lane->join, 0));
+        if (int rc = a3r_ga_accumulate(&q, modes[k], stream)) return rc;
+        k_exchange<<<grid, 256, 0, st>>>(*peers, tag, p->acc_slot);
+        A3R_CUDA(cudaGetLastError());
+        if (int rc = update_forked(p, modes[k], &steps[k], st, lane, &pending)) return rc;
+    }
+    if (pending) A3R_CUDA(cudaStreamWaitEvent(st, lane->join, 0));
+    return A3R_OK;
+}
+
 int a3r_ga_unproject(const A3rProblem* p, float* pts3d, void* stream) {
     if (int rc = check_problem(p)) return rc;
     if (!pts3d) return a3r_fail(A3R_E_ARG, "pts3d is NULL");

@@ -189,6 +189,33 @@ int a3r_ga_update(const A3rProblem *p, uint32_t mode, const A3rAdamStep *adam, v
  * global_alignment_loop, base_opt.py:513-547).  steps/modes are host arrays of length count. */
 int a3r_ga_run(const A3rProblem *p, int32_t count, const uint32_t *modes, const A3rAdamStep *steps, void *stream);
 
+/* ---- multi-GPU exchange over peer memory (NVLink / NVSwitch; one process per GPU on one node) ----
+ * The only thing that crosses GPUs is the fp64 accumulator block (acc_slot | acc_frame | prior_acc).  Instead of a
+ * library all-reduce between two kernels, every rank's scan writes its partial sums into a CUDA-IPC shared region of its
+ * own memory, and ONE kernel per iteration (a) flags "my sums of iteration t are complete" into every peer's region,
+ * (b) waits for the peers' flags, (c) reads all ranks' partial sums over NVLink and adds them in rank order (bit-identical
+ * on every rank) into the private block the update kernels read.  Two partial-sum buffers alternate by iteration parity,
+ * so no second barrier is needed (a rank cannot overwrite a buffer a peer may still be reading: it only reaches that
+ * buffer again after the peer flagged the iteration in between).
+ * Region layout (bytes): [A3R_MAX_PEERS flags, 128 B apart][partial sums, parity 0][partial sums, parity 1]. */
+#define A3R_MAX_PEERS 8
+typedef struct A3rPeers {
+    int32_t world, rank;
+    int64_t n_acc;                          /* doubles in the accumulator block */
+    void *base[A3R_MAX_PEERS];              /* every rank's region mapped into this process (base[rank] = own) */
+} A3rPeers;
+size_t a3r_peer_region_bytes(int64_t n_acc);
+/* own region: cudaMalloc + zero + cudaIpcGetMemHandle (64-byte handle to hand to the other ranks) */
+int a3r_peer_alloc(int64_t n_acc, void **region, unsigned char handle[64]);
+int a3r_peer_open(const unsigned char handle[64], void **region);       /* a peer's region (cudaIpcOpenMemHandle) */
+int a3r_peer_close(void *region);
+int a3r_peer_free(void *region);
+/* a3r_ga_run for a frame-window sharded problem: prepare, scan into the shared partial-sum buffer, exchange kernel,
+ * update.  `tag0`: iteration tags tag0+1 .. tag0+count must be larger than any tag used before on these regions and
+ * identical on all ranks (they run the same iterations in lockstep). */
+int a3r_ga_run_peers(const A3rProblem *p, const A3rPeers *peers, uint32_t tag0, int32_t count, const uint32_t *modes,
+                     const A3rAdamStep *steps, void *stream);
+
 /* ---- read-out (reference optimizer.py:468-478 depth_to_pts3d) ----
  * world points [n_local_frames][pix_stride][3] from logdepth + frame_par (call a3r_ga_prepare first) */
 int a3r_ga_unproject(const A3rProblem *p, float *pts3d, void *stream);

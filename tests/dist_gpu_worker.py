@@ -43,7 +43,8 @@ def main():
     gathered = [None] * world
     dist.all_gather_object(gathered, (lo, hi, depth_local.cpu(), same, loss, bool(net.flow_loss_flag)))
     if rank == 0:
-        torch.save(dict(parts=gathered, im_poses=net.get_im_poses().detach().cpu(), focals=net.get_focals().detach().cpu()), sys.argv[2])
+        torch.save(dict(parts=gathered, im_poses=net.get_im_poses().detach().cpu(), focals=net.get_focals().detach().cpu(),
+                        exchange="peer" if net._peers is not None else "nccl"), sys.argv[2])
     dist.barrier()
     dist.destroy_process_group()
 

@@ -22,16 +22,20 @@ def _free_port():
     return p
 
 
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
 @pytest.mark.parametrize("name", ["small_flow"])
-def test_nccl_sharded_alignment_matches_reference(cuda_device, name, tmp_path):
+def test_sharded_alignment_matches_reference(cuda_device, name, exchange, tmp_path):
+    """exchange='peer': the accumulator block crosses GPUs inside our own kernel over CUDA-IPC peer memory
+    (a3r_ga_run_peers); 'nccl': torch.distributed all-reduce between the scan and the update."""
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs at least 2 GPUs")
     out = str(tmp_path / "res.pt")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "dist_gpu_worker.py"), name, out]
-    subprocess.run(cmd, check=True, timeout=600, cwd=ROOT)
+    subprocess.run(cmd, check=True, timeout=600, cwd=ROOT, env=dict(os.environ, A3R_EXCHANGE=exchange))
     res = torch.load(out, weights_only=False)
+    assert res["exchange"] == exchange
     fx, scene, prob = golden_case(name)
     parts = sorted(res["parts"], key=lambda t: t[0])
     assert parts[0][0] == 0 and parts[-1][1] == prob.n_imgs and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
