@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SOURCES = ["a3r_common.cu", "ga_kernels.cu", "mst_kernels.cu"]
-HEADERS = ["a3r_common.cuh", "ga_math.cuh", "ga_scan_v2.cuh", "ga_scan_v3.cuh", "ga_scan_v4.cuh"]
+HEADERS = ["a3r_common.cuh", "ga_math.cuh", "ptx_helpers.cuh", "ga_scan_v4.cuh"]
 
 
 def lib_path():
@@ -33,7 +33,7 @@ def build(force=False, verbose=False):
     cmd = [nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
            "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(HERE, "csrc"),
            "-o", out] + [os.path.join(HERE, "csrc", f) for f in SOURCES]
-    for macro in ("A3R_V2_T", "A3R_V2_STAGES", "A3R_V3_T", "A3R_V3_WARPS", "A3R_V4_WARPS", "A3R_V4_SLOTS", "A3R_V4_STAGES", "A3R_V3_STAGES", "A3R_EXP_CHEAP_C", "A3R_EXP_CHEAP_B", "A3R_V2_TRACE"):      # tuning knobs of the scan kernel (see csrc/ga_scan_v2.cuh)
+    for macro in ("A3R_V4_WARPS", "A3R_V4_SLOTS", "A3R_V4_STAGES"):      # tuning knobs of the scan kernel (csrc/ga_scan_v4.cuh)
         if os.environ.get(macro):
             cmd.append(f"-D{macro}={os.environ[macro]}")
     if verbose:

@@ -9,8 +9,6 @@
 #include "a3r_ga.h"
 #include "ga_math.cuh"
 #include "a3r_common.cuh"
-#include "ga_scan_v2.cuh"
-#include "ga_scan_v3.cuh"
 #include "ga_scan_v4.cuh"
 #include <stdlib.h>
 
@@ -543,20 +541,18 @@ __global__ void __launch_bounds__(256) k_pack_flow(const float* __restrict__ src
 // ==========================================================================================
 // C ABI
 // ==========================================================================================
-// Scan kernel variant.  v4 (independent warps, private TMA rings, shared-memory slot table, half-warp transpose
-// reduction) is the product path; v3 is its predecessor (same organisation, ~25 % more instructions per chunk).  A3R_SCAN=v1 selects the simple thread-owns-pixels kernel (on-device cross-check in the GPU tests);
-// A3R_SCAN=v2 the warp-owns-slot / pixel-warp pipeline (kept for the record: fewer instructions per pixel-slot,
-// but its per-tile hand-offs leave the slot warps idle half of the time - see DESIGN.md section 8).
+// Scan kernel variant.  v4 (ga_scan_v4.cuh: independent warps, private cp.async rings, shared-memory slot table,
+// half-warp transpose reduction) is the product path.  A3R_SCAN=v1 selects the simple thread-owns-pixels kernel above:
+// the on-device cross-check of v4 in the GPU tests (same per-element math header, different organisation).
 static int scan_variant() {
     static int v = [] {
         const char* e = getenv("A3R_SCAN");
-        if (e && e[0] == 'v' && e[1] >= '1' && e[1] <= '4') return e[1] - '0';
-        return 4;
+        return (e && e[0] == 'v' && e[1] == '1') ? 1 : 4;
     }();
     return v;
 }
-static int scan_tile() { const int v = scan_variant(); return v == 1 ? K1_TILE : (v == 2 ? V2_T : (v == 3 ? V3_T : V4_T)); }
-static int scan_slots() { const int v = scan_variant(); return v == 1 ? K1_MAXS : (v == 2 ? V2_SLOTS : (v == 3 ? V3_SLOTS : V4_SLOTS)); }
+static int scan_tile() { return scan_variant() == 1 ? K1_TILE : V4_T; }
+static int scan_slots() { return scan_variant() == 1 ? K1_MAXS : V4_SLOTS; }
 
 static int check_problem(const A3rProblem* p) {
     if (!p) return a3r_fail(A3R_E_ARG, "problem is NULL");
@@ -580,32 +576,6 @@ static int launch_accumulate(const A3rProblem* p, cudaStream_t st) {
             configured = true;
         }
         k_accumulate_v1<FLOW, L2D><<<p->n_ctas, K1_THREADS, smem, st>>>(*p);
-    } else if (scan_variant() == 2) {
-        const size_t smem = sizeof(V2Smem);
-        static bool configured = false;
-        if (!configured) {
-            A3R_CUDA(cudaFuncSetAttribute(k_accumulate_v2<FLOW, L2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = true;
-        }
-        k_accumulate_v2<FLOW, L2D><<<p->n_ctas, V2_THREADS, smem, st>>>(*p);
-    } else if (scan_variant() == 3) {
-        if (p->n_ctas % V3_WARPS != 0) return a3r_fail(A3R_E_ARG, "n_ctas must be a multiple of %d for the v3 scan", V3_WARPS);
-        const size_t smem = sizeof(V3Smem);
-        // copy engine of the private rings: TMA bulk copies for the flow-active scan, per-lane cp.async otherwise
-        // (measured, see ga_scan_v3.cuh); A3R_V3_COPY=tma|ldgsts forces one
-        static const int forced = [] {
-            const char* e = getenv("A3R_V3_COPY");
-            return (!e || !e[0]) ? 0 : (e[0] == 't' ? 1 : 2);
-        }();
-        const bool tma = forced ? forced == 1 : FLOW;
-        static bool configured = false;
-        if (!configured) {
-            A3R_CUDA(cudaFuncSetAttribute(k_accumulate_v3<FLOW, L2D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            A3R_CUDA(cudaFuncSetAttribute(k_accumulate_v3<FLOW, L2D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = true;
-        }
-        if (tma) k_accumulate_v3<FLOW, L2D, true><<<p->n_ctas / V3_WARPS, V3_THREADS, smem, st>>>(*p);
-        else k_accumulate_v3<FLOW, L2D, false><<<p->n_ctas / V3_WARPS, V3_THREADS, smem, st>>>(*p);
     } else {
         if (p->n_ctas % V4_WARPS != 0) return a3r_fail(A3R_E_ARG, "n_ctas must be a multiple of %d for the v4 scan", V4_WARPS);
         // copy engine of the private rings (A3R_V4_COPY=tma|ldgsts forces one; default: per-lane cp.async)
@@ -646,9 +616,9 @@ int a3r_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
 int a3r_max_ctas(int device) {
     int sm = 0;
     if (a3r_device_info(device, &sm, nullptr, nullptr) != A3R_OK) return A3R_E_CUDA;
-    // v1: 2 resident CTAs per SM; v2: one persistent CTA per SM; v3: every warp has its own range of the plan
+    // v1: 2 resident CTAs per SM; v4: every warp has its own range of the plan
     const int v = scan_variant();
-    return v == 1 ? sm * 2 : (v == 2 ? sm : (v == 3 ? sm * V3_WARPS : sm * V4_WARPS));
+    return v == 1 ? sm * 2 : sm * V4_WARPS;
 }
 
 int a3r_pack_pred(const float* pts, const float* conf, int32_t n, int64_t P, const int32_t* dst_slot,

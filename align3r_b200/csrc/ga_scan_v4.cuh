@@ -1,6 +1,6 @@
-// ga_scan_v4.cuh - K1 (v4): the fused forward+backward scan, v3's organisation with the per-chunk overhead cut.
+// ga_scan_v4.cuh - K1 (v4): the fused forward+backward scan (product path).
 //
-// As in v3 every warp is an independent stream: it owns a contiguous range of 128-pixel tiles (4 pixels per lane,
+// Every warp is an independent stream: it owns a contiguous range of 128-pixel tiles (4 pixels per lane,
 // per-pixel state in registers) and walks, per tile, the slots living on that frame; the (X,Y,Z,w) + flow chunk of
 // every (tile, slot) - 3 KB - lands in the warp's private shared-memory ring STAGES chunks ahead of the one being
 // computed (per-lane cp.async - a lane only ever reads what it copied itself, completion is cp.async.wait_group; or TMA
@@ -12,9 +12,11 @@
 // and try_wait loop per chunk).  The kernel is bound by instruction issue, not by HBM: warps per scheduler matter
 // more than prefetch depth.
 //
-// v3 spent 630 warp instructions per chunk (4 pixel-slots per lane) of which ~210 were not arithmetic
-// (profiles/r01_scan_v3c_*): re-materialised addresses, a dependent global-load chain for the slot constants, the
-// copy-issue sequence and the cross-lane reduction.  v4 removes most of that:
+// History (git log, profiles/r01_scan_v{1,2,3,3c}_*): v1 = thread owns pixels, shuffle reduction (33 % of the HBM roofline);
+// v2 = warp owns slot + pixel warps + TMA producer with mbarrier hand-offs (37 %: hand-off latency); v3 = this
+// organisation at 12 warps with TMA rings, 630 warp instructions per chunk (4 pixel-slots per lane) of which ~210 were
+// not arithmetic: re-materialised addresses, a dependent global-load chain for the slot constants, the copy-issue
+// sequence and the cross-lane reduction (54 %).  v4 removes most of that:
 //   * everything a warp owns lives in ONE contiguous shared-memory block (ring, slot table, running sums, transpose
 //     buffer, barriers): a single base register + compile-time offsets;
 //   * the constants of the frame's slots (-M, s t, flow homography, 1/area, global slot) are staged once per
@@ -30,8 +32,7 @@
 #pragma once
 #include "ga_math.cuh"
 #include "a3r_common.cuh"
-#include "ga_scan_v2.cuh"     // PTX helpers (mbarrier, bulk copy, raw shared-memory accesses)
-#include "ga_scan_v3.cuh"     // cp.async helpers
+#include "ptx_helpers.cuh"    // mbarrier, bulk copy, cp.async, raw shared-memory accesses
 
 namespace a3r {
 

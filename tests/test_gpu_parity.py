@@ -381,3 +381,42 @@ def test_depth_prior_teacher_forced_and_free_run(cuda_device):
     assert abs(final - fr["loss"]) <= 2e-3 * abs(fr["loss"])
     d = (net2.im_depthmaps.detach().cpu()[:, :P] - fr["params"]["im_depthmaps"]).abs()
     assert float(d.median()) < 2e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the two organisations of the scan (A3R_SCAN=v1: thread owns pixels; default v4: warp streams) agree on the device
+# ---------------------------------------------------------------------------------------------------------------
+_V1_SNIPPET = """
+import sys, torch
+sys.path.insert(0, {root!r})
+from tests.test_gpu_parity import build, set_params, grads_of
+from tests.helpers import golden_case
+from align3r_b200 import _lib
+assert _lib.load().a3r_tile_pixels() == 1024          # the v1 kernel's tile
+fx, scene, prob = golden_case("small_flow")
+net = build(scene, fx["kw"])
+set_params(net, fx["init_params"])
+loss = net(epoch=fx["tf32_flow"]["epoch"])
+loss.backward()
+torch.save(dict(loss=float(loss.detach()), grads=grads_of(net, prob.P)), {out!r})
+"""
+
+
+def test_scan_v1_cross_checks_v4(cuda_device, tmp_path):
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "v1.pt")
+    subprocess.run([sys.executable, "-c", _V1_SNIPPET.format(root=root, out=out)], check=True, timeout=600,
+                   env=dict(os.environ, A3R_SCAN="v1"), cwd=root)
+    v1 = torch.load(out, weights_only=False)
+    assert _lib.load().a3r_tile_pixels() == 128
+    fx, scene, prob = golden_case("small_flow")
+    net = build(scene, fx["kw"])
+    set_params(net, fx["init_params"])
+    loss = net(epoch=fx["tf32_flow"]["epoch"])
+    loss.backward()
+    assert abs(float(loss.detach()) - v1["loss"]) <= 1e-6 * abs(v1["loss"])
+    mine = grads_of(net, prob.P)
+    for k in mine:
+        assert rel_err(mine[k], v1["grads"][k]) <= 2e-5, (k, rel_err(mine[k], v1["grads"][k]))
