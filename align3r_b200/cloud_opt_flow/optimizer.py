@@ -653,6 +653,26 @@ class PointCloudOptimizer(nn.Module):
             _lib.check(self._lib.a3r_ga_unproject(C.byref(st), _lib.ptr(out), self._stream()), "a3r_ga_unproject")
         return out
 
+    @torch.no_grad()
+    def clean_pointcloud(self, tol=0.001, bad_conf=0, dbg=()):
+        """reference base_opt.py:293-303,587-623: lower ``im_conf`` where a point of one frame lands in front of another
+        frame's depth map while being less confident.  One kernel launch per frame (a3r_clean_pointcloud); single device."""
+        if self._shard is not None and int(self._shard['world']) > 1:
+            raise NotImplementedError("clean_pointcloud on a frame-window sharded problem (every frame meets every other)")
+        assert 0 <= tol < 1
+        dev, plan = self._device, self._plan
+        cams = torch.linalg.inv(self.get_im_poses().detach()).float().contiguous()            # world to camera
+        K = self.get_intrinsics().detach()
+        intr = torch.stack((K[:, 0, 0], K[:, 1, 1], K[:, 0, 2], K[:, 1, 2]), dim=1).float().contiguous()
+        pts = self.depth_to_pts3d().contiguous()
+        depth = self.im_depthmaps.detach().exp().contiguous()
+        hw = torch.tensor(self.imshapes, dtype=torch.int32).to(dev)
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.a3r_clean_pointcloud(_lib.ptr(pts), _lib.ptr(depth), _lib.ptr(cams), _lib.ptr(intr), _lib.ptr(hw),
+                                                      self.n_imgs, plan.pix_stride, float(tol), float(bad_conf),
+                                                      _lib.ptr(self._im_conf_plane), self._stream()), "a3r_clean_pointcloud")
+        return self
+
     def get_pts3d(self, raw=False, **kwargs):
         res = self.depth_to_pts3d()
         if not raw:

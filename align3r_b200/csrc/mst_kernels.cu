@@ -207,7 +207,47 @@ __global__ void __launch_bounds__(256) k_init_depth(const float* __restrict__ pr
 
 }  // namespace
 
+// confidence clean-up of frame i against all other frames (reference base_opt.py:587-623)
+__global__ void __launch_bounds__(256) k_clean_frame(const float* __restrict__ pts3d, const float* __restrict__ depth,
+                                                     const float* __restrict__ w2c, const float* __restrict__ intr,
+                                                     const int32_t* __restrict__ hw, int n, int i, int64_t pix_stride,
+                                                     float tol, float bad_conf, float* conf) {
+    const int P = hw[2 * i] * hw[2 * i + 1];
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < P; q += gridDim.x * blockDim.x) {
+        const float* X = pts3d + ((int64_t)i * pix_stride + q) * 3;
+        const float x = X[0], y = X[1], z = X[2];
+        float c = conf[(int64_t)i * pix_stride + q];
+        for (int j = 0; j < n; ++j) {
+            if (j == i) continue;
+            const float* M = w2c + 16 * j;
+            // geotrf(cams[j], pts3d): R x + t, then geotrf(K[j], ., norm=1, ncol=2): (K p)_xy / (K p)_z, rounded half-to-even
+            const float px = M[0] * x + M[1] * y + M[2] * z + M[3];
+            const float py = M[4] * x + M[5] * y + M[6] * z + M[7];
+            const float pz = M[8] * x + M[9] * y + M[10] * z + M[11];
+            const float* K = intr + 4 * j;
+            const float uu = (K[0] * px + K[2] * pz) / pz, vv = (K[1] * py + K[3] * pz) / pz;
+            const long long u = (long long)rintf(uu), v = (long long)rintf(vv);
+            const int Hj = hw[2 * j], Wj = hw[2 * j + 1];
+            if (!(pz > 0.f) || u < 0 || u >= Wj || v < 0 || v >= Hj) continue;       // NaN coordinates fail the range test
+            const int64_t o = (int64_t)j * pix_stride + v * Wj + u;
+            if (pz < (1.0f - tol) * depth[o] && c < conf[o]) c = fminf(c, bad_conf);
+        }
+        conf[(int64_t)i * pix_stride + q] = c;
+    }
+}
+
 extern "C" {
+
+int a3r_clean_pointcloud(const float* pts3d, const float* depth, const float* w2c, const float* intr, const int32_t* hw,
+                         int32_t n, int64_t pix_stride, float tol, float bad_conf, float* conf, void* stream) {
+    if (!pts3d || !depth || !w2c || !intr || !hw || !conf || n <= 0) return a3r_fail(A3R_E_ARG, "a3r_clean_pointcloud: bad arguments");
+    if (!(tol >= 0.f && tol < 1.f)) return a3r_fail(A3R_E_ARG, "a3r_clean_pointcloud: tol must be in [0, 1)");
+    for (int i = 0; i < n; ++i)          // frame i reads the confidences frames < i ended with: one launch per frame, in order
+        k_clean_frame<<<592, 256, 0, (cudaStream_t)stream>>>(pts3d, depth, w2c, intr, hw, n, i, pix_stride, tol, bad_conf, conf);
+    A3R_CUDA(cudaGetLastError());
+    return A3R_OK;
+}
+
 
 int a3r_procrustes_batched(const float* predw, int64_t pix_stride, const int32_t* xs, const int32_t* ys,
                            const int32_t* npix, int32_t count, int32_t conf_mode, double* sums, double* out,

@@ -117,6 +117,7 @@ def build_plan(edges, frame_hw, tile_pixels: int, max_slots: int, n_ctas: int, f
     N, E = len(frame_hw), len(edges)
     assert check_edges(edges.tolist()) == N, "frame_hw does not match the edge list"
     areas = frame_hw[:, 0].astype(np.int64) * frame_hw[:, 1]
+    assert int(areas.max()) < (1 << 24), "frames of 2^24 pixels or more are not supported (the scan derives (u, v) from a float quotient)"
     # whole tiles per plane: the TMA-fed scan copies full tiles, padding is zero (weight 0, not static)
     unit = int(np.lcm(4, int(tile_pixels)))
     pix_stride = int((areas.max() + unit - 1) // unit * unit)

@@ -220,6 +220,15 @@ int a3r_ga_run_peers(const A3rProblem *p, const A3rPeers *peers, uint32_t tag0, 
  * world points [n_local_frames][pix_stride][3] from logdepth + frame_par (call a3r_ga_prepare first) */
 int a3r_ga_unproject(const A3rProblem *p, float *pts3d, void *stream);
 
+/* ---- post-step: confidence clean-up (reference base_opt.py:293-303, 587-623 clean_pointcloud) ----
+ * For i = 0..n-1 in order, every point of frame i is projected into every other camera j (in order); where it lands
+ * in front of j's depth map ((1-tol) factor) while being less confident than the pixel it lands on, its confidence is
+ * clipped to bad_conf.  One launch per frame i (a pixel's j-loop is sequential, frames are sequential, pixels of one
+ * frame are independent).  pts3d [n][pix_stride][3] world points, depth [n][pix_stride], w2c [n][16] row-major
+ * world-to-camera, intr [n][4] = fx fy cx cy, hw [n][2] (device int32), conf [n][pix_stride] in/out. */
+int a3r_clean_pointcloud(const float *pts3d, const float *depth, const float *w2c, const float *intr, const int32_t *hw,
+                         int32_t n, int64_t pix_stride, float tol, float bad_conf, float *conf, void *stream);
+
 /* ---- MST initialisation solves (reference init_im_poses.py:446-465, post_process.py:36-58) ---- */
 /* count weighted similarity registrations y ~ s R x + t between two slots living on the same frame:
  * x = slot xs[k] (weights = raw conf = conf_untrf(w)), y = slot ys[k]; P[k] valid pixels.

@@ -126,3 +126,16 @@ def test_depth_prior_loss_and_grads_match_reference():
     assert abs(float(loss64) - float(g64["loss"])) <= 1e-10 * abs(float(g64["loss"]))
     for k, ref in g64["grads"].items():
         assert rel_err(grads64[k], ref) <= 1e-9, k
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clean_pointcloud: fixture from the real reference, oracle/make_golden_clean.py
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tol", [0.001, 0.05])
+def test_clean_pointcloud_matches_reference(tol):
+    fx, scene, prob = golden_case("small_clean_pointcloud")
+    b = fx["before"]
+    res = go.clean_pointcloud(b["im_conf"], b["K"], b["c2w"], b["depth"], b["pts3d"], tol=tol)
+    ref = fx[f"after_tol{tol}"]
+    assert int((ref != b["im_conf"]).sum()) > 1000, "the fixture must exercise the clean-up"
+    assert torch.equal(res, ref)
