@@ -910,6 +910,11 @@ class PointCloudOptimizer(nn.Module):
         return [np.stack(tum, 0), tt]
 
 
+from . import writeout as _writeout      # noqa: E402   save_tum_poses, save_focals, save_intrinsics, save_conf_maps, ...
+for _m in _writeout.METHODS:
+    setattr(PointCloudOptimizer, _m.__name__, _m)
+
+
 def _rgb(ftensor, true_shape=None):
     """reference dust3r/utils/image.py:44-61: network-normalised images -> [0,1] HWC numpy."""
     if isinstance(ftensor, list):

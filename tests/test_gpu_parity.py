@@ -453,3 +453,37 @@ def test_clean_pointcloud(cuda_device, tol):
     differ = (after - ref).abs() > 1e-6
     assert float(differ.float().mean()) <= 2e-3, int(differ.sum())
     assert int(((after - before).abs() > 1e-6).sum()) > 1000
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# result write-out: the on-disk formats of reference base_opt.py:332-427 / vo_eval.py:308-316
+# ---------------------------------------------------------------------------------------------------------------
+def test_result_write_out(cuda_device, tmp_path):
+    scene = make_scene(5, 40, 56, "swin-2-noncyclic", seed=2, with_flow=True, with_img=True)
+    net = build(scene, dict(CANONICAL_KW, num_total_iter=5))
+    net.compute_global_alignment(init="mst", niter=5, schedule="linear", lr=0.01)
+    d = str(tmp_path)
+    tum = net.save_tum_poses(f"{d}/pred_traj.txt")
+    rows = [l.split() for l in open(f"{d}/pred_traj.txt").read().splitlines()]
+    assert len(rows) == 5 and all(len(r) == 8 for r in rows) and [float(r[0]) for r in rows] == [0, 1, 2, 3, 4]
+    back = np.array([[float(x) for x in r[1:]] for r in rows])
+    assert np.allclose(back, tum, rtol=0, atol=1e-12)                      # x y z qw qx qy qz, full precision
+    c2w = net.get_im_poses().detach().cpu().numpy()
+    assert np.allclose(back[:, :3], c2w[:, :3, 3], atol=1e-6)
+    from scipy.spatial.transform import Rotation
+    assert np.allclose(Rotation.from_quat(back[:, [4, 5, 6, 3]]).as_matrix(), c2w[:, :3, :3], atol=1e-5)
+    net.save_focals(f"{d}/pred_focal.txt")
+    assert np.allclose(np.loadtxt(f"{d}/pred_focal.txt"), net.get_focals().detach().cpu().numpy().ravel(), atol=1e-6 + 5e-7)
+    net.save_intrinsics(f"{d}/pred_intrinsics.txt")
+    net.save_intrinsics(f"{d}/pred_intrinsics.txt")                        # appended: two clips, one file
+    K = np.loadtxt(f"{d}/pred_intrinsics.txt")
+    assert K.shape == (10, 9) and np.allclose(K[:5], K[5:]) and np.allclose(K[:5].reshape(5, 3, 3), net.get_intrinsics().detach().cpu().numpy(), atol=1e-6)
+    net.save_conf_maps(d, 3)
+    net.save_init_conf_maps(d, 3)
+    assert np.allclose(np.load(f"{d}/conf_3.npy"), net.get_conf()[0].cpu().numpy()) and os.path.exists(f"{d}/init_conf_7.npy")
+    net.save_depth_maps(d, 0)
+    assert np.allclose(np.load(f"{d}/frame_0004.npy"), net.get_depthmaps()[4].detach().cpu().numpy())
+    assert os.path.exists(f"{d}/frame_0000.png") and os.path.exists(f"{d}/_depth_maps.gif")
+    net.save_dynamic_masks(d, 0)
+    net.save_rgb_imgs(d, 0)
+    assert os.path.exists(f"{d}/dynamic_mask_4.png") and os.path.exists(f"{d}/frame_0002_rgb.png") and os.path.exists(f"{d}/_rgb.gif")
