@@ -487,3 +487,45 @@ def test_result_write_out(cuda_device, tmp_path):
     net.save_dynamic_masks(d, 0)
     net.save_rgb_imgs(d, 0)
     assert os.path.exists(f"{d}/dynamic_mask_4.png") and os.path.exists(f"{d}/frame_0002_rgb.png") and os.path.exists(f"{d}/_rgb.gif")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the plain aligner of tool/depth_test.py (reference dust3r/cloud_opt): same kernels, flow / temporal terms off,
+# non-symmetrised complete clip graph, cosine schedule down to 1e-6
+# ---------------------------------------------------------------------------------------------------------------
+def test_cloud_opt_variant_against_live_oracle(cuda_device):
+    from align3r_b200 import cloud_opt
+    from align3r_b200.synth import make_edge_list
+    edges = make_edge_list(6, "complete", symmetrize=False)
+    scene = make_scene(6, 48, 64, "complete", seed=4, with_flow=False, edges=edges)
+    assert len(scene.edges) == 15
+    net = cloud_opt.global_aligner(scene.output, False, [], "cuda", mode=cloud_opt.GlobalAlignerMode.PointCloudOptimizer,
+                                   verbose=False, min_conf_thr=3)
+    assert not net.is_symmetrized and net.flow_loss_weight == 0 and net.temporal_smoothing_weight == 0
+    prob = go.problem_from_output(scene.output, None, None, flow_loss_weight=0.0, temporal_smoothing_weight=0.0)
+    params, _ = go.mst_init(prob)
+    # teacher-forced at the oracle's initialisation: loss and gradients on a graph whose frames carry unequal numbers
+    # of side-i and side-j slots (frame 0 has no side-i slot at all)
+    p64 = {k: v.double() for k, v in params.items()}
+    loss64, g64, _ = go.loss_and_grads(prob.to(torch.float64), p64, 9999)
+    _, g32, _ = go.loss_and_grads(prob, params, 9999)
+    set_params(net, params)
+    l0 = net(epoch=9999)
+    l0.backward()
+    assert abs(float(l0.detach()) - float(loss64)) <= 2e-6 * abs(float(loss64))
+    mine = grads_of(net, prob.P)
+    for k in mine:
+        ok, err, ref_err = grad_close(k, mine[k], g32[k], g64[k])
+        assert ok, (k, err, ref_err)
+    # the loop from that initialisation (lr 0.05, cosine to 1e-6) ends where the oracle ends
+    loss = net.compute_global_alignment(init=None, niter=30, schedule="cosine", lr=0.05)
+    final, losses, _ = go.run_alignment(prob, params, niter=30, schedule="cosine", lr=0.05, lr_min=1e-6)
+    assert abs(loss - losses[-1]) <= 1e-3 * abs(losses[-1]), (loss, losses[-1])
+    d = (net.im_depthmaps.detach().cpu()[:, :prob.P] - final["im_depthmaps"]).abs()
+    assert float(d.median()) < 1e-4
+    # and the canonical call through our own initialisation ends on a finite, comparable loss
+    net2 = cloud_opt.global_aligner(scene.output, False, [], "cuda", verbose=False, min_conf_thr=3)
+    loss2 = net2.compute_global_alignment(init="mst", niter=30, schedule="cosine", lr=0.05)
+    assert math.isfinite(loss2) and loss2 < 5 * losses[-1], (loss2, losses[-1])
+    with pytest.raises(NotImplementedError):
+        cloud_opt.global_aligner(scene.output, True, [], "cuda")
