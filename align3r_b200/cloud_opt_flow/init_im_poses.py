@@ -180,9 +180,6 @@ def fast_pnp(pts3d, focal, msk, pp=None, niter_PnP=10):
 def init_minimum_spanning_tree(self, save_score_path=None, save_score_only=False, init_priors=None, niter_PnP=10):
     """Init all camera poses (image-wise and pairwise poses) given an initial set of pairwise
     estimations - reference init_im_poses.py:88-104,157-284 followed by init_from_pts3d (:107-154)."""
-    if init_priors is not None:
-        raise NotImplementedError("init_priors (hierarchical clip driver, reference init_im_poses.py:173-215) is a "
-                                  "'next' row of the scope table")
     ph = Phases('mst-init', self.device)
     scores = compute_edge_scores(self)
     ph.mark('scores')
@@ -198,21 +195,39 @@ def init_minimum_spanning_tree(self, save_score_path=None, save_score_only=False
     todo = sorted(zip(-msp.data, msp.row, msp.col))
 
     # ---- pass 1: traversal order (pure graph logic) ----
-    score, i, j = todo.pop()
+    key_sim, key_pose, fixed_focal = None, None, {}
+    if init_priors is None:
+        score, i, j = todo.pop()
+    else:
+        # hierarchical clip driver (reference init_im_poses.py:173-215): the tree starts at an edge touching frame 0 - the
+        # key frame - whose pose and focal come from the key-frame alignment: init_priors = [pose 4x4, depth, [focal, ...]]
+        key_pose = np.array(init_priors[0]).astype(np.float32).astype(np.float64)
+        key_sim = (1.0, key_pose[:3, :3].copy(), key_pose[:3, 3].copy())
+        fixed_focal[0] = float(init_priors[2][0])
+        score, i, j = None, None, None
+        while todo:
+            score, i, j = todo.pop()
+            if i == 0 or j == 0:
+                break
+            todo.insert(0, (score, i, j))
     if self.verbose:
         print(f' init edge ({i}*,{j}*) {score=}')
     k0 = eid[(int(i), int(j))]
-    src = {int(i): 2 * k0, int(j): 2 * k0 + 1}          # frame -> slot its world pointmap is made of
+    if key_sim is None or int(i) == 0:
+        src = {int(i): 2 * k0, int(j): 2 * k0 + 1}      # frame -> slot its world pointmap is made of
+    else:                                                # j is the key frame: the reference reads the mirrored edge (:207-209)
+        kr = eid[(int(j), int(i))]
+        src = {int(i): 2 * kr + 1, int(j): 2 * kr}
     done = {int(i), int(j)}
     first = (int(i), int(j))
-    focal_slot = {int(i): 2 * k0}                        # frame -> slot whose Weiszfeld focal it takes
+    focal_slot = {} if key_sim is not None else {int(i): 2 * k0}      # frame -> slot whose Weiszfeld focal it takes
     stale_k = k0
     steps = []                                           # (anchor frame, new frame, x slot, new src slot, pose frame)
     msp_edges = [first]
     while todo:
         score, i, j = todo.pop()
         i, j = int(i), int(j)
-        if i not in focal_slot:
+        if i not in focal_slot and i not in fixed_focal:
             focal_slot[i] = 2 * stale_k                  # the reference's stale ``i_j`` (init_im_poses.py:223-224)
         if i in done:
             if self.verbose:
@@ -240,7 +255,7 @@ def init_minimum_spanning_tree(self, save_score_path=None, save_score_only=False
     pair_scores = list(sparse_graph.values())
     edges_from_best_to_worse = np.array(list(sparse_graph.keys()))[np.argsort(pair_scores)]
     for i, j in edges_from_best_to_worse.tolist():
-        if i not in focal_slot:
+        if i not in focal_slot and i not in fixed_focal:
             focal_slot[i] = 2 * eid[(i, j)]
 
     ph.mark('tree')
@@ -255,6 +270,7 @@ def init_minimum_spanning_tree(self, save_score_path=None, save_score_only=False
     ph.mark('procrustes')
     frames_f = sorted(focal_slot)
     focals = dict(zip(frames_f, _run_focals(self, [focal_slot[n] for n in frames_f]).tolist()))
+    focals.update(fixed_focal)
 
     ph.mark('focals')
 
@@ -262,10 +278,13 @@ def init_minimum_spanning_tree(self, save_score_path=None, save_score_only=False
         return float(row[0]), row[1:10].reshape(3, 3), row[10:13]
 
     # ---- pass 3: compose in tree order (fp64, host) ----
-    ident = (1.0, np.eye(3), np.zeros(3))
+    ident = (1.0, np.eye(3), np.zeros(3)) if key_sim is None else key_sim
     T = {first[0]: ident, first[1]: ident}
     im_poses = [None] * N
-    im_poses[first[0]] = np.eye(4)
+    if key_sim is None:
+        im_poses[first[0]] = np.eye(4)
+    else:
+        im_poses[0] = key_pose.copy()                    # first[0] == 0 or first[1] == 0
     for t, (anchor, new, xs, new_src, pose_frame) in enumerate(steps):
         s, R, tt = _compose(T[anchor], sim(reg[t]))
         T[new] = (s, R, tt)

@@ -529,3 +529,25 @@ def test_cloud_opt_variant_against_live_oracle(cuda_device):
     assert math.isfinite(loss2) and loss2 < 5 * losses[-1], (loss2, losses[-1])
     with pytest.raises(NotImplementedError):
         cloud_opt.global_aligner(scene.output, True, [], "cuda")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# init_priors (hierarchical clip driver start from the key frame)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_mst_initialisation_with_priors(cuda_device, tag):
+    fx, scene, prob = golden_case(f"small_init_priors_{tag}")
+    ref = fx["params"]
+    net = build(scene, fx["kw"])
+    init_fun.init_minimum_spanning_tree(net, niter_PnP=10, init_priors=fx["init_priors"])
+    T_ref = go.pw_pose_matrices(prob, ref["pw_poses"])
+    assert float((net.get_pw_poses().detach().cpu() - T_ref).abs().max()) < 5e-5
+    P_ref = go.poses_to_matrices(ref["im_poses"])
+    Pm = net.get_im_poses().detach().cpu()
+    assert float((Pm - P_ref).abs().max()) < 2e-3
+    # the key frame keeps the prior pose up to the scale normalisation of its translation
+    key = torch.from_numpy(fx["init_priors"][0])
+    assert float((Pm[0, :3, :3] - key[:3, :3]).abs().max()) < 1e-5
+    assert rel_err(net.get_focals().detach().cpu(), go.focals(prob, ref["im_focals"])) < 1e-5
+    d = (net.im_depthmaps.detach().cpu()[:, :prob.P] - ref["im_depthmaps"]).abs()
+    assert float(d.median()) < 1e-5 and float(d.max()) < 2e-3

@@ -139,3 +139,19 @@ def test_clean_pointcloud_matches_reference(tol):
     ref = fx[f"after_tol{tol}"]
     assert int((ref != b["im_conf"]).sum()) > 1000, "the fixture must exercise the clean-up"
     assert torch.equal(res, ref)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# init_priors (hierarchical clip driver): fixtures from the real reference,
+# oracle/make_golden_priors.py - "a" starts at (0*, k*), "b" at (k*, 0*) (the mirrored-edge branch)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_mst_init_with_priors_matches_reference(tag):
+    fx, scene, prob = golden_case(f"small_init_priors_{tag}")
+    assert ("(0*," in fx["first_edge"]) == (tag == "a")
+    params, info = go.mst_init(prob, init_priors=fx["init_priors"])
+    for k, ref in fx["params"].items():
+        assert torch.allclose(params[k], ref, rtol=1e-5, atol=2e-6), (k, float((params[k] - ref).abs().max()))
+    key = torch.from_numpy(fx["init_priors"][0])
+    # the key frame keeps the prior rotation; its translation is rescaled by init_from_pts3d's scale normalisation
+    assert float((go.poses_to_matrices(params["im_poses"])[0, :3, :3] - key[:3, :3]).abs().max()) < 1e-6
