@@ -17,9 +17,9 @@ using namespace a3r;
 // ==========================================================================================
 // K0: parameter maps  (reference base_opt.py:195-247, optimizer.py:398-428)
 // ==========================================================================================
-__global__ void __launch_bounds__(256) k_prepare(const A3rProblem p) {
-    __shared__ double s_red[32];
-    __shared__ double s_mean;
+// body shared by the stand-alone launch and the tail of the fused update kernel (256 threads per CTA in both, so the
+// mean of the pair log-scales is the same number, bit for bit, wherever it is evaluated)
+__device__ __forceinline__ void prepare_body(const A3rProblem& p, const int gid, const int gstride, double* s_red, double* s_mean) {
     const int tid = threadIdx.x;
     const int E = p.n_edges, N = p.n_frames;
     const bool shared_focal = p.flags & A3R_F_SHARED_FOCAL;
@@ -29,12 +29,9 @@ __global__ void __launch_bounds__(256) k_prepare(const A3rProblem p) {
     double part = 0.0;
     for (int e = tid; e < E; e += blockDim.x) part += (double)p.pw_poses[8 * e + 7];
     part = block_sum(part, s_red);
-    if (tid == 0) s_mean = part / (double)E;
+    if (tid == 0) *s_mean = part / (double)E;
     __syncthreads();
-    const double log_norm = norm_scale ? (log((double)p.base_scale) - s_mean) : 0.0;
-
-    const int gid = blockIdx.x * blockDim.x + tid;
-    const int gstride = gridDim.x * blockDim.x;
+    const double log_norm = norm_scale ? (log((double)p.base_scale) - *s_mean) : 0.0;
 
     for (int n = gid; n < N; n += gstride) {
         FrameD F;
@@ -53,6 +50,12 @@ __global__ void __launch_bounds__(256) k_prepare(const A3rProblem p) {
             derive_slot_par(S, T, p.slot_par + SP_STRIDE * gs);
         }
     }
+}
+
+__global__ void __launch_bounds__(256) k_prepare(const A3rProblem p) {
+    __shared__ double s_red[32];
+    __shared__ double s_mean;
+    prepare_body(p, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, s_red, &s_mean);
 }
 
 // ==========================================================================================
@@ -274,99 +277,36 @@ __global__ void __launch_bounds__(256) k_depth_prior(const A3rProblem p) {
     }
 }
 
-// K2a: loss assembly + gate (one small CTA: 3 sums over 2E slots, N-1 temporal pairs)
-__global__ void __launch_bounds__(512, 1) k_loss_scalars(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam) {
-    __shared__ double s_red[32];
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int N = p.n_frames, E = p.n_edges;
-    const bool shared_focal = p.flags & A3R_F_SHARED_FOCAL;
-    const bool flow_active = (mode & A3R_M_FLOW_ACTIVE) && (p.flags & A3R_F_HAS_FLOW) && p.flow_loss_weight > 0.f;
-    const double fb = (double)p.focal_break;
-    const double tsw = (double)p.temporal_smoothing_weight, tw = (double)p.translation_weight;
-    double l_align = 0, num_i = 0, cnt_i = 0, num_j = 0, cnt_j = 0, l_temp = 0, l_prior = 0;
-    if (p.depth_regularize_weight > 0.f)
-        for (int n = tid; n < N; n += nt)
-            l_prior += prior_frame(p.prior_acc + (int64_t)n * PR_N, (double)p.frame_hw[2 * n] * p.frame_hw[2 * n + 1]).loss;
-    for (int gs = tid; gs < 2 * E; gs += nt) {
+// ==========================================================================================
+// K2: loss, gate, every parameter chain, Adam on the small parameters and the parameter maps of the NEXT iteration in
+// ONE launch: a thread-block cluster of 8 CTAs x 256 threads whose phases are separated by the hardware cluster barrier
+// (barrier.cluster arrive.release / wait.acquire orders the global-memory traffic of the phases), instead of five
+// launches + a memset separated by kernel boundaries.  This chain is pure latency (a few thousand items of fp64
+// arithmetic) and sits on the critical path between two scans.
+//   phase 0  zero frame_grad | loss sums + gate: every CTA evaluates them in the same order, CTA 0 publishes p.scal
+//   phase 1  chains that end in a camera (fp64 atomics into frame_grad) + dL/dlog s_e
+//   phase 2  gradients of pw_poses / im_poses (/ per-frame focal, pp) + torch.optim.Adam
+//   phase 3  the shared focal (one scalar that every frame read in phase 2)
+//   phase 4  (tail) parameter maps of the updated parameters = k_prepare of the next iteration
+// ==========================================================================================
+constexpr int K2_CLUSTER = 8;
+constexpr int K2_THREADS = 256;
+
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// the four flow sums (numerator / per-channel mask count of both sides) over all 2E slots in a fixed 256-thread order:
+// K2 and the depth-plane Adam kernel K3 both evaluate them (K3 must not wait for K2) and must agree bit for bit
+__device__ __forceinline__ void flow_sums_256(const A3rProblem& p, double* s_red, double out[4]) {
+    double num_i = 0, cnt_i = 0, num_j = 0, cnt_j = 0;
+    for (int gs = threadIdx.x; gs < 2 * p.n_edges; gs += 256) {
         const double* a = p.acc_slot + (int64_t)gs * ACC_STRIDE;
-        l_align += a[ACC_LOSS];
         if (gs & 1) { num_j += a[ACC_FNUM]; cnt_j += a[ACC_FCNT]; }
         else        { num_i += a[ACC_FNUM]; cnt_i += a[ACC_FCNT]; }
     }
-    if (tsw > 0) {
-        for (int n = tid; n < N - 1; n += nt) {
-            FrameD T, S;
-            load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n, shared_focal, fb, T);
-            load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n + 1, shared_focal, fb, S);
-            l_temp += temporal_pair(S, T, tsw, tw, nullptr);
-        }
-    }
-    l_align = block_sum(l_align, s_red);
-    num_i = block_sum(num_i, s_red); cnt_i = block_sum(cnt_i, s_red);
-    num_j = block_sum(num_j, s_red); cnt_j = block_sum(cnt_j, s_red);
-    l_temp = block_sum(l_temp, s_red);
-    l_prior = block_sum(l_prior, s_red) / (double)N;
-    if (tid == 0) {
-        LossScalars r = assemble_loss(l_align, l_temp, num_i, cnt_i, num_j, cnt_j, flow_active,
-                                            (double)p.flow_loss_weight, (double)p.flow_loss_thre, tsw);
-        r.loss += (double)p.depth_regularize_weight * l_prior;           // optimizer.py:554-557
-        p.scal[A3R_S_PRIOR] = l_prior;
-        p.scal[A3R_S_LOSS] = r.loss; p.scal[A3R_S_ALIGN] = l_align; p.scal[A3R_S_TEMPORAL] = l_temp;
-        p.scal[A3R_S_FLOW] = r.floss; p.scal[A3R_S_FLOW_DROPPED] = r.dropped;
-        p.scal[A3R_S_SC_I] = r.sc_i; p.scal[A3R_S_SC_J] = r.sc_j;
-        if (r.dropped != 0) p.scal[A3R_S_FLAG_STICKY] = 1.0;
-        p.scal[S_GSUM] = 0.0; p.scal[S_GPHI] = 0.0;
-        if (p.loss_hist && adam.iter >= 0) p.loss_hist[adam.iter] = (float)r.loss;
-    }
-}
-
-// K2b: every chain that ends in a camera (frame_grad, zeroed beforehand; fp64 atomics) + dL/dlog s_e
-//   items: [0,N) alignment part of frame n | [N, N+2E) flow chain of a slot | [.., +N-1) temporal pair | [.., +E) edge
-__global__ void __launch_bounds__(128) k_chain(const A3rProblem p, const uint32_t mode) {
-    const int N = p.n_frames, E = p.n_edges;
-    const bool shared_focal = p.flags & A3R_F_SHARED_FOCAL;
-    const bool flow_active = (mode & A3R_M_FLOW_ACTIVE) && (p.flags & A3R_F_HAS_FLOW) && p.flow_loss_weight > 0.f;
-    const double fb = (double)p.focal_break;
-    const double tsw = (double)p.temporal_smoothing_weight, tw = (double)p.translation_weight;
-    const double sc_i = p.scal[A3R_S_SC_I], sc_j = p.scal[A3R_S_SC_J];
-    const int total = N + 2 * E + (N - 1) + E;
-    for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < total; it += gridDim.x * blockDim.x) {
-        if (it < N) {
-            const int n = it;
-            FrameD F;
-            load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n, shared_focal, fb, F);
-            double fg[FG_STRIDE];
-            frame_align_grad(F, p.acc_frame + (int64_t)n * FACC_N, fg);
-            double* dst = p.frame_grad + (int64_t)n * FG_STRIDE;
-            for (int k = 0; k < 15; ++k) atomicAdd(&dst[k], fg[k]);
-        } else if (it < N + 2 * E) {
-            if (!(flow_active && (sc_i != 0 || sc_j != 0))) continue;
-            const int gs = it - N, e = gs >> 1, side = gs & 1;
-            const int i = p.edge_ij[2 * e], j = p.edge_ij[2 * e + 1];
-            const int sI = side ? j : i, tI = side ? i : j;
-            FrameD S, T;
-            load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, sI, shared_focal, fb, S);
-            load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, tI, shared_focal, fb, T);
-            PairGrad g;
-            slot_flow_chain(S, T, p.acc_slot + (int64_t)gs * ACC_STRIDE, side ? sc_j : sc_i, g);
-            scatter_pair(g, p.frame_grad + (int64_t)sI * FG_STRIDE, p.frame_grad + (int64_t)tI * FG_STRIDE);
-        } else if (it < N + 2 * E + N - 1) {
-            if (!(tsw > 0)) continue;
-            const int n = it - N - 2 * E;
-            FrameD T, S;
-            load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n, shared_focal, fb, T);
-            load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n + 1, shared_focal, fb, S);
-            PairGrad g;
-            temporal_pair(S, T, tsw, tw, &g);
-            scatter_pair(g, p.frame_grad + (int64_t)(n + 1) * FG_STRIDE, p.frame_grad + (int64_t)n * FG_STRIDE);
-        } else {
-            const int e = it - N - 2 * E - (N - 1);
-            const double* a0 = p.acc_slot + (int64_t)(2 * e) * ACC_STRIDE;
-            const double g = edge_logscale_grad(p.edge_par + EP_STRIDE * e, a0, a0 + ACC_STRIDE);
-            p.edge_scratch[e] = g;
-            atomicAdd(&p.scal[S_GSUM], g);
-        }
-    }
+    out[0] = block_sum(num_i, s_red); out[1] = block_sum(cnt_i, s_red);
+    out[2] = block_sum(num_j, s_red); out[3] = block_sum(cnt_j, s_red);
 }
 
 __device__ __forceinline__ void adam_vec(float* prm, float* m, float* v, const float* g, int cnt,
@@ -375,52 +315,155 @@ __device__ __forceinline__ void adam_vec(float* prm, float* m, float* v, const f
         adam_update(prm[k], m[k], v[k], g[k], p.adam_beta1, p.adam_beta2, p.adam_eps, a.step_size, a.bc2_sqrt);
 }
 
-// K2c: gradients of the small parameters + torch.optim.Adam.  items: [0,E) pairwise pose | [E, E+N) image pose
-__global__ void __launch_bounds__(128) k_adam_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam) {
+__global__ void __cluster_dims__(K2_CLUSTER, 1, 1) __launch_bounds__(K2_THREADS, 1)
+k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const uint32_t prepare_next) {
+    __shared__ double s_red[32];
+    __shared__ double s_sc[2];
+    __shared__ double s_mean;
+    const int tid = threadIdx.x;
+    const int vt = blockIdx.x * K2_THREADS + tid, nvt = gridDim.x * K2_THREADS;      // the grid is one cluster
     const int N = p.n_frames, E = p.n_edges;
     const bool shared_focal = p.flags & A3R_F_SHARED_FOCAL;
     const bool norm_scale = p.flags & A3R_F_NORM_PW_SCALE;
+    const bool flow_active = (mode & A3R_M_FLOW_ACTIVE) && (p.flags & A3R_F_HAS_FLOW) && p.flow_loss_weight > 0.f;
     const bool apply = mode & A3R_M_APPLY_ADAM;
     const double fb = (double)p.focal_break;
-    const double gmean = norm_scale ? p.scal[S_GSUM] / (double)E : 0.0;
-    for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < E + N; it += gridDim.x * blockDim.x) {
-        if (it < E) {
-            const int e = it;
-            const double* a0 = p.acc_slot + (int64_t)(2 * e) * ACC_STRIDE;
-            float g[8], ga[2];
-            edge_pose_grad(p.pw_poses + 8 * e, p.edge_par + EP_STRIDE * e, a0, a0 + ACC_STRIDE, p.edge_scratch[e] - gmean,
-                           p.flags & A3R_F_TRAIN_ADAPTORS, norm_scale, (double)p.pw_break, g, ga);
-            for (int k = 0; k < 8; ++k) p.g_pw_poses[8 * e + k] = g[k];
-            p.g_pw_adaptors[2 * e] = ga[0]; p.g_pw_adaptors[2 * e + 1] = ga[1];
-            if (apply && (p.flags & A3R_F_TRAIN_PW_POSES)) adam_vec(p.pw_poses + 8 * e, p.pw_poses_m + 8 * e, p.pw_poses_v + 8 * e, g, 8, p, adam);
-            if (apply && (p.flags & A3R_F_TRAIN_ADAPTORS)) adam_vec(p.pw_adaptors + 2 * e, p.pw_adaptors_m + 2 * e, p.pw_adaptors_v + 2 * e, ga, 2, p, adam);
-        } else {
-            const int n = it - E;
-            FrameD F;
-            load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n, shared_focal, fb, F);
-            float g[7], gpp[2];
-            double gphi;
-            frame_pose_grad(p.im_poses + 7 * n, F, p.frame_grad + (int64_t)n * FG_STRIDE, fb, p.flags & A3R_F_TRAIN_PP, g, &gphi, gpp);
-            for (int k = 0; k < 7; ++k) p.g_im_poses[7 * n + k] = g[k];
-            p.g_im_pp[2 * n] = gpp[0]; p.g_im_pp[2 * n + 1] = gpp[1];
-            if (shared_focal) atomicAdd(&p.scal[S_GPHI], gphi);     // applied by k_adam_focal once every frame has read f
-            else {
-                float gf = (float)gphi;
-                p.g_im_focals[n] = gf;
-                if (apply && (p.flags & A3R_F_TRAIN_FOCALS)) adam_vec(p.im_focals + n, p.im_focals_m + n, p.im_focals_v + n, &gf, 1, p, adam);
+    const double tsw = (double)p.temporal_smoothing_weight, tw = (double)p.translation_weight;
+
+    // ---------------- phase 0: loss assembly + gate (reference optimizer.py:538-557) ----------------
+    for (int i = vt; i < N * FG_STRIDE; i += nvt) p.frame_grad[i] = 0.0;
+    {
+        double l_align = 0, l_temp = 0, l_prior = 0;
+        if (p.depth_regularize_weight > 0.f)
+            for (int n = tid; n < N; n += K2_THREADS)
+                l_prior += prior_frame(p.prior_acc + (int64_t)n * PR_N, (double)p.frame_hw[2 * n] * p.frame_hw[2 * n + 1]).loss;
+        for (int gs = tid; gs < 2 * E; gs += K2_THREADS) l_align += p.acc_slot[(int64_t)gs * ACC_STRIDE + ACC_LOSS];
+        if (tsw > 0) {
+            for (int n = tid; n < N - 1; n += K2_THREADS) {
+                FrameD T, S;
+                load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n, shared_focal, fb, T);
+                load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n + 1, shared_focal, fb, S);
+                l_temp += temporal_pair(S, T, tsw, tw, nullptr);
             }
-            if (apply && (p.flags & A3R_F_TRAIN_PP)) adam_vec(p.im_pp + 2 * n, p.im_pp_m + 2 * n, p.im_pp_v + 2 * n, gpp, 2, p, adam);
-            if (apply && (p.flags & A3R_F_TRAIN_IM_POSES)) adam_vec(p.im_poses + 7 * n, p.im_poses_m + 7 * n, p.im_poses_v + 7 * n, g, 7, p, adam);
+        }
+        double fs[4];
+        flow_sums_256(p, s_red, fs);
+        l_align = block_sum(l_align, s_red);
+        l_temp = block_sum(l_temp, s_red);
+        l_prior = block_sum(l_prior, s_red) / (double)N;
+        if (tid == 0) {
+            LossScalars r = assemble_loss(l_align, l_temp, fs[0], fs[1], fs[2], fs[3], flow_active,
+                                          (double)p.flow_loss_weight, (double)p.flow_loss_thre, tsw);
+            s_sc[0] = r.sc_i; s_sc[1] = r.sc_j;
+            if (blockIdx.x == 0) {
+                r.loss += (double)p.depth_regularize_weight * l_prior;           // optimizer.py:554-557
+                p.scal[A3R_S_PRIOR] = l_prior;
+                p.scal[A3R_S_LOSS] = r.loss; p.scal[A3R_S_ALIGN] = l_align; p.scal[A3R_S_TEMPORAL] = l_temp;
+                p.scal[A3R_S_FLOW] = r.floss; p.scal[A3R_S_FLOW_DROPPED] = r.dropped;
+                p.scal[A3R_S_SC_I] = r.sc_i; p.scal[A3R_S_SC_J] = r.sc_j;
+                if (r.dropped != 0) p.scal[A3R_S_FLAG_STICKY] = 1.0;
+                p.scal[S_GSUM] = 0.0; p.scal[S_GPHI] = 0.0;
+                if (p.loss_hist && adam.iter >= 0) p.loss_hist[adam.iter] = (float)r.loss;
+            }
         }
     }
-}
+    cluster_barrier();
 
-// K2d: the shared focal (one scalar that every frame reads)
-__global__ void k_adam_focal(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        float gf = (float)p.scal[S_GPHI];
-        p.g_im_focals[0] = gf;
-        if ((mode & A3R_M_APPLY_ADAM) && (p.flags & A3R_F_TRAIN_FOCALS)) adam_vec(p.im_focals, p.im_focals_m, p.im_focals_v, &gf, 1, p, adam);
+    // ---------------- phase 1: every chain that ends in a camera + dL/dlog s_e ----------------
+    //   items: [0,N) alignment part of frame n | [N, N+2E) flow chain of a slot | [.., +N-1) temporal pair | [.., +E) edge
+    {
+        const double sc_i = s_sc[0], sc_j = s_sc[1];
+        const int total = N + 2 * E + (N - 1) + E;
+        for (int it = vt; it < total; it += nvt) {
+            if (it < N) {
+                const int n = it;
+                FrameD F;
+                load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n, shared_focal, fb, F);
+                double fg[FG_STRIDE];
+                frame_align_grad(F, p.acc_frame + (int64_t)n * FACC_N, fg);
+                double* dst = p.frame_grad + (int64_t)n * FG_STRIDE;
+                for (int k = 0; k < 15; ++k) atomicAdd(&dst[k], fg[k]);
+            } else if (it < N + 2 * E) {
+                if (!(flow_active && (sc_i != 0 || sc_j != 0))) continue;
+                const int gs = it - N, e = gs >> 1, side = gs & 1;
+                const int i = p.edge_ij[2 * e], j = p.edge_ij[2 * e + 1];
+                const int sI = side ? j : i, tI = side ? i : j;
+                FrameD S, T;
+                load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, sI, shared_focal, fb, S);
+                load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, tI, shared_focal, fb, T);
+                PairGrad g;
+                slot_flow_chain(S, T, p.acc_slot + (int64_t)gs * ACC_STRIDE, side ? sc_j : sc_i, g);
+                scatter_pair(g, p.frame_grad + (int64_t)sI * FG_STRIDE, p.frame_grad + (int64_t)tI * FG_STRIDE);
+            } else if (it < N + 2 * E + N - 1) {
+                if (!(tsw > 0)) continue;
+                const int n = it - N - 2 * E;
+                FrameD T, S;
+                load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n, shared_focal, fb, T);
+                load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n + 1, shared_focal, fb, S);
+                PairGrad g;
+                temporal_pair(S, T, tsw, tw, &g);
+                scatter_pair(g, p.frame_grad + (int64_t)(n + 1) * FG_STRIDE, p.frame_grad + (int64_t)n * FG_STRIDE);
+            } else {
+                const int e = it - N - 2 * E - (N - 1);
+                const double* a0 = p.acc_slot + (int64_t)(2 * e) * ACC_STRIDE;
+                const double g = edge_logscale_grad(p.edge_par + EP_STRIDE * e, a0, a0 + ACC_STRIDE);
+                p.edge_scratch[e] = g;
+                atomicAdd(&p.scal[S_GSUM], g);
+            }
+        }
+    }
+    cluster_barrier();
+
+    // ---------------- phase 2: gradients of the small parameters + torch.optim.Adam ----------------
+    //   items: [0,E) pairwise pose | [E, E+N) image pose
+    {
+        const double gmean = norm_scale ? p.scal[S_GSUM] / (double)E : 0.0;
+        for (int it = vt; it < E + N; it += nvt) {
+            if (it < E) {
+                const int e = it;
+                const double* a0 = p.acc_slot + (int64_t)(2 * e) * ACC_STRIDE;
+                float g[8], ga[2];
+                edge_pose_grad(p.pw_poses + 8 * e, p.edge_par + EP_STRIDE * e, a0, a0 + ACC_STRIDE, p.edge_scratch[e] - gmean,
+                               p.flags & A3R_F_TRAIN_ADAPTORS, norm_scale, (double)p.pw_break, g, ga);
+                for (int k = 0; k < 8; ++k) p.g_pw_poses[8 * e + k] = g[k];
+                p.g_pw_adaptors[2 * e] = ga[0]; p.g_pw_adaptors[2 * e + 1] = ga[1];
+                if (apply && (p.flags & A3R_F_TRAIN_PW_POSES)) adam_vec(p.pw_poses + 8 * e, p.pw_poses_m + 8 * e, p.pw_poses_v + 8 * e, g, 8, p, adam);
+                if (apply && (p.flags & A3R_F_TRAIN_ADAPTORS)) adam_vec(p.pw_adaptors + 2 * e, p.pw_adaptors_m + 2 * e, p.pw_adaptors_v + 2 * e, ga, 2, p, adam);
+            } else {
+                const int n = it - E;
+                FrameD F;
+                load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n, shared_focal, fb, F);
+                float g[7], gpp[2];
+                double gphi;
+                frame_pose_grad(p.im_poses + 7 * n, F, p.frame_grad + (int64_t)n * FG_STRIDE, fb, p.flags & A3R_F_TRAIN_PP, g, &gphi, gpp);
+                for (int k = 0; k < 7; ++k) p.g_im_poses[7 * n + k] = g[k];
+                p.g_im_pp[2 * n] = gpp[0]; p.g_im_pp[2 * n + 1] = gpp[1];
+                if (shared_focal) atomicAdd(&p.scal[S_GPHI], gphi);     // applied in phase 3, once every frame has read f
+                else {
+                    float gf = (float)gphi;
+                    p.g_im_focals[n] = gf;
+                    if (apply && (p.flags & A3R_F_TRAIN_FOCALS)) adam_vec(p.im_focals + n, p.im_focals_m + n, p.im_focals_v + n, &gf, 1, p, adam);
+                }
+                if (apply && (p.flags & A3R_F_TRAIN_PP)) adam_vec(p.im_pp + 2 * n, p.im_pp_m + 2 * n, p.im_pp_v + 2 * n, gpp, 2, p, adam);
+                if (apply && (p.flags & A3R_F_TRAIN_IM_POSES)) adam_vec(p.im_poses + 7 * n, p.im_poses_m + 7 * n, p.im_poses_v + 7 * n, g, 7, p, adam);
+            }
+        }
+    }
+
+    // ---------------- phase 3: the shared focal ----------------
+    if (shared_focal) {
+        cluster_barrier();
+        if (vt == 0) {
+            float gf = (float)p.scal[S_GPHI];
+            p.g_im_focals[0] = gf;
+            if (apply && (p.flags & A3R_F_TRAIN_FOCALS)) adam_vec(p.im_focals, p.im_focals_m, p.im_focals_v, &gf, 1, p, adam);
+        }
+    }
+
+    // ---------------- phase 4: parameter maps of the next iteration (reference base_opt.py:195-247) ----------------
+    if (prepare_next) {
+        cluster_barrier();
+        prepare_body(p, vt, nvt, s_red, &s_mean);
     }
 }
 
@@ -431,7 +474,22 @@ template <bool FLOW>
 __global__ void __launch_bounds__(256) k_update_depth(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam) {
     const int64_t total4 = (int64_t)p.n_local_frames * p.pix_stride / 4;
     const bool prior = p.depth_regularize_weight > 0.f;
-    const float sc_i = (float)p.scal[A3R_S_SC_I], sc_j = (float)p.scal[A3R_S_SC_J];
+    // the flow normalisers and the gate, evaluated here exactly as K2 evaluates them: K3 starts right after the scan,
+    // beside K2, instead of waiting for K2's scalars
+    float sc_i = 0.f, sc_j = 0.f;
+    if (FLOW) {
+        __shared__ double s_red[32];
+        __shared__ float s_sc[2];
+        double fs[4];
+        flow_sums_256(p, s_red, fs);
+        if (threadIdx.x == 0) {
+            const LossScalars r = assemble_loss(0.0, 0.0, fs[0], fs[1], fs[2], fs[3], true, (double)p.flow_loss_weight,
+                                                (double)p.flow_loss_thre, 0.0);
+            s_sc[0] = (float)r.sc_i; s_sc[1] = (float)r.sc_j;
+        }
+        __syncthreads();
+        sc_i = s_sc[0]; sc_j = s_sc[1];
+    }
     const bool apply = mode & A3R_M_APPLY_ADAM;
     float4* ld = reinterpret_cast<float4*>(p.logdepth);
     float4* mm = reinterpret_cast<float4*>(p.logdepth_m);
@@ -685,9 +743,9 @@ int a3r_ga_accumulate(const A3rProblem* p, uint32_t mode, void* stream) {
     return l2 ? launch_accumulate<false, true>(p, st) : launch_accumulate<false, false>(p, st);
 }
 
-// The depth-plane Adam step (K3, HBM-bound, ~38 us on C2) only needs the flow normalisers of k_loss_scalars; the chain /
-// small-parameter Adam / next prepare kernels (latency-bound, ~40 us together) never touch the depth planes.  They run
-// side by side: K3 on a library-owned auxiliary stream, forked after k_loss_scalars and joined before the next scan.
+// The depth-plane Adam step (K3, HBM-bound, ~38 us on C2) needs only the flow normalisers, which it evaluates itself from
+// the slot accumulators; K2 (latency-bound) never touches the depth planes.  They run side by side: K3 on a library-owned
+// auxiliary stream, forked right after the scan (or the exchange) and joined before the next scan.
 struct AuxLane {
     cudaStream_t stream = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
@@ -707,11 +765,11 @@ static int aux_lane(AuxLane** out) {
     return A3R_OK;
 }
 
-// update without the final join: *pending_join is set when K3 is still running on the auxiliary stream
-static int update_forked(const A3rProblem* p, uint32_t mode, const A3rAdamStep* adam, cudaStream_t st, AuxLane* lane, bool* pending_join) {
+// update without the final join: *pending_join is set when K3 is still running on the auxiliary stream.
+// prepare_next: K2's tail writes the parameter maps of the updated parameters (the next iteration's k_prepare).
+static int update_forked(const A3rProblem* p, uint32_t mode, const A3rAdamStep* adam, cudaStream_t st, AuxLane* lane, bool* pending_join,
+                         bool prepare_next) {
     *pending_join = false;
-    A3R_CUDA(cudaMemsetAsync(p->frame_grad, 0, sizeof(double) * FG_STRIDE * (size_t)p->n_frames, st));
-    k_loss_scalars<<<1, 512, 0, st>>>(*p, mode, *adam);
     const bool apply = mode & A3R_M_APPLY_ADAM;
     if (p->n_local_frames > 0 && (!apply || (p->flags & A3R_F_TRAIN_DEPTH))) {
         A3R_CUDA(cudaEventRecord(lane->fork, st));
@@ -726,12 +784,7 @@ static int update_forked(const A3rProblem* p, uint32_t mode, const A3rAdamStep* 
         A3R_CUDA(cudaEventRecord(lane->join, lane->stream));
         *pending_join = true;
     }
-    {
-        const int items = p->n_frames + 2 * p->n_edges + (p->n_frames - 1) + p->n_edges;
-        k_chain<<<(items + 127) / 128, 128, 0, st>>>(*p, mode);
-        k_adam_small<<<(p->n_edges + p->n_frames + 127) / 128, 128, 0, st>>>(*p, mode, *adam);
-        if (p->flags & A3R_F_SHARED_FOCAL) k_adam_focal<<<1, 32, 0, st>>>(*p, mode, *adam);
-    }
+    k_small<<<K2_CLUSTER, K2_THREADS, 0, st>>>(*p, mode, *adam, prepare_next ? 1u : 0u);
     A3R_CUDA(cudaGetLastError());
     return A3R_OK;
 }
@@ -743,7 +796,7 @@ int a3r_ga_update(const A3rProblem* p, uint32_t mode, const A3rAdamStep* adam, v
     AuxLane* lane = nullptr;
     if (int rc = aux_lane(&lane)) return rc;
     bool pending = false;
-    if (int rc = update_forked(p, mode, adam, st, lane, &pending)) return rc;
+    if (int rc = update_forked(p, mode, adam, st, lane, &pending, false)) return rc;
     if (pending) A3R_CUDA(cudaStreamWaitEvent(st, lane->join, 0));      // everything is ordered in the caller's stream on return
     return A3R_OK;
 }
@@ -755,12 +808,12 @@ int a3r_ga_run(const A3rProblem* p, int32_t count, const uint32_t* modes, const 
     AuxLane* lane = nullptr;
     if (int rc = aux_lane(&lane)) return rc;
     bool pending = false;
+    if (count > 0)
+        if (int rc = a3r_ga_prepare(p, modes[0], stream)) return rc;                 // later ones: the tail of K2
     for (int32_t k = 0; k < count; ++k) {
-        if (int rc = a3r_ga_prepare(p, modes[k], stream)) return rc;                 // overlaps the previous iteration's K3
         if (pending) A3R_CUDA(cudaStreamWaitEvent(st, lane->join, 0));               // the scan reads the depth planes
         if (int rc = a3r_ga_accumulate(p, modes[k], stream)) return rc;
-        if (!steps) return a3r_fail(A3R_E_ARG, "steps is NULL");
-        if (int rc = update_forked(p, modes[k], &steps[k], st, lane, &pending)) return rc;
+        if (int rc = update_forked(p, modes[k], &steps[k], st, lane, &pending, k + 1 < count)) return rc;
     }
     if (pending) A3R_CUDA(cudaStreamWaitEvent(st, lane->join, 0));
     return A3R_OK;
@@ -864,12 +917,13 @@ int a3r_ga_run_peers(const A3rProblem* p, const A3rPeers* peers, uint32_t tag0, 
         q.acc_slot = part;
         q.acc_frame = part + (int64_t)2 * p->n_edges * A3R_SLOT_ACC;
         if (prior) q.prior_acc = q.acc_frame + (int64_t)p->n_frames * A3R_FRAME_ACC;
-        if (int rc = a3r_ga_prepare(p, modes[k], stream)) return rc;
+        if (k == 0)
+            if (int rc = a3r_ga_prepare(p, modes[k], stream)) return rc;             // later ones: the tail of K2
         if (pending) A3R_CUDA(cudaStreamWaitEvent(st, lane->join, 0));
         if (int rc = a3r_ga_accumulate(&q, modes[k], stream)) return rc;
         k_exchange<<<grid, 256, 0, st>>>(*peers, tag, p->acc_slot);
         A3R_CUDA(cudaGetLastError());
-        if (int rc = update_forked(p, modes[k], &steps[k], st, lane, &pending)) return rc;
+        if (int rc = update_forked(p, modes[k], &steps[k], st, lane, &pending, k + 1 < count)) return rc;
     }
     if (pending) A3R_CUDA(cudaStreamWaitEvent(st, lane->join, 0));
     return A3R_OK;

@@ -384,7 +384,8 @@ def run_ours(args, cfg, name):
             "config": {"workload": f"{name}: {n}-frame {H}x{W} {graph} PointCloudOptimizer alignment ({E} directed edges, "
                                    f"{E * P} pixel-edges), shared focal, flow 0.01 + temporal 0.01, linear lr 0.01->1e-3, init=mst",
                        "iterations_with_flow": n_flow, "parallelism": "single GPU" if world == 1 else f"{world} frame windows, "
-                       "one NCCL all-reduce of the fp64 accumulator block per iteration",
+                       + ("one NCCL all-reduce" if os.environ.get("A3R_EXCHANGE") == "nccl" else "one peer-memory exchange kernel (NVLink loads)")
+                       + " of the fp64 accumulator block per iteration",
                        "l2": "inputs exceed L2 (per-iteration scan >> 126 MB)"},
             "pixel_edges_per_sec": E * P * K / (ms * 1e-3),
             "final_loss": final_loss,
@@ -397,7 +398,7 @@ def run_ours(args, cfg, name):
             "roofline_iteration": {"bytes_per_iteration": blended_bytes, "achieved": blended_bytes / world / (ms / K * 1e-3) / 1e9,
                                    "frac": blended_bytes / (ms / K * 1e-3) / 1e9 / peak / world,
                                    "note": "whole iteration (all kernels), SURVEY 8(d) bytes, per GPU"},
-            "gpu_launches": 7 * K,
+            "gpu_launches": (3 if world == 1 else 4) * K + 1,      # scan + K2 + K3 (+ exchange) per iteration, one k_prepare
             "clocks": clocks,
         }
         if e2e is not None:
