@@ -282,15 +282,22 @@ __global__ void __launch_bounds__(256) k_depth_prior(const A3rProblem p) {
 // ONE launch: a thread-block cluster of 8 CTAs x 256 threads whose phases are separated by the hardware cluster barrier
 // (barrier.cluster arrive.release / wait.acquire orders the global-memory traffic of the phases), instead of five
 // launches + a memset separated by kernel boundaries.  This chain is pure latency (a few thousand items of fp64
-// arithmetic) and sits on the critical path between two scans.
-//   phase 0  zero frame_grad | loss sums + gate: every CTA evaluates them in the same order, CTA 0 publishes p.scal
-//   phase 1  chains that end in a camera (fp64 atomics into frame_grad) + dL/dlog s_e
-//   phase 2  gradients of pw_poses / im_poses (/ per-frame focal, pp) + torch.optim.Adam
-//   phase 3  the shared focal (one scalar that every frame read in phase 2)
-//   phase 4  (tail) parameter maps of the updated parameters = k_prepare of the next iteration
+// arithmetic, instruction fetch of run-once code, dependent L2 round trips) and sits on the critical path between two
+// scans, so the kernel is organised around doing every expensive thing once:
+//   * the fp64 camera of every frame (quaternion -> R, signed_expm1 translations, exp focal: FrameD) is evaluated ONCE
+//     per CTA into shared memory and every chain reads it from there; once more after the update for the maps;
+//   * the shared focal's Adam step is evaluated redundantly by every CTA from values it read before anyone writes
+//     them, so it needs no phase (and no barrier) of its own;
+//   * frame_grad is zeroed in the tail for the next call (the entry points zero it once before the first).
+//   phase A  cameras -> shared memory | loss sums + gate: every CTA in the same order, CTA 0 publishes p.scal |
+//            chains that end in a camera (fp64 atomics into frame_grad) + dL/dlog s_e
+//   phase B  gradients of pw_poses / im_poses (/ per-frame focal, pp) + torch.optim.Adam
+//   phase C  the shared focal | cameras of the updated parameters -> shared memory | parameter maps (= k_prepare of the
+//            next iteration) | zero frame_grad
 // ==========================================================================================
 constexpr int K2_CLUSTER = 8;
 constexpr int K2_THREADS = 256;
+constexpr int K2_MAX_FRAMES = 1280;        // cameras in shared memory: 160 B each (200 KB of the 227 KB opt-in limit)
 
 __device__ __forceinline__ void cluster_barrier() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -315,11 +322,23 @@ __device__ __forceinline__ void adam_vec(float* prm, float* m, float* v, const f
         adam_update(prm[k], m[k], v[k], g[k], p.adam_beta1, p.adam_beta2, p.adam_eps, a.step_size, a.bc2_sqrt);
 }
 
+// every frame's fp64 camera into shared memory; `focals` may point at a shared-memory copy of the shared focal
+// (one copy of this code, called twice; plain arguments so that the parameter block is not spilled to pass a reference)
+__device__ __noinline__ void fill_cameras(const float* im_poses, const float* focals, const float* im_pp, const int32_t* frame_hw,
+                                          int N, bool shared_focal, double focal_break, FrameD* fr) {
+    for (int n = threadIdx.x; n < N; n += K2_THREADS)
+        load_frame(im_poses, focals, im_pp, frame_hw, n, shared_focal, focal_break, fr[n]);
+    __syncthreads();
+}
+
 __global__ void __cluster_dims__(K2_CLUSTER, 1, 1) __launch_bounds__(K2_THREADS, 1)
 k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const uint32_t prepare_next) {
+    extern __shared__ __align__(16) unsigned char k2_smem[];
+    FrameD* fr = reinterpret_cast<FrameD*>(k2_smem);
     __shared__ double s_red[32];
     __shared__ double s_sc[2];
     __shared__ double s_mean;
+    __shared__ float s_foc[3];                 // the shared focal: parameter, m, v as they were when the kernel started
     const int tid = threadIdx.x;
     const int vt = blockIdx.x * K2_THREADS + tid, nvt = gridDim.x * K2_THREADS;      // the grid is one cluster
     const int N = p.n_frames, E = p.n_edges;
@@ -330,22 +349,17 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
     const double fb = (double)p.focal_break;
     const double tsw = (double)p.temporal_smoothing_weight, tw = (double)p.translation_weight;
 
-    // ---------------- phase 0: loss assembly + gate (reference optimizer.py:538-557) ----------------
-    for (int i = vt; i < N * FG_STRIDE; i += nvt) p.frame_grad[i] = 0.0;
+    // ---------------- phase A: cameras, loss assembly + gate (reference optimizer.py:538-557), chains ----------------
+    if (shared_focal && tid == 0) { s_foc[0] = p.im_focals[0]; s_foc[1] = p.im_focals_m[0]; s_foc[2] = p.im_focals_v[0]; }
+    fill_cameras(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, N, shared_focal, fb, fr);
     {
         double l_align = 0, l_temp = 0, l_prior = 0;
         if (p.depth_regularize_weight > 0.f)
             for (int n = tid; n < N; n += K2_THREADS)
                 l_prior += prior_frame(p.prior_acc + (int64_t)n * PR_N, (double)p.frame_hw[2 * n] * p.frame_hw[2 * n + 1]).loss;
         for (int gs = tid; gs < 2 * E; gs += K2_THREADS) l_align += p.acc_slot[(int64_t)gs * ACC_STRIDE + ACC_LOSS];
-        if (tsw > 0) {
-            for (int n = tid; n < N - 1; n += K2_THREADS) {
-                FrameD T, S;
-                load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n, shared_focal, fb, T);
-                load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n + 1, shared_focal, fb, S);
-                l_temp += temporal_pair(S, T, tsw, tw, nullptr);
-            }
-        }
+        if (tsw > 0)
+            for (int n = tid; n < N - 1; n += K2_THREADS) l_temp += temporal_pair(fr[n + 1], fr[n], tsw, tw, nullptr);
         double fs[4];
         flow_sums_256(p, s_red, fs);
         l_align = block_sum(l_align, s_red);
@@ -362,25 +376,21 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
                 p.scal[A3R_S_FLOW] = r.floss; p.scal[A3R_S_FLOW_DROPPED] = r.dropped;
                 p.scal[A3R_S_SC_I] = r.sc_i; p.scal[A3R_S_SC_J] = r.sc_j;
                 if (r.dropped != 0) p.scal[A3R_S_FLAG_STICKY] = 1.0;
-                p.scal[S_GSUM] = 0.0; p.scal[S_GPHI] = 0.0;
                 if (p.loss_hist && adam.iter >= 0) p.loss_hist[adam.iter] = (float)r.loss;
             }
         }
+        __syncthreads();
     }
-    cluster_barrier();
-
-    // ---------------- phase 1: every chain that ends in a camera + dL/dlog s_e ----------------
-    //   items: [0,N) alignment part of frame n | [N, N+2E) flow chain of a slot | [.., +N-1) temporal pair | [.., +E) edge
+    //   chain items: [0,N) alignment part of frame n | [N, N+2E) flow chain of a slot | [.., +N-1) temporal pair | [.., +E) edge
+    //   (frame_grad, scal[S_GSUM] and scal[S_GPHI] are zero on entry: zeroed by the previous call's tail / the entry point)
     {
         const double sc_i = s_sc[0], sc_j = s_sc[1];
         const int total = N + 2 * E + (N - 1) + E;
         for (int it = vt; it < total; it += nvt) {
             if (it < N) {
                 const int n = it;
-                FrameD F;
-                load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n, shared_focal, fb, F);
                 double fg[FG_STRIDE];
-                frame_align_grad(F, p.acc_frame + (int64_t)n * FACC_N, fg);
+                frame_align_grad(fr[n], p.acc_frame + (int64_t)n * FACC_N, fg);
                 double* dst = p.frame_grad + (int64_t)n * FG_STRIDE;
                 for (int k = 0; k < 15; ++k) atomicAdd(&dst[k], fg[k]);
             } else if (it < N + 2 * E) {
@@ -388,20 +398,14 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
                 const int gs = it - N, e = gs >> 1, side = gs & 1;
                 const int i = p.edge_ij[2 * e], j = p.edge_ij[2 * e + 1];
                 const int sI = side ? j : i, tI = side ? i : j;
-                FrameD S, T;
-                load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, sI, shared_focal, fb, S);
-                load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, tI, shared_focal, fb, T);
                 PairGrad g;
-                slot_flow_chain(S, T, p.acc_slot + (int64_t)gs * ACC_STRIDE, side ? sc_j : sc_i, g);
+                slot_flow_chain(fr[sI], fr[tI], p.acc_slot + (int64_t)gs * ACC_STRIDE, side ? sc_j : sc_i, g);
                 scatter_pair(g, p.frame_grad + (int64_t)sI * FG_STRIDE, p.frame_grad + (int64_t)tI * FG_STRIDE);
             } else if (it < N + 2 * E + N - 1) {
                 if (!(tsw > 0)) continue;
                 const int n = it - N - 2 * E;
-                FrameD T, S;
-                load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n, shared_focal, fb, T);
-                load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n + 1, shared_focal, fb, S);
                 PairGrad g;
-                temporal_pair(S, T, tsw, tw, &g);
+                temporal_pair(fr[n + 1], fr[n], tsw, tw, &g);
                 scatter_pair(g, p.frame_grad + (int64_t)(n + 1) * FG_STRIDE, p.frame_grad + (int64_t)n * FG_STRIDE);
             } else {
                 const int e = it - N - 2 * E - (N - 1);
@@ -414,7 +418,7 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
     }
     cluster_barrier();
 
-    // ---------------- phase 2: gradients of the small parameters + torch.optim.Adam ----------------
+    // ---------------- phase B: gradients of the small parameters + torch.optim.Adam ----------------
     //   items: [0,E) pairwise pose | [E, E+N) image pose
     {
         const double gmean = norm_scale ? p.scal[S_GSUM] / (double)E : 0.0;
@@ -431,14 +435,12 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
                 if (apply && (p.flags & A3R_F_TRAIN_ADAPTORS)) adam_vec(p.pw_adaptors + 2 * e, p.pw_adaptors_m + 2 * e, p.pw_adaptors_v + 2 * e, ga, 2, p, adam);
             } else {
                 const int n = it - E;
-                FrameD F;
-                load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n, shared_focal, fb, F);
                 float g[7], gpp[2];
                 double gphi;
-                frame_pose_grad(p.im_poses + 7 * n, F, p.frame_grad + (int64_t)n * FG_STRIDE, fb, p.flags & A3R_F_TRAIN_PP, g, &gphi, gpp);
+                frame_pose_grad(p.im_poses + 7 * n, fr[n], p.frame_grad + (int64_t)n * FG_STRIDE, fb, p.flags & A3R_F_TRAIN_PP, g, &gphi, gpp);
                 for (int k = 0; k < 7; ++k) p.g_im_poses[7 * n + k] = g[k];
                 p.g_im_pp[2 * n] = gpp[0]; p.g_im_pp[2 * n + 1] = gpp[1];
-                if (shared_focal) atomicAdd(&p.scal[S_GPHI], gphi);     // applied in phase 3, once every frame has read f
+                if (shared_focal) atomicAdd(&p.scal[S_GPHI], gphi);     // applied in phase C
                 else {
                     float gf = (float)gphi;
                     p.g_im_focals[n] = gf;
@@ -449,22 +451,42 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
             }
         }
     }
+    cluster_barrier();
 
-    // ---------------- phase 3: the shared focal ----------------
-    if (shared_focal) {
-        cluster_barrier();
-        if (vt == 0) {
-            float gf = (float)p.scal[S_GPHI];
+    // ---------------- phase C: the shared focal, the parameter maps of the next iteration, zero the scratch ----------------
+    // Every CTA steps the shared focal from the values it saved in phase A (nobody has written them yet) and the complete
+    // sum of phase B: the same number on every CTA; CTA 0 stores it.
+    if (shared_focal && tid == 0) {
+        float gf = (float)p.scal[S_GPHI];
+        if (apply && (p.flags & A3R_F_TRAIN_FOCALS)) adam_vec(&s_foc[0], &s_foc[1], &s_foc[2], &gf, 1, p, adam);
+        if (blockIdx.x == 0) {
             p.g_im_focals[0] = gf;
-            if (apply && (p.flags & A3R_F_TRAIN_FOCALS)) adam_vec(p.im_focals, p.im_focals_m, p.im_focals_v, &gf, 1, p, adam);
+            p.im_focals[0] = s_foc[0]; p.im_focals_m[0] = s_foc[1]; p.im_focals_v[0] = s_foc[2];
         }
     }
-
-    // ---------------- phase 4: parameter maps of the next iteration (reference base_opt.py:195-247) ----------------
-    if (prepare_next) {
-        cluster_barrier();
-        prepare_body(p, vt, nvt, s_red, &s_mean);
+    __syncthreads();
+    if (prepare_next) {       // reference base_opt.py:195-247, optimizer.py:398-428 of the updated parameters
+        const float* focals = shared_focal ? s_foc : p.im_focals;
+        fill_cameras(p.im_poses, focals, p.im_pp, p.frame_hw, N, shared_focal, fb, fr);
+        double part = 0.0;    // every CTA recomputes mean_e(log scale) in k_prepare's order -> the same number everywhere
+        for (int e = tid; e < E; e += K2_THREADS) part += (double)p.pw_poses[8 * e + 7];
+        part = block_sum(part, s_red);
+        if (tid == 0) s_mean = part / (double)E;
+        __syncthreads();
+        const double log_norm = norm_scale ? (log((double)p.base_scale) - s_mean) : 0.0;
+        for (int n = vt; n < N; n += nvt) derive_frame_par(fr[n], p.frame_par + FP_STRIDE * n);
+        for (int e = vt; e < E; e += nvt)
+            derive_edge_par(p.pw_poses + 8 * e, p.pw_adaptors + 2 * e, log_norm, norm_scale, (double)p.pw_break, p.edge_par + EP_STRIDE * e);
+        if (p.flags & A3R_F_HAS_FLOW) {
+            for (int gs = vt; gs < 2 * E; gs += nvt) {
+                const int e = gs >> 1, side = gs & 1;
+                const int i = p.edge_ij[2 * e], j = p.edge_ij[2 * e + 1];
+                derive_slot_par(fr[side ? j : i], fr[side ? i : j], p.slot_par + SP_STRIDE * gs);
+            }
+        }
     }
+    for (int i = vt; i < N * FG_STRIDE; i += nvt) p.frame_grad[i] = 0.0;
+    if (vt == 0) { p.scal[S_GSUM] = 0.0; p.scal[S_GPHI] = 0.0; }
 }
 
 // ==========================================================================================
@@ -765,6 +787,29 @@ static int aux_lane(AuxLane** out) {
     return A3R_OK;
 }
 
+// K2 reads frame_grad / scal[S_GSUM] / scal[S_GPHI] as zero and leaves them zero: once per entry point, before the first launch
+static int zero_small_scratch(const A3rProblem* p, cudaStream_t st) {
+    A3R_CUDA(cudaMemsetAsync(p->frame_grad, 0, sizeof(double) * FG_STRIDE * (size_t)p->n_frames, st));
+    A3R_CUDA(cudaMemsetAsync(p->scal + S_GSUM, 0, sizeof(double) * 2, st));
+    return A3R_OK;
+}
+
+static int launch_small(const A3rProblem* p, uint32_t mode, const A3rAdamStep* adam, cudaStream_t st, bool prepare_next) {
+    if (p->n_frames > K2_MAX_FRAMES)
+        return a3r_fail(A3R_E_UNSUPPORTED, "%d frames: the small-parameter kernel keeps every camera in shared memory (at most %d)",
+                        p->n_frames, K2_MAX_FRAMES);
+    static bool attr_set[64] = {};
+    int dev = 0;
+    A3R_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        A3R_CUDA(cudaFuncSetAttribute(k_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FrameD) * K2_MAX_FRAMES)));
+        attr_set[dev] = true;
+    }
+    k_small<<<K2_CLUSTER, K2_THREADS, sizeof(FrameD) * (size_t)p->n_frames, st>>>(*p, mode, *adam, prepare_next ? 1u : 0u);
+    A3R_CUDA(cudaGetLastError());
+    return A3R_OK;
+}
+
 // update without the final join: *pending_join is set when K3 is still running on the auxiliary stream.
 // prepare_next: K2's tail writes the parameter maps of the updated parameters (the next iteration's k_prepare).
 static int update_forked(const A3rProblem* p, uint32_t mode, const A3rAdamStep* adam, cudaStream_t st, AuxLane* lane, bool* pending_join,
@@ -784,8 +829,7 @@ static int update_forked(const A3rProblem* p, uint32_t mode, const A3rAdamStep* 
         A3R_CUDA(cudaEventRecord(lane->join, lane->stream));
         *pending_join = true;
     }
-    k_small<<<K2_CLUSTER, K2_THREADS, 0, st>>>(*p, mode, *adam, prepare_next ? 1u : 0u);
-    A3R_CUDA(cudaGetLastError());
+    if (int rc = launch_small(p, mode, adam, st, prepare_next)) return rc;
     return A3R_OK;
 }
 
@@ -796,6 +840,7 @@ int a3r_ga_update(const A3rProblem* p, uint32_t mode, const A3rAdamStep* adam, v
     AuxLane* lane = nullptr;
     if (int rc = aux_lane(&lane)) return rc;
     bool pending = false;
+    if (int rc = zero_small_scratch(p, st)) return rc;
     if (int rc = update_forked(p, mode, adam, st, lane, &pending, false)) return rc;
     if (pending) A3R_CUDA(cudaStreamWaitEvent(st, lane->join, 0));      // everything is ordered in the caller's stream on return
     return A3R_OK;
@@ -808,6 +853,7 @@ int a3r_ga_run(const A3rProblem* p, int32_t count, const uint32_t* modes, const 
     AuxLane* lane = nullptr;
     if (int rc = aux_lane(&lane)) return rc;
     bool pending = false;
+    if (int rc = zero_small_scratch(p, st)) return rc;
     if (count > 0)
         if (int rc = a3r_ga_prepare(p, modes[0], stream)) return rc;                 // later ones: the tail of K2
     for (int32_t k = 0; k < count; ++k) {
@@ -910,6 +956,7 @@ int a3r_ga_run_peers(const A3rProblem* p, const A3rPeers* peers, uint32_t tag0, 
     int grid = (int)((n_acc + 255) / 256);
     if (grid > sm) grid = sm;
     bool pending = false;
+    if (int rc = zero_small_scratch(p, st)) return rc;
     for (int32_t k = 0; k < count; ++k) {
         const uint32_t tag = tag0 + 1u + (uint32_t)k;
         A3rProblem q = *p;                               // the scan adds into this rank's shared partial-sum buffer

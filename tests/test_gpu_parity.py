@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.helpers import CANONICAL_KW, go, golden_case, grad_close, make_scene, rel_err
+from tests.helpers import CANONICAL_KW, go, golden_case, grad_close, load_golden, make_scene, rel_err, scene_checksum
 from align3r_b200 import _lib
 from align3r_b200.cloud_opt_flow import GlobalAlignerMode, global_aligner
 from align3r_b200.cloud_opt_flow import init_im_poses as init_fun
@@ -551,3 +551,40 @@ def test_mst_initialisation_with_priors(cuda_device, tag):
     assert rel_err(net.get_focals().detach().cpu(), go.focals(prob, ref["im_focals"])) < 1e-5
     d = (net.im_depthmaps.detach().cpu()[:, :prob.P] - ref["im_depthmaps"]).abs()
     assert float(d.median()) < 1e-5 and float(d.max()) < 2e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[0] at FULL size against the real reference's own 300-iteration run
+# (fixture: oracle/make_golden_c1.py, 6.4 minutes of the unmodified reference on 8 host threads)
+# ---------------------------------------------------------------------------------------------------------------
+def test_c1_full_size_against_reference_run(cuda_device):
+    """10-frame 288x512 swin-3 sequence, init='mst', niter=300, canonical hyper-parameters: what a user reads out after
+    the run equals what the reference produced.  Stated tolerances (end state after 300 Adam steps from an MST init that
+    differs by fp32 rounding): final loss 2e-3 relative, median |log-depth| 2e-3, camera matrices 1e-2, focal 5e-3
+    relative, Abs Rel / log RMSE / delta<1.25 2e-3 absolute, ATE 5e-3 scene units, RPE rotation 0.1 degree."""
+    fx = load_golden("c1_reference_run")
+    scene = make_scene(**fx["recipe"])
+    assert scene.edges == [tuple(e) for e in fx["edges"]]
+    assert abs(scene_checksum(scene) - fx["checksum"]) <= 1e-9 * abs(fx["checksum"]), "synthetic generator drifted"
+    torch.manual_seed(fx["seed"])
+    net = build(scene, fx["kw"])
+    loss = net.compute_global_alignment(init='mst', niter=fx["niter"], schedule='linear', lr=0.01)
+    assert net.flow_loss_flag == fx["flow_dropped"]
+    assert abs(loss - fx["loss"]) <= 2e-3 * abs(fx["loss"]), (loss, fx["loss"])
+    n, H, W = fx["recipe"]["n_frames"], fx["recipe"]["H"], fx["recipe"]["W"]
+    depth = torch.stack(net.get_depthmaps()).detach().cpu()
+    assert depth.shape == (n, H, W)
+    s = fx["stride"]
+    d = (depth[:, ::s, ::s].log() - fx["logdepth_sample"]).abs()
+    assert float(d.median()) < 2e-3 and float(d.max()) < 5e-2, (float(d.median()), float(d.max()))
+    assert abs(float(depth.log().double().mean()) - fx["logdepth_mean"]) < 2e-3
+    poses = net.get_im_poses().detach().cpu()
+    assert float((poses - fx["im_poses_4x4"]).abs().max()) < 1e-2
+    assert rel_err(net.get_focals().detach().cpu(), fx["focals"]) < 5e-3
+    assert float((net.get_pw_poses().detach().cpu() - fx["pw_poses_4x4"]).abs().max()) < 1e-2
+    gt_depth = np.stack([scene.gt.depth(k).numpy() for k in range(n)])
+    dm = go.depth_metrics(depth.numpy(), gt_depth)
+    for k in ("abs_rel", "log_rmse", "d1"):
+        assert abs(dm[k] - fx["depth_metrics"][k]) <= 2e-3, (k, dm[k], fx["depth_metrics"][k])
+    pm = go.pose_metrics(poses.numpy(), scene.gt.cam2world)
+    assert abs(pm["ate"] - fx["pose_metrics"]["ate"]) <= 5e-3 and abs(pm["rpe_rot"] - fx["pose_metrics"]["rpe_rot"]) <= 0.1, (pm, fx["pose_metrics"])
