@@ -304,16 +304,43 @@ __device__ __forceinline__ void cluster_barrier() {
 }
 
 // the four flow sums (numerator / per-channel mask count of both sides) over all 2E slots in a fixed 256-thread order:
-// K2 and the depth-plane Adam kernel K3 both evaluate them (K3 must not wait for K2) and must agree bit for bit
-__device__ __forceinline__ void flow_sums_256(const A3rProblem& p, double* s_red, double out[4]) {
-    double num_i = 0, cnt_i = 0, num_j = 0, cnt_j = 0;
-    for (int gs = threadIdx.x; gs < 2 * p.n_edges; gs += 256) {
-        const double* a = p.acc_slot + (int64_t)gs * ACC_STRIDE;
-        if (gs & 1) { num_j += a[ACC_FNUM]; cnt_j += a[ACC_FCNT]; }
-        else        { num_i += a[ACC_FNUM]; cnt_i += a[ACC_FCNT]; }
+// K2 and the depth-plane Adam kernel K3 both evaluate them (K3 must not wait for K2) and must agree bit for bit.
+// Element k = 2 gs + which of the (FNUM, FCNT) pairs; with a stride of 256 a thread only ever sees category k & 3 =
+// (side, which), so it carries ONE running sum, all loads are independent, and one shuffle tree + one block barrier
+// finish all four sums.  out = num_i, cnt_i, num_j, cnt_j.  `red`: >= 32 doubles of shared memory.
+__device__ __forceinline__ void flow_sums_256(const A3rProblem& p, double* red, double out[4]) {
+    static_assert(ACC_FCNT == ACC_FNUM + 1, "flow numerator and count are adjacent in a slot's accumulator row");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int total = 4 * p.n_edges;
+    double acc = 0.0;
+#pragma unroll 4
+    for (int k = tid; k < total; k += 256) acc += p.acc_slot[(int64_t)(k >> 1) * ACC_STRIDE + ACC_FNUM + (k & 1)];
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+    if (lane < 4) red[warp * 4 + lane] = acc;
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        double r = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) r += red[w * 4 + c];
+        out[c] = r;
     }
-    out[0] = block_sum(num_i, s_red); out[1] = block_sum(cnt_i, s_red);
-    out[2] = block_sum(num_j, s_red); out[3] = block_sum(cnt_j, s_red);
+    __syncthreads();
+}
+
+// three CTA-wide sums with one block barrier (256 threads; fixed order, every thread gets the results)
+__device__ __forceinline__ void block_sum3_256(double& a, double& b, double& c, double* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+    if (lane == 0) { red[warp * 3] = a; red[warp * 3 + 1] = b; red[warp * 3 + 2] = c; }
+    __syncthreads();
+    double ra = 0.0, rb = 0.0, rc = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { ra += red[w * 3]; rb += red[w * 3 + 1]; rc += red[w * 3 + 2]; }
+    __syncthreads();
+    a = ra; b = rb; c = rc;
 }
 
 __device__ __forceinline__ void adam_vec(float* prm, float* m, float* v, const float* g, int cnt,
@@ -362,9 +389,8 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
             for (int n = tid; n < N - 1; n += K2_THREADS) l_temp += temporal_pair(fr[n + 1], fr[n], tsw, tw, nullptr);
         double fs[4];
         flow_sums_256(p, s_red, fs);
-        l_align = block_sum(l_align, s_red);
-        l_temp = block_sum(l_temp, s_red);
-        l_prior = block_sum(l_prior, s_red) / (double)N;
+        block_sum3_256(l_align, l_temp, l_prior, s_red);
+        l_prior /= (double)N;
         if (tid == 0) {
             LossScalars r = assemble_loss(l_align, l_temp, fs[0], fs[1], fs[2], fs[3], flow_active,
                                           (double)p.flow_loss_weight, (double)p.flow_loss_thre, tsw);
@@ -493,7 +519,7 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
 // K3: Adam on the log-depth planes (or, without A3R_M_APPLY_ADAM, total depth gradient -> g_align)
 // ==========================================================================================
 template <bool FLOW>
-__global__ void __launch_bounds__(256) k_update_depth(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam) {
+__global__ void __launch_bounds__(256, 4) k_update_depth(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam) {
     const int64_t total4 = (int64_t)p.n_local_frames * p.pix_stride / 4;
     const bool prior = p.depth_regularize_weight > 0.f;
     // the flow normalisers and the gate, evaluated here exactly as K2 evaluates them: K3 starts right after the scan,
@@ -822,7 +848,7 @@ static int update_forked(const A3rProblem* p, uint32_t mode, const A3rAdamStep* 
         const bool flow = (mode & A3R_M_FLOW_ACTIVE) && (p->flags & A3R_F_HAS_FLOW) && p->flow_loss_weight > 0.f;
         const int64_t total4 = (int64_t)p->n_local_frames * p->pix_stride / 4;
         int64_t grid = (total4 + 255) / 256;
-        if (grid > 148 * 8) grid = 148 * 8;
+        if (grid > 148 * 4) grid = 148 * 4;              // one resident wave (62 registers: 4 CTAs per SM)
         if (flow) k_update_depth<true><<<(unsigned)grid, 256, 0, lane->stream>>>(*p, mode, *adam);
         else k_update_depth<false><<<(unsigned)grid, 256, 0, lane->stream>>>(*p, mode, *adam);
         A3R_CUDA(cudaGetLastError());
