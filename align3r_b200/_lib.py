@@ -7,7 +7,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("A3R_LIB") or os.path.join(HERE, "lib", "liba3r_ga.so")   # A3R_LIB: tuning builds
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # A3rProblem.flags
 F_SHARED_FOCAL, F_NORM_PW_SCALE, F_DIST_L2 = 1 << 0, 1 << 1, 1 << 2
@@ -84,6 +84,8 @@ _SIGNATURES = {
     "a3r_procrustes_batched": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "a3r_weiszfeld_focal_batched": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp]),
     "a3r_init_depth": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "a3r_motion_minmax": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "a3r_motion_masks": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _vp, _vp, _vp]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

@@ -294,16 +294,18 @@ class PointCloudOptimizer(nn.Module):
         # ---------------- flow term inputs (reference optimizer.py:104-116) ----------------
         self.sam2_dynamic_masks = None
         if want_flow:
-            if use_self_mask:
-                raise NotImplementedError("use_self_mask=True (get_motion_mask_from_pairs, reference optimizer.py:156-235) "
-                                          "is a 'next' row of the scope table; pass dynamic_mask in the views instead")
-            if self.dynamic_masks is None:
-                raise ValueError("the flow term needs dynamic masks: put 'dynamic_mask' into view1/view2 "
-                                 "(the reference fails with torch.stack(None) here, optimizer.py:533)")
             assert len(set(self.imshapes)) == 1, "the flow term requires uniform image shapes (reference optimizer.py:528)"
-            with torch.cuda.stream(self._upload_stream):
-                self._upload_masks()
+            if use_self_mask:
+                # reference optimizer.py:106: the masks are estimated from the pairs themselves (device pre-step)
                 self._uploads_ready = self._upload_stream.record_event()
+                self.get_motion_mask_from_pairs(view1, view2, pred1, pred2)
+            else:
+                if self.dynamic_masks is None:
+                    raise ValueError("the flow term needs dynamic masks: put 'dynamic_mask' into view1/view2 "
+                                     "(the reference fails with torch.stack(None) here, optimizer.py:533)")
+                with torch.cuda.stream(self._upload_stream):
+                    self._upload_masks()
+                    self._uploads_ready = self._upload_stream.record_event()
         if want_prior and not want_flow:
             if self.dynamic_masks is None:
                 raise ValueError("depth_regularize_weight > 0 weighs pixels by 1 + dynamic_mask: put 'dynamic_mask' into "
@@ -441,6 +443,11 @@ class PointCloudOptimizer(nn.Module):
         for k, n in enumerate(lfr):
             m = torch.as_tensor(masks[n]).to(self._device).bool().reshape(-1)
             b.static_mask[k, :m.numel()] = (~m).to(torch.uint8)
+
+    def get_motion_mask_from_pairs(self, view1, view2, pred1, pred2):
+        """reference optimizer.py:156-235 (``use_self_mask=True``): see cloud_opt_flow/motion_mask.py."""
+        from .motion_mask import get_motion_mask_from_pairs
+        return get_motion_mask_from_pairs(self, view1, view2, pred1, pred2)
 
     def get_flow(self, sintel_ckpt=False):
         """reference optimizer.py:118-154 runs RAFT here.  RAFT (and its weights) are outside this

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define A3R_ABI_VERSION 4
+#define A3R_ABI_VERSION 5
 
 /* error codes */
 #define A3R_OK 0
@@ -228,6 +228,26 @@ int a3r_ga_unproject(const A3rProblem *p, float *pts3d, void *stream);
  * world-to-camera, intr [n][4] = fx fy cx cy, hw [n][2] (device int32), conf [n][pix_stride] in/out. */
 int a3r_clean_pointcloud(const float *pts3d, const float *depth, const float *w2c, const float *intr, const int32_t *hw,
                          int32_t n, int64_t pix_stride, float tol, float bad_conf, float *conf, void *stream);
+
+/* ---- pre-step: self-estimated dynamic masks (reference optimizer.py:156-235 get_motion_mask_from_pairs, use_self_mask=True;
+ *      ego flow = goem_opt.py:195-236 warp_by_disp) ----
+ * An item is one side of a symmetric pair: the flow plane of local slot item_slot[k] is compared, on that slot's frame, with
+ * the ego flow induced by the pair's two-view cameras (pair_viewer.py:21-78; PnP solved on the host).  item_cam [k][16] fp32:
+ * homography H = K_t relR K_s^-1 (9, row-major), K_t relt (3), depth row (4): depth = row . (X, Y, Z, 1) of the points in
+ * local slot item_dslot[k] (the same frame's grid).  item_hw [k][2] = (H, W).  All index arrays are device int32.
+ * a3r_motion_minmax: per item min / max of the error map |ego - flow|_2 -> minmax [k][2] = (~bits(min), bits(max)).
+ * a3r_motion_masks: per local frame and pixel the mean over the frame's items (frame_items[frame_item_begin[f] ..
+ * frame_item_begin[f+1]), in the reference's stacking order) of (err - min) / (max - min), compared with `thre`:
+ * dynamic_mask [n_local_frames][pix_stride] (1 = dynamic), static_mask = its complement (A3rProblem.static_mask),
+ * mean_out the mean itself (optional, may be NULL). */
+int a3r_motion_minmax(const float *predw, const float *flow, int64_t pix_stride, const int32_t *item_slot,
+                      const int32_t *item_dslot, const int32_t *item_hw, const float *item_cam, int32_t n_items,
+                      uint32_t *minmax, void *stream);
+int a3r_motion_masks(const float *predw, const float *flow, int64_t pix_stride, const int32_t *item_slot,
+                     const int32_t *item_dslot, const float *item_cam, const uint32_t *minmax,
+                     const int32_t *frame_item_begin, const int32_t *frame_items, const int32_t *lframe_hw,
+                     int32_t n_local_frames, float thre, uint8_t *static_mask, uint8_t *dynamic_mask, float *mean_out,
+                     void *stream);
 
 /* ---- MST initialisation solves (reference init_im_poses.py:446-465, post_process.py:36-58) ---- */
 /* count weighted similarity registrations y ~ s R x + t between two slots living on the same frame:

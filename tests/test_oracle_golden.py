@@ -176,3 +176,19 @@ def test_c1_reference_run_fixture_is_reproducible():
     assert abs(dm["abs_rel"] - fx["depth_metrics"]["abs_rel"]) < 5e-4 and dm["d1"] > 0.999
     pm = go.pose_metrics(fx["im_poses_4x4"].numpy(), scene.gt.cam2world)
     assert abs(pm["ate"] - fx["pose_metrics"]["ate"]) < 1e-9
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# use_self_mask=True: get_motion_mask_from_pairs, fixtures from the real
+# reference (oracle/make_golden_self_mask.py)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_self_estimated_masks_match_reference(tag):
+    fx, scene, prob = golden_case(f"small_self_mask_{tag}")
+    masks, mean = go.motion_masks_from_pairs(prob, motion_mask_thre=0.35)
+    assert 0.02 < float(fx["dynamic_masks"].float().mean()) < 0.5, "the fixture must contain dynamic pixels"
+    assert torch.equal(masks, fx["dynamic_masks"])
+    _, _, cams = go.motion_error_maps(prob)
+    assert torch.equal(cams["K_i"], fx["cams"]["K_i"]) and torch.equal(cams["K_j"], fx["cams"]["K_j"])
+    assert float((cams["P_i"][:, :3, :3] - fx["cams"]["R_i"]).abs().max()) < 1e-6
+    assert float((cams["P_j"][:, :3, 3:] - fx["cams"]["T_j"]).abs().max()) < 1e-6
