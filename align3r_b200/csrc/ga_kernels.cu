@@ -711,11 +711,14 @@ int a3r_tile_pixels(void) { return scan_tile(); }
 int a3r_max_slots(void) { return scan_slots(); }
 
 int a3r_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
-    cudaDeviceProp prop;
-    A3R_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (sm_count) *sm_count = prop.multiProcessorCount;
-    if (cc_major) *cc_major = prop.major;
-    if (cc_minor) *cc_minor = prop.minor;
+    // three attribute queries (microseconds); cudaGetDeviceProperties takes tens of milliseconds on these boxes
+    int sm = 0, major = 0, minor = 0;
+    A3R_CUDA(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device));
+    A3R_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    A3R_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+    if (sm_count) *sm_count = sm;
+    if (cc_major) *cc_major = major;
+    if (cc_minor) *cc_minor = minor;
     return A3R_OK;
 }
 

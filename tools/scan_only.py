@@ -15,12 +15,25 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--mode", default="both")
 ap.add_argument("--workload", default="c2")
+ap.add_argument("--world", type=int, default=1, help="time the scan of ONE frame-window shard of `world` (rank-emulated on this GPU)")
+ap.add_argument("--rank", type=int, default=0)
 a = ap.parse_args()
 n, H, W, graph = CONFIGS[a.workload]
 sc = make_scene(n, H, W, graph, seed=0, with_flow=True)
 net = global_aligner(sc.output, "cuda", flow=(sc.flow_ij, sc.flow_ji), **dict(CANONICAL_KW))
 net.verbose = False
 net.compute_global_alignment(init="mst", niter=0)
+if a.world > 1:        # one shard of a `world`-way frame-window partition, with the full problem's initial parameters
+    full = net
+    net = global_aligner(sc.output, "cuda", flow=(sc.flow_ij, sc.flow_ji), shard=dict(world=a.world, rank=a.rank, group=None),
+                         **dict(CANONICAL_KW))
+    net.verbose = False
+    with torch.no_grad():
+        for k in ("pw_poses", "im_poses", "im_focals"):
+            getattr(net, k).data.copy_(getattr(full, k).data)
+        net.im_depthmaps.data.copy_(full.im_depthmaps.data[torch.as_tensor(net._plan.lframe_id.tolist(), device="cuda")])
+    net._join_uploads() if hasattr(net, "_join_uploads") else None
+    del full
 st = net._bufs.struct(net._trainable())
 stream = net._stream()
 ps, nl, P = net._plan.pixel_slots(), net._plan.n_local_frames, H * W
