@@ -294,7 +294,7 @@ def init_minimum_spanning_tree(self, save_score_path=None, save_score_only=False
 
     # ---- frames the tree left without a pose: RANSAC-PnP on the host (init_im_poses.py:272-279).  The calls are
     # independent (cv2 seeds its RANSAC generator per call) and release the GIL: run them on a thread pool.
-    pnp = np.zeros((N, 17))
+    pnp = np.zeros((N, 18))          # [solved, cam-to-world (16), focal the solve settled on]
     jobs = []
     for n in range(N):
         if im_poses[n] is None and n in self._lframe:
@@ -320,12 +320,17 @@ def init_minimum_spanning_tree(self, save_score_path=None, save_score_only=False
             for n, res in pool.map(_solve, jobs):
                 if res:
                     pnp[n, 0] = 1
-                    pnp[n, 1:] = res[1].ravel()
+                    pnp[n, 1:17] = res[1].ravel()
+                    pnp[n, 17] = res[0]
     ph.mark('pnp-solve')
     pnp = _allreduce_np(self, pnp)
     for n in range(N):
         if im_poses[n] is None:
-            im_poses[n] = pnp[n, 1:].reshape(4, 4) if pnp[n, 0] > 0 else np.eye(4)
+            im_poses[n] = pnp[n, 1:17].reshape(4, 4) if pnp[n, 0] > 0 else np.eye(4)
+            if pnp[n, 0] > 0:
+                # a frame that is never the first image of a pair (non-symmetrised graphs) has no Weiszfeld focal: it takes
+                # the tentative focal RANSAC-PnP scored best (init_im_poses.py:276-277, 487-504)
+                im_focals[n] = float(pnp[n, 17])
     im_poses = np.stack(im_poses)
     res = init_from_pts3d(self, T, src, reg[len(steps):], im_focals, im_poses)
     ph.mark('init_from_pts3d')

@@ -21,14 +21,20 @@ def _np(t):
     return t.detach().cpu().numpy() if hasattr(t, "detach") else np.asarray(t)
 
 
-def save_tum_poses(self, path):
-    poses, tt = self.get_tum_poses()
+def save_trajectory_tum_format(traj, path, verbose=True):
+    """reference utils/vo_eval.py:308-316 for traj = [poses (M,7) x y z qw qx qy qz, timestamps (M,)]."""
+    poses, tt = traj
     with open(path, "w") as f:
         for t, p in zip(tt, np.asarray(poses, dtype=np.float64)):
             f.write(f"{t} " + " ".join(map(str, p[:3])) + " " + " ".join(map(str, p[3:7])) + "\n")
-    if self.verbose:
+    if verbose:
         print(f"Saved trajectory to {path}")
-    return poses
+
+
+def save_tum_poses(self, path):
+    traj = self.get_tum_poses()
+    save_trajectory_tum_format(traj, path, self.verbose)
+    return traj[0]
 
 
 def save_focals(self, path):

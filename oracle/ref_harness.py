@@ -56,7 +56,8 @@ def import_reference():
         except Exception:
             plt = _stub("matplotlib.pyplot", grid=_noop, ion=_noop, imsave=_noop, figure=_noop, savefig=_noop,
                         title=_noop, xlabel=_noop, ylabel=_noop)
-            _stub("matplotlib", pyplot=plt)
+            mpl = _stub("matplotlib", pyplot=plt)
+            mpl.scale = _stub("matplotlib.scale", scale_factory=_noop)       # dust3r/cloud_opt/__init__.py:10 (unused import)
     if "seaborn" not in sys.modules:
         try:
             import seaborn  # noqa: F401
@@ -74,6 +75,10 @@ def import_reference():
     tools.file_interface = _stub("evo.tools.file_interface")
     tools.plot = _stub("evo.tools.plot")
     _stub("evo", core=core, tools=tools, main_ape=_stub("evo.main_ape"), main_rpe=_stub("evo.main_rpe"))
+    if "wandb" not in sys.modules:      # dust3r/cloud_opt/__init__.py:11 imports torch through wandb (an IDE auto-import)
+        import torch as _torch
+        wb = _stub("wandb")
+        wb.wandb_torch = _stub("wandb.wandb_torch", torch=_torch)
     sam2 = _stub("sam2")
     sam2.build_sam = _stub("sam2.build_sam", build_sam2_video_predictor=_noop)
 

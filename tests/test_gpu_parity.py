@@ -659,3 +659,22 @@ def test_long_video_small_frames_against_live_oracle(cuda_device):
     ours = net2._bufs.loss_hist[:10].cpu().tolist()
     for it, (a, b) in enumerate(zip(ours, ref_full)):       # 5e-5 while the runs are in lockstep, 2e-3 over all ten
         assert abs(a - b) <= (5e-5 if it < 3 else 2e-3) * abs(b), (it, ours, ref_full)
+
+
+def test_mst_initialisation_on_a_non_symmetrised_graph(cuda_device):
+    """Edges (0,1), (0,2), (1,2): frame 2 is never the first image of a pair, so it has no Weiszfeld focal and takes the
+    tentative focal its RANSAC-PnP solve scored best (reference init_im_poses.py:272-279, 482-504); the oracle's
+    initialisation equals the real flow-free reference's bit for bit on this case (oracle/make_golden_hierarchical.py)."""
+    import copy
+    from align3r_b200.cloud_opt import global_aligner as plain_aligner
+    sc = make_scene(11, 32, 48, "complete", seed=4, with_flow=False, edges=[(0, 4), (0, 8), (4, 8)])
+    out = copy.deepcopy(sc.output)
+    out["view1"]["idx"], out["view2"]["idx"] = [0, 0, 1], [1, 2, 2]
+    prob = go.problem_from_output(out, None, None, min_conf_thr=3.0)
+    params, _ = go.mst_init(prob)
+    net = plain_aligner(copy.deepcopy(out), False, [], "cuda", mode=GlobalAlignerMode.PointCloudOptimizer, verbose=False, min_conf_thr=3)
+    net.compute_global_alignment(init="mst", niter=0)
+    assert float((net.im_focals.detach().cpu().reshape(-1) - params["im_focals"].reshape(-1)).abs().max()) < 1e-4
+    assert float((net.im_poses.detach().cpu() - params["im_poses"]).abs().max()) < 1e-5
+    assert float((net.pw_poses.detach().cpu() - params["pw_poses"]).abs().max()) < 1e-5
+    assert float((net.im_depthmaps.detach().cpu()[:, :prob.P] - params["im_depthmaps"]).abs().max()) < 1e-5
