@@ -112,6 +112,15 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_name(name, cfg):
+    """One description of the workload for both arms (config.workload)."""
+    from align3r_b200.synth import make_edge_list
+    n, H, W, graph = cfg
+    E = len(make_edge_list(n, graph))
+    return (f"{name}: {n}-frame {H}x{W} {graph} PointCloudOptimizer alignment ({E} directed edges, {E * H * W} pixel-edges), "
+            "shared focal, flow 0.01 + temporal 0.01, linear lr 0.01->1e-3, init=mst")
+
+
 def algorithmic_bytes(E, N, P, flow):
     """SURVEY.md section 8(d).  Returns (bytes per whole iteration, bytes of the accumulate kernel alone)."""
     it = E * P * 32 + N * P * 24 + (E * P * 16 + N * P if flow else 0)
@@ -184,7 +193,7 @@ def run_reference(args, cfg, name):
         "impl": "reference", "metric": "ga_iterations_per_sec", "value": r["value"], "unit": "iterations/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / r["value"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{name}: {n}-frame {H}x{W} {graph} PointCloudOptimizer alignment, flow+temporal, linear lr"},
+        "config": {"workload": workload_name(name, cfg)},
         "cpu_baseline": {"value": r["value"], "unit": "iterations/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -381,8 +390,7 @@ def run_ours(args, cfg, name):
             "metric": "ga_iterations_per_sec", "value": K / (ms * 1e-3), "unit": "iterations/s", "n_gpus": world,
             "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{name}: {n}-frame {H}x{W} {graph} PointCloudOptimizer alignment ({E} directed edges, "
-                                   f"{E * P} pixel-edges), shared focal, flow 0.01 + temporal 0.01, linear lr 0.01->1e-3, init=mst",
+            "config": {"workload": workload_name(name, cfg),
                        "iterations_with_flow": n_flow, "parallelism": "single GPU" if world == 1 else f"{world} frame windows, "
                        + ("one NCCL all-reduce" if os.environ.get("A3R_EXCHANGE") == "nccl" else "one peer-memory exchange kernel (NVLink loads)")
                        + " of the fp64 accumulator block per iteration",
