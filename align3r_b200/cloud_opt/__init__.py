@@ -43,6 +43,9 @@ def global_aligner(dust3r_output, if_use_mono, mono_depths, device, mode=GlobalA
     view1, view2, pred1, pred2 = [dust3r_output[k] for k in 'view1 view2 pred1 pred2'.split()]
     if mode == GlobalAlignerMode.PointCloudOptimizer:
         return PointCloudOptimizer(view1, view2, pred1, pred2, if_use_mono, mono_depths, device=device, **optim_kw).to(device)
-    if mode in (GlobalAlignerMode.ModularPointCloudOptimizer, GlobalAlignerMode.PairViewer):
+    if mode == GlobalAlignerMode.PairViewer:                # reference cloud_opt/pair_viewer.py = cloud_opt_flow/pair_viewer.py
+        from ..cloud_opt_flow.pair_viewer import PairViewer
+        return PairViewer(view1, view2, pred1, pred2, device=device, **optim_kw).to(device)
+    if mode == GlobalAlignerMode.ModularPointCloudOptimizer:
         raise NotImplementedError(f'{mode} is outside the B200 hot path (SURVEY.md section 8(b))')
     raise NotImplementedError(f'Unknown mode {mode}')

@@ -13,15 +13,17 @@ class GlobalAlignerMode(Enum):
 def global_aligner(dust3r_output, device, mode=GlobalAlignerMode.PointCloudOptimizer, **optim_kw):
     """Build the scene optimiser from the pairwise inference dict (reference __init__.py:20-33).
 
-    Only ``GlobalAlignerMode.PointCloudOptimizer`` is built here: it is the mode every caller of the
-    flow-aware aligner uses (tool/demo.py:150, tool/pose_test.py:169).  The other two members are kept
-    so that existing call sites import cleanly; selecting them raises NotImplementedError, as the
-    reference does for unknown modes.
+    ``GlobalAlignerMode.PointCloudOptimizer`` is the mode every caller of the flow-aware aligner uses for more than two
+    images (tool/demo.py:150, tool/pose_test.py:169); ``PairViewer`` is what they select for two (tool/demo.py:151-153).
+    ``ModularPointCloudOptimizer`` (no caller) raises NotImplementedError, as the reference does for unknown modes.
     """
     view1, view2, pred1, pred2 = [dust3r_output[k] for k in 'view1 view2 pred1 pred2'.split()]
     if mode == GlobalAlignerMode.PointCloudOptimizer:
         net = PointCloudOptimizer(view1, view2, pred1, pred2, device=device, **optim_kw).to(device)
-    elif mode in (GlobalAlignerMode.ModularPointCloudOptimizer, GlobalAlignerMode.PairViewer):
+    elif mode == GlobalAlignerMode.PairViewer:
+        from .pair_viewer import PairViewer
+        net = PairViewer(view1, view2, pred1, pred2, device=device, **optim_kw).to(device)
+    elif mode == GlobalAlignerMode.ModularPointCloudOptimizer:
         raise NotImplementedError(f'{mode} is outside the B200 hot path (SURVEY.md section 8(b)); '
                                   'use GlobalAlignerMode.PointCloudOptimizer')
     else:

@@ -80,12 +80,14 @@ def hierarchical_alignment(imgs, inference, device='cuda', clip_size=10, niter=3
 
     clip_size = choose_clip_size(len(imgs), clip_size)
     coarse_init_pairs, keyframes_id, all_clips_pairs, all_clips_id = my_make_pairs(imgs, clip_size)
-    if len(keyframes_id) <= 2:
-        raise NotImplementedError("two or fewer key frames: the reference switches to PairViewer here (tool/demo.py:211-213), "
-                                  "which is outside the B200 hot path")
     key_out, key_flow = run_inference(coarse_init_pairs)
-    scene = build(key_out, key_flow)
-    losses = [scene.compute_global_alignment(init='mst', niter=niter, schedule=schedule, lr=lr)]
+    if len(imgs) > 2:                                        # tool/demo.py:204-216, depth_test.py:641-647
+        scene = build(key_out, key_flow)
+        losses = [scene.compute_global_alignment(init='mst', niter=niter, schedule=schedule, lr=lr)]
+    else:
+        scene = _ga(key_out, device, mode=GlobalAlignerMode.PairViewer, **aligner_kw) if flow else \
+            _ga(key_out, False, [], device, mode=GlobalAlignerMode.PairViewer, **aligner_kw)
+        losses = [float('nan')]
     key_poses = _np(scene.get_im_poses()).tolist()
     key_depths = [_np(d) for d in scene.get_depthmaps()]
     key_focals = _np(scene.get_focals()).tolist()

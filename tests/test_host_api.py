@@ -45,7 +45,7 @@ def test_cpu_device_is_refused_loudly():
     with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
         global_aligner(scene.output, "cpu", mode=GlobalAlignerMode.PointCloudOptimizer, verbose=False)
     with pytest.raises(NotImplementedError):
-        global_aligner(scene.output, "cuda", mode=GlobalAlignerMode.PairViewer)
+        global_aligner(scene.output, "cuda", mode=GlobalAlignerMode.ModularPointCloudOptimizer)
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure path")
