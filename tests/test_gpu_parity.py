@@ -678,3 +678,69 @@ def test_mst_initialisation_on_a_non_symmetrised_graph(cuda_device):
     assert float((net.im_poses.detach().cpu() - params["im_poses"]).abs().max()) < 1e-5
     assert float((net.pw_poses.detach().cpu() - params["pw_poses"]).abs().max()) < 1e-5
     assert float((net.im_depthmaps.detach().cpu()[:, :prob.P] - params["im_depthmaps"]).abs().max()) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# variable image shapes (reference optimizer.py:66-92, 601-607): fixture from the real reference, oracle/make_golden_ragged.py
+# ---------------------------------------------------------------------------------------------------------------
+def test_ragged_image_shapes_against_reference(cuda_device):
+    """Frames of 40x56 and 32x56 pixels in one scene, inputs as per-edge lists (flow off: the reference's flow term needs
+    uniform shapes).  MST initialisation, teacher-forced loss / gradients (fp64 arbiter criterion) and a 15-iteration free
+    run against the reference's own numbers."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    from make_golden_ragged import RECIPE, ragged_output
+    fx = load_golden("small_ragged")
+    scene = make_scene(**RECIPE)
+    assert abs(scene_checksum(scene) - fx["checksum"]) <= 1e-9 * abs(fx["checksum"])
+    out = ragged_output(scene)
+
+    def fresh():
+        import copy
+        return global_aligner(copy.deepcopy(out), "cuda", mode=GlobalAlignerMode.PointCloudOptimizer, **fx["kw"])
+    net = fresh()
+    assert [tuple(s) for s in net.imshapes] == fx["imshapes"]
+    areas = [h * w for h, w in fx["imshapes"]]
+    P = max(areas)
+    # MST initialisation
+    init_fun.init_minimum_spanning_tree(net, niter_PnP=10)
+    ref = fx["init_params"]
+    assert float((net.pw_poses.detach().cpu() - ref["pw_poses"]).abs().max()) < 5e-5
+    assert float((net.im_poses.detach().cpu() - ref["im_poses"]).abs().max()) < 5e-5
+    assert float((net.im_focals.detach().cpu().reshape(-1) - ref["im_focals"].reshape(-1)).abs().max()) < 1e-4
+    for n, a in enumerate(areas):
+        d = (net.im_depthmaps.detach().cpu()[n, :a] - ref["im_depthmaps"][n, :a]).abs()
+        assert float(d.max()) < 2e-3 and float(d.median()) < 1e-5, (n, float(d.max()))
+    # teacher-forced loss and gradients at the reference's initial parameters
+    net = fresh()
+    set_params(net, ref)
+    loss = net(epoch=9999)
+    loss.backward()
+    assert abs(float(loss.detach()) - float(fx["tf64"]["loss"])) <= 2e-6 * abs(float(fx["tf64"]["loss"]))
+    for k in ("pw_poses", "im_depthmaps", "im_poses", "im_focals"):
+        m = getattr(net, k).grad.detach().cpu()
+        g32, g64 = fx["tf32"]["grads"][k], fx["tf64"]["grads"][k]
+        if k == "im_depthmaps":
+            m = m[:, :P].clone()
+            for n, a in enumerate(areas):
+                assert float(m[n, a:].abs().max()) == 0 if a < P else True      # the padding carries no gradient
+        else:
+            m = m.reshape(g64.shape)
+        ok, err, ref_err = grad_close(k, m, g32, g64)
+        assert ok, (k, err, ref_err)
+    # free run: from the reference's initial parameters the loop ends on the reference's result (5e-5); through our own MST
+    # initialisation (canonical call) within the end-state tolerance of a 15-iteration, still fast-moving run (1e-2)
+    fr = fx["free_run"]
+    net = fresh()
+    set_params(net, ref)
+    final = net.compute_global_alignment(init=None, niter=fx["niter"], schedule='linear', lr=0.01)
+    assert abs(final - fr["loss"]) <= 5e-5 * abs(fr["loss"]), (final, fr["loss"])
+    assert float((net.get_im_poses().detach().cpu() - fr["im_poses_4x4"]).abs().max()) < 1e-4
+    net = fresh()
+    final = net.compute_global_alignment(init='mst', niter=fx["niter"], schedule='linear', lr=0.01)
+    assert abs(final - fr["loss"]) <= 1e-2 * abs(fr["loss"]), (final, fr["loss"])
+    assert float((net.get_im_poses().detach().cpu() - fr["im_poses_4x4"]).abs().max()) < 1e-2
+    for d, r in zip(net.get_depthmaps(), fr["depths"]):
+        assert d.shape == r.shape
+        assert float((d.detach().cpu().log() - r.log()).abs().median()) < 2e-3
