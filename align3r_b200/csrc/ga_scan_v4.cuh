@@ -47,6 +47,9 @@ constexpr int V4_THREADS = V4_WARPS * 32;
 #define A3R_V4_STAGES 2
 #endif
 constexpr int V4_STAGES = A3R_V4_STAGES;
+#ifndef A3R_V4_EVICT_FIRST
+#define A3R_V4_EVICT_FIRST 0
+#endif
 #ifndef A3R_V4_SLOTS
 #define A3R_V4_SLOTS 20
 #endif
@@ -128,6 +131,9 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
     for (int k = lane; k < (V4_SLOTS + 1) * V4_ROW; k += 32) sts32(wb + V4_WACC + k * 4, 0.f);
     __syncwarp();
 
+#if A3R_V4_EVICT_FIRST
+    const uint64_t stream_policy = l2_policy_evict_first();      // predw / flow are read once per scan
+#endif
     // ---- copy cursor: next chunk = (l_tile, l_s) at pixel offset l_off of the slot-major planes ----
     int l_tile = t0, l_wf = 0, l_wf_end = -1, l_s = 0, l_deg = 1;
     int64_t l_off = 0;
@@ -153,8 +159,13 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
                 const uint32_t fd = wb + V4_FL + (stage_off >> 1) + lane * 8;
 #pragma unroll
                 for (int j = 0; j < V4_PPL; ++j) {
+#if A3R_V4_EVICT_FIRST
+                    cp_async16_hint(xd + j * 512, xw_g + l_off + lane + j * 32, stream_policy);
+                    if (FLOW) cp_async8_hint(fd + j * 256, fl_g + l_off + lane + j * 32, stream_policy);
+#else
                     cp_async16(xd + j * 512, xw_g + l_off + lane + j * 32);
                     if (FLOW) cp_async8(fd + j * 256, fl_g + l_off + lane + j * 32);
+#endif
                 }
             }
             if (++l_s >= l_deg) { l_s = 0; ++l_tile; l_off += V4_T - (int64_t)(l_deg - 1) * stride; }
