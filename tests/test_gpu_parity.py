@@ -744,3 +744,9 @@ def test_ragged_image_shapes_against_reference(cuda_device):
     for d, r in zip(net.get_depthmaps(), fr["depths"]):
         assert d.shape == r.shape
         assert float((d.detach().cpu().log() - r.log()).abs().median()) < 2e-3
+
+
+def test_graft_entry_smoke(cuda_device):
+    """The driver's smoke() entry point stays green (it runs before the bench at round end)."""
+    import __graft_entry__ as entry
+    entry.smoke()
