@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(256) k_depth_prior(const A3rProblem p) {
 // ==========================================================================================
 constexpr int K2_CLUSTER = 8;
 constexpr int K2_THREADS = 256;
-constexpr int K2_MAX_FRAMES = 1280;        // cameras in shared memory: 160 B each (200 KB of the 227 KB opt-in limit)
+constexpr int K2_MAX_FRAMES = 1280;        // cameras in shared memory: 160 B each (200 KB of the 227 KB opt-in limit); more: global scratch
 
 __device__ __forceinline__ void cluster_barrier() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -359,9 +359,11 @@ __device__ __noinline__ void fill_cameras(const float* im_poses, const float* fo
 }
 
 __global__ void __cluster_dims__(K2_CLUSTER, 1, 1) __launch_bounds__(K2_THREADS, 1)
-k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const uint32_t prepare_next) {
+k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const uint32_t prepare_next, FrameD* const cam_scratch) {
     extern __shared__ __align__(16) unsigned char k2_smem[];
-    FrameD* fr = reinterpret_cast<FrameD*>(k2_smem);
+    // cameras: shared memory up to K2_MAX_FRAMES frames; beyond that a library-owned global scratch every CTA fills with the
+    // same values (identical writes; a CTA reads what it wrote itself after its own block barrier)
+    FrameD* fr = cam_scratch ? cam_scratch : reinterpret_cast<FrameD*>(k2_smem);
     __shared__ double s_red[32];
     __shared__ double s_sc[2];
     __shared__ double s_mean;
@@ -823,18 +825,42 @@ static int zero_small_scratch(const A3rProblem* p, cudaStream_t st) {
     return A3R_OK;
 }
 
+// cameras of problems with more than K2_MAX_FRAMES frames: one lazily grown global scratch per device (never shrinks)
+struct CamScratch { void* ptr = nullptr; size_t bytes = 0; };
+static int camera_scratch(int dev, size_t bytes, void** out) {
+    static CamScratch scratch[64];
+    CamScratch& c = scratch[dev];
+    if (c.bytes < bytes) {
+        if (c.ptr) { A3R_CUDA(cudaDeviceSynchronize()); A3R_CUDA(cudaFree(c.ptr)); c.ptr = nullptr; c.bytes = 0; }
+        A3R_CUDA(cudaMalloc(&c.ptr, bytes));
+        c.bytes = bytes;
+    }
+    *out = c.ptr;
+    return A3R_OK;
+}
+
 static int launch_small(const A3rProblem* p, uint32_t mode, const A3rAdamStep* adam, cudaStream_t st, bool prepare_next) {
-    if (p->n_frames > K2_MAX_FRAMES)
-        return a3r_fail(A3R_E_UNSUPPORTED, "%d frames: the small-parameter kernel keeps every camera in shared memory (at most %d)",
-                        p->n_frames, K2_MAX_FRAMES);
     static bool attr_set[64] = {};
+    static int max_smem_frames = -1;
     int dev = 0;
     A3R_CUDA(cudaGetDevice(&dev));
-    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    if (dev < 0 || dev >= 64) return a3r_fail(A3R_E_ARG, "device index %d out of range", dev);
+    if (!attr_set[dev]) {
         A3R_CUDA(cudaFuncSetAttribute(k_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FrameD) * K2_MAX_FRAMES)));
         attr_set[dev] = true;
     }
-    k_small<<<K2_CLUSTER, K2_THREADS, sizeof(FrameD) * (size_t)p->n_frames, st>>>(*p, mode, *adam, prepare_next ? 1u : 0u);
+    if (max_smem_frames < 0) {        // A3R_K2_SMEM_FRAMES: lower the switch-over point (tests exercise the global-scratch path)
+        const char* e = getenv("A3R_K2_SMEM_FRAMES");
+        max_smem_frames = e ? atoi(e) : K2_MAX_FRAMES;
+        if (max_smem_frames > K2_MAX_FRAMES || max_smem_frames < 0) max_smem_frames = K2_MAX_FRAMES;
+    }
+    void* scratch = nullptr;
+    size_t smem = sizeof(FrameD) * (size_t)p->n_frames;
+    if (p->n_frames > max_smem_frames) {
+        if (int rc = camera_scratch(dev, sizeof(FrameD) * (size_t)p->n_frames, &scratch)) return rc;
+        smem = 0;
+    }
+    k_small<<<K2_CLUSTER, K2_THREADS, smem, st>>>(*p, mode, *adam, prepare_next ? 1u : 0u, static_cast<FrameD*>(scratch));
     A3R_CUDA(cudaGetLastError());
     return A3R_OK;
 }

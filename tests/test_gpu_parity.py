@@ -750,3 +750,36 @@ def test_graft_entry_smoke(cuda_device):
     """The driver's smoke() entry point stays green (it runs before the bench at round end)."""
     import __graft_entry__ as entry
     entry.smoke()
+
+
+_K2_SCRATCH_SNIPPET = """
+import sys, torch
+sys.path.insert(0, {root!r})
+from tests.test_gpu_parity import build, set_params
+from tests.helpers import golden_case
+fx, scene, prob = golden_case("small_flow")
+net = build(scene, fx["kw"])
+set_params(net, fx["init_params"])
+loss = net.compute_global_alignment(init=None, niter=fx["niter"], schedule="linear", lr=0.01)
+torch.save(dict(loss=loss, hist=net._bufs.loss_hist[:fx["niter"]].cpu(), im_poses=net.im_poses.detach().cpu(),
+                pw_poses=net.pw_poses.detach().cpu(), depth=net.im_depthmaps.detach().cpu()), {out!r})
+"""
+
+
+def test_k2_global_camera_scratch_matches_shared_memory(cuda_device, tmp_path):
+    """Beyond 1280 frames K2 keeps its cameras in a library-owned global scratch instead of shared memory; forced here on a
+    small scene (A3R_K2_SMEM_FRAMES=2, separate process): the whole run is bit-identical to the shared-memory one."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "scratch.pt")
+    subprocess.run([sys.executable, "-c", _K2_SCRATCH_SNIPPET.format(root=root, out=out)], check=True, timeout=600,
+                   env=dict(os.environ, A3R_K2_SMEM_FRAMES="2"), cwd=root)
+    alt = torch.load(out, weights_only=False)
+    fx, scene, prob = golden_case("small_flow")
+    net = build(scene, fx["kw"])
+    set_params(net, fx["init_params"])
+    loss = net.compute_global_alignment(init=None, niter=fx["niter"], schedule="linear", lr=0.01)
+    assert torch.equal(net._bufs.loss_hist[:fx["niter"]].cpu(), alt["hist"]) and loss == alt["loss"]
+    assert torch.equal(net.im_poses.detach().cpu(), alt["im_poses"]) and torch.equal(net.pw_poses.detach().cpu(), alt["pw_poses"])
+    assert torch.equal(net.im_depthmaps.detach().cpu(), alt["depth"])
