@@ -41,7 +41,8 @@ def main():
     same = torch.equal(ref, small)
     depth_local = net.im_depthmaps.detach()[:, :prob.P].contiguous()
     gathered = [None] * world
-    dist.all_gather_object(gathered, (lo, hi, depth_local.cpu(), same, loss, bool(net.flow_loss_flag)))
+    masks = torch.stack([net.dynamic_masks[n] for n in range(lo, hi)]).cpu() if kw.get("use_self_mask") else None
+    dist.all_gather_object(gathered, (lo, hi, depth_local.cpu(), same, loss, bool(net.flow_loss_flag), masks))
     if rank == 0:
         torch.save(dict(parts=gathered, im_poses=net.get_im_poses().detach().cpu(), focals=net.get_focals().detach().cpu(),
                         exchange="peer" if net._peers is not None else "nccl"), sys.argv[2])

@@ -49,3 +49,23 @@ def test_sharded_alignment_matches_reference(cuda_device, name, exchange, tmp_pa
     assert float((depth - ref["params"]["im_depthmaps"]).abs().median()) < 2e-3
     assert float((res["im_poses"] - ref["im_poses_4x4"]).abs().max()) < 1e-2
     assert rel_err(res["focals"], ref["focals"]) < 5e-3
+
+
+def test_sharded_self_estimated_masks(cuda_device, tmp_path):
+    """use_self_mask=True on frame windows: every rank estimates the dynamic masks of its own frames from the slots living on
+    them (no exchange beyond the focals / confidences the initialisation already shares); together they are the reference's."""
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    out = str(tmp_path / "res.pt")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "dist_gpu_worker.py"), "small_self_mask_a", out]
+    subprocess.run(cmd, check=True, timeout=600, cwd=ROOT, env=dict(os.environ))
+    res = torch.load(out, weights_only=False)
+    fx, scene, prob = golden_case("small_self_mask_a")
+    parts = sorted(res["parts"], key=lambda t: t[0])
+    masks = torch.cat([p[6] for p in parts])
+    assert masks.shape == fx["dynamic_masks"].shape
+    assert int((masks != fx["dynamic_masks"]).sum()) <= 1e-3 * masks.numel()
+    assert all(p[3] for p in parts) and len({p[4] for p in parts}) == 1
+    assert abs(parts[0][4] - fx["free_run"]["loss"]) <= 1e-2 * abs(fx["free_run"]["loss"])
