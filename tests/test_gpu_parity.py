@@ -783,3 +783,52 @@ def test_k2_global_camera_scratch_matches_shared_memory(cuda_device, tmp_path):
     assert torch.equal(net._bufs.loss_hist[:fx["niter"]].cpu(), alt["hist"]) and loss == alt["loss"]
     assert torch.equal(net.im_poses.detach().cpu(), alt["im_poses"]) and torch.equal(net.pw_poses.detach().cpu(), alt["pw_poses"])
     assert torch.equal(net.im_depthmaps.detach().cpu(), alt["depth"])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE configs[2] and [3] at full size: size-independent properties and the read-out metrics
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["c3", "c4"])
+def test_full_size_properties_c3_c4(cuda_device, name):
+    """c3 = DAVIS-shaped 90 frames 288x512 with per-frame-coherent ("Depth-Pro-conditioned") pointmap noise; c4 = Bonn/TUM-shaped
+    110 frames 384x512 with the pose-metric read-out.  The loss is reproducible (only the order of the fp64 atomics may
+    differ), a frame-window shard's accumulators add up to the unsharded ones (what the multi-GPU exchange relies on), and
+    40 iterations of the canonical schedule end with sane depth (Sintel protocol) and pose (ATE / RPE) metrics."""
+    from align3r_b200.synth import CONFIGS
+    n, H, W, graph = CONFIGS[name]
+    extra = dict(frame_noise=0.02, pixel_noise=0.003) if name == "c3" else {}
+    scene = make_scene(n, H, W, graph, seed=2, with_flow=True, **extra)
+    kw = dict(CANONICAL_KW, num_total_iter=40)
+    net = build(scene, kw)
+    net.verbose = False
+    E = {"c3": 870, "c4": 1070}[name]
+    assert net.n_edges == E and net._plan.pixel_slots() == 2 * E * H * W
+    net.compute_global_alignment(init='mst', niter=0)
+    l0, l0b = float(net(epoch=9999)), float(net(epoch=9999))
+    assert math.isfinite(l0) and abs(l0 - l0b) <= 1e-6 * abs(l0)
+    # additivity over frame windows: two shards, same parameters, accumulator blocks summed = the unsharded block
+    full_acc = net._bufs.acc.clone()
+    total = torch.zeros_like(full_acc)
+    for r in range(2):
+        sh = build(scene, kw, shard=dict(world=2, rank=r, group=None))
+        sh._reduce_accumulators = lambda: None
+        with torch.no_grad():
+            for k in ("pw_poses", "im_poses", "im_focals"):
+                getattr(sh, k).data.copy_(getattr(net, k).data)
+            sh.im_depthmaps.data.copy_(net.im_depthmaps.data[torch.as_tensor(sh._plan.lframe_id.tolist(), device=net.device)])
+        sh._phase_accumulate(_lib.M_FLOW_ACTIVE)
+        total += sh._bufs.acc
+        del sh
+    scale = full_acc.abs().max()
+    assert float((total - full_acc).abs().max()) <= 1e-6 * float(scale)
+    final = net.compute_global_alignment(init=None, niter=40, schedule='linear', lr=0.01)
+    hist = net._bufs.loss_hist[:40].cpu()
+    assert math.isfinite(final) and bool(torch.isfinite(hist).all()) and not net.flow_loss_flag
+    depth = torch.stack(net.get_depthmaps()).detach()
+    assert bool(torch.isfinite(depth).all()) and float(depth.min()) > 0
+    gt_depth = torch.stack([scene.gt.depth(k) for k in range(n)]).float()
+    dm = go.depth_metrics(depth.cpu().numpy()[::10], gt_depth.numpy()[::10])
+    pm = go.pose_metrics(net.get_im_poses().detach().cpu().numpy(), scene.gt.cam2world)
+    print(name, "after 40 iterations:", dm, pm)
+    assert dm["abs_rel"] < 0.1 and dm["d1"] > 0.9, dm
+    assert pm["ate"] < 0.3 and pm["rpe_rot"] < 2.0, pm
