@@ -54,6 +54,46 @@ def compute_edge_scores(self):
     return scores
 
 
+def _is_rank0(self):
+    return self._shard is None or int(self._shard.get('rank', 0)) == 0
+
+
+def edge_score_matrix(edge_scores, n_imgs=None):
+    """(n_imgs, n_imgs) matrix of the directed edge scores, NaN where the graph has no edge - what the reference's
+    draw_edge_scores_map (init_im_poses.py:24-34) renders."""
+    if n_imgs is None:
+        n_imgs = max(max(edge) for edge in edge_scores) + 1
+    m = np.full((n_imgs, n_imgs), np.nan)
+    for (i, j), score in edge_scores.items():
+        m[i, j] = score
+    return m
+
+
+def save_edge_scores_map(edge_scores, save_path, n_imgs=None):
+    """reference draw_edge_scores_map (init_im_poses.py:24-42): the annotated seaborn heat-map of the score matrix at
+    ``save_path``.  The data behind the picture is always written next to it (``<save_path minus .png>.npy``); the picture
+    itself needs matplotlib + seaborn, which this image does not have - without them only the matrix is written."""
+    import os
+    m = edge_score_matrix(edge_scores, n_imgs)
+    np.save(os.path.splitext(save_path)[0] + ".npy", m)
+    try:
+        import matplotlib
+        matplotlib.use("Agg")
+        import matplotlib.pyplot as plt
+        import seaborn as sns
+    except ImportError:
+        return m
+    n = m.shape[0]
+    fig = plt.figure(figsize=(int(5.5 * np.log(n) - 2), int((5.5 * np.log(n) - 2) * 3 / 4)))
+    sns.heatmap(m, annot=True, fmt=".1f", cmap="viridis", cbar=True, annot_kws={"fontsize": int(-4.2 * np.log(n) + 22.4)})
+    plt.title("Heatmap of Edge Scores")
+    plt.xlabel("Node")
+    plt.ylabel("Node")
+    plt.savefig(save_path)
+    plt.close(fig)
+    return m
+
+
 def dict_to_sparse_graph(dic):
     """reference init_im_poses.py:438-443."""
     n_imgs = max(max(e) for e in dic) + 1
@@ -183,9 +223,9 @@ def init_minimum_spanning_tree(self, save_score_path=None, save_score_only=False
     ph = Phases('mst-init', self.device)
     scores = compute_edge_scores(self)
     ph.mark('scores')
-    if save_score_only or save_score_path is not None:
-        raise NotImplementedError("save_score_path / save_score_only draw a seaborn heat-map in the reference "
-                                  "(init_im_poses.py:24-42); plotting is out of scope")
+    if save_score_only:                                  # reference init_im_poses.py:94-97: scores only, no initialisation
+        save_edge_scores_map(scores, save_score_path)
+        return
     N, E = self.n_imgs, self.n_edges
     eid = {ij: e for e, ij in enumerate(self.edges)}
 
@@ -212,6 +252,7 @@ def init_minimum_spanning_tree(self, save_score_path=None, save_score_only=False
             todo.insert(0, (score, i, j))
     if self.verbose:
         print(f' init edge ({i}*,{j}*) {score=}')
+    tree_log = [f'init edge ({i}*,{j}*) {score=}\n']       # the reference's <save_score_path>_tree.txt (:185-190)
     k0 = eid[(int(i), int(j))]
     if key_sim is None or int(i) == 0:
         src = {int(i): 2 * k0, int(j): 2 * k0 + 1}      # frame -> slot its world pointmap is made of
@@ -232,6 +273,7 @@ def init_minimum_spanning_tree(self, save_score_path=None, save_score_only=False
         if i in done:
             if self.verbose:
                 print(f' init edge ({i},{j}*) {score=}')
+            tree_log.append(f'init edge ({i},{j}*) {score=}\n')
             assert j not in done
             k = eid[(i, j)]
             stale_k = k
@@ -242,6 +284,7 @@ def init_minimum_spanning_tree(self, save_score_path=None, save_score_only=False
         elif j in done:
             if self.verbose:
                 print(f' init edge ({i}*,{j}) {score=}')
+            tree_log.append(f'init edge ({i}*,{j}) {score=}\n')
             assert i not in done
             k = eid[(i, j)]
             stale_k = k
@@ -258,6 +301,10 @@ def init_minimum_spanning_tree(self, save_score_path=None, save_score_only=False
         if i not in focal_slot and i not in fixed_focal:
             focal_slot[i] = 2 * eid[(i, j)]
 
+    if save_score_path is not None and _is_rank0(self):
+        save_edge_scores_map(scores, save_score_path, n_imgs=N)
+        with open(save_score_path.replace(".png", "_tree.txt"), "w") as f:
+            f.writelines(tree_log)
     ph.mark('tree')
     # ---- pass 2: every pointmap reduction in two batched launches ----
     pairs = []

@@ -832,3 +832,31 @@ def test_full_size_properties_c3_c4(cuda_device, name):
     print(name, "after 40 iterations:", dm, pm)
     assert dm["abs_rel"] < 0.1 and dm["d1"] > 0.9, dm
     assert pm["ate"] < 0.3 and pm["rpe_rot"] < 2.0, pm
+
+
+def test_edge_score_map_and_tree_file(cuda_device, tmp_path):
+    """compute_global_alignment(init='mst', save_score_path=..., save_score_only=...) (reference base_opt.py:460-466,
+    init_im_poses.py:94-97,185-190,229-250): the score matrix equals the oracle's edge scores, the tree file lists the
+    spanning tree in the oracle's order with the reference's star notation, and saving does not change the initialisation."""
+    fx, scene, prob = golden_case("small_flow")
+    ref = go.edge_scores(prob)
+    net = build(scene, fx["kw"])
+    before = net.im_poses.detach().clone()
+    path = str(tmp_path / "scores.png")
+    assert net.compute_global_alignment(init='mst', save_score_path=path, save_score_only=True) is None
+    assert torch.equal(net.im_poses.detach(), before)                  # scores only: nothing initialised
+    m = np.load(str(tmp_path / "scores.npy"))
+    assert int((~np.isnan(m)).sum()) == len(ref)
+    for (i, j), s in ref.items():
+        assert abs(m[i, j] - s) <= 1e-5 * abs(s), ((i, j), m[i, j], s)
+
+    init_fun.init_minimum_spanning_tree(net, save_score_path=path, niter_PnP=10)
+    lines = open(str(tmp_path / "scores_tree.txt")).read().splitlines()
+    tree = go.mst_init(prob)[1]["tree"]
+    assert len(lines) == len(tree) == prob.n_imgs - 1
+    assert lines[0].startswith(f"init edge ({tree[0][0]}*,{tree[0][1]}*) score=")
+    for line, (i, j) in zip(lines[1:], tree[1:]):
+        assert line.startswith(f"init edge ({i}*,{j}) score=") or line.startswith(f"init edge ({i},{j}*) score="), line
+    plain = build(scene, fx["kw"])
+    init_fun.init_minimum_spanning_tree(plain, niter_PnP=10)
+    assert float((plain.pw_poses.detach() - net.pw_poses.detach()).abs().max()) < 1e-5

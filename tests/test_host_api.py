@@ -94,3 +94,59 @@ def test_synthetic_scene_is_reproducible_and_sliceable():
     b = make_scene(5, 16, 24, "swin-2-noncyclic", seed=4, edges=sub)
     assert torch.equal(b.pred1["pts3d"][0], a.pred1["pts3d"][3]) and torch.equal(b.flow_ji[1], a.flow_ji[0])
     assert set(CANONICAL_KW) >= {"shared_focal", "flow_loss_weight", "temporal_smoothing_weight"}
+
+
+def test_edge_score_map_writer(tmp_path):
+    """save_score_path / save_score_only (reference init_im_poses.py:24-42,94-97): the matrix behind the reference's
+    heat-map, NaN where the graph has no edge; the picture itself only where matplotlib + seaborn exist."""
+    from align3r_b200.cloud_opt_flow.init_im_poses import edge_score_matrix, save_edge_scores_map
+    scores = {(0, 1): 2.5, (1, 0): 2.25, (1, 2): 3.0, (3, 1): 1.5}
+    m = edge_score_matrix(scores)
+    assert m.shape == (4, 4) and np.isnan(m).sum() == 12
+    assert m[0, 1] == 2.5 and m[1, 0] == 2.25 and m[1, 2] == 3.0 and m[3, 1] == 1.5
+    assert edge_score_matrix(scores, n_imgs=6).shape == (6, 6)
+    path = str(tmp_path / "scores.png")
+    out = save_edge_scores_map(scores, path, n_imgs=5)
+    back = np.load(str(tmp_path / "scores.npy"))
+    assert back.shape == (5, 5) and np.array_equal(back, out, equal_nan=True)
+
+
+def test_tree_file_lists_the_oracle_spanning_tree(tmp_path, monkeypatch):
+    """The graph pass of the MST initialisation is host logic: run it on a stand-in object (confidence sums of a fixture
+    scene on the CPU, stopped before the first device launch) and compare the tree file it writes
+    (reference init_im_poses.py:185-190,229-250) with the oracle's spanning tree."""
+    import types
+    from tests.helpers import go, golden_case
+    from align3r_b200.cloud_opt_flow import init_im_poses as init_fun
+    fx, scene, prob = golden_case("small_flow")
+    E, N = prob.n_edges, prob.n_imgs
+    conf_sum = torch.zeros(2 * E, dtype=torch.float64)
+    conf_sum[0::2] = prob.conf_i.reshape(E, -1).double().sum(1)
+    conf_sum[1::2] = prob.conf_j.reshape(E, -1).double().sum(1)
+    stand_in = types.SimpleNamespace(_shard=None, _conf_sum=conf_sum, _lslot={g: g for g in range(2 * E)},
+                                     imshapes=[(prob.H, prob.W)] * N, edges=list(prob.edges), n_imgs=N, n_edges=E,
+                                     verbose=False, device='cpu')
+
+    class DeviceWorkStarts(Exception):
+        pass
+
+    def stop(*a, **k):
+        raise DeviceWorkStarts
+
+    monkeypatch.setattr(init_fun, "_run_procrustes", stop)
+    path = str(tmp_path / "scores.png")
+    with pytest.raises(DeviceWorkStarts):
+        init_fun.init_minimum_spanning_tree(stand_in, save_score_path=path)
+    m = np.load(str(tmp_path / "scores.npy"))
+    for (i, j), s in go.edge_scores(prob).items():
+        assert abs(m[i, j] - s) <= 1e-6 * abs(s)
+    lines = open(str(tmp_path / "scores_tree.txt")).read().splitlines()
+    tree = go.mst_init(prob)[1]["tree"]
+    assert len(lines) == len(tree) == N - 1
+    assert lines[0].startswith(f"init edge ({tree[0][0]}*,{tree[0][1]}*) score=")
+    for line, (i, j) in zip(lines[1:], tree[1:]):
+        assert line.startswith(f"init edge ({i}*,{j}) score=") or line.startswith(f"init edge ({i},{j}*) score="), line
+    # scores only: nothing but the matrix is produced
+    only = str(tmp_path / "only.png")
+    assert init_fun.init_minimum_spanning_tree(stand_in, save_score_path=only, save_score_only=True) is None
+    assert np.array_equal(np.load(str(tmp_path / "only.npy"))[~np.isnan(m)], m[~np.isnan(m)])
