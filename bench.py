@@ -10,8 +10,8 @@ started from the MST initialisation, so the flow term switches on at iteration 0
 reference's canonical 300-iteration run.  One JSON line is printed by rank 0.
 
 N > 1 (launched by torchrun): the scene is cut into N contiguous frame windows; a rank owns the slots
-living on its frames; one NCCL all-reduce of the small-parameter accumulators per iteration; total work is
-fixed ("scaling": "strong").
+living on its frames; the fp64 accumulator block of the small parameters is exchanged once per iteration inside our own
+kernel over NVLink peer memory (A3R_EXCHANGE=nccl: one NCCL all-reduce instead); total work is fixed ("scaling": "strong").
 
 ``--impl reference`` times the CPU oracle port of the reference implementation (oracle/ga_oracle.py: same
 torch ops + autograd + torch.optim.Adam as the reference, all host threads) on a bounded sample of the
