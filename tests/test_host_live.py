@@ -110,3 +110,39 @@ def test_schedules_and_small_maps_equal_the_reference():
     y = torch.tensor([-3.5, -1e-9, -0.0, 0.0, 1e-9, 0.25, 40.0])
     assert torch.equal(our_c.signed_log1p(y), ref_c.signed_log1p(y)) and torch.equal(our_c.signed_expm1(y), ref_c.signed_expm1(y))
     assert our_c.edge_str(3, 14) == ref_c.edge_str(3, 14) and our_c.i_j_ij((3, 14)) == ref_c.i_j_ij((3, 14))
+
+
+def test_clip_pairs_equal_the_reference_on_a_sweep():
+    """hierarchical.my_make_pairs / choose_clip_size against the reference's own my_make_pairs (tool/depth_test.py, taken from its
+    source with ast: the tool loads networks at import) and clip-size rule (tool/depth_test.py:626-628) over a sweep of video
+    lengths and clip sizes."""
+    import ast
+    import copy
+    from align3r_b200 import hierarchical as hi
+    path = os.path.join(rh.REFERENCE_ROOT, "tool", "depth_test.py")
+    tree = ast.parse(open(path).read())
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "my_make_pairs"][0]
+    ns = {}
+    exec(compile(ast.Module([fn], []), path, "exec"), ns)
+    ref_pairs = ns["my_make_pairs"]
+
+    def ident(pairs):
+        return [(a["idx"], b["idx"], a["frame"], b["frame"]) for a, b in pairs]
+
+    checked = 0
+    for n in list(range(4, 34)) + [50, 90, 110]:
+        for clip in (3, 4, 5, 8, 10, 20):
+            imgs = [dict(idx=k, frame=k) for k in range(n)]
+            want = clip
+            while want > 1 and (n % want == 1 or n % want == 0 or want > n):
+                want -= 1
+            if want <= 1:
+                continue
+            assert hi.choose_clip_size(n, clip) == want, (n, clip)
+            r_key, r_kid, r_clips, r_cid = ref_pairs(copy.deepcopy(imgs), want)
+            o_key, o_kid, o_clips, o_cid = hi.my_make_pairs(imgs, want)
+            assert list(o_kid) == list(r_kid) and [list(c) for c in o_cid] == [list(c) for c in r_cid], (n, clip)
+            assert ident(o_key) == ident(r_key), (n, clip)
+            assert [ident(c) for c in o_clips] == [ident(c) for c in r_clips], (n, clip)
+            checked += 1
+    assert checked > 100
