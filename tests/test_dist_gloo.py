@@ -1,6 +1,6 @@
-"""Frame-window sharding over 2 ranks on CPU (gloo): every rank scans only the slots living on its frames,
+"""Frame-window sharding over 2 and 3 ranks on CPU (gloo): every rank scans only the slots living on its frames,
 the fp64 accumulator block is summed with one all-reduce, and the (replicated) small-parameter update is
-then bit-identical on both ranks and equal to the single-shard result.  The per-rank work is re-enacted by
+then bit-identical on all ranks and equal to the single-shard result.  The per-rank work is re-enacted by
 the CPU emulation harness; the GPU path runs the same plan/reduce code with NCCL (test_gpu_parity.py)."""
 import os
 import socket
@@ -53,10 +53,12 @@ def _worker(rank, world, port, name, out):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("world", [2, 3])
 @pytest.mark.parametrize("name", ["small_flow"])
-def test_two_rank_sharded_iterations_equal_single_shard(name, tmp_path):
+def test_sharded_iterations_equal_single_shard(name, world, tmp_path):
+    """2 ranks (one boundary) and 3 ranks (the middle window has slots of boundary edges on both sides)."""
     emul_lib()                                   # build once before forking
-    world, out = 2, str(tmp_path / "res.pt")
+    out = str(tmp_path / "res.pt")
     mp.spawn(_worker, args=(world, _free_port(), name, out), nprocs=world, join=True)
     res = torch.load(out, weights_only=False)
 
@@ -67,12 +69,16 @@ def test_two_rank_sharded_iterations_equal_single_shard(name, tmp_path):
         l, _, _ = emul_eval(bufs, True, apply=True, lr=0.01, step=it)
         ref_losses.append(l)
 
-    (w0, l0, s0, d0), (w1, l1, s1, d1) = res
-    assert w0[1] == w1[0] and w0[0] == 0 and w1[1] == prob.n_imgs
-    assert l0 == l1                                              # replicated state stays bit-identical
+    wins = [r[0] for r in res]
+    assert wins[0][0] == 0 and wins[-1][1] == prob.n_imgs and all(wins[r][1] == wins[r + 1][0] for r in range(world - 1))
+    assert all(b > a for a, b in wins)
+    l0, s0 = res[0][1], res[0][2]
+    for _, lr_, sr, _ in res[1:]:
+        assert lr_ == l0                                             # replicated state stays bit-identical
+        for k in s0:
+            assert torch.equal(s0[k], sr[k]), k
     for k in s0:
-        assert torch.equal(s0[k], s1[k]), k
         assert torch.allclose(s0[k], bufs.params[k], rtol=0, atol=2e-6), k
     assert np.allclose(l0, ref_losses, rtol=1e-9, atol=0)
-    depth = torch.cat((d0, d1))
+    depth = torch.cat([r[3] for r in res])
     assert torch.allclose(depth, bufs.params["im_depthmaps"][:, :prob.P], rtol=0, atol=2e-6)
