@@ -7,7 +7,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("A3R_LIB") or os.path.join(HERE, "lib", "liba3r_ga.so")   # A3R_LIB: tuning builds
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # A3rProblem.flags
 F_SHARED_FOCAL, F_NORM_PW_SCALE, F_DIST_L2 = 1 << 0, 1 << 1, 1 << 2
@@ -60,6 +60,10 @@ class A3rAdamStep(C.Structure):
     _fields_ = [("step_size", _f32), ("bc2_sqrt", _f32), ("iter", _i32), ("_pad", _i32)]
 
 
+class A3rGrads(C.Structure):
+    _fields_ = [(n, _vp) for n in ("pw_poses", "pw_adaptors", "im_poses", "im_focals", "im_pp", "logdepth", "scal")]
+
+
 _SIGNATURES = {
     "a3r_abi_version": (C.c_int, []),
     "a3r_last_error": (C.c_char_p, []),
@@ -74,6 +78,16 @@ _SIGNATURES = {
     "a3r_ga_update": (C.c_int, [C.POINTER(A3rProblem), _u32, C.POINTER(A3rAdamStep), _vp]),
     "a3r_ga_run": (C.c_int, [C.POINTER(A3rProblem), _i32, C.POINTER(_u32), C.POINTER(A3rAdamStep), _vp]),
     "a3r_ga_unproject": (C.c_int, [C.POINTER(A3rProblem), _vp, _vp]),
+    # handle layer (SURVEY.md section 8(b) export set)
+    "a3r_ga_create": (C.c_int, [C.POINTER(A3rProblem), C.POINTER(_vp)]),
+    "a3r_ga_destroy": (C.c_int, [_vp]),
+    "a3r_ga_problem": (C.POINTER(A3rProblem), [_vp]),
+    "a3r_ga_pack_inputs": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "a3r_ga_reset_adam": (C.c_int, [_vp, _vp]),
+    "a3r_ga_step": (C.c_int, [_vp, _i32, _i32, _f32, _u32, _vp]),
+    "a3r_ga_forward": (C.c_int, [_vp, _u32, _vp, _vp]),
+    "a3r_ga_grads": (C.c_int, [_vp, C.POINTER(A3rGrads)]),
+    "a3r_mst_edge_scores": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
     "a3r_peer_region_bytes": (C.c_size_t, [_i64]),
     "a3r_peer_alloc": (C.c_int, [_i64, C.POINTER(_vp), C.c_char_p]),
     "a3r_peer_open": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define A3R_ABI_VERSION 5
+#define A3R_ABI_VERSION 6
 
 /* error codes */
 #define A3R_OK 0
@@ -165,14 +165,14 @@ int a3r_device_info(int device, int *sm_count, int *cc_major, int *cc_minor);
 
 /* ---- one-off packing (replaces the ParameterStack buffers of reference optimizer.py:80-92,
  *      _compute_img_conf base_opt.py:187-193 and compute_edge_scores commons.py:21-31) ----
- * pts [n][P][3], conf [n][P] raw network outputs of n edge-sides (device, fp32); dst_slot[n] (host)
+ * pts [n][P][3], conf [n][P] raw network outputs of n edge-sides (device, fp32); dst_slot[n] (device int32)
  * local slot index of each; conf_mode 0=log 1=sqrt 2=m1 3=id.  Writes predw, max-merges raw conf into
- * im_conf[lframe][pix_stride] (frame index per slot in dst_lframe, host) and adds sum(conf) into
+ * im_conf[lframe][pix_stride] (local frame index of each row in dst_lframe[n], device int32) and adds sum(conf) into
  * conf_sum[dst_slot] (fp64, device). */
 int a3r_pack_pred(const float *pts, const float *conf, int32_t n, int64_t P, const int32_t *dst_slot,
                   const int32_t *dst_lframe, int64_t pix_stride, int32_t conf_mode, float *predw,
                   float *im_conf, double *conf_sum, void *stream);
-/* flow [n][2][P] (reference get_flow layout, optimizer.py:118-154) -> flow plane [slot][pix_stride][2] */
+/* flow [n][2][P] (reference get_flow layout, optimizer.py:118-154) -> flow plane [slot][pix_stride][2]; dst_slot device int32 */
 int a3r_pack_flow(const float *flow_src, int32_t n, int64_t P, const int32_t *dst_slot, int64_t pix_stride,
                   float *flow_dst, void *stream);
 
@@ -188,6 +188,41 @@ int a3r_ga_update(const A3rProblem *p, uint32_t mode, const A3rAdamStep *adam, v
 /* prepare + accumulate + update, `count` consecutive iterations (single-device loop of
  * global_alignment_loop, base_opt.py:513-547).  steps/modes are host arrays of length count. */
 int a3r_ga_run(const A3rProblem *p, int32_t count, const uint32_t *modes, const A3rAdamStep *steps, void *stream);
+
+/* ---- handle layer: the export set SURVEY.md section 8(b) names, over the stateless entry points above ----
+ * A handle is a validated copy of the descriptor + the Adam step count (torch's state['step']); it owns no device memory
+ * (every pointer in the descriptor stays the caller's) and belongs to the device that was current at creation.  One device
+ * holding every frame only: a frame-window shard uses the three-phase calls with an all-reduce, or a3r_ga_run_peers. */
+typedef struct A3rHandle A3rHandle;
+int a3r_ga_create(const A3rProblem *desc, A3rHandle **out);
+int a3r_ga_destroy(A3rHandle *h);
+const A3rProblem *a3r_ga_problem(const A3rHandle *h);
+/* a3r_pack_pred (+ a3r_pack_flow when `flow` [n][2][P] is not NULL) of n edge-side rows into the descriptor's predw / flow
+ * planes; arguments as for a3r_pack_pred. */
+int a3r_ga_pack_inputs(A3rHandle *h, const float *pts, const float *conf, const float *flow, int32_t n, int64_t P,
+                       const int32_t *dst_slot, const int32_t *dst_lframe, int32_t conf_mode, float *im_conf, double *conf_sum,
+                       void *stream);
+/* a fresh torch.optim.Adam (reference base_opt.py:524): zero every moment buffer of the descriptor, step count 0 */
+int a3r_ga_reset_adam(A3rHandle *h, void *stream);
+/* one iteration of global_alignment_iter (base_opt.py:550-583) at learning rate lr: parameter maps, scan, loss + gate +
+ * chains + Adam.  flags: A3R_M_FLOW_ACTIVE or 0.  The loss lands in scal[A3R_S_LOSS] and loss_hist[iter] (when not NULL).
+ * The bias corrections use the handle's step count and the decimal betas the fp32 fields stand for, like torch. */
+int a3r_ga_step(A3rHandle *h, int32_t iter, int32_t niter, float lr, uint32_t flags, void *stream);
+/* loss + every gradient of the current parameters, no update (reference forward + loss.backward()); the fp64 loss is
+ * also copied to loss_out (device or pinned host, may be NULL) on the stream. */
+int a3r_ga_forward(A3rHandle *h, uint32_t flags, double *loss_out, void *stream);
+/* where the gradients of the last a3r_ga_forward live (device pointers into the descriptor's buffers; test hook) */
+typedef struct A3rGrads {
+    const float *pw_poses, *pw_adaptors, *im_poses, *im_focals, *im_pp;   /* shapes of the parameters */
+    const float *logdepth;                                                 /* [n_local_frames][pix_stride] */
+    const double *scal;                                                    /* [A3R_SCAL], A3R_S_* */
+} A3rGrads;
+int a3r_ga_grads(const A3rHandle *h, A3rGrads *out);
+/* compute_edge_scores (reference commons.py:21-31): scores[e] = fp32(mean conf_i) * fp32(mean conf_j) from the per-slot
+ * confidence sums a3r_pack_pred accumulated, indexed by GLOBAL slot 2e+side (conf_sum [2E] fp64, device); edge_ij [E][2],
+ * frame_hw [N][2] device int32; scores [E] fp64 (device). */
+int a3r_mst_edge_scores(const double *conf_sum, const int32_t *edge_ij, const int32_t *frame_hw, int32_t n_edges,
+                        double *scores, void *stream);
 
 /* ---- multi-GPU exchange over peer memory (NVLink / NVSwitch; one process per GPU on one node) ----
  * The only thing that crosses GPUs is the fp64 accumulator block (acc_slot | acc_frame | prior_acc).  Instead of a
