@@ -945,7 +945,8 @@ def _rgb(ftensor, true_shape=None):
 def global_alignment_loop(net, lr=0.01, niter=300, schedule='cosine', lr_min=1e-3, temporal_smoothing_weight=0,
                           depth_map_save_dir=None):
     """Adam loop of the global alignment.  ``temporal_smoothing_weight`` is accepted and ignored exactly as in
-    the reference (base_opt.py:513,550): the constructor attribute is what counts."""
+    the reference (base_opt.py:513,550): the constructor attribute is what counts.  ``depth_map_save_dir`` (verbose runs
+    only, as in the reference, base_opt.py:531-540): jet-coloured pictures of the depth maps before iterations 0, 500, ..."""
     trainable = net._trainable()
     if not any(trainable.values()):
         return net
@@ -977,8 +978,14 @@ def global_alignment_loop(net, lr=0.01, niter=300, schedule='cosine', lr_min=1e-
         st = b.struct(trainable)
         s = net._stream()
         it = 0
+        dump = net.verbose and depth_map_save_dir is not None
         while it < niter:
             n = min(chunk, niter - it)
+            if dump:
+                if it % 500 == 0:
+                    _writeout.save_depthmap_pictures(net.get_depthmaps(), depth_map_save_dir, it)
+                    print(f"Saved depthmaps at iteration {it} to {depth_map_save_dir}")
+                n = min(n, 500 - it % 500)                      # the next picture is due on a chunk boundary
             if sharded and peers is not None:
                 sub_m = (C.c_uint32 * n).from_buffer(marr, 4 * it)
                 sub_s = (_lib.A3rAdamStep * n).from_buffer(steps, C.sizeof(_lib.A3rAdamStep) * it)

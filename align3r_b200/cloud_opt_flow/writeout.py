@@ -7,6 +7,7 @@
     conf_<k>.npy / init_conf_<k>.npy        transformed confidence maps
     frame_<k:04d>.npy (+ .png JET colour map, + _depth_maps.gif)   depth maps
     frame_<k:04d>_rgb.png (+ _rgb.gif), dynamic_mask_<k>.png
+    depthmaps_<i>_iter_<n>.png           progress pictures of the loop (depth_map_save_dir, verbose runs)
 
 Host code only (numpy / cv2 / PIL); bound to PointCloudOptimizer as methods of the same names.
 """
@@ -105,6 +106,31 @@ def save_depth_maps(self, path, start, depth_maps_init=None):
         files.append(name + '.png')
     _append_gif(os.path.join(path, '_depth_maps_refine.gif' if refine else '_depth_maps.gif'), files)
     return depth_maps
+
+
+def save_depthmap_pictures(depth_maps, save_dir, iteration):
+    """reference base_opt.py:531-540: ``depthmaps_<i>_iter_<n>.png`` of every frame, min-max normalised and jet-coloured
+    (matplotlib's ``imsave(cmap='jet')`` where matplotlib exists, OpenCV's JET colour map otherwise)."""
+    os.makedirs(save_dir, exist_ok=True)
+    try:
+        import matplotlib
+        matplotlib.use("Agg")
+        import matplotlib.pyplot as plt
+    except ImportError:
+        plt = None
+    files = []
+    for i, d in enumerate(depth_maps):
+        d = _np(d).astype(np.float64)
+        path = os.path.join(save_dir, f'depthmaps_{i}_iter_{iteration}.png')
+        if plt is not None:
+            plt.imsave(path, d, cmap='jet')
+        else:
+            import cv2
+            lo, hi = float(d.min()), float(d.max())
+            norm = (d - lo) / (hi - lo) if hi > lo else np.zeros_like(d)
+            cv2.imwrite(path, cv2.applyColorMap(np.round(norm * 255).astype(np.uint8), cv2.COLORMAP_JET))
+        files.append(path)
+    return files
 
 
 METHODS = (save_tum_poses, save_focals, save_intrinsics, save_conf_maps, save_init_conf_maps, save_rgb_imgs,

@@ -150,3 +150,17 @@ def test_tree_file_lists_the_oracle_spanning_tree(tmp_path, monkeypatch):
     only = str(tmp_path / "only.png")
     assert init_fun.init_minimum_spanning_tree(stand_in, save_score_path=only, save_score_only=True) is None
     assert np.array_equal(np.load(str(tmp_path / "only.npy"))[~np.isnan(m)], m[~np.isnan(m)])
+
+
+def test_progress_pictures_of_the_loop(tmp_path):
+    """depth_map_save_dir (reference base_opt.py:531-540): one jet-coloured picture per frame, named like the reference's."""
+    import cv2
+    from align3r_b200.cloud_opt_flow.writeout import save_depthmap_pictures
+    maps = [torch.linspace(1, 3, 20 * 30).reshape(20, 30), torch.full((20, 30), 2.0)]
+    d = str(tmp_path / "progress")
+    files = save_depthmap_pictures(maps, d, 500)
+    assert [f.split("/")[-1] for f in files] == ["depthmaps_0_iter_500.png", "depthmaps_1_iter_500.png"]
+    a, b = cv2.imread(files[0]), cv2.imread(files[1])
+    assert a.shape[:2] == (20, 30) and b.shape[:2] == (20, 30)
+    assert int(a[0, 0, 0]) > int(a[0, 0, 2]) and int(a[-1, -1, 2]) > int(a[-1, -1, 0])      # near = blue, far = red (BGR)
+    assert len(np.unique(b.reshape(-1, 3), axis=0)) == 1                                      # a constant map is one colour
