@@ -88,3 +88,56 @@ def test_canonical_aligner_on_a_fresh_scene():
         final = ref.compute_global_alignment(init=None, niter=12, schedule="linear", lr=0.01)
     _, losses, dropped = go.run_alignment(prob, params, niter=12, schedule="linear", lr=0.01)
     assert abs(losses[-1] - float(final)) <= 1e-4 * abs(float(final)) and dropped == bool(ref.flow_loss_flag)
+
+
+@pytest.mark.parametrize("variant", ["l2", "adaptors_pp", "conf_sqrt", "conf_m1", "conf_id", "perframe_focal_base_scale"])
+def test_variant_switches_teacher_forced(variant):
+    """The constructor switches no committed fixture turns: dist='l2', trainable adaptors + principal points (with non-zero
+    values), the confidence transforms, per-frame focals with another base_scale.  Oracle loss and gradients against the
+    real reference's forward + autograd at the same parameters (fp32: loss 2e-6, gradients 2e-4 of the tensor's norm - the
+    reference's own fp32 noise level)."""
+    rh.import_reference()
+    import dust3r.cloud_opt_flow.init_im_poses as init_fun
+    sc = make_scene(5, 32, 48, "swin-2-noncyclic", seed=71, with_flow=True)
+    kw = dict(CANONICAL_KW, num_total_iter=10, flow_loss_thre=0)
+    names = list(go.TRAINABLE)
+    if variant == "l2":
+        kw["dist"] = "l2"
+    elif variant == "adaptors_pp":
+        kw.update(allow_pw_adaptors=True, optimize_pp=True)
+        names += ["pw_adaptors", "im_pp"]
+    elif variant.startswith("conf_"):
+        kw["conf"] = variant[5:]
+    else:
+        kw.update(shared_focal=False, base_scale=0.8)
+    ref = rh.build_reference_scene(sc, **kw)
+    with rh.quiet():
+        init_fun.init_minimum_spanning_tree(ref, niter_PnP=10)
+    g = torch.Generator().manual_seed(2)
+    with torch.no_grad():
+        if variant == "adaptors_pp":
+            ref.pw_adaptors.data.copy_(0.3 * torch.randn(ref.pw_adaptors.shape, generator=g))
+            ref.im_pp.data.copy_(0.2 * torch.randn(ref.im_pp.shape, generator=g))
+    all_names = ("pw_poses", "pw_adaptors", "im_depthmaps", "im_poses", "im_focals", "im_pp")
+    params = {k: getattr(ref, k).detach().clone() for k in all_names}
+    ref.zero_grad()
+    with rh.quiet():
+        loss_ref = ref(epoch=9999)
+    loss_ref.backward()
+
+    prob = go.problem_from_output(sc.output, sc.flow_ij, sc.flow_ji, **kw)
+    mine = {k: v.reshape(go_shape(prob, k, v)) for k, v in params.items()}
+    loss, grads, _ = go.loss_and_grads(prob, mine, 9999, trainable=names)
+    loss, loss_ref = float(loss.detach()), float(loss_ref.detach())
+    assert abs(loss - loss_ref) <= 2e-6 * abs(loss_ref), (loss, loss_ref)
+    for k in names:
+        r = getattr(ref, k).grad.detach()
+        m = grads[k].reshape(r.shape)
+        assert float((m - r).norm()) <= 2e-4 * float(r.norm()) + 1e-9, (k, float((m - r).norm()), float(r.norm()))
+
+
+def go_shape(prob, name, value):
+    """Shapes of the oracle's parameter dict (mst_init's): the reference stacks its parameters the same way except the focal."""
+    if name == "im_focals":
+        return (-1, 1)
+    return tuple(value.shape)
