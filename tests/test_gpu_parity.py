@@ -860,3 +860,34 @@ def test_edge_score_map_and_tree_file(cuda_device, tmp_path):
     plain = build(scene, fx["kw"])
     init_fun.init_minimum_spanning_tree(plain, niter_PnP=10)
     assert float((plain.pw_poses.detach() - net.pw_poses.detach()).abs().max()) < 1e-5
+
+
+@pytest.mark.xfail(strict=False, reason="added after round 1's GPU minutes were spent: first hardware run pending (an XPASS means confirmed)")
+@pytest.mark.parametrize("conf", ["sqrt", "m1", "id"])
+def test_confidence_transforms_against_live_oracle(cuda_device, conf):
+    """conf='sqrt' | 'm1' | 'id' (reference commons.py:53-64): the pack kernel's weight, the raw confidence the Procrustes
+    kernel recovers from it (MST initialisation against the oracle's) and the teacher-forced loss / gradients.  The oracle is
+    pinned on these switches against the real reference (test_oracle_live.py::test_variant_switches_teacher_forced)."""
+    scene = make_scene(6, 48, 64, "swin-2-noncyclic", seed=23, with_flow=True)
+    kw = dict(CANONICAL_KW, num_total_iter=10, flow_loss_thre=0, conf=conf)
+    prob = go.problem_from_output(scene.output, scene.flow_ij, scene.flow_ji, **kw)
+    params, _ = go.mst_init(prob)
+    net = build(scene, kw)
+    init_fun.init_minimum_spanning_tree(net, niter_PnP=10)
+    T_ref = go.pw_pose_matrices(prob, params["pw_poses"])
+    assert float((net.get_pw_poses().detach().cpu() - T_ref).abs().max()) < 5e-5
+    for c, r in zip(net.get_conf(), [prob.conf_trf(x) for x in prob.im_conf] if hasattr(prob, "conf_trf") else []):
+        assert torch.allclose(c.cpu(), r.reshape(c.shape), rtol=1e-6, atol=1e-6)
+    p64 = {k: v.double() for k, v in params.items()}
+    names = list(go.TRAINABLE)
+    loss64, g64, _ = go.loss_and_grads(prob.to(torch.float64), p64, 9999, trainable=names)
+    _, g32, _ = go.loss_and_grads(prob, params, 9999, trainable=names)
+    set_params(net, params)
+    loss = net(epoch=9999)
+    loss.backward()
+    assert abs(float(loss.detach()) - float(loss64)) <= 2e-6 * abs(float(loss64))
+    for k in names:
+        m = getattr(net, k).grad.detach().cpu()
+        m = m[:, :prob.P] if k == "im_depthmaps" else m.reshape(g64[k].shape)
+        ok, err, ref_err = grad_close(k, m, g32[k], g64[k])
+        assert ok, (k, err, ref_err)
