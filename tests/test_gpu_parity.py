@@ -876,8 +876,6 @@ def test_confidence_transforms_against_live_oracle(cuda_device, conf):
     init_fun.init_minimum_spanning_tree(net, niter_PnP=10)
     T_ref = go.pw_pose_matrices(prob, params["pw_poses"])
     assert float((net.get_pw_poses().detach().cpu() - T_ref).abs().max()) < 5e-5
-    for c, r in zip(net.get_conf(), [prob.conf_trf(x) for x in prob.im_conf] if hasattr(prob, "conf_trf") else []):
-        assert torch.allclose(c.cpu(), r.reshape(c.shape), rtol=1e-6, atol=1e-6)
     p64 = {k: v.double() for k, v in params.items()}
     names = list(go.TRAINABLE)
     loss64, g64, _ = go.loss_and_grads(prob.to(torch.float64), p64, 9999, trainable=names)
