@@ -889,3 +889,31 @@ def test_confidence_transforms_against_live_oracle(cuda_device, conf):
         m = m[:, :prob.P] if k == "im_depthmaps" else m.reshape(g64[k].shape)
         ok, err, ref_err = grad_close(k, m, g32[k], g64[k])
         assert ok, (k, err, ref_err)
+
+
+@pytest.mark.xfail(strict=False, reason="added after round 1's GPU minutes were spent: first hardware run pending (an XPASS means confirmed)")
+def test_preset_frozen_focals_like_use_gt_focal(cuda_device):
+    """tool/pose_test.py:181-193 (--use_gt_focal): per-frame focals preset and frozen, then the canonical init='mst' run.  The
+    initialisation leaves the preset focals alone, the loop does not step them, and the run follows the oracle's (which is
+    pinned on this flow against the real reference: test_oracle_live.py::test_preset_frozen_focals_like_use_gt_focal)."""
+    scene = make_scene(5, 32, 48, "swin-2-noncyclic", seed=83, with_flow=True)
+    kw = dict(CANONICAL_KW, num_total_iter=10, shared_focal=False)
+    gt_focals = [0.9 * 48 * (1 + 0.01 * n) for n in range(5)]
+    net = build(scene, kw)
+    net.preset_focal(gt_focals, requires_grad=False)
+    assert not net.im_focals.requires_grad
+    net.compute_global_alignment(init='mst', niter=0)
+    want = torch.tensor(gt_focals)
+    assert torch.allclose(net.get_focals().detach().cpu().reshape(-1), want, rtol=1e-6)
+
+    prob = go.problem_from_output(scene.output, scene.flow_ij, scene.flow_ji, **kw)
+    params, _ = go.mst_init(prob)
+    params["im_focals"] = (prob.focal_break * torch.log(want)).reshape(params["im_focals"].shape).float()
+    T_ref = go.pw_pose_matrices(prob, params["pw_poses"])
+    assert float((net.get_pw_poses().detach().cpu() - T_ref).abs().max()) < 5e-5
+    set_params(net, params)                                   # the same start for the loop
+    trainable = [k for k in go.TRAINABLE if k != "im_focals"]
+    _, losses, _ = go.run_alignment(prob, params, niter=10, schedule="linear", lr=0.01, trainable=trainable)
+    loss = net.compute_global_alignment(init=None, niter=10, schedule="linear", lr=0.01)
+    assert abs(loss - losses[-1]) <= 5e-5 * abs(losses[-1]), (loss, losses[-1])
+    assert torch.equal(net.im_focals.detach().cpu().reshape(-1), params["im_focals"].reshape(-1))     # never stepped

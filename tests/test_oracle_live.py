@@ -141,3 +141,34 @@ def go_shape(prob, name, value):
     if name == "im_focals":
         return (-1, 1)
     return tuple(value.shape)
+
+
+def test_preset_frozen_focals_like_use_gt_focal():
+    """tool/pose_test.py:181-193 (--use_gt_focal): per-frame focals preset and frozen (preset_focal(..., requires_grad=False),
+    optimizer.py:352-363), then the canonical init='mst' run.  The MST initialisation leaves the preset focals alone
+    (_set_focal only writes trainable parameters, :392-396) and the loop does not step them."""
+    rh.import_reference()
+    import dust3r.cloud_opt_flow.init_im_poses as init_fun
+    sc = make_scene(5, 32, 48, "swin-2-noncyclic", seed=83, with_flow=True)
+    kw = dict(CANONICAL_KW, num_total_iter=10, shared_focal=False)
+    gt_focals = [0.9 * 48 * (1 + 0.01 * n) for n in range(5)]
+    ref = rh.build_reference_scene(sc, **kw)
+    with rh.quiet():
+        ref.preset_focal(gt_focals, requires_grad=False)
+        init_fun.init_minimum_spanning_tree(ref, niter_PnP=10)
+    assert not ref.im_focals.requires_grad
+    assert torch.allclose(ref.get_focals().detach().reshape(-1), torch.tensor(gt_focals), rtol=1e-6)
+
+    prob = go.problem_from_output(sc.output, sc.flow_ij, sc.flow_ji, **kw)
+    params, _ = go.mst_init(prob)
+    params["im_focals"] = (prob.focal_break * torch.log(torch.tensor(gt_focals))).reshape(params["im_focals"].shape).float()
+    for k in ("pw_poses", "im_poses", "im_focals", "im_depthmaps"):
+        r = getattr(ref, k).detach()
+        assert torch.allclose(params[k].reshape(r.shape), r, rtol=1e-5, atol=1e-6), k
+    trainable = [k for k in go.TRAINABLE if k != "im_focals"]
+    with rh.quiet():
+        final = ref.compute_global_alignment(init=None, niter=10, schedule="linear", lr=0.01)
+    end, losses, _ = go.run_alignment(prob, params, niter=10, schedule="linear", lr=0.01, trainable=trainable)
+    assert abs(losses[-1] - float(final)) <= 1e-4 * abs(float(final))
+    assert torch.equal(end["im_focals"], params["im_focals"])
+    assert torch.allclose(ref.get_focals().detach().reshape(-1), torch.tensor(gt_focals), rtol=1e-6)
