@@ -212,7 +212,8 @@ class PointCloudOptimizer(nn.Module):
         self._peers, self._peers_tried = None, False
         self._prior_ready = False
         if want_flow:
-            self.flow_ij, self.flow_ji, self.flow_valid_mask_i, self.flow_valid_mask_j = self.get_flow(sintel_ckpt)
+            self.flow_ij, self.flow_ji, valid_i, valid_j = self.get_flow(sintel_ckpt)
+            self._flow_valid = [valid_i, valid_j]     # None: evaluated from the packed flow planes when somebody reads them
             # on a side stream: the initialisation does not read the flow planes, its kernels need not queue behind
             # these copies; the hot loop joins (self._join_uploads)
             self._upload_stream = torch.cuda.Stream(device)
@@ -457,11 +458,44 @@ class PointCloudOptimizer(nn.Module):
             raise NotImplementedError("flow_loss_weight > 0 needs optical flow: pass flow=(flow_ij, flow_ji) to "
                                       "global_aligner / PointCloudOptimizer (RAFT inference is out of scope)")
         flow_ij, flow_ji = self._injected_flow[:2]
-        n = flow_ij.shape[0]
-        H, W = flow_ij.shape[-2:]
-        # the reference stores OccMask validity maps it never reads (optimizer.py:105-111): all-true, broadcast views
-        ones = torch.ones((1, 1, 1, 1), dtype=torch.bool).expand(n, 1, H, W)
-        return flow_ij, flow_ji, ones, ones
+        # the reference also returns OccMask validity maps, which it stores and never reads (optimizer.py:105-111,146-147):
+        # None here - flow_valid_mask_i / _j evaluate them on the device from the packed flow planes on first access
+        return flow_ij, flow_ji, None, None
+
+    def _flow_valid_mask(self, side):
+        """reference goem_opt.py:575-618 (OccMask, th = 3): (E,1,H,W) bool, forward flow = this side's, backward = the other's."""
+        if getattr(self, '_flow_valid', None) is None:
+            return None
+        if self._flow_valid[side] is None:
+            if self._shard is not None and int(self._shard['world']) > 1:
+                raise NotImplementedError("flow validity maps on a frame-window sharded problem (an edge's two flow planes may "
+                                          "live on different GPUs)")
+            E, (H, W) = self.n_edges, self.imshape
+            fwd = torch.tensor([self._lslot[2 * e + side] for e in range(E)], dtype=torch.int32).to(self._device)
+            bwd = torch.tensor([self._lslot[2 * e + 1 - side] for e in range(E)], dtype=torch.int32).to(self._device)
+            valid = torch.empty((E, H * W), dtype=torch.uint8, device=self._device)
+            with torch.cuda.device(self._device):
+                self._join_uploads()
+                _lib.check(self._lib.a3r_occ_masks(_lib.ptr(self._bufs.flow), self._plan.pix_stride, _lib.ptr(fwd), _lib.ptr(bwd), E, H, W,
+                                                   3.0, _lib.ptr(valid), self._stream()), "a3r_occ_masks")
+            self._flow_valid[side] = valid.view(E, 1, H, W).bool()
+        return self._flow_valid[side]
+
+    @property
+    def flow_valid_mask_i(self):
+        return self._flow_valid_mask(0)
+
+    @flow_valid_mask_i.setter
+    def flow_valid_mask_i(self, v):
+        self._flow_valid = [v, (getattr(self, '_flow_valid', None) or [None, None])[1]]
+
+    @property
+    def flow_valid_mask_j(self):
+        return self._flow_valid_mask(1)
+
+    @flow_valid_mask_j.setter
+    def flow_valid_mask_j(self, v):
+        self._flow_valid = [(getattr(self, '_flow_valid', None) or [None, None])[0], v]
 
     # =====================================================================================
     # properties (reference base_opt.py:159-173)

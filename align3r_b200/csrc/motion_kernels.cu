@@ -98,9 +98,57 @@ __global__ void __launch_bounds__(256) k_motion_masks(const float* __restrict__ 
     }
 }
 
+// ---- flow validity maps (reference goem_opt.py:575-618 OccMask, called by get_flow, optimizer.py:146-147) ----
+// valid = |(fwd + bwd(p + fwd)).x + (...).y| < th  and  p + fwd inside the image; bwd sampled bilinearly with zero padding
+// through torch.grid_sample's align_corners=True coordinate round trip (x -> x / ((W-1)/2) - 1 -> ((g + 1) / 2) (W-1)).
+__global__ void __launch_bounds__(256) k_occ_mask(const float* __restrict__ flow, int64_t pix_stride, const int32_t* __restrict__ fwd_slot,
+                                                  const int32_t* __restrict__ bwd_slot, int H, int W, float th, uint8_t* __restrict__ valid) {
+    const int k = blockIdx.y, P = H * W;
+    const float2* fw = reinterpret_cast<const float2*>(flow) + (int64_t)fwd_slot[k] * pix_stride;
+    const float2* bw = reinterpret_cast<const float2*>(flow) + (int64_t)bwd_slot[k] * pix_stride;
+    const float hx = (float)((double)(W - 1) / 2.0), hy = (float)((double)(H - 1) / 2.0);
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < P; pix += gridDim.x * blockDim.x) {
+        const int v = pix / W, u = pix - v * W;
+        const float2 f = fw[pix];
+        const float x = (float)u + f.x, y = (float)v + f.y;
+        const bool inside = !(x < 0.f || x > (float)(W - 1) || y < 0.f || y > (float)(H - 1));
+        const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(__fsub_rn(__fdiv_rn(x, hx), 1.f), 1.f), 2.f), (float)(W - 1));
+        const float iy = __fmul_rn(__fdiv_rn(__fadd_rn(__fsub_rn(__fdiv_rn(y, hy), 1.f), 1.f), 2.f), (float)(H - 1));
+        const float fx0 = floorf(ix), fy0 = floorf(iy);
+        const float wx1 = ix - fx0, wy1 = iy - fy0, wx0 = (fx0 + 1.f) - ix, wy0 = (fy0 + 1.f) - iy;
+        float sx = 0.f, sy = 0.f;
+        if (fabsf(fx0) < 1e9f && fabsf(fy0) < 1e9f) {               // NaN / huge flows sample nothing
+            const int x0 = (int)fx0, y0 = (int)fy0;
+            const float wgt[4] = {wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1};            // nw, ne, sw, se
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int xx = x0 + (t & 1), yy = y0 + (t >> 1);
+                if (xx >= 0 && xx < W && yy >= 0 && yy < H) {
+                    const float2 b = bw[yy * W + xx];
+                    sx += b.x * wgt[t];
+                    sy += b.y * wgt[t];
+                }
+            }
+        }
+        const float inc = fabsf((sx + f.x) + (sy + f.y));
+        valid[(int64_t)k * P + pix] = (inc < th && inside) ? 1 : 0;
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+int a3r_occ_masks(const float* flow, int64_t pix_stride, const int32_t* fwd_slot, const int32_t* bwd_slot, int32_t n_items, int32_t H,
+                  int32_t W, float th, uint8_t* valid, void* stream) {
+    if (n_items < 0 || H < 2 || W < 2 || (int64_t)H * W > pix_stride)
+        return a3r_fail(A3R_E_ARG, "a3r_occ_masks: n_items %d, image %dx%d, pix_stride %lld", n_items, H, W, (long long)pix_stride);
+    if (n_items == 0) return A3R_OK;
+    if (!flow || !fwd_slot || !bwd_slot || !valid) return a3r_fail(A3R_E_ARG, "a3r_occ_masks: NULL argument");
+    k_occ_mask<<<dim3(32, (unsigned)n_items), 256, 0, (cudaStream_t)stream>>>(flow, pix_stride, fwd_slot, bwd_slot, H, W, th, valid);
+    A3R_CUDA(cudaGetLastError());
+    return A3R_OK;
+}
 
 int a3r_motion_minmax(const float* predw, const float* flow, int64_t pix_stride, const int32_t* item_slot, const int32_t* item_dslot,
                       const int32_t* item_hw, const float* item_cam, int32_t n_items, uint32_t* minmax, void* stream) {

@@ -284,6 +284,15 @@ int a3r_motion_masks(const float *predw, const float *flow, int64_t pix_stride, 
                      int32_t n_local_frames, float thre, uint8_t *static_mask, uint8_t *dynamic_mask, float *mean_out,
                      void *stream);
 
+/* ---- pre-step: flow validity maps (reference goem_opt.py:575-618 OccMask, computed by get_flow, optimizer.py:146-147, and
+ *      stored as flow_valid_mask_i / _j; the loss never reads them) ----
+ * Item k: forward flow = the flow plane of local slot fwd_slot[k], backward flow = the plane of bwd_slot[k] (the edge's other
+ * side; uniform H x W).  valid [n_items][H*W] = 1 where the forward-backward inconsistency |sum over both channels of
+ * (fwd + bwd sampled at p + fwd)| is below th (3 in the reference) and p + fwd stays inside the image.  Index arrays are
+ * device int32. */
+int a3r_occ_masks(const float *flow, int64_t pix_stride, const int32_t *fwd_slot, const int32_t *bwd_slot, int32_t n_items,
+                  int32_t H, int32_t W, float th, uint8_t *valid, void *stream);
+
 /* ---- MST initialisation solves (reference init_im_poses.py:446-465, post_process.py:36-58) ---- */
 /* count weighted similarity registrations y ~ s R x + t between two slots living on the same frame:
  * x = slot xs[k] (weights = raw conf = conf_untrf(w)), y = slot ys[k]; P[k] valid pixels.

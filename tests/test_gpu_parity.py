@@ -917,3 +917,27 @@ def test_preset_frozen_focals_like_use_gt_focal(cuda_device):
     loss = net.compute_global_alignment(init=None, niter=10, schedule="linear", lr=0.01)
     assert abs(loss - losses[-1]) <= 5e-5 * abs(losses[-1]), (loss, losses[-1])
     assert torch.equal(net.im_focals.detach().cpu().reshape(-1), params["im_focals"].reshape(-1))     # never stepped
+
+
+@pytest.mark.xfail(strict=False, reason="added after round 1's GPU minutes were spent: first hardware run pending (an XPASS means confirmed)")
+def test_flow_validity_maps(cuda_device):
+    """flow_valid_mask_i / _j (reference get_flow -> OccMask, goem_opt.py:575-618; stored, never read by the loss): evaluated
+    by k_occ_mask from the packed flow planes on first access, against the oracle's restatement (pinned live on the reference's
+    OccMask).  Noisy flows exercise both outcomes; a pixel may differ only inside a rounding band around the threshold / border."""
+    scene = make_scene(5, 32, 48, "swin-2-noncyclic", seed=91, with_flow=True)
+    g = torch.Generator().manual_seed(5)
+    scene.flow_ij = scene.flow_ij + 6 * torch.randn(scene.flow_ij.shape, generator=g)
+    scene.flow_ji = scene.flow_ji + 6 * torch.randn(scene.flow_ji.shape, generator=g)
+    net = build(scene, dict(CANONICAL_KW, num_total_iter=10))
+    H, W = 32, 48
+    vv, uu = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    for mine, a, b in ((net.flow_valid_mask_i, scene.flow_ij, scene.flow_ji), (net.flow_valid_mask_j, scene.flow_ji, scene.flow_ij)):
+        want, inc = go.occ_mask(a, b, th=3.0)
+        mine = mine.cpu()
+        assert mine.dtype == torch.bool and mine.shape == want.shape
+        assert 0.02 < float(want.float().mean()) < 0.98
+        x, y = uu + a[:, 0], vv + a[:, 1]
+        border = torch.minimum(torch.minimum(x.abs(), (x - (W - 1)).abs()), torch.minimum(y.abs(), (y - (H - 1)).abs()))[:, None]
+        band = ((inc - 3.0).abs() < 1e-3) | (border < 1e-4)
+        assert bool(((mine == want) | band).all()), int(((mine != want) & ~band).sum())
+    assert net.flow_valid_mask_i is net.flow_valid_mask_i                      # evaluated once

@@ -172,3 +172,19 @@ def test_preset_frozen_focals_like_use_gt_focal():
     assert abs(losses[-1] - float(final)) <= 1e-4 * abs(float(final))
     assert torch.equal(end["im_focals"], params["im_focals"])
     assert torch.allclose(ref.get_focals().detach().reshape(-1), torch.tensor(gt_focals), rtol=1e-6)
+
+
+def test_flow_validity_maps():
+    """oracle occ_mask against the reference's OccMask (dust3r/utils/goem_opt.py:575-618) on the flows of a synthetic scene and
+    on flows that leave the image / disagree between the two directions."""
+    rh.import_reference()
+    from dust3r.utils.goem_opt import OccMask
+    sc = make_scene(5, 32, 48, "swin-2-noncyclic", seed=91, with_flow=True)
+    g = torch.Generator().manual_seed(5)
+    wild_ij = sc.flow_ij + 6 * torch.randn(sc.flow_ij.shape, generator=g)
+    wild_ji = sc.flow_ji + 6 * torch.randn(sc.flow_ji.shape, generator=g)
+    for a, b in ((sc.flow_ij, sc.flow_ji), (sc.flow_ji, sc.flow_ij), (wild_ij, wild_ji)):
+        want = OccMask(th=3.0)(a.clone(), b.clone())
+        mine, _ = go.occ_mask(a, b, th=3.0)
+        assert mine.shape == want.shape == (a.shape[0], 1, 32, 48) and torch.equal(mine, want.bool())
+    assert 0.02 < float(go.occ_mask(wild_ij, wild_ji)[0].float().mean()) < 0.98          # both outcomes are exercised
