@@ -112,3 +112,46 @@ def test_zero_weight_and_masked_pixels_have_no_gradient():
     assert loss == 0.0
     for k, v in grads.items():
         assert float(v.abs().max()) == 0.0, k
+
+
+def test_flow_validity_kernel_arithmetic_restated():
+    """k_occ_mask (csrc/motion_kernels.cu) restated operation by operation in numpy fp32 - the grid_sample coordinate round
+    trip, tap order nw / ne / sw / se with zero padding, |(sx + fx) + (sy + fy)| < th and the bounds test - against the oracle's
+    occ_mask (which equals the reference's OccMask, tests/test_oracle_live.py)."""
+    import numpy as np
+    import torch
+    from tests.helpers import go, make_scene
+    f32 = np.float32
+
+    def kernel(fw, bw, th=3.0):
+        _, H, W = fw.shape
+        hx, hy = f32((W - 1) / 2.0), f32((H - 1) / 2.0)
+        v, u = np.meshgrid(np.arange(H, dtype=f32), np.arange(W, dtype=f32), indexing="ij")
+        x, y = (u + fw[0]).astype(f32), (v + fw[1]).astype(f32)
+        inside = ~((x < 0) | (x > f32(W - 1)) | (y < 0) | (y > f32(H - 1)))
+        ix = ((((x / hx).astype(f32) - f32(1)) + f32(1)) / f32(2)).astype(f32) * f32(W - 1)
+        iy = ((((y / hy).astype(f32) - f32(1)) + f32(1)) / f32(2)).astype(f32) * f32(H - 1)
+        fx0, fy0 = np.floor(ix), np.floor(iy)
+        wx1, wy1, wx0, wy0 = ix - fx0, iy - fy0, (fx0 + 1) - ix, (fy0 + 1) - iy
+        x0, y0 = fx0.astype(np.int64), fy0.astype(np.int64)
+        sx, sy = np.zeros_like(x), np.zeros_like(x)
+        for t, wg in enumerate((wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1)):
+            xx, yy = x0 + (t & 1), y0 + (t >> 1)
+            ok = (xx >= 0) & (xx < W) & (yy >= 0) & (yy < H)
+            xs, ys = np.clip(xx, 0, W - 1), np.clip(yy, 0, H - 1)
+            sx = sx + np.where(ok, bw[0][ys, xs] * wg, 0).astype(f32)
+            sy = sy + np.where(ok, bw[1][ys, xs] * wg, 0).astype(f32)
+        inc = np.abs((sx + fw[0]) + (sy + fw[1]))
+        return (inc < th) & inside, inc
+
+    sc = make_scene(5, 32, 48, "swin-2-noncyclic", seed=91, with_flow=True)
+    g = torch.Generator().manual_seed(5)
+    wij = sc.flow_ij + 6 * torch.randn(sc.flow_ij.shape, generator=g)
+    wji = sc.flow_ji + 6 * torch.randn(sc.flow_ji.shape, generator=g)
+    for a, b in ((sc.flow_ij, sc.flow_ji), (wij, wji)):
+        want, inc = go.occ_mask(a, b)
+        for e in range(a.shape[0]):
+            m, i2 = kernel(a[e].numpy(), b[e].numpy())
+            band = np.abs(inc[e, 0].numpy() - 3.0) < 1e-3
+            assert ((m == want[e, 0].numpy()) | band).all()
+            assert float(np.abs(i2 - inc[e, 0].numpy()).max()) < 1e-4
