@@ -63,3 +63,7 @@ def test_argument_errors_are_reported_not_crashed():
     assert rc == -1 and b"NULL" in lib.a3r_last_error()
     with pytest.raises(RuntimeError, match="a3r_ga_prepare"):
         _lib.check(rc, "a3r_ga_prepare")
+    assert lib.a3r_occ_masks(None, 128, None, None, 1, 1, 8, 3.0, None, None) == -1 and b"a3r_occ_masks" in lib.a3r_last_error()
+    assert lib.a3r_occ_masks(None, 128, None, None, 1, 8, 8, 3.0, None, None) == -1 and b"NULL" in lib.a3r_last_error()
+    assert lib.a3r_occ_masks(None, 128, None, None, 0, 8, 8, 3.0, None, None) == 0
+    assert lib.a3r_occ_masks(None, 32, None, None, 1, 8, 8, 3.0, None, None) == -1          # the image does not fit the planes
