@@ -26,3 +26,14 @@ class Phases:
     def done(self):
         if self.on:
             print(f"[a3r {self.name} ms] " + "  ".join(self.rows), file=sys.stderr, flush=True)
+
+
+def host_workers(n_jobs, shard=None):
+    """Size of a host thread pool (RANSAC-PnP solves): the box's cores are shared by the ranks of a frame-window sharded
+    job - every rank starting cpu_count() workers oversubscribes the host 8x at 8 GPUs.  A3R_HOST_THREADS overrides."""
+    import os
+    env = os.environ.get("A3R_HOST_THREADS")
+    if env:
+        return max(1, min(int(n_jobs), int(env)))
+    world = int(shard['world']) if shard is not None else 1
+    return max(1, min(int(n_jobs), (os.cpu_count() or 1) // max(world, 1)))

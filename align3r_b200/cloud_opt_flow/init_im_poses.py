@@ -22,7 +22,7 @@ import scipy.sparse as sp
 import torch
 
 from .. import _lib
-from .._timing import Phases
+from .._timing import Phases, host_workers
 from .commons import edge_str, signed_log1p
 
 
@@ -363,7 +363,7 @@ def init_minimum_spanning_tree(self, save_score_path=None, save_score_only=False
             pts = (Xn[:, 0:1] * A[:, 0] + Xn[:, 1:2] * A[:, 1] + Xn[:, 2:3] * A[:, 2] + t32).reshape(h, w, 3)
             return n, fast_pnp(pts, im_focals[n], msk.numpy(), niter_PnP=niter_PnP)
 
-        with ThreadPoolExecutor(max_workers=min(len(jobs), _os.cpu_count() or 1)) as pool:
+        with ThreadPoolExecutor(max_workers=host_workers(len(jobs), self._shard)) as pool:
             for n, res in pool.map(_solve, jobs):
                 if res:
                     pnp[n, 0] = 1
@@ -491,7 +491,7 @@ def init_from_known_poses(self, niter_PnP=10, min_conf_thr=3):
 
     pw = np.zeros((E, 8), dtype=np.float32)
     best = {}
-    with ThreadPoolExecutor(max_workers=min(len(jobs), _os.cpu_count() or 1)) as pool:
+    with ThreadPoolExecutor(max_workers=host_workers(len(jobs), self._shard)) as pool:
         results = dict(pool.map(_solve, jobs))
     for e, (i, j) in enumerate(self.edges):
         res = results[e]

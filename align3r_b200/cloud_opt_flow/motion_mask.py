@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from .. import _lib
-from .._timing import Phases
+from .._timing import Phases, host_workers
 
 PAIR_MIN_CONF_THR = 3.0      # the PairViewer is built with the base class default (reference base_opt.py:66, optimizer.py:188)
 
@@ -86,7 +86,7 @@ def get_motion_mask_from_pairs(self, view1, view2, pred1, pred2):
             k, first, r, conf, focal = job
             return k, first, _pair_pnp(_row(pts2, r).reshape(H, W, 3), conf.reshape(H, W) > PAIR_MIN_CONF_THR, float(focal), H, W)
 
-        with ThreadPoolExecutor(max_workers=min(len(jobs), _os.cpu_count() or 1)) as pool:
+        with ThreadPoolExecutor(max_workers=host_workers(len(jobs), self._shard)) as pool:
             for k, first, pose in pool.map(_solve, jobs):
                 rel[k] = (first, pose)
     ph.mark(f'pnp({len(jobs)})')

@@ -32,6 +32,20 @@ from . import init_im_poses as init_fun
 _TRAIN_ORDER = ("pw_poses", "im_depthmaps", "im_poses", "im_focals")   # reference base_opt.py:514 order
 
 
+def _row_hw(rows, r):
+    """(H, W) of row r of a stack of pointmaps: one (E,H,W,3) array-like (a tensor, or rows drawn on demand) or a list of
+    per-edge (H,W,3) tensors of varying shapes."""
+    shp = getattr(rows, 'shape', None)
+    if shp is not None and len(shp) == 4:
+        return (int(shp[1]), int(shp[2]))
+    return tuple(rows[r].shape[0:2])
+
+
+def _is_stack(rows):
+    shp = getattr(rows, 'shape', None)
+    return shp is not None and hasattr(rows, '__getitem__') and not isinstance(rows, (list, tuple)) and len(shp) >= 3
+
+
 class _SlotDict:
     """Read-only dict-like view ``'i_j' -> tensor`` over the packed slot planes (the reference keeps
     ParameterDicts pred_i / pred_j / conf_i / conf_j, base_opt.py:88-100)."""
@@ -338,7 +352,7 @@ class PointCloudOptimizer(nn.Module):
         imshapes = [None] * self.n_imgs
         for e, r in self._row_of_edge.items():
             i, j = self.edges[e]
-            for n, shp in ((i, tuple(pred_i[r].shape[0:2])), (j, tuple(pred_j[r].shape[0:2]))):
+            for n, shp in ((i, _row_hw(pred_i, r)), (j, _row_hw(pred_j, r))):
                 if imshapes[n]:
                     assert imshapes[n] == shp, f'incorrect shape for image {n}'
                 imshapes[n] = shp
@@ -387,16 +401,16 @@ class PointCloudOptimizer(nn.Module):
                 k = 0
                 while k < len(todo):
                     e0, r0 = todo[k]
-                    shp = tuple(pts[r0].shape[0:2])
+                    shp = _row_hw(pts, r0)
                     m = 1
                     while (k + m < len(todo) and m < chunk and todo[k + m][1] == r0 + m
-                           and tuple(pts[r0 + m].shape[0:2]) == shp):
+                           and _row_hw(pts, r0 + m) == shp):
                         m += 1
                     P = shp[0] * shp[1]
                     # staged through the problem's one staging area: copy(k+1) queues behind pack(k) on this stream
                     dp = b.stage[:m * P * 3].view(m, P, 3)
                     dc = b.stage[m * P * 3:m * P * 4].view(m, P)
-                    if isinstance(pts, torch.Tensor):
+                    if _is_stack(pts) and _is_stack(conf):      # one (E,H,W,3) tensor, or rows drawn on the device on demand
                         dp.copy_(pts[r0:r0 + m].reshape(m, P, 3), non_blocking=True)
                         dc.copy_(conf[r0:r0 + m].reshape(m, P), non_blocking=True)
                     else:
@@ -868,6 +882,36 @@ class PointCloudOptimizer(nn.Module):
                 return None
         self._peers, self._peer_region, self._peer_opened, self._peer_tag = peers, region, opened, 0
         return peers
+
+    def close(self):
+        """Releases what a frame-window sharded run holds outside torch's allocator: the CUDA-IPC mappings of the peers'
+        exchange regions and this rank's own region (a3r_peer_alloc).  Collective on sharded problems (every rank calls it:
+        a barrier makes sure no peer still reads the region); a no-op otherwise.  The optimiser stays usable - the next
+        sharded loop maps the peers again."""
+        if getattr(self, '_peers', None) is None:
+            return
+        import torch.distributed as dist
+        torch.cuda.synchronize(self._device)
+        if dist.is_available() and dist.is_initialized():
+            dist.barrier(group=self._shard.get('group'))
+        with torch.cuda.device(self._device):
+            for ptr in self._peer_opened:
+                self._lib.a3r_peer_close(ptr)
+            if self._peer_region.value:
+                self._lib.a3r_peer_free(self._peer_region)
+        self._peers, self._peers_tried, self._peer_opened = None, False, []
+
+    def __del__(self):
+        # not collective: only this process's mappings of the peers' regions are dropped here; the own region is released
+        # by close() (a peer may still be reading it)
+        try:
+            if getattr(self, '_peers', None) is not None:
+                with torch.cuda.device(self._device):
+                    for ptr in self._peer_opened:
+                        self._lib.a3r_peer_close(ptr)
+                self._peer_opened = []
+        except Exception:
+            pass
 
     def _phase_accumulate(self, mode):
         """parameter maps + fused forward/backward scan over this device's pixel-slots."""

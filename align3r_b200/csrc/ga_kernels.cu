@@ -299,6 +299,17 @@ constexpr int K2_CLUSTER = 8;
 constexpr int K2_THREADS = 256;
 constexpr int K2_MAX_FRAMES = 1280;        // cameras in shared memory: 160 B each (200 KB of the 227 KB opt-in limit); more: global scratch
 
+// diagnostic phase trace of K2 (a3r_debug_k2_trace): globaltimer stamps of thread 0 of every CTA at the phase boundaries
+__device__ unsigned long long g_k2_trace[K2_CLUSTER * 8];
+__device__ int g_k2_trace_on = 0;
+__device__ __forceinline__ void k2_stamp(int slot) {
+    if (g_k2_trace_on && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_k2_trace[blockIdx.x * 8 + slot] = t;
+    }
+}
+
 __device__ __forceinline__ void cluster_barrier() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -379,8 +390,10 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
     const double tsw = (double)p.temporal_smoothing_weight, tw = (double)p.translation_weight;
 
     // ---------------- phase A: cameras, loss assembly + gate (reference optimizer.py:538-557), chains ----------------
+    k2_stamp(0);
     if (shared_focal && tid == 0) { s_foc[0] = p.im_focals[0]; s_foc[1] = p.im_focals_m[0]; s_foc[2] = p.im_focals_v[0]; }
     fill_cameras(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, N, shared_focal, fb, fr);
+    k2_stamp(1);
     {
         double l_align = 0, l_temp = 0, l_prior = 0;
         if (p.depth_regularize_weight > 0.f)
@@ -409,6 +422,7 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
         }
         __syncthreads();
     }
+    k2_stamp(2);
     //   chain items: [0,N) alignment part of frame n | [N, N+2E) flow chain of a slot | [.., +N-1) temporal pair | [.., +E) edge
     //   (frame_grad, scal[S_GSUM] and scal[S_GPHI] are zero on entry: zeroed by the previous call's tail / the entry point)
     {
@@ -444,7 +458,9 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
             }
         }
     }
+    k2_stamp(3);
     cluster_barrier();
+    k2_stamp(4);
 
     // ---------------- phase B: gradients of the small parameters + torch.optim.Adam ----------------
     //   items: [0,E) pairwise pose | [E, E+N) image pose
@@ -479,7 +495,9 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
             }
         }
     }
+    k2_stamp(5);
     cluster_barrier();
+    k2_stamp(6);
 
     // ---------------- phase C: the shared focal, the parameter maps of the next iteration, zero the scratch ----------------
     // Every CTA steps the shared focal from the values it saved in phase A (nobody has written them yet) and the complete
@@ -515,6 +533,7 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
     }
     for (int i = vt; i < N * FG_STRIDE; i += nvt) p.frame_grad[i] = 0.0;
     if (vt == 0) { p.scal[S_GSUM] = 0.0; p.scal[S_GPHI] = 0.0; }
+    k2_stamp(7);
 }
 
 // ==========================================================================================
@@ -1028,6 +1047,15 @@ int a3r_ga_run_peers(const A3rProblem* p, const A3rPeers* peers, uint32_t tag0, 
         if (int rc = update_forked(p, modes[k], &steps[k], st, lane, &pending, k + 1 < count)) return rc;
     }
     if (pending) A3R_CUDA(cudaStreamWaitEvent(st, lane->join, 0));
+    return A3R_OK;
+}
+
+// diagnostic: switch the K2 phase trace on / off and read the stamps of the last launch (nanoseconds of %globaltimer;
+// [cta][8]: start, cameras, loss + gate, chains, barrier 1, phase B, barrier 2, end).  Synchronises the device.
+int a3r_debug_k2_trace(int enable, unsigned long long* out) {
+    A3R_CUDA(cudaDeviceSynchronize());
+    if (out) A3R_CUDA(cudaMemcpyFromSymbol(out, g_k2_trace, sizeof(unsigned long long) * K2_CLUSTER * 8));
+    A3R_CUDA(cudaMemcpyToSymbol(g_k2_trace_on, &enable, sizeof(int)));
     return A3R_OK;
 }
 

@@ -191,13 +191,14 @@ def _edge_generator(seed: int, i: int, j: int, n: int) -> torch.Generator:
 def make_scene(n_frames: int, H: int, W: int, scene_graph: str = "swin-5-noncyclic", seed: int = 0,
                with_flow: bool = True, with_img: bool = False, edges=None,
                pixel_noise: float = 0.01, frame_noise: float = 0.0, flow_noise: float = 0.5,
-               motion: float = 1.0, pin_memory: bool = False) -> SyntheticScene:
+               motion: float = 1.0, pin_memory: bool = False, workers: int = 1) -> SyntheticScene:
     """Build the pairwise-prediction dict for a synthetic video.
 
     ``edges`` restricts generation to a subset of the graph's directed edges (used by the
     frame-window sharded multi-GPU path: each rank generates only the edges it touches).
     ``frame_noise`` > 0 makes the noise per-frame coherent (X_n (1+eps_n)), the
     "Depth-Pro-conditioned" variant of SURVEY.md section 8(d).
+    ``workers`` > 1 draws the edges on a thread pool (every edge has its own generator: same tensors, bit for bit).
     """
     all_edges = make_edge_list(n_frames, scene_graph)
     edges = list(all_edges) if edges is None else [tuple(e) for e in edges]
@@ -218,18 +219,37 @@ def make_scene(n_frames: int, H: int, W: int, scene_graph: str = "swin-5-noncycl
         g = torch.Generator().manual_seed(seed * 31 + 5)
         feps = 1 + frame_noise * torch.randn(n_frames, generator=g, dtype=torch.float64)
 
+    import threading
+    lock = threading.Lock()
     cam_cache: dict = {}
 
     def cam_pts(n):
-        if n not in cam_cache:
-            if len(cam_cache) > 16:
-                cam_cache.pop(next(iter(cam_cache)))
+        with lock:
+            p = cam_cache.get(n)
+        if p is None:
             p = gt.cam_points(n)
-            cam_cache[n] = p * feps[n] if feps is not None else p
-        return cam_cache[n]
+            p = p * feps[n] if feps is not None else p
+            with lock:
+                if len(cam_cache) > 32:
+                    cam_cache.pop(next(iter(cam_cache)))
+                cam_cache[n] = p
+        return p
 
     flow_cache: dict = {}
-    for e, (i, j) in enumerate(edges):
+
+    def flow_of(s, t):
+        with lock:
+            f = flow_cache.get((s, t))
+        if f is None:
+            f = ego_flow(gt, s, t).float()
+            with lock:
+                if len(flow_cache) > 96:
+                    flow_cache.pop(next(iter(flow_cache)))
+                flow_cache[(s, t)] = f
+        return f
+
+    def draw(e):
+        i, j = edges[e]
         g = _edge_generator(seed, i, j, n_frames)
         s_ij = 1.0 + 0.1 * float(torch.rand(1, generator=g))
         Ti, Tj = torch.from_numpy(gt.cam2world[i]), torch.from_numpy(gt.cam2world[j])
@@ -242,13 +262,22 @@ def make_scene(n_frames: int, H: int, W: int, scene_graph: str = "swin-5-noncycl
         conf2[e] = 1 + 3 * torch.rand(H, W, generator=g)
         if with_flow:
             for (s, t, dst) in ((i, j, flow_ij), (j, i, flow_ji)):
-                if (s, t) not in flow_cache:
-                    if len(flow_cache) > 64:
-                        flow_cache.pop(next(iter(flow_cache)))
-                    flow_cache[(s, t)] = ego_flow(gt, s, t).float()
-                f = flow_cache[(s, t)] + flow_noise * torch.randn(2, H, W, generator=g)
+                f = flow_of(s, t) + flow_noise * torch.randn(2, H, W, generator=g)
                 f = f + masks[s][None] * (20 * torch.rand(2, H, W, generator=g) - 10)
                 dst[e] = f
+
+    if workers > 1 and E > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        nthr = torch.get_num_threads()
+        torch.set_num_threads(1)                 # the pool is the parallelism; per-edge ops are small
+        try:
+            with ThreadPoolExecutor(max_workers=int(workers)) as pool:
+                list(pool.map(draw, range(E)))
+        finally:
+            torch.set_num_threads(nthr)
+    else:
+        for e in range(E):
+            draw(e)
 
     idx1 = [i for i, _ in edges]
     idx2 = [j for _, j in edges]
@@ -267,6 +296,189 @@ def make_scene(n_frames: int, H: int, W: int, scene_graph: str = "swin-5-noncycl
     pred2 = {"pts3d_in_other_view": pts2, "conf": conf2}
     meta = dict(n_frames=n_frames, H=H, W=W, scene_graph=scene_graph, seed=seed, n_edges_total=len(all_edges))
     return SyntheticScene(edges, view1, view2, pred1, pred2, flow_ij, flow_ji, masks, gt, meta)
+
+
+# ---------------------------------------------------------------------------------------
+# long videos: the same recipe drawn on the GPU, row by row, when the aligner packs them
+# ---------------------------------------------------------------------------------------
+class DeviceRows:
+    """(E, *row_shape) float32 rows that are drawn on a CUDA device when somebody indexes them.
+
+    The 1000-frame workload (BASELINE configs[4]) has 70 GB of pairwise predictions: drawing them with the host
+    generator takes minutes per rank and a pinned host copy of that size.  This sequence hands the aligner's packing
+    loop device tensors instead: ``rows[k]``, ``rows[a:b]`` and ``rows[[k0, k1, ...]]`` return freshly drawn rows; every
+    row has its own Philox stream seeded by (seed, i, j, kind), so any rank draws the same values for the same edge.
+    Input fabrication, not part of the alignment path.
+    """
+
+    def __init__(self, n_rows, row_shape, draw, device):
+        self.shape = (int(n_rows),) + tuple(row_shape)
+        self._draw, self.device, self.dtype = draw, torch.device(device), torch.float32
+
+    def __len__(self):
+        return self.shape[0]
+
+    def numel(self):
+        return int(np.prod(self.shape))
+
+    def element_size(self):
+        return 4
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            k = list(range(*k.indices(self.shape[0])))
+        if isinstance(k, (list, tuple)):
+            return torch.stack([self._draw(int(r)) for r in k]) if len(k) else torch.empty((0,) + self.shape[1:], device=self.device)
+        return self._draw(int(k))
+
+
+def make_scene_device(n_frames: int, H: int, W: int, scene_graph: str = "swin-5-noncyclic", seed: int = 0, device="cuda",
+                      edges=None, pixel_noise: float = 0.01, flow_noise: float = 0.5, motion: float = 1.0) -> SyntheticScene:
+    """``make_scene``'s recipe (same ground truth, same noise model, same per-pair scales) with every per-edge tensor a
+    ``DeviceRows`` sequence drawn on ``device`` on demand.  The values differ from the host generator's (another random
+    stream); ranks agree with each other.  The dynamic masks are host tensors as in ``make_scene``."""
+    device = torch.device(device)
+    all_edges = make_edge_list(n_frames, scene_graph)
+    edges = list(all_edges) if edges is None else [tuple(e) for e in edges]
+    E = len(edges)
+    gt = make_ground_truth(n_frames, H, W, motion)
+    masks = [frame_dynamic_mask(seed, n, H, W) for n in range(n_frames)]
+    cams = torch.from_numpy(gt.cam2world).to(device)
+    K = torch.from_numpy(gt.intrinsics()).to(device)
+    v, u = torch.meshgrid(torch.arange(H, dtype=torch.float64, device=device), torch.arange(W, dtype=torch.float64, device=device), indexing="ij")
+    cache: dict = {}
+
+    def cached(key, fn, limit=64):
+        if key not in cache:
+            if len(cache) > limit:
+                cache.pop(next(iter(cache)))
+            cache[key] = fn()
+        return cache[key]
+
+    def depth(n):
+        return 2 + 0.5 * torch.sin(u / 60 + 0.2 * n) * torch.cos(v / 45) + 0.05 * n
+
+    def cam_pts(n):
+        def fn():
+            d = depth(n)
+            return torch.stack((d * (u - gt.pp[0]) / gt.focal, d * (v - gt.pp[1]) / gt.focal, d), dim=-1)
+        return cached(("X", n), fn)
+
+    def flow_gt(s, t):
+        def fn():
+            relR = cams[t, :3, :3].T @ cams[s, :3, :3]
+            relt = cams[t, :3, :3].T @ (cams[s, :3, 3] - cams[t, :3, 3])
+            A = K @ relR @ torch.linalg.inv(K)
+            b = K @ relt
+            disp = 1.0 / (depth(s) + 1e-6)
+            q = [A[r, 0] * u + A[r, 1] * v + A[r, 2] + disp * b[r] for r in range(3)]
+            den = q[2] + 1e-6
+            return torch.stack((q[0] / den - u, q[1] / den - v), dim=0).float()
+        return cached(("F", s, t), fn)
+
+    def mask_dev(n):
+        return cached(("M", n), lambda: masks[n].to(device))
+
+    def gen(i, j, kind):
+        g = torch.Generator(device=device)
+        g.manual_seed((((seed * 1000003 + i) * 1000003 + j) * 16 + kind) % (1 << 62))
+        return g
+
+    def scale(i, j):
+        return 1.0 + 0.1 * float(torch.rand(1, generator=_edge_generator(seed, i, j, n_frames)))
+
+    def pts1(e):
+        i, j = edges[e]
+        return (scale(i, j) * cam_pts(i)).float() + pixel_noise * torch.randn(H, W, 3, generator=gen(i, j, 0), device=device)
+
+    def pts2(e):
+        i, j = edges[e]
+        rel = torch.linalg.inv(cams[i]) @ cams[j]
+        x = cam_pts(j) @ rel[:3, :3].T + rel[:3, 3]
+        return (scale(i, j) * x).float() + pixel_noise * torch.randn(H, W, 3, generator=gen(i, j, 1), device=device)
+
+    def conf(kind):
+        def fn(e):
+            i, j = edges[e]
+            return 1 + 3 * torch.rand(H, W, generator=gen(i, j, kind), device=device)
+        return fn
+
+    def flow(kind):
+        def fn(e):
+            i, j = edges[e]
+            s, t = (i, j) if kind == 4 else (j, i)
+            g = gen(i, j, kind)
+            f = flow_gt(s, t) + flow_noise * torch.randn(2, H, W, generator=g, device=device)
+            return f + mask_dev(s)[None] * (20 * torch.rand(2, H, W, generator=g, device=device) - 10)
+        return fn
+
+    idx1 = [i for i, _ in edges]
+    idx2 = [j for _, j in edges]
+    mstack = torch.stack(masks)
+    view1 = {"idx": idx1, "dynamic_mask": mstack[idx1]}
+    view2 = {"idx": idx2, "dynamic_mask": mstack[idx2]}
+    pred1 = {"pts3d": DeviceRows(E, (H, W, 3), pts1, device), "conf": DeviceRows(E, (H, W), conf(2), device)}
+    pred2 = {"pts3d_in_other_view": DeviceRows(E, (H, W, 3), pts2, device), "conf": DeviceRows(E, (H, W), conf(3), device)}
+    meta = dict(n_frames=n_frames, H=H, W=W, scene_graph=scene_graph, seed=seed, n_edges_total=len(all_edges), drawn_on=str(device))
+    return SyntheticScene(edges, view1, view2, pred1, pred2, DeviceRows(E, (2, H, W), flow(4), device),
+                          DeviceRows(E, (2, H, W), flow(5), device), masks, gt, meta)
+
+
+# ---------------------------------------------------------------------------------------
+# parameters by recipe: a point near the solution, reproducible anywhere without running an initialisation
+# ---------------------------------------------------------------------------------------
+def near_solution_params(gt: GroundTruth, edges, seed: int = 0, base_scale: float = 0.5, focal_break: float = 20.0,
+                         shared_focal: bool = True, wobble: float = 0.02):
+    """Parameter values of the aligner (the reference's parameterisation, base_opt.py:202-247, optimizer.py:392-436)
+    derived in closed form from the ground truth plus a small deterministic wobble, so that a teacher-forced evaluation
+    can be repeated on another machine from the recipe alone (a 1000-frame depth stack does not fit a fixture).
+    The scene is rescaled by c = base_scale * exp(mean log s_ij) so that the pair scales need no normalisation shift.
+    Returns (small, logdepth): small = dict(pw_poses (E,8), im_poses (N,7), im_focals (1|N,1)) fp32 CPU tensors,
+    logdepth(n, device='cpu') -> (H*W,) fp32 log-depth of frame n."""
+    from scipy.spatial.transform import Rotation
+    N, E = gt.n_frames, len(edges)
+    s_ij = np.array([1.0 + 0.1 * float(torch.rand(1, generator=_edge_generator(seed, i, j, N))) for i, j in edges])
+    c = base_scale * float(np.exp(np.mean(np.log(s_ij))))
+    rng = np.random.RandomState(seed * 7 + 11)
+
+    def slog1p(x):
+        return np.sign(x) * np.log1p(np.abs(x))
+
+    im = np.zeros((N, 7))
+    for n in range(N):
+        rv = Rotation.from_matrix(gt.cam2world[n, :3, :3]) * Rotation.from_rotvec(wobble * 0.1 * rng.randn(3))
+        im[n, :4] = rv.as_quat() * (1.0 + 0.3 * rng.rand())              # raw quaternions are not unit in the reference either
+        im[n, 4:] = slog1p(c * gt.cam2world[n, :3, 3] + wobble * 0.05 * rng.randn(3))
+    pw = np.zeros((E, 8))
+    for e, (i, j) in enumerate(edges):
+        s = c / s_ij[e] * np.exp(wobble * rng.randn())
+        rv = Rotation.from_matrix(gt.cam2world[i, :3, :3]) * Rotation.from_rotvec(wobble * 0.1 * rng.randn(3))
+        pw[e, :4] = rv.as_quat() * (1.0 + 0.3 * rng.rand())
+        pw[e, 4:7] = slog1p((c * gt.cam2world[i, :3, 3] + wobble * 0.05 * rng.randn(3)) / s)      # y = s (R x + T / s)
+        pw[e, 7] = np.log(s)
+    nf = 1 if shared_focal else N
+    foc = focal_break * np.log(gt.focal * (1.0 + wobble * 0.1 * rng.randn(nf, 1)))
+    small = dict(pw_poses=torch.from_numpy(pw).float(), im_poses=torch.from_numpy(im).float(), im_focals=torch.from_numpy(foc).float())
+
+    def logdepth(n, device="cpu"):
+        v, u = torch.meshgrid(torch.arange(gt.H, dtype=torch.float64, device=device),
+                              torch.arange(gt.W, dtype=torch.float64, device=device), indexing="ij")
+        d = 2 + 0.5 * torch.sin(u / 60 + 0.2 * n) * torch.cos(v / 45) + 0.05 * n
+        wob = wobble * torch.sin(0.05 * u + 0.07 * v + 1.3 * n)
+        return (torch.log(c * d) + wob).float().reshape(-1)
+
+    return small, logdepth
+
+
+def load_params(net, small, logdepth):
+    """Writes near_solution_params' values into an aligner (ours; the frames this device owns)."""
+    with torch.no_grad():
+        net.pw_poses.data.copy_(small["pw_poses"].to(net.device))
+        net.im_poses.data.copy_(small["im_poses"].to(net.device))
+        net.im_focals.data.copy_(small["im_focals"].reshape(net.im_focals.shape).to(net.device))
+        for k, n in enumerate(net._plan.lframe_id.tolist()):
+            ld = logdepth(n, net.device)
+            net.im_depthmaps.data[k, :ld.numel()] = ld
 
 
 # canonical hyper-parameters used by every caller of the reference (SURVEY.md section 3.1)

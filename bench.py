@@ -13,9 +13,11 @@ N > 1 (launched by torchrun): the scene is cut into N contiguous frame windows; 
 living on its frames; the fp64 accumulator block of the small parameters is exchanged once per iteration inside our own
 kernel over NVLink peer memory (A3R_EXCHANGE=nccl: one NCCL all-reduce instead); total work is fixed ("scaling": "strong").
 
-``--impl reference`` times the CPU oracle port of the reference implementation (oracle/ga_oracle.py: same
-torch ops + autograd + torch.optim.Adam as the reference, all host threads) on a bounded sample of the
-same workload and scales by pixel-edges; rank 0 only.
+``--impl reference`` times the UNMODIFIED reference (dust3r.cloud_opt_flow PointCloudOptimizer + global_alignment_iter,
+imported from /root/reference or its verbatim git-ignored copy oracle/_ref made by oracle/build_ref.py) on the host cores,
+on the same workload: its own MST initialisation, warm-up iterations, then as many of the K iterations as fit the run's
+time budget (never fewer than 5; `steps` in its line is what was timed); rank 0 only.  The ``cpu_baseline`` leg of our arm
+runs the same function with 1 warm-up + 5 timed iterations.
 """
 from __future__ import annotations
 
@@ -41,8 +43,11 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline leg")
-    ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds for the whole --impl reference run")
+    ap.add_argument("--synth", default="auto", choices=["auto", "host", "device"],
+                    help="where the synthetic pair predictions are drawn: host (pinned memory, the default workload) or "
+                         "device (rows drawn on the GPU while they are packed: the 1000-frame workload; no e2e leg)")
+    ap.add_argument("--cpu-budget", type=float, default=75.0, help="seconds for the cpu_baseline leg (reference construction + MST init + iterations)")
+    ap.add_argument("--ref-budget", type=float, default=240.0, help="seconds for the whole --impl reference run")
     return ap.parse_args()
 
 
@@ -129,10 +134,82 @@ def algorithmic_bytes(E, N, P, flow):
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port on the host cores
+# reference arm / cpu baseline: the reference's own CPU implementation on the host cores
 # ------------------------------------------------------------------------------------------------
+def reference_rate(cfg, budget_s, steps, warmup, seed, scene=None):
+    """Times the UNMODIFIED reference (dust3r/cloud_opt_flow: PointCloudOptimizer + global_alignment_iter,
+    base_opt.py:550-583; imported from /root/reference or its verbatim copy oracle/_ref) on the host cores, on the SAME
+    workload as our arm: MST initialisation, then `steps` iterations of the canonical loop (linear schedule, lr 0.01, flow
+    term on from iteration 0.1*steps) after `warmup` untimed iterations (flow on; parameters and a fresh Adam restored
+    afterwards).  `steps` is cut down to what fits `budget_s` (never below 5; the blend of align-only and flow-active
+    iterations stays 10 % / 90 % because the reference is built with num_total_iter = the steps actually run).
+    Falls back to the oracle port (kind "port") only when the reference cannot be imported."""
+    import torch
+    from align3r_b200.synth import make_scene, make_edge_list, CANONICAL_KW
+    here = os.path.join(ROOT, "oracle")
+    if here not in sys.path:
+        sys.path.insert(0, here)
+    import ref_harness as rh
+    if not rh.reference_available():
+        return oracle_rate(cfg, budget_s, min(steps, 3), min(warmup, 1), seed)
+    n, H, W, graph = cfg
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    t_start = time.perf_counter()
+    _, _, _, base_opt = rh.import_reference()
+    if scene is None:
+        scene = make_scene(n, H, W, graph, seed=seed, with_flow=True, workers=cores)
+    E = len(make_edge_list(n, graph))
+
+    def fresh(k_total):
+        torch.manual_seed(seed)
+        ref = rh.build_reference_scene(scene, **dict(CANONICAL_KW, num_total_iter=k_total))
+        with rh.quiet():
+            ref.compute_global_alignment(init="mst", niter=0)            # the reference's own MST initialisation, no iteration
+        return ref
+
+    ref = fresh(steps)
+    t_init = time.perf_counter() - t_start
+    params = [p for p in ref.parameters() if p.requires_grad]
+    snap = [p.detach().clone() for p in params]
+    opt = torch.optim.Adam(params, lr=0.01, betas=(0.9, 0.9))
+    t_w = []
+    for w in range(max(1, warmup)):
+        t0 = time.perf_counter()
+        with rh.quiet():
+            base_opt.global_alignment_iter(ref, steps - 1, steps, 0.01, 1e-3, opt, "linear")       # flow on
+        t_w.append(time.perf_counter() - t0)
+        if w >= 1 and time.perf_counter() - t_start > 0.4 * budget_s:
+            break
+    with torch.no_grad():
+        for p, v in zip(params, snap):
+            p.copy_(v)
+    left = budget_s - (time.perf_counter() - t_start)
+    k_run = min(steps, int(max(5, left / max(min(t_w), 1e-3))))
+    ref.num_total_iter = k_run                              # optimizer.py:520: flow on from 0.1 * num_total_iter
+    ref.flow_loss_flag = False
+    opt = torch.optim.Adam(params, lr=0.01, betas=(0.9, 0.9))          # a fresh Adam, like global_alignment_loop (base_opt.py:524)
+    losses = []
+    t0 = time.perf_counter()
+    for it in range(k_run):
+        with rh.quiet():
+            loss, _ = base_opt.global_alignment_iter(ref, it, k_run, 0.01, 1e-3, opt, "linear")
+        losses.append(loss)
+    dt = time.perf_counter() - t0
+    n_flow = sum(1 for it in range(k_run) if it >= k_run * CANONICAL_KW["flow_loss_start_epoch"])
+    return dict(value=k_run / dt, unit="iterations/s", cores=cores, kind="reference", steps_run=k_run,
+                sample=(f"the unmodified reference (dust3r.cloud_opt_flow PointCloudOptimizer, global_alignment_iter) from "
+                        f"{os.path.relpath(rh.REFERENCE_ROOT, ROOT) if rh.REFERENCE_ROOT.startswith(ROOT) else rh.REFERENCE_ROOT} "
+                        f"on the full workload ({n} frames {H}x{W}, {E} edges): its own MST init ({t_init:.1f} s incl. construction), "
+                        f"{len(t_w)} warm-up + {k_run} timed iterations ({n_flow} with the flow term) in {dt:.1f} s on {cores} host threads; "
+                        f"roma restated by oracle/roma_shim.py"),
+                ms_per_step_sample=1e3 * dt / k_run, torch_threads=torch.get_num_threads(), final_loss=losses[-1],
+                same_config=True)
+
+
 def oracle_rate(cfg, budget_s, steps, warmup, seed):
-    """Times `steps` iterations (after `warmup`) of the oracle port on a sample of workload cfg sized to the
+    """Fallback of reference_rate when the reference tree is neither at /root/reference nor copied to oracle/_ref: times
+    `steps` iterations (after `warmup`) of the oracle PORT (oracle/ga_oracle.py) on a sample of workload cfg sized to the
     budget.  Returns dict(value = iterations/s scaled to the full workload, sample description, ...)."""
     import torch
     from align3r_b200.synth import make_scene, make_edge_list, CANONICAL_KW
@@ -176,27 +253,31 @@ def oracle_rate(cfg, budget_s, steps, warmup, seed):
     dt = time.perf_counter() - t0
     sample_pe = prob.n_edges * prob.P
     rate_sample = steps / dt
-    return dict(value=rate_sample * sample_pe / full_pe, unit="iterations/s", cores=cores, kind="port",
-                sample=(f"{steps} iterations (flow on from 0.1*{steps}) of the oracle port on a {ns}-frame {hs}x{ws} {graph} sample "
-                        f"({prob.n_edges} edges, {sample_pe} pixel-edges, {rate_sample:.3f} it/s), scaled by pixel-edges "
-                        f"{sample_pe}/{full_pe} to the full workload"),
-                ms_per_step_sample=1e3 * dt / steps, torch_threads=torch.get_num_threads())
+    return dict(value=rate_sample * sample_pe / full_pe, unit="iterations/s", cores=cores, kind="port", steps_run=steps,
+                sample=(f"REFERENCE TREE UNAVAILABLE - {steps} iterations (flow on from 0.1*{steps}) of the oracle port on a {ns}-frame "
+                        f"{hs}x{ws} {graph} sample ({prob.n_edges} edges, {sample_pe} pixel-edges, {rate_sample:.3f} it/s), scaled by "
+                        f"pixel-edges {sample_pe}/{full_pe} to the full workload"),
+                ms_per_step_sample=1e3 * dt / steps, torch_threads=torch.get_num_threads(), same_config=False)
 
 
 def run_reference(args, cfg, name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = oracle_rate(cfg, args.ref_budget, args.steps, args.warmup, args.seed)
+    t0 = time.perf_counter()
+    r = reference_rate(cfg, args.ref_budget, args.steps, args.warmup, args.seed)
     n, H, W, graph = cfg
     line = {
         "impl": "reference", "metric": "ga_iterations_per_sec", "value": r["value"], "unit": "iterations/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / r["value"],
+        "n_gpus": args.gpus, "steps": r["steps_run"], "warmup": args.warmup, "ms_per_step": 1e3 / r["value"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(name, cfg)},
+        "config": {"workload": workload_name(name, cfg), "same_config": r["same_config"],
+                   "steps_requested": args.steps, "steps_run": r["steps_run"],
+                   "note": "CPU run of the reference's own code on the host cores; the timed steps are cut to the run's time budget "
+                           f"({args.ref_budget:.0f} s), `steps` is what was timed"},
         "cpu_baseline": {"value": r["value"], "unit": "iterations/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "final_loss": r.get("final_loss"), "seconds_total": time.perf_counter() - t0,
     }
     print(json.dumps(line), flush=True)
 
@@ -212,7 +293,7 @@ def run_ours(args, cfg, name):
     from align3r_b200.cloud_opt_flow.optimizer import global_alignment_loop
     from align3r_b200.plan import frame_costs, partition_frames
     from align3r_b200.problem import adam_schedule
-    from align3r_b200.synth import CANONICAL_KW, make_edge_list, make_scene
+    from align3r_b200.synth import CANONICAL_KW, make_edge_list, make_scene, make_scene_device
     import numpy as np
     import ctypes as C
 
@@ -240,9 +321,19 @@ def run_ours(args, cfg, name):
         lo, hi = wins[rank]
         rows = [e for e, (i, j) in enumerate(all_edges) if lo <= i < hi or lo <= j < hi]
         shard = dict(world=world, rank=rank, group=None)
-    scene = make_scene(n, H, W, graph, seed=args.seed, with_flow=True, pin_memory=True,
-                       edges=None if rows is None else [all_edges[e] for e in rows])
+    device_synth = args.synth == "device" or (args.synth == "auto" and n >= 400)
+    t_synth = time.perf_counter()
+    if device_synth:
+        args.no_e2e = True                 # no host copy of the inputs exists: nothing to upload
+        scene = make_scene_device(n, H, W, graph, seed=args.seed, device=dev,
+                                  edges=None if rows is None else [all_edges[e] for e in rows])
+    else:
+        scene = make_scene(n, H, W, graph, seed=args.seed, with_flow=True, pin_memory=True, workers=max(1, (os.cpu_count() or 1) // world),
+                           edges=None if rows is None else [all_edges[e] for e in rows])
+    t_synth = time.perf_counter() - t_synth
     kw = dict(CANONICAL_KW, num_total_iter=K)
+    if world > 1:                      # host threads of this rank: the box's cores are shared by the ranks
+        torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))
 
     def output_dict():
         out = scene.output
@@ -277,56 +368,67 @@ def run_ours(args, cfg, name):
              wnet._bufs.loss_hist[:10].cpu())
         del wnet, tiny, _
         # ... and one untimed job on the workload itself (3 iterations): first-touch page faults of the host-side temporaries,
-        # the PnP thread pool and cv2's buffers at this size, the arena / staging allocations - the timed job measures a
-        # steady-state job, like the W warm-up steps do for the device-timed loop
-        if world == 1:
-            wnet = build()
-            wnet.compute_global_alignment(init="mst", niter=3, schedule="linear", lr=0.01)
-            torch.cuda.synchronize(dev)
-            del wnet
+        # the PnP thread pool and cv2's buffers at this size, the arena / staging allocations, the peer mappings - the timed job
+        # measures a steady-state job, like the W warm-up steps do for the device-timed loop (every world size)
+        wnet = build()
+        wnet.compute_global_alignment(init="mst", niter=3, schedule="linear", lr=0.01)
+        torch.cuda.synchronize(dev)
+        wnet.close()
+        del wnet
         if world > 1:
             warm = torch.zeros(1024, device=dev, dtype=torch.float64)
             dist.all_reduce(warm)
         # the caller's result buffers (pinned, like the inputs): allocated once, outside the job
         n_own = n if world == 1 else wins[rank][1] - wins[rank][0]
         res_depth = torch.empty((n_own, (P + 127) // 128 * 128), dtype=torch.float32, pin_memory=True)
-        barrier()
-        t0 = time.perf_counter()
-        net = build()
-        t_c = time.perf_counter()                      # no synchronisation between the phases: the uploads of the
-        net.compute_global_alignment(init="mst", niter=0)      # constructor drain while the initialisation runs
-        t_i = time.perf_counter()
-        loss_e2e = net.compute_global_alignment(init=None, niter=K, schedule="linear", lr=0.01)    # returns float(loss): syncs
-        t_l = time.perf_counter()
-        dd = net.get_depthmaps(raw=True).detach()                      # (frames, pix_stride) in one copy
-        if res_depth.shape != dd.shape:
-            res_depth = torch.empty(dd.shape, dtype=torch.float32, pin_memory=True)     # (plan padded differently)
-        res_depth.copy_(dd, non_blocking=True)
-        depth_h = [res_depth]
-        poses_h = net.get_im_poses().detach().cpu()
-        foc_h = net.get_focals().detach().cpu()
-        hist_h = net._bufs.loss_hist[:K].cpu()
-        torch.cuda.synchronize(dev)
-        phases = {"construct_upload_pack_s": t_c - t0, "mst_init_s": t_i - t_c, "loop_s": t_l - t_i, "readback_s": time.perf_counter() - t_l,
-                  "note": "host-side wall clock per call, no synchronisation in between (asynchronous uploads overlap the next call)"}
-        barrier()
-        t_e2e = time.perf_counter() - t0
-        if world > 1:
-            tt = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            t_e2e = float(tt)
-            hh = torch.tensor([float(h2d)], device=dev, dtype=torch.float64)
-            dist.all_reduce(hh)
-            h2d_total = float(hh)
-        else:
-            h2d_total = float(h2d)
-        d2h = sum(d.numel() * 4 for d in depth_h) + poses_h.numel() * 4 + foc_h.numel() * 4 + hist_h.numel() * 4
-        e2e = {"value": K / t_e2e, "unit": "iterations/s", "h2d_bytes_per_step": h2d_total / K, "d2h_bytes_per_step": d2h / K,
-               "seconds_total": t_e2e, "phases": phases, "final_loss": loss_e2e,
-               "what": "global_aligner(host dict) + compute_global_alignment(init='mst', niter=K) + depth/pose/focal/loss read-back, "
-                       "whole job / K; inputs are uploaded once per job (they are constant across iterations)"
-                       + ("; one untimed 3-iteration job on the same inputs runs first (process warm-up)" if world == 1 else "")}
-        del depth_h
+
+        def e2e_job(Kj, keep):
+            nonlocal res_depth
+            kwj = dict(CANONICAL_KW, num_total_iter=Kj)
+            barrier()
+            t0 = time.perf_counter()
+            netj = global_aligner(output_dict(), dev, mode=GlobalAlignerMode.PointCloudOptimizer,
+                                  flow=(scene.flow_ij, scene.flow_ji), shard=shard, edge_rows=rows, **kwj)
+            t_c = time.perf_counter()                      # no synchronisation between the phases: the uploads of the
+            netj.compute_global_alignment(init="mst", niter=0)      # constructor drain while the initialisation runs
+            t_i = time.perf_counter()
+            loss_j = netj.compute_global_alignment(init=None, niter=Kj, schedule="linear", lr=0.01)    # returns float(loss): syncs
+            t_l = time.perf_counter()
+            dd = netj.get_depthmaps(raw=True).detach()                      # (frames, pix_stride) in one copy
+            if res_depth.shape != dd.shape:
+                res_depth = torch.empty(dd.shape, dtype=torch.float32, pin_memory=True)     # (plan padded differently)
+            res_depth.copy_(dd, non_blocking=True)
+            poses_h = netj.get_im_poses().detach().cpu()
+            foc_h = netj.get_focals().detach().cpu()
+            hist_h = netj._bufs.loss_hist[:Kj].cpu()
+            torch.cuda.synchronize(dev)
+            phases = {"construct_upload_pack_s": t_c - t0, "mst_init_s": t_i - t_c, "loop_s": t_l - t_i, "readback_s": time.perf_counter() - t_l,
+                      "note": "host-side wall clock per call, no synchronisation in between (asynchronous uploads overlap the next call)"}
+            barrier()
+            t_j = time.perf_counter() - t0
+            if world > 1:
+                tt = torch.tensor([t_j], device=dev, dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                t_j = float(tt)
+                hh = torch.tensor([float(h2d)], device=dev, dtype=torch.float64)
+                dist.all_reduce(hh)
+                h2d_total = float(hh)
+            else:
+                h2d_total = float(h2d)
+            d2h = res_depth.numel() * 4 + poses_h.numel() * 4 + foc_h.numel() * 4 + hist_h.numel() * 4
+            rec = {"value": Kj / t_j, "unit": "iterations/s", "h2d_bytes_per_step": h2d_total / Kj, "d2h_bytes_per_step": d2h / Kj,
+                   "iterations": Kj, "seconds_total": t_j, "phases": phases, "final_loss": loss_j}
+            if not keep:
+                netj.close()
+                netj = None
+            return rec, netj
+
+        e2e, net = e2e_job(K, True)
+        e2e["what"] = ("global_aligner(host dict) + compute_global_alignment(init='mst', niter=K) + depth/pose/focal/loss read-back, "
+                       "whole job / K; inputs are uploaded once per job (they are constant across iterations); one untimed "
+                       "3-iteration job on the same inputs runs first (process warm-up)")
+        if K != 300:        # the reference's canonical job length beside the driver's K
+            e2e["canonical_300_iterations"], _ = e2e_job(300, False)
     if net is None:
         net = build()
         net.compute_global_alignment(init="mst", niter=0)
@@ -348,19 +450,40 @@ def run_ours(args, cfg, name):
     net.flow_loss_flag = False
 
     # ---------------- timed region: K iterations, device time, max over ranks ----------------
+    # The K-step loop is timed exactly as the contract says (barrier + synchronize on both sides, CUDA events on the launching
+    # stream, max over ranks).  When K steps take less than 0.5 s the loop is REPEATED from the restored initial state until
+    # at least 1 s of device time has been spent (at most 400 loops), so that the clock sampler sees a loaded GPU for several
+    # samples; value = K / median loop time, the spread is reported.
+    def restore():
+        with torch.no_grad():
+            for k, v in snap.items():
+                getattr(net, k).data.copy_(v)
+        net.flow_loss_flag = False
+
     sampler = ClockSampler(local).start() if rank == 0 else None
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(torch.cuda.current_stream(dev))
-    final_loss = global_alignment_loop(net, lr=0.01, niter=K, schedule="linear")
-    ev1.record(torch.cuda.current_stream(dev))
-    barrier()
-    ms = ev0.elapsed_time(ev1)
+    loops, final_loss, spent = [], None, 0.0
+    while True:
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(torch.cuda.current_stream(dev))
+        fl = global_alignment_loop(net, lr=0.01, niter=K, schedule="linear")
+        ev1.record(torch.cuda.current_stream(dev))
+        barrier()
+        t_ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            tt = torch.tensor([t_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_ms = float(tt)
+        if final_loss is None:
+            final_loss = fl
+            loss_head = [float(x) for x in net._bufs.loss_hist[:min(K, 24)].cpu()]
+        loops.append(t_ms)
+        spent += t_ms
+        if loops[0] >= 500.0 or spent >= 1000.0 or len(loops) >= 400:        # the same decision on every rank (max over ranks)
+            break
+        restore()
     clocks = sampler.stop() if sampler is not None else None
-    if world > 1:
-        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt)
+    ms = sorted(loops)[len(loops) // 2]
     n_flow = sum(1 for it in range(K) if net._flow_active(it))
 
     # ---------------- roofline of the dominant kernel: the accumulate scan, timed alone ----------------
@@ -405,9 +528,13 @@ def run_ours(args, cfg, name):
                        + " of the fp64 accumulator block per iteration",
                        "l2": "inputs exceed L2 (per-iteration scan >> 126 MB)"},
             "pixel_edges_per_sec": E * P * K / (ms * 1e-3),
-            "final_loss": final_loss,
+            "final_loss": final_loss, "loss_hist_head": loss_head,
+            "timed_loops": {"count": len(loops), "ms_median": ms, "ms_min": min(loops), "ms_max": max(loops), "ms_first": loops[0],
+                            "note": "K-step loops from the restored MST initialisation; value = K / median"},
+            "synth": {"where": "device rows" if device_synth else "host, pinned", "seconds": t_synth},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": (traffic or {}).get("accumulate_flow_bytes_per_launch") if world == 1 else None,
+                         "traffic": (traffic or {}).get("accumulate_flow_bytes_per_launch") if world == 1 and name == "c2" else None,
+                         "traffic_source": "recorded: profiles/traffic.json (ncu --set full of this kernel on this workload), not measured in this run",
                          "kernel": "k_accumulate (flow active), timed alone over %d launches" % reps,
                          "ms_per_launch": roof["flow"], "algorithmic_bytes_per_launch": k1_bytes_flow, "peak_source": peak_src,
                          "align_only": {"ms_per_launch": roof["align"], "achieved": k1_bytes_align / (roof["align"] * 1e-3) / 1e9,
@@ -424,7 +551,7 @@ def run_ours(args, cfg, name):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         del net
         torch.cuda.empty_cache()
-        cb = oracle_rate(cfg, args.cpu_budget, 3, 1, args.seed)
+        cb = reference_rate(cfg, args.cpu_budget, 5, 1, args.seed, scene=scene)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -251,6 +251,11 @@ int a3r_peer_free(void *region);
 int a3r_ga_run_peers(const A3rProblem *p, const A3rPeers *peers, uint32_t tag0, int32_t count, const uint32_t *modes,
                      const A3rAdamStep *steps, void *stream);
 
+/* diagnostic (no reference counterpart): phase trace of the small-parameter kernel.  enable != 0 switches the stamps on for
+ * the following launches; out (host, 64 entries, may be NULL) receives the %globaltimer stamps [cta][8] of the last
+ * traced launch.  Synchronises the device. */
+int a3r_debug_k2_trace(int enable, unsigned long long *out);
+
 /* ---- read-out (reference optimizer.py:468-478 depth_to_pts3d) ----
  * world points [n_local_frames][pix_stride][3] from logdepth + frame_par (call a3r_ga_prepare first) */
 int a3r_ga_unproject(const A3rProblem *p, float *pts3d, void *stream);

@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE - runs the UNMODIFIED reference global aligner from /root/reference on CPU.
 
-Only usable in the build container (``/root/reference`` does not exist on the GPU box).  Used by
+The reference tree is ``/root/reference`` in the build container and its verbatim git-ignored copy ``oracle/_ref``
+(made by ``oracle/build_ref.py``) on the GPU box.  Used by
 ``oracle/make_golden.py`` to generate the committed fixtures in ``tests/golden/`` and by the
 ``not gpu`` tests to cross-check ``oracle/ga_oracle.py`` live when the reference tree is present.
 
@@ -17,7 +18,22 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("A3R_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _reference_root() -> str:
+    """/root/reference in the build container; on the GPU box the verbatim, git-ignored copy oracle/_ref made by
+    oracle/build_ref.py (it travels with the snapshot)."""
+    env = os.environ.get("A3R_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", os.path.join(_HERE, "_ref")):
+        if os.path.isdir(os.path.join(cand, "dust3r", "cloud_opt_flow")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _reference_root()
 
 
 def reference_available() -> bool:

@@ -862,7 +862,6 @@ def test_edge_score_map_and_tree_file(cuda_device, tmp_path):
     assert float((plain.pw_poses.detach() - net.pw_poses.detach()).abs().max()) < 1e-5
 
 
-@pytest.mark.xfail(strict=False, reason="added after round 1's GPU minutes were spent: first hardware run pending (an XPASS means confirmed)")
 @pytest.mark.parametrize("conf", ["sqrt", "m1", "id"])
 def test_confidence_transforms_against_live_oracle(cuda_device, conf):
     """conf='sqrt' | 'm1' | 'id' (reference commons.py:53-64): the pack kernel's weight, the raw confidence the Procrustes
@@ -891,7 +890,6 @@ def test_confidence_transforms_against_live_oracle(cuda_device, conf):
         assert ok, (k, err, ref_err)
 
 
-@pytest.mark.xfail(strict=False, reason="added after round 1's GPU minutes were spent: first hardware run pending (an XPASS means confirmed)")
 def test_preset_frozen_focals_like_use_gt_focal(cuda_device):
     """tool/pose_test.py:181-193 (--use_gt_focal): per-frame focals preset and frozen, then the canonical init='mst' run.  The
     initialisation leaves the preset focals alone, the loop does not step them, and the run follows the oracle's (which is
@@ -919,7 +917,6 @@ def test_preset_frozen_focals_like_use_gt_focal(cuda_device):
     assert torch.equal(net.im_focals.detach().cpu().reshape(-1), params["im_focals"].reshape(-1))     # never stepped
 
 
-@pytest.mark.xfail(strict=False, reason="added after round 1's GPU minutes were spent: first hardware run pending (an XPASS means confirmed)")
 def test_flow_validity_maps(cuda_device):
     """flow_valid_mask_i / _j (reference get_flow -> OccMask, goem_opt.py:575-618; stored, never read by the loss): evaluated
     by k_occ_mask from the packed flow planes on first access, against the oracle's restatement (pinned live on the reference's

@@ -37,8 +37,6 @@ def test_argument_errors_of_the_handle_layer():
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="the handle layer was added after round 1's GPU minutes were spent: first hardware run pending "
-                                        "(an XPASS here means it is confirmed - drop the marker)")
 def test_handle_layer_against_the_stateless_entry_points(cuda_device):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "handle_api_worker.py")], capture_output=True, text=True,
                        timeout=600, cwd=ROOT)

@@ -5,12 +5,13 @@
 #   gpurun --gpus 8 --timeout 900 -- 'bash tools/c5_scaling.sh 8'        # 8 frame windows, ~8.8 GB of planes per GPU
 #   gpurun          --timeout 1500 -- 'bash tools/c5_scaling.sh 1'       # the same scene on one GPU (fits in 180 GB)
 #
-# Every rank draws only the edges living on its frame window (40 ms per edge on one host core: ~1 minute per rank at 8
-# GPUs, ~7 minutes on one GPU, before anything is timed).  The end-to-end leg is skipped: at one GPU its untimed warm-up
-# job would hold a second 70 GB arena.  Output: one bench JSON line in gpurun_out/c5_n<N>.json.
+# Every rank draws only the edges living on its frame window, on its GPU, row by row while they are packed
+# (synth.make_scene_device: the 70 GB of pair predictions never exist on the host).  No end-to-end leg (there is no host
+# copy of the inputs to upload).  Output: one bench JSON line in gpurun_out/c5_n<N>.json; its loss_hist_head is what
+# tools/c5_compare.py compares between the 1-GPU and the 8-GPU run.
 set -euo pipefail
 N="${1:-8}"
-STEPS="${2:-100}"
+STEPS="${2:-40}"
 mkdir -p gpurun_out
 if [ "$N" -gt 1 ]; then
   python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port 29531 \

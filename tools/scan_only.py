@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from align3r_b200 import _lib
 from align3r_b200.cloud_opt_flow import global_aligner
-from align3r_b200.synth import CANONICAL_KW, CONFIGS, make_scene
+from align3r_b200.synth import CANONICAL_KW, CONFIGS, load_params, make_edge_list, make_scene, make_scene_device, near_solution_params
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--reps", type=int, default=20)
@@ -17,12 +17,34 @@ ap.add_argument("--mode", default="both")
 ap.add_argument("--workload", default="c2")
 ap.add_argument("--world", type=int, default=1, help="time the scan of ONE frame-window shard of `world` (rank-emulated on this GPU)")
 ap.add_argument("--rank", type=int, default=0)
+ap.add_argument("--recipe", action="store_true", help="device-drawn inputs (only this shard's edges) + parameters by recipe "
+                "(synth.near_solution_params) instead of host inputs + MST initialisation: the 1000-frame workload")
 a = ap.parse_args()
 n, H, W, graph = CONFIGS[a.workload]
-sc = make_scene(n, H, W, graph, seed=0, with_flow=True)
-net = global_aligner(sc.output, "cuda", flow=(sc.flow_ij, sc.flow_ji), **dict(CANONICAL_KW))
-net.verbose = False
-net.compute_global_alignment(init="mst", niter=0)
+if a.recipe:
+    import numpy as np
+    from align3r_b200.plan import frame_costs, partition_frames
+    all_edges = make_edge_list(n, graph)
+    rows, shard = None, None
+    if a.world > 1:
+        lo, hi = partition_frames(frame_costs(np.asarray(all_edges, dtype=np.int32), np.asarray([(H, W)] * n, dtype=np.int32)), a.world)[a.rank]
+        rows = [e for e, (i, j) in enumerate(all_edges) if lo <= i < hi or lo <= j < hi]
+        shard = dict(world=a.world, rank=a.rank, group=None)
+    sc = make_scene_device(n, H, W, graph, seed=0, device="cuda", edges=None if rows is None else [all_edges[e] for e in rows])
+    out = sc.output
+    if rows is not None:
+        out = dict(out, view1=dict(out["view1"], idx=[i for i, _ in all_edges]), view2=dict(out["view2"], idx=[j for _, j in all_edges]))
+    net = global_aligner(out, "cuda", flow=(sc.flow_ij, sc.flow_ji), shard=shard, edge_rows=rows, **dict(CANONICAL_KW))
+    net.verbose = False
+    load_params(net, *near_solution_params(sc.gt, all_edges, seed=0))
+    net._join_uploads()
+    a.world = 1          # built: skip the host-input shard path below
+else:
+    sc = make_scene(n, H, W, graph, seed=0, with_flow=True)
+if not a.recipe:
+    net = global_aligner(sc.output, "cuda", flow=(sc.flow_ij, sc.flow_ji), **dict(CANONICAL_KW))
+    net.verbose = False
+    net.compute_global_alignment(init="mst", niter=0)
 if a.world > 1:        # one shard of a `world`-way frame-window partition, with the full problem's initial parameters
     full = net
     net = global_aligner(sc.output, "cuda", flow=(sc.flow_ij, sc.flow_ji), shard=dict(world=a.world, rank=a.rank, group=None),

@@ -28,3 +28,16 @@ for rep in range(3):
     e1.record()
     torch.cuda.synchronize()
     print(f"rep {rep}: {a.iters} iterations, {1e3 * e0.elapsed_time(e1) / a.iters:.1f} us / iteration (tiny images: the small-parameter chain dominates)  loss {loss:.6f}")
+
+# phase trace of the last K2 launch (a3r_debug_k2_trace): nanoseconds relative to the earliest CTA's start
+import ctypes as C
+lib = net._lib
+buf = (C.c_ulonglong * 64)()
+lib.a3r_debug_k2_trace(1, None)
+global_alignment_loop(net, lr=0.01, niter=a.iters, schedule="linear")
+lib.a3r_debug_k2_trace(0, buf)
+rows = [[buf[c * 8 + k] for k in range(8)] for c in range(8)]
+t0 = min(r[0] for r in rows)
+print("K2 phase trace (us since the first CTA started): start cameras loss+gate chains | barrier1 | phaseB | barrier2 | end")
+for c, r in enumerate(rows):
+    print(f"  cta {c}: " + "  ".join(f"{(x - t0) / 1e3:7.2f}" for x in r))
