@@ -95,6 +95,7 @@ _SIGNATURES = {
     "a3r_peer_free": (C.c_int, [_vp]),
     "a3r_ga_run_peers": (C.c_int, [C.POINTER(A3rProblem), C.POINTER(A3rPeers), _u32, _i32, C.POINTER(_u32), C.POINTER(A3rAdamStep), _vp]),
     "a3r_clean_pointcloud": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _f32, _f32, _vp, _vp]),
+    "a3r_clean_pointcloud_range": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, _f32, _f32, _vp, _vp]),
     "a3r_procrustes_batched": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "a3r_weiszfeld_focal_batched": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp]),
     "a3r_init_depth": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, _vp, _vp]),

@@ -476,24 +476,76 @@ class PointCloudOptimizer(nn.Module):
         # None here - flow_valid_mask_i / _j evaluate them on the device from the packed flow planes on first access
         return flow_ij, flow_ji, None, None
 
+    def _owner_of_frame(self, n):
+        for r, (a, b) in enumerate(self._windows):
+            if a <= n < b:
+                return r
+        raise ValueError(n)
+
+    def _fetch_remote_planes(self, planes, want):
+        """Frame-window shards: the rows of ``planes`` ([local slots][pix_stride](,C)) of the global slots in ``want`` that
+        live on other GPUs, fetched from their owners (point-to-point, one batch).  Collective: every rank calls it with
+        its own wish list.  Returns {global slot: tensor}."""
+        import torch.distributed as dist
+        world, rank, group = int(self._shard['world']), int(self._shard['rank']), self._shard.get('group')
+        want = sorted(int(g) for g in want)
+        wishes = [None] * world
+        dist.all_gather_object(wishes, want, group=group)
+        ops, got = [], {}
+        for r, wl in enumerate(wishes):              # the same order on sender and receiver: (receiver rank, slot)
+            for gs in wl:
+                owner = self._owner_of_frame(self.edges[gs >> 1][gs & 1])
+                peer_g = (lambda q: dist.get_global_rank(group, q) if group is not None else q)
+                if owner == rank and r != rank:
+                    ops.append(dist.P2POp(dist.isend, planes[self._lslot[gs]].contiguous(), peer_g(r), group=group))
+                elif r == rank and owner != rank:
+                    got[gs] = torch.empty_like(planes[0])
+                    ops.append(dist.P2POp(dist.irecv, got[gs], peer_g(owner), group=group))
+        if ops:
+            for q in dist.batch_isend_irecv(ops):
+                q.wait()
+        return got
+
     def _flow_valid_mask(self, side):
-        """reference goem_opt.py:575-618 (OccMask, th = 3): (E,1,H,W) bool, forward flow = this side's, backward = the other's."""
+        """reference goem_opt.py:575-618 (OccMask, th = 3): (E,1,H,W) bool, forward flow = this side's, backward = the other's.
+        Frame-window shards evaluate the rows whose forward flow lives here (``flow_valid_rows(side)``; the other rows stay
+        False); the backward planes of the pairs that straddle a window boundary are fetched from the neighbour."""
         if getattr(self, '_flow_valid', None) is None:
             return None
         if self._flow_valid[side] is None:
-            if self._shard is not None and int(self._shard['world']) > 1:
-                raise NotImplementedError("flow validity maps on a frame-window sharded problem (an edge's two flow planes may "
-                                          "live on different GPUs)")
             E, (H, W) = self.n_edges, self.imshape
-            fwd = torch.tensor([self._lslot[2 * e + side] for e in range(E)], dtype=torch.int32).to(self._device)
-            bwd = torch.tensor([self._lslot[2 * e + 1 - side] for e in range(E)], dtype=torch.int32).to(self._device)
-            valid = torch.empty((E, H * W), dtype=torch.uint8, device=self._device)
-            with torch.cuda.device(self._device):
-                self._join_uploads()
-                _lib.check(self._lib.a3r_occ_masks(_lib.ptr(self._bufs.flow), self._plan.pix_stride, _lib.ptr(fwd), _lib.ptr(bwd), E, H, W,
-                                                   3.0, _lib.ptr(valid), self._stream()), "a3r_occ_masks")
+            dev = self._device
+            rows = self.flow_valid_rows(side)
+            valid = torch.zeros((E, H * W), dtype=torch.uint8, device=dev)
+
+            def run(table, fwd_idx, bwd_idx, dst_rows):
+                if not dst_rows:
+                    return
+                fwd = torch.tensor(fwd_idx, dtype=torch.int32).to(dev)
+                bwd = torch.tensor(bwd_idx, dtype=torch.int32).to(dev)
+                part = valid if len(dst_rows) == E else torch.empty((len(dst_rows), H * W), dtype=torch.uint8, device=dev)
+                with torch.cuda.device(dev):
+                    _lib.check(self._lib.a3r_occ_masks(_lib.ptr(table), self._plan.pix_stride, _lib.ptr(fwd), _lib.ptr(bwd), len(dst_rows),
+                                                       H, W, 3.0, _lib.ptr(part), self._stream()), "a3r_occ_masks")
+                if part is not valid:
+                    valid[torch.tensor(dst_rows, device=dev)] = part
+
+            self._join_uploads()
+            here = [e for e in rows if (2 * e + 1 - side) in self._lslot]
+            run(self._bufs.flow, [self._lslot[2 * e + side] for e in here], [self._lslot[2 * e + 1 - side] for e in here], here)
+            if self._shard is not None and int(self._shard['world']) > 1:
+                away = [e for e in rows if (2 * e + 1 - side) not in self._lslot]         # pairs that straddle a window boundary
+                remote = self._fetch_remote_planes(self._bufs.flow, [2 * e + 1 - side for e in away])
+                if away:                     # a small table: [forward planes of those rows | the fetched backward planes]
+                    table = torch.stack([self._bufs.flow[self._lslot[2 * e + side]] for e in away] + [remote[2 * e + 1 - side] for e in away])
+                    run(table, list(range(len(away))), list(range(len(away), 2 * len(away))), away)
             self._flow_valid[side] = valid.view(E, 1, H, W).bool()
         return self._flow_valid[side]
+
+    def flow_valid_rows(self, side):
+        """Edges whose row of flow_valid_mask_i (side 0) / _j (side 1) this device evaluates: all of them on one GPU, the
+        edges whose side-`side` frame lives here on a frame-window shard."""
+        return [e for e in range(self.n_edges) if (2 * e + side) in self._lslot]
 
     @property
     def flow_valid_mask_i(self):
@@ -711,9 +763,11 @@ class PointCloudOptimizer(nn.Module):
     @torch.no_grad()
     def clean_pointcloud(self, tol=0.001, bad_conf=0, dbg=()):
         """reference base_opt.py:293-303,587-623: lower ``im_conf`` where a point of one frame lands in front of another
-        frame's depth map while being less confident.  One kernel launch per frame (a3r_clean_pointcloud); single device."""
-        if self._shard is not None and int(self._shard['world']) > 1:
-            raise NotImplementedError("clean_pointcloud on a frame-window sharded problem (every frame meets every other)")
+        frame's depth map while being less confident.  One kernel launch per frame (a3r_clean_pointcloud).
+        Frame-window shards: every frame meets every other frame's depth map and confidence, and frame i reads the FINAL
+        confidences of the frames before it - the depth and confidence planes of all frames are gathered on every rank
+        (N x P floats each), then the windows are cleaned in rank order, each rank broadcasting its frames' confidences
+        when it is done (the reference's sequential semantics, exactly)."""
         assert 0 <= tol < 1
         dev, plan = self._device, self._plan
         cams = torch.linalg.inv(self.get_im_poses().detach()).float().contiguous()            # world to camera
@@ -722,6 +776,30 @@ class PointCloudOptimizer(nn.Module):
         pts = self.depth_to_pts3d().contiguous()
         depth = self.im_depthmaps.detach().exp().contiguous()
         hw = torch.tensor(self.imshapes, dtype=torch.int32).to(dev)
+        if self._shard is not None and int(self._shard['world']) > 1:
+            import torch.distributed as dist
+            group, rank = self._shard.get('group'), int(self._shard['rank'])
+            depth_all = torch.zeros(self.n_imgs, plan.pix_stride, device=dev)
+            conf_all = torch.zeros(self.n_imgs, plan.pix_stride, device=dev)
+            lo, hi = self._windows[rank]
+            depth_all[lo:hi] = depth
+            conf_all[lo:hi] = self._im_conf_plane[:hi - lo]
+            for r, (a, b) in enumerate(self._windows):                  # everybody's depth maps and initial confidences
+                if b > a:
+                    dist.broadcast(depth_all[a:b], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+                    dist.broadcast(conf_all[a:b], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+            for r, (a, b) in enumerate(self._windows):                  # windows in frame order; the results travel on
+                if b <= a:
+                    continue
+                if r == rank:
+                    with torch.cuda.device(dev):
+                        _lib.check(self._lib.a3r_clean_pointcloud_range(_lib.ptr(pts), _lib.ptr(depth_all), _lib.ptr(cams), _lib.ptr(intr),
+                                                                        _lib.ptr(hw), self.n_imgs, a, b, plan.pix_stride, float(tol),
+                                                                        float(bad_conf), _lib.ptr(conf_all), self._stream()),
+                                   "a3r_clean_pointcloud_range")
+                dist.broadcast(conf_all[a:b], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+            self._im_conf_plane[:hi - lo] = conf_all[lo:hi]
+            return self
         with torch.cuda.device(dev):
             _lib.check(self._lib.a3r_clean_pointcloud(_lib.ptr(pts), _lib.ptr(depth), _lib.ptr(cams), _lib.ptr(intr), _lib.ptr(hw),
                                                       self.n_imgs, plan.pix_stride, float(tol), float(bad_conf),

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256) k_motion_minmax(const float* __restrict__
                                                        const int32_t* __restrict__ item_hw, const float* __restrict__ item_cam,
                                                        uint32_t* __restrict__ minmax) {
     __shared__ float s_lo[8], s_hi[8];
-    const int k = blockIdx.y;
+    const int k = blockIdx.x;
     const int W = item_hw[2 * k + 1], P = item_hw[2 * k] * W;
     const float4* xw = reinterpret_cast<const float4*>(predw) + (int64_t)item_dslot[k] * pix_stride;
     const float2* fl = reinterpret_cast<const float2*>(flow) + (int64_t)item_slot[k] * pix_stride;
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) k_motion_minmax(const float* __restrict__
     if (threadIdx.x < CAM) c[threadIdx.x] = item_cam[(int64_t)k * CAM + threadIdx.x];
     __syncthreads();
     float lo = INFINITY, hi = 0.0f;
-    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < P; pix += gridDim.x * blockDim.x) {
+    for (int pix = blockIdx.y * blockDim.x + threadIdx.x; pix < P; pix += gridDim.y * blockDim.x) {
         const float e = motion_err(xw, fl, c, pix, W);
         lo = fminf(lo, e); hi = fmaxf(hi, e);
     }
@@ -103,11 +103,11 @@ __global__ void __launch_bounds__(256) k_motion_masks(const float* __restrict__ 
 // through torch.grid_sample's align_corners=True coordinate round trip (x -> x / ((W-1)/2) - 1 -> ((g + 1) / 2) (W-1)).
 __global__ void __launch_bounds__(256) k_occ_mask(const float* __restrict__ flow, int64_t pix_stride, const int32_t* __restrict__ fwd_slot,
                                                   const int32_t* __restrict__ bwd_slot, int H, int W, float th, uint8_t* __restrict__ valid) {
-    const int k = blockIdx.y, P = H * W;
+    const int k = blockIdx.x, P = H * W;
     const float2* fw = reinterpret_cast<const float2*>(flow) + (int64_t)fwd_slot[k] * pix_stride;
     const float2* bw = reinterpret_cast<const float2*>(flow) + (int64_t)bwd_slot[k] * pix_stride;
     const float hx = (float)((double)(W - 1) / 2.0), hy = (float)((double)(H - 1) / 2.0);
-    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < P; pix += gridDim.x * blockDim.x) {
+    for (int pix = blockIdx.y * blockDim.x + threadIdx.x; pix < P; pix += gridDim.y * blockDim.x) {
         const int v = pix / W, u = pix - v * W;
         const float2 f = fw[pix];
         const float x = (float)u + f.x, y = (float)v + f.y;
@@ -145,7 +145,7 @@ int a3r_occ_masks(const float* flow, int64_t pix_stride, const int32_t* fwd_slot
         return a3r_fail(A3R_E_ARG, "a3r_occ_masks: n_items %d, image %dx%d, pix_stride %lld", n_items, H, W, (long long)pix_stride);
     if (n_items == 0) return A3R_OK;
     if (!flow || !fwd_slot || !bwd_slot || !valid) return a3r_fail(A3R_E_ARG, "a3r_occ_masks: NULL argument");
-    k_occ_mask<<<dim3(32, (unsigned)n_items), 256, 0, (cudaStream_t)stream>>>(flow, pix_stride, fwd_slot, bwd_slot, H, W, th, valid);
+    k_occ_mask<<<dim3((unsigned)n_items, 32), 256, 0, (cudaStream_t)stream>>>(flow, pix_stride, fwd_slot, bwd_slot, H, W, th, valid);
     A3R_CUDA(cudaGetLastError());
     return A3R_OK;
 }
@@ -158,7 +158,7 @@ int a3r_motion_minmax(const float* predw, const float* flow, int64_t pix_stride,
         return a3r_fail(A3R_E_ARG, "a3r_motion_minmax: NULL argument");
     cudaStream_t st = (cudaStream_t)stream;
     A3R_CUDA(cudaMemsetAsync(minmax, 0, sizeof(uint32_t) * 2 * (size_t)n_items, st));     // (~min bits, max bits) = (0, 0)
-    k_motion_minmax<<<dim3(32, (unsigned)n_items), 256, 0, st>>>(predw, flow, pix_stride, item_slot, item_dslot, item_hw, item_cam, minmax);
+    k_motion_minmax<<<dim3((unsigned)n_items, 32), 256, 0, st>>>(predw, flow, pix_stride, item_slot, item_dslot, item_hw, item_cam, minmax);
     A3R_CUDA(cudaGetLastError());
     return A3R_OK;
 }

@@ -31,14 +31,14 @@ __global__ void __launch_bounds__(256) k_procrustes_moments(const float* __restr
                                                             const int32_t* __restrict__ npix, int conf_mode,
                                                             double* __restrict__ sums) {
     __shared__ double s_red[32];
-    const int k = blockIdx.y;
+    const int k = blockIdx.x;
     const int P = npix[k];
     const float4* X = reinterpret_cast<const float4*>(predw) + (int64_t)xs[k] * pix_stride;
     const float4* Y = reinterpret_cast<const float4*>(predw) + (int64_t)ys[k] * pix_stride;
     double a[PR_USED];
 #pragma unroll
     for (int i = 0; i < PR_USED; ++i) a[i] = 0.0;
-    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < P; pix += gridDim.x * blockDim.x) {
+    for (int pix = blockIdx.y * blockDim.x + threadIdx.x; pix < P; pix += gridDim.y * blockDim.x) {
         const float4 x = ld_stream4(X + pix), y = ld_stream4(Y + pix);
         const double w = (double)conf_untrf(x.w, conf_mode);
         const double x0 = x.x, x1 = x.y, x2 = x.z, y0 = y.x, y1 = y.y, y2 = y.z;
@@ -149,13 +149,13 @@ __global__ void __launch_bounds__(256) k_focal_pass(const float* __restrict__ pr
                                                     const int32_t* __restrict__ sl, const int32_t* __restrict__ hw,
                                                     const double* __restrict__ focal, int first, double* __restrict__ sums) {
     __shared__ double s_red[32];
-    const int k = blockIdx.y;
+    const int k = blockIdx.x;
     const int H = hw[2 * k], W = hw[2 * k + 1], P = H * W;
     const float4* X = reinterpret_cast<const float4*>(predw) + (int64_t)sl[k] * pix_stride;
     const float f = first ? 0.f : (float)focal[k];
     const float ppx = 0.5f * W, ppy = 0.5f * H;
     double num = 0.0, den = 0.0;
-    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < P; pix += gridDim.x * blockDim.x) {
+    for (int pix = blockIdx.y * blockDim.x + threadIdx.x; pix < P; pix += gridDim.y * blockDim.x) {
         const float4 x = ld_stream4(X + pix);
         const int v = pix / W, u = pix - v * W;
         const float pu = (float)u - ppx, pv = (float)v - ppy;
@@ -208,13 +208,15 @@ __global__ void __launch_bounds__(256) k_init_depth(const float* __restrict__ pr
 }  // namespace
 
 // confidence clean-up of frame i against all other frames (reference base_opt.py:587-623)
+// pts3d holds the frames [i0, ...) only (row i - i0 is frame i): a frame-window shard cleans its own frames against the
+// depth maps / confidences of ALL frames (gathered by the caller)
 __global__ void __launch_bounds__(256) k_clean_frame(const float* __restrict__ pts3d, const float* __restrict__ depth,
                                                      const float* __restrict__ w2c, const float* __restrict__ intr,
-                                                     const int32_t* __restrict__ hw, int n, int i, int64_t pix_stride,
+                                                     const int32_t* __restrict__ hw, int n, int i, int i0, int64_t pix_stride,
                                                      float tol, float bad_conf, float* conf) {
     const int P = hw[2 * i] * hw[2 * i + 1];
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < P; q += gridDim.x * blockDim.x) {
-        const float* X = pts3d + ((int64_t)i * pix_stride + q) * 3;
+        const float* X = pts3d + ((int64_t)(i - i0) * pix_stride + q) * 3;
         const float x = X[0], y = X[1], z = X[2];
         float c = conf[(int64_t)i * pix_stride + q];
         for (int j = 0; j < n; ++j) {
@@ -238,14 +240,21 @@ __global__ void __launch_bounds__(256) k_clean_frame(const float* __restrict__ p
 
 extern "C" {
 
-int a3r_clean_pointcloud(const float* pts3d, const float* depth, const float* w2c, const float* intr, const int32_t* hw,
-                         int32_t n, int64_t pix_stride, float tol, float bad_conf, float* conf, void* stream) {
-    if (!pts3d || !depth || !w2c || !intr || !hw || !conf || n <= 0) return a3r_fail(A3R_E_ARG, "a3r_clean_pointcloud: bad arguments");
+int a3r_clean_pointcloud_range(const float* pts3d, const float* depth, const float* w2c, const float* intr, const int32_t* hw,
+                               int32_t n, int32_t i0, int32_t i1, int64_t pix_stride, float tol, float bad_conf, float* conf,
+                               void* stream) {
+    if (!pts3d || !depth || !w2c || !intr || !hw || !conf || n <= 0 || i0 < 0 || i1 > n || i0 > i1)
+        return a3r_fail(A3R_E_ARG, "a3r_clean_pointcloud: bad arguments");
     if (!(tol >= 0.f && tol < 1.f)) return a3r_fail(A3R_E_ARG, "a3r_clean_pointcloud: tol must be in [0, 1)");
-    for (int i = 0; i < n; ++i)          // frame i reads the confidences frames < i ended with: one launch per frame, in order
-        k_clean_frame<<<592, 256, 0, (cudaStream_t)stream>>>(pts3d, depth, w2c, intr, hw, n, i, pix_stride, tol, bad_conf, conf);
+    for (int i = i0; i < i1; ++i)        // frame i reads the confidences frames < i ended with: one launch per frame, in order
+        k_clean_frame<<<592, 256, 0, (cudaStream_t)stream>>>(pts3d, depth, w2c, intr, hw, n, i, i0, pix_stride, tol, bad_conf, conf);
     A3R_CUDA(cudaGetLastError());
     return A3R_OK;
+}
+
+int a3r_clean_pointcloud(const float* pts3d, const float* depth, const float* w2c, const float* intr, const int32_t* hw,
+                         int32_t n, int64_t pix_stride, float tol, float bad_conf, float* conf, void* stream) {
+    return a3r_clean_pointcloud_range(pts3d, depth, w2c, intr, hw, n, 0, n, pix_stride, tol, bad_conf, conf, stream);
 }
 
 
@@ -257,7 +266,7 @@ int a3r_procrustes_batched(const float* predw, int64_t pix_stride, const int32_t
     cudaStream_t st = (cudaStream_t)stream;
     A3R_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * PR_SUMS * (size_t)count, st));
     const int chunks = count >= 592 ? 8 : (count >= 148 ? 16 : 64);
-    k_procrustes_moments<<<dim3(chunks, count), 256, 0, st>>>(predw, pix_stride, xs, ys, npix, conf_mode, sums);
+    k_procrustes_moments<<<dim3(count, chunks), 256, 0, st>>>(predw, pix_stride, xs, ys, npix, conf_mode, sums);
     A3R_CUDA(cudaGetLastError());
     k_procrustes_solve<<<(count + 63) / 64, 64, 0, st>>>(sums, count, out);
     A3R_CUDA(cudaGetLastError());
@@ -272,7 +281,7 @@ int a3r_weiszfeld_focal_batched(const float* predw, int64_t pix_stride, const in
     const int chunks = count >= 592 ? 8 : (count >= 148 ? 16 : 64);
     for (int pass = 0; pass <= 10; ++pass) {
         A3R_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)count, st));
-        k_focal_pass<<<dim3(chunks, count), 256, 0, st>>>(predw, pix_stride, sl, hw, out_focal, pass == 0, sums);
+        k_focal_pass<<<dim3(count, chunks), 256, 0, st>>>(predw, pix_stride, sl, hw, out_focal, pass == 0, sums);
         A3R_CUDA(cudaGetLastError());
         k_focal_finish<<<(count + 127) / 128, 128, 0, st>>>(sums, count, out_focal);
         A3R_CUDA(cudaGetLastError());

@@ -25,19 +25,33 @@ def choose_clip_size(n_imgs, clip_size=10):
     return clip_size
 
 
-def my_make_pairs(imgs, clip_size):
-    """tool/demo.py:357-397 / depth_test.py:395-435.  Returns (coarse_init_pairs, keyframes_id, all_clips_pairs, all_clips_id).
+def my_make_pairs(imgs, clip_size, variant='depth_test'):
+    """Returns (coarse_init_pairs, keyframes_id, all_clips_pairs, all_clips_id).  The reference has two drivers with two pair
+    builders of this name:
+      ``variant='depth_test'``  tool/depth_test.py:395-435 (flow-free aligner): complete, NON-symmetrised graphs for the key
+                                frames and for every clip;
+      ``variant='demo'``        tool/demo.py:357-397 (flow aligner): the key-frame pairs are symmetrised, a clip pairs image i
+                                with i+1, i+3, i+5, ... (stride 2) and mirrors those pairs - the symmetric graphs
+                                ``use_self_mask=True`` (demo.py's default) asserts on (optimizer.py:157).
     The key frames and the images of a clip are re-indexed from 0 (``'idx'``) on copies: the caller's dicts are left alone
     (the reference renumbers them in place)."""
+    if variant not in ('depth_test', 'demo'):
+        raise ValueError(f'bad {variant=}')
+    demo = variant == 'demo'
     keyframes_id = list(range(0, len(imgs), clip_size))
     key_imgs = [dict(imgs[i], idx=k) for k, i in enumerate(keyframes_id)]
     coarse_init_pairs = [(key_imgs[a], key_imgs[b]) for a in range(len(key_imgs) - 1) for b in range(a + 1, len(key_imgs))]
+    if demo:
+        coarse_init_pairs += [(b, a) for a, b in coarse_init_pairs]
     all_clips_pairs, all_clips_id = [], []
     for start in keyframes_id:
         clip = imgs[start:start + clip_size]
         all_clips_id.append([im['idx'] for im in clip])
         local = [dict(im, idx=k) for k, im in enumerate(clip)]
-        all_clips_pairs.append([(dict(local[a]), dict(local[b])) for a in range(len(local) - 1) for b in range(a + 1, len(local))])
+        pairs = [(dict(local[a]), dict(local[b])) for a in range(len(local) - 1) for b in range(a + 1, len(local), 2 if demo else 1)]
+        if demo:
+            pairs += [(b, a) for a, b in pairs]
+        all_clips_pairs.append(pairs)
     return coarse_init_pairs, keyframes_id, all_clips_pairs, all_clips_id
 
 
@@ -46,11 +60,13 @@ def _np(t):
 
 
 def hierarchical_alignment(imgs, inference, device='cuda', clip_size=10, niter=300, schedule='cosine', lr=0.05,
-                           flow=False, conf_to=None, save_folder=None, **aligner_kw):
+                           flow=False, conf_to=None, save_folder=None, pairs=None, **aligner_kw):
     """Key-frame alignment, then one alignment per clip started from its key frame.
 
-    ``flow=False``: the flow-free aligner of tool/depth_test.py (``align3r_b200.cloud_opt``, lr 0.05, cosine);
-    ``flow=True``: ``align3r_b200.cloud_opt_flow`` as in tool/demo.py (pass lr=0.01 and its keyword arguments).
+    ``flow=False``: the flow-free aligner of tool/depth_test.py (``align3r_b200.cloud_opt``, lr 0.05, cosine) on that
+    tool's pair graphs (complete, not symmetrised);
+    ``flow=True``: ``align3r_b200.cloud_opt_flow`` as in tool/demo.py (pass lr=0.01 and its keyword arguments) on demo.py's
+    pair graphs (symmetrised; clips pair every image with every second later one) - ``pairs=`` overrides the choice.
     ``conf_to``: depth_test.py:638-639,659-660 sets every confidence above 1 to 10 before the alignment (``conf_to=10``).
     Returns a dict: ``traj`` = [tum poses (M,7), timestamps (M,)], ``depths`` / ``confs`` lists over all frames of all
     clips, ``focals``, ``key_poses``, ``losses`` (key alignment first).  With ``save_folder`` the per-clip results are also
@@ -79,7 +95,8 @@ def hierarchical_alignment(imgs, inference, device='cuda', clip_size=10, niter=3
         return out, fl
 
     clip_size = choose_clip_size(len(imgs), clip_size)
-    coarse_init_pairs, keyframes_id, all_clips_pairs, all_clips_id = my_make_pairs(imgs, clip_size)
+    coarse_init_pairs, keyframes_id, all_clips_pairs, all_clips_id = my_make_pairs(
+        imgs, clip_size, variant=pairs or ('demo' if flow else 'depth_test'))
     key_out, key_flow = run_inference(coarse_init_pairs)
     if len(imgs) > 2:                                        # tool/demo.py:204-216, depth_test.py:641-647
         scene = build(key_out, key_flow)
@@ -117,6 +134,8 @@ def hierarchical_alignment(imgs, inference, device='cuda', clip_size=10, niter=3
             clip.save_depth_maps(save_folder, offset)
             clip.save_conf_maps(save_folder, offset)
             clip.save_init_conf_maps(save_folder, offset)
+            if flow and getattr(clip, 'dynamic_masks', None) is not None:
+                clip.save_dynamic_masks(save_folder, offset)                 # tool/demo.py:240
         offset += t[0].shape[0]
         del clip
     return dict(traj=traj, depths=depths, confs=confs, focals=focals, key_poses=key_poses, key_focals=key_focals,

@@ -423,12 +423,15 @@ def run_ours(args, cfg, name):
                 netj = None
             return rec, netj
 
+        canon = None
+        if K != 300:        # the reference's canonical job length beside the driver's K (first: the kept job below holds its arena)
+            canon, _ = e2e_job(300, False)
         e2e, net = e2e_job(K, True)
         e2e["what"] = ("global_aligner(host dict) + compute_global_alignment(init='mst', niter=K) + depth/pose/focal/loss read-back, "
                        "whole job / K; inputs are uploaded once per job (they are constant across iterations); one untimed "
                        "3-iteration job on the same inputs runs first (process warm-up)")
-        if K != 300:        # the reference's canonical job length beside the driver's K
-            e2e["canonical_300_iterations"], _ = e2e_job(300, False)
+        if canon is not None:
+            e2e["canonical_300_iterations"] = canon
     if net is None:
         net = build()
         net.compute_global_alignment(init="mst", niter=0)

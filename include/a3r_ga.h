@@ -268,6 +268,12 @@ int a3r_ga_unproject(const A3rProblem *p, float *pts3d, void *stream);
  * world-to-camera, intr [n][4] = fx fy cx cy, hw [n][2] (device int32), conf [n][pix_stride] in/out. */
 int a3r_clean_pointcloud(const float *pts3d, const float *depth, const float *w2c, const float *intr, const int32_t *hw,
                          int32_t n, int64_t pix_stride, float tol, float bad_conf, float *conf, void *stream);
+/* the same for frames i0 <= i < i1 only (a frame-window shard): pts3d holds just those frames ([i1-i0][pix_stride][3], row
+ * i - i0), depth / conf / w2c / intr / hw cover all n frames (gathered by the caller; frames < i0 must already hold their
+ * final confidences - the windows are processed in rank order). */
+int a3r_clean_pointcloud_range(const float *pts3d, const float *depth, const float *w2c, const float *intr, const int32_t *hw,
+                               int32_t n, int32_t i0, int32_t i1, int64_t pix_stride, float tol, float bad_conf, float *conf,
+                               void *stream);
 
 /* ---- pre-step: self-estimated dynamic masks (reference optimizer.py:156-235 get_motion_mask_from_pairs, use_self_mask=True;
  *      ego flow = goem_opt.py:195-236 warp_by_disp) ----

@@ -33,6 +33,8 @@ def main():
                pred1={k: v[rows] for k, v in out["pred1"].items()}, pred2={k: v[rows] for k, v in out["pred2"].items()})
     net = global_aligner(sub, dev, mode=GlobalAlignerMode.PointCloudOptimizer, flow=(scene.flow_ij[rows], scene.flow_ji[rows]),
                          shard=dict(world=world, rank=rank, group=None), edge_rows=rows, **kw)
+    if len(sys.argv) > 3 and sys.argv[3] == "readout":
+        return readout(net, scene, prob, rank, world, lo, hi)
     loss = net.compute_global_alignment(init="mst", niter=fx["niter"], schedule="linear", lr=0.01)
     # replicated parameters must be bit-identical on every rank
     small = torch.cat([net.pw_poses.detach().flatten(), net.im_poses.detach().flatten(), net.im_focals.detach().flatten()])
@@ -46,6 +48,25 @@ def main():
     if rank == 0:
         torch.save(dict(parts=gathered, im_poses=net.get_im_poses().detach().cpu(), focals=net.get_focals().detach().cpu(),
                         exchange="peer" if net._peers is not None else "nccl"), sys.argv[2])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def readout(net, scene, prob, rank, world, lo, hi):
+    """The post-step and the lazy pre-step read-outs on frame windows, at parameters both sides build from the same recipe:
+    clean_pointcloud (every frame meets every other frame's depth map) and the flow validity maps (a pair's two flow planes
+    may live on different GPUs)."""
+    from align3r_b200.synth import load_params, near_solution_params
+    load_params(net, *near_solution_params(scene.gt, scene.edges, seed=0))
+    net.clean_pointcloud()
+    conf = torch.stack([c.detach().cpu() for c in net.im_conf])
+    vi, vj = net.flow_valid_mask_i, net.flow_valid_mask_j
+    rows_i, rows_j = net.flow_valid_rows(0), net.flow_valid_rows(1)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (lo, hi, conf, rows_i, vi[rows_i].cpu(), rows_j, vj[rows_j].cpu()))
+    net.close()
+    if rank == 0:
+        torch.save(dict(parts=gathered), sys.argv[2])
     dist.barrier()
     dist.destroy_process_group()
 

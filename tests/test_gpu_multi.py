@@ -69,3 +69,36 @@ def test_sharded_self_estimated_masks(cuda_device, tmp_path):
     assert int((masks != fx["dynamic_masks"]).sum()) <= 1e-3 * masks.numel()
     assert all(p[3] for p in parts) and len({p[4] for p in parts}) == 1
     assert abs(parts[0][4] - fx["free_run"]["loss"]) <= 1e-2 * abs(fx["free_run"]["loss"])
+
+
+def test_sharded_readouts_equal_the_single_device_ones(cuda_device, tmp_path):
+    """clean_pointcloud (reference base_opt.py:587-623, the step right after the loop in tool/pose_test.py:202-216) and the
+    flow validity maps (OccMask, goem_opt.py:575-618) on frame windows: bit-equal to the single-device product path at the
+    same parameters (which tests/test_gpu_parity.py pins on the reference's fixtures)."""
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    from align3r_b200.cloud_opt_flow import GlobalAlignerMode, global_aligner
+    from align3r_b200.synth import load_params, near_solution_params
+    out = str(tmp_path / "res.pt")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "dist_gpu_worker.py"), "small_flow", out, "readout"]
+    subprocess.run(cmd, check=True, timeout=600, cwd=ROOT, env=dict(os.environ))
+    res = torch.load(out, weights_only=False)
+    fx, scene, prob = golden_case("small_flow")
+    net = global_aligner(scene.output, cuda_device, mode=GlobalAlignerMode.PointCloudOptimizer, flow=(scene.flow_ij, scene.flow_ji),
+                         **dict(fx["kw"]))
+    load_params(net, *near_solution_params(scene.gt, scene.edges, seed=0))
+    before = torch.stack([c.detach().cpu().clone() for c in net.im_conf])
+    net.clean_pointcloud()
+    conf = torch.stack([c.detach().cpu() for c in net.im_conf])
+    assert int((conf != before).sum()) > 0, "the clean-up changed nothing: the test scene does not exercise it"
+    parts = sorted(res["parts"], key=lambda t: t[0])
+    assert torch.equal(torch.cat([p[2] for p in parts]), conf)
+    vi, vj = net.flow_valid_mask_i.cpu(), net.flow_valid_mask_j.cpu()
+    seen_i, seen_j = set(), set()
+    for _, _, _, rows_i, part_i, rows_j, part_j in parts:
+        assert torch.equal(part_i, vi[rows_i]) and torch.equal(part_j, vj[rows_j])
+        seen_i |= set(rows_i)
+        seen_j |= set(rows_j)
+    assert seen_i == set(range(prob.n_edges)) and seen_j == set(range(prob.n_edges))

@@ -30,6 +30,71 @@ def test_clip_pairs_match_the_reference():
     assert hi.choose_clip_size(50, 10) == 9 and hi.choose_clip_size(110, 50) == 50 and hi.choose_clip_size(7, 10) == 5
 
 
+def _reference_function(path, name):
+    """Source of ONE top-level function of a reference tool script, compiled on its own (the tool scripts import gradio,
+    the network, ... at module scope and cannot be imported here)."""
+    import ast
+    import os
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not present (build container only)")
+    tree = ast.parse(open(path).read())
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == name)
+    ns = {}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    return ns[name]
+
+
+@pytest.mark.parametrize("variant,tool", [("demo", "tool/demo.py"), ("depth_test", "tool/depth_test.py")])
+@pytest.mark.parametrize("n,clip", [(23, 10), (12, 5), (7, 4)])
+def test_pair_builders_match_the_reference_tools_live(variant, tool, n, clip):
+    """my_make_pairs of BOTH reference drivers (tool/demo.py:357-397: symmetrised key pairs, stride-2 mirrored clip pairs;
+    tool/depth_test.py:395-435: complete unsymmetrised graphs), executed from the reference's own source."""
+    ref_fn = _reference_function("/root/reference/" + tool, "my_make_pairs")
+    clip = hi.choose_clip_size(n, clip)
+    ours = hi.my_make_pairs(imgs_of(n), clip, variant=variant)
+    ref = ref_fn([dict(idx=k, frame=k) for k in range(n)], clip)
+    assert ours[1] == ref[1] and ours[3] == ref[3]
+    sig = lambda pairs: [(a["idx"], b["idx"], a["frame"], b["frame"]) for a, b in pairs]      # noqa: E731
+    assert sig(ours[0]) == sig(ref[0])
+    assert [sig(c) for c in ours[2]] == [sig(c) for c in ref[2]]
+    if variant == "demo":          # what use_self_mask=True asserts on (reference optimizer.py:157)
+        for pairs in [ours[0]] + [c for c in ours[2] if c]:
+            e = {(a["idx"], b["idx"]) for a, b in pairs}
+            assert e == {(j, i) for i, j in e}
+
+
+@pytest.mark.gpu
+def test_hierarchical_flow_arm_with_self_masks(cuda_device, tmp_path):
+    """tool/demo.py's arm of the driver: the flow aligner with use_self_mask=True (demo.py's default) on demo.py's symmetrised
+    pair graphs, key frames then clips.  Checked against the synthetic ground truth: the run completes on every clip (the
+    self-mask pre-step asserts symmetric graphs), the trajectory is complete and the depth maps are sane."""
+    from align3r_b200.synth import CANONICAL_KW
+    N, H, W = 14, 48, 64
+
+    def inference(pairs):
+        edges = [(a["frame"], b["frame"]) for a, b in pairs]
+        sc = make_scene(N, H, W, "complete", seed=5, with_flow=True, edges=edges)
+        out = copy.deepcopy(sc.output)
+        out["view1"]["idx"] = [a["idx"] for a, _ in pairs]
+        out["view2"]["idx"] = [b["idx"] for _, b in pairs]
+        return out, (sc.flow_ij, sc.flow_ji)
+
+    kw = dict(CANONICAL_KW, use_self_mask=True, num_total_iter=30)
+    res = hi.hierarchical_alignment(imgs_of(N), inference, device="cuda", clip_size=5, niter=30, schedule="linear", lr=0.01,
+                                    flow=True, save_folder=str(tmp_path), **kw)
+    assert res["clip_size"] == 5 and res["keyframes_id"] == [0, 5, 10]
+    tum, tt = res["traj"]
+    assert tum.shape == (N, 7) and tt.tolist() == list(range(N))
+    assert all(np.isfinite(l) for l in res["losses"]) and len(res["losses"]) == 4
+    gt = make_scene(N, H, W, "complete", seed=5, with_flow=False, edges=[(0, 1)]).gt
+    d = np.stack(res["depths"])
+    ratio = np.stack([d[n] / gt.depth(n).numpy() for n in range(N)])
+    # depth up to one global scale per clip: the spread of the ratio inside a frame is small
+    assert float(np.median(ratio.std(axis=(1, 2)) / ratio.mean(axis=(1, 2)))) < 0.05
+    assert (tmp_path / "pred_traj.txt").read_text().count("\n") == N
+    assert (tmp_path / "dynamic_mask_0.png").exists() and (tmp_path / f"dynamic_mask_{N - 1}.png").exists()
+
+
 @pytest.mark.gpu
 def test_hierarchical_alignment_against_reference_run(cuda_device, tmp_path):
     """Key frames, then clips started from the key poses (init_priors).  The protocol's lr = 0.05 makes the 30 iterations a
