@@ -7,7 +7,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("A3R_LIB") or os.path.join(HERE, "lib", "liba3r_ga.so")   # A3R_LIB: tuning builds
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 # A3rProblem.flags
 F_SHARED_FOCAL, F_NORM_PW_SCALE, F_DIST_L2 = 1 << 0, 1 << 1, 1 << 2
@@ -15,7 +15,8 @@ F_TRAIN_PW_POSES, F_TRAIN_DEPTH, F_TRAIN_IM_POSES, F_TRAIN_FOCALS = 1 << 3, 1 <<
 F_TRAIN_PP, F_TRAIN_ADAPTORS, F_HAS_FLOW = 1 << 7, 1 << 8, 1 << 9
 # mode bits
 M_FLOW_ACTIVE, M_APPLY_ADAM = 1 << 0, 1 << 1
-SLOT_ACC, FRAME_ACC, PRIOR_ACC, SCAL = 28, 12, 4, 16
+SLOT_ACC, FRAME_ACC, PRIOR_ACC, GLOB_ACC, SCAL = 28, 12, 4, 8, 16
+PAIR_ROW, CAM_ROW = 32, 20
 S_LOSS, S_ALIGN, S_TEMPORAL, S_FLOW, S_FLOW_DROPPED, S_SC_I, S_SC_J, S_FLAG_STICKY = range(8)
 S_PRIOR = 10
 CONF_MODES = {"log": 0, "sqrt": 1, "m1": 2, "id": 3, "none": 3}
@@ -34,6 +35,7 @@ _POINTER_FIELDS = [
     "logdepth", "logdepth_m", "logdepth_v", "g_align", "g_flow_i", "g_flow_j",
     "acc_slot", "acc_frame", "frame_grad", "edge_scratch", "scal", "loss_hist",
     "logdepth_init", "prior_acc",
+    "acc_glob", "acc_alt", "pair_scratch", "cam_cache", "inc_begin", "inc_items", "sync_ctr",
 ]
 
 
@@ -53,7 +55,7 @@ MAX_PEERS = 8
 
 
 class A3rPeers(C.Structure):
-    _fields_ = [("world", _i32), ("rank", _i32), ("n_acc", _i64), ("base", _vp * MAX_PEERS)]
+    _fields_ = [("world", _i32), ("rank", _i32), ("n_acc", _i64), ("base", _vp * MAX_PEERS), ("win", _i32 * (MAX_PEERS + 1))]
 
 
 class A3rAdamStep(C.Structure):

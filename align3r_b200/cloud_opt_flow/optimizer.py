@@ -928,7 +928,7 @@ class PointCloudOptimizer(nn.Module):
         if not (dist.is_available() and dist.is_initialized()):
             return None
         want = os.environ.get("A3R_EXCHANGE", "peer") != "nccl" and world <= _lib.MAX_PEERS
-        n_acc = int(self._bufs.acc.numel())
+        n_acc = int(self._bufs.n_acc)
         region, handle, ok = C.c_void_p(), C.create_string_buffer(64), want
         with torch.cuda.device(self._device):
             if want and self._lib.a3r_peer_alloc(n_acc, C.byref(region), handle) != 0:
@@ -938,6 +938,8 @@ class PointCloudOptimizer(nn.Module):
             ok = all(h[0] for h in handles)
             peers = _lib.A3rPeers()
             peers.world, peers.rank, peers.n_acc = world, rank, n_acc
+            for r, (lo, hi) in enumerate(self._windows):
+                peers.win[r], peers.win[r + 1] = lo, hi
             opened = []
             if ok:
                 for r in range(world):

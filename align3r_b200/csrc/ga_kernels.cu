@@ -10,53 +10,10 @@
 #include "ga_math.cuh"
 #include "a3r_common.cuh"
 #include "ga_scan_v4.cuh"
+#include "ga_small.cuh"     // K0 (parameter maps) and K2 (loss, gate, chains, small Adam, exchange)
 #include <stdlib.h>
 
 using namespace a3r;
-
-// ==========================================================================================
-// K0: parameter maps  (reference base_opt.py:195-247, optimizer.py:398-428)
-// ==========================================================================================
-// body shared by the stand-alone launch and the tail of the fused update kernel (256 threads per CTA in both, so the
-// mean of the pair log-scales is the same number, bit for bit, wherever it is evaluated)
-__device__ __forceinline__ void prepare_body(const A3rProblem& p, const int gid, const int gstride, double* s_red, double* s_mean) {
-    const int tid = threadIdx.x;
-    const int E = p.n_edges, N = p.n_frames;
-    const bool shared_focal = p.flags & A3R_F_SHARED_FOCAL;
-    const bool norm_scale = p.flags & A3R_F_NORM_PW_SCALE;
-
-    // every CTA recomputes mean_e(log scale) in the same order -> identical on all CTAs
-    double part = 0.0;
-    for (int e = tid; e < E; e += blockDim.x) part += (double)p.pw_poses[8 * e + 7];
-    part = block_sum(part, s_red);
-    if (tid == 0) *s_mean = part / (double)E;
-    __syncthreads();
-    const double log_norm = norm_scale ? (log((double)p.base_scale) - *s_mean) : 0.0;
-
-    for (int n = gid; n < N; n += gstride) {
-        FrameD F;
-        load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n, shared_focal, (double)p.focal_break, F);
-        derive_frame_par(F, p.frame_par + FP_STRIDE * n);
-    }
-    for (int e = gid; e < E; e += gstride)
-        derive_edge_par(p.pw_poses + 8 * e, p.pw_adaptors + 2 * e, log_norm, norm_scale, (double)p.pw_break, p.edge_par + EP_STRIDE * e);
-    if (p.flags & A3R_F_HAS_FLOW) {
-        for (int gs = gid; gs < 2 * E; gs += gstride) {
-            const int e = gs >> 1, side = gs & 1;
-            const int i = p.edge_ij[2 * e], j = p.edge_ij[2 * e + 1];
-            FrameD S, T;
-            load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, side ? j : i, shared_focal, (double)p.focal_break, S);
-            load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, side ? i : j, shared_focal, (double)p.focal_break, T);
-            derive_slot_par(S, T, p.slot_par + SP_STRIDE * gs);
-        }
-    }
-}
-
-__global__ void __launch_bounds__(256) k_prepare(const A3rProblem p) {
-    __shared__ double s_red[32];
-    __shared__ double s_mean;
-    prepare_body(p, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, s_red, &s_mean);
-}
 
 // ==========================================================================================
 // K1 (v1): fused forward + backward over pixel-slots, frame-major, thread-owns-pixels.
@@ -103,7 +60,12 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k_accumulate_v1(const A3rProble
             double sum = 0.0;
 #pragma unroll
             for (int w = 0; w < K1_WARPS; ++w) sum += s_wacc[(w * K1_MAXS + s) * ACC_STRIDE + i];
-            if (sum != 0.0) atomicAdd(&p.acc_slot[(int64_t)sh.gslot[s] * ACC_STRIDE + i], sum);
+            if (sum != 0.0) {
+                atomicAdd(&p.acc_slot[(int64_t)sh.gslot[s] * ACC_STRIDE + i], sum);
+                // the whole-problem sums the gate and the loss need (acc_glob)
+                if (i == ACC_LOSS) atomicAdd(&p.acc_glob[GL_LOSS], sum);
+                else if (i == ACC_FNUM || i == ACC_FCNT) atomicAdd(&p.acc_glob[((sh.gslot[s] & 1) ? GL_FNUM_J : GL_FNUM_I) + (i - ACC_FNUM)], sum);
+            }
         }
 #pragma unroll
         for (int k = 0; k < FACC_N; ++k) {
@@ -244,21 +206,6 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k_accumulate_v1(const A3rProble
 }
 
 // ==========================================================================================
-// K2: loss assembly, gate, temporal term, parameter-chain gradients, Adam on the small parameters.
-//     O(E + N) small fp64 blocks, split at its two global dependencies into four tiny launches:
-//     scalars/gate -> camera chains (atomics) -> gradients + Adam -> shared focal.
-// ==========================================================================================
-__device__ __forceinline__ void scatter_pair(const PairGrad& g, double* fgS, double* fgT) {
-    for (int k = 0; k < 15; ++k) {
-        if (g.s[k] != 0.0) atomicAdd(&fgS[k], g.s[k]);
-        if (g.t[k] != 0.0) atomicAdd(&fgT[k], g.t[k]);
-    }
-}
-
-// extra scratch scalars of the update step (A3rProblem.scal)
-constexpr int S_GSUM = 8;      // sum_e dL/dlog s_e  (mean coupling of the pair scales)
-constexpr int S_GPHI = 9;      // sum_n dL/dphi_n    (shared focal)
-
 // depth prior: 4 sums per local frame (grid: chunks x local frames), fp64 atomics into prior_acc
 __global__ void __launch_bounds__(256) k_depth_prior(const A3rProblem p) {
     __shared__ double s_red[32];
@@ -278,287 +225,15 @@ __global__ void __launch_bounds__(256) k_depth_prior(const A3rProblem p) {
 }
 
 // ==========================================================================================
-// K2: loss, gate, every parameter chain, Adam on the small parameters and the parameter maps of the NEXT iteration in
-// ONE launch: a thread-block cluster of 8 CTAs x 256 threads whose phases are separated by the hardware cluster barrier
-// (barrier.cluster arrive.release / wait.acquire orders the global-memory traffic of the phases), instead of five
-// launches + a memset separated by kernel boundaries.  This chain is pure latency (a few thousand items of fp64
-// arithmetic, instruction fetch of run-once code, dependent L2 round trips) and sits on the critical path between two
-// scans, so the kernel is organised around doing every expensive thing once:
-//   * the fp64 camera of every frame (quaternion -> R, signed_expm1 translations, exp focal: FrameD) is evaluated ONCE
-//     per CTA into shared memory and every chain reads it from there; once more after the update for the maps;
-//   * the shared focal's Adam step is evaluated redundantly by every CTA from values it read before anyone writes
-//     them, so it needs no phase (and no barrier) of its own;
-//   * frame_grad is zeroed in the tail for the next call (the entry points zero it once before the first).
-//   phase A  cameras -> shared memory | loss sums + gate: every CTA in the same order, CTA 0 publishes p.scal |
-//            chains that end in a camera (fp64 atomics into frame_grad) + dL/dlog s_e
-//   phase B  gradients of pw_poses / im_poses (/ per-frame focal, pp) + torch.optim.Adam
-//   phase C  the shared focal | cameras of the updated parameters -> shared memory | parameter maps (= k_prepare of the
-//            next iteration) | zero frame_grad
-// ==========================================================================================
-constexpr int K2_CLUSTER = 8;
-constexpr int K2_THREADS = 256;
-constexpr int K2_MAX_FRAMES = 1280;        // cameras in shared memory: 160 B each (200 KB of the 227 KB opt-in limit); more: global scratch
-
-// diagnostic phase trace of K2 (a3r_debug_k2_trace): globaltimer stamps of thread 0 of every CTA at the phase boundaries
-__device__ unsigned long long g_k2_trace[K2_CLUSTER * 8];
-__device__ int g_k2_trace_on = 0;
-__device__ __forceinline__ void k2_stamp(int slot) {
-    if (g_k2_trace_on && threadIdx.x == 0) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        g_k2_trace[blockIdx.x * 8 + slot] = t;
-    }
-}
-
-__device__ __forceinline__ void cluster_barrier() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
-// the four flow sums (numerator / per-channel mask count of both sides) over all 2E slots in a fixed 256-thread order:
-// K2 and the depth-plane Adam kernel K3 both evaluate them (K3 must not wait for K2) and must agree bit for bit.
-// Element k = 2 gs + which of the (FNUM, FCNT) pairs; with a stride of 256 a thread only ever sees category k & 3 =
-// (side, which), so it carries ONE running sum, all loads are independent, and one shuffle tree + one block barrier
-// finish all four sums.  out = num_i, cnt_i, num_j, cnt_j.  `red`: >= 32 doubles of shared memory.
-__device__ __forceinline__ void flow_sums_256(const A3rProblem& p, double* red, double out[4]) {
-    static_assert(ACC_FCNT == ACC_FNUM + 1, "flow numerator and count are adjacent in a slot's accumulator row");
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int total = 4 * p.n_edges;
-    double acc = 0.0;
-#pragma unroll 4
-    for (int k = tid; k < total; k += 256) acc += p.acc_slot[(int64_t)(k >> 1) * ACC_STRIDE + ACC_FNUM + (k & 1)];
-    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 8);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-    if (lane < 4) red[warp * 4 + lane] = acc;
-    __syncthreads();
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        double r = 0.0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) r += red[w * 4 + c];
-        out[c] = r;
-    }
-    __syncthreads();
-}
-
-// three CTA-wide sums with one block barrier (256 threads; fixed order, every thread gets the results)
-__device__ __forceinline__ void block_sum3_256(double& a, double& b, double& c, double* red) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
-    if (lane == 0) { red[warp * 3] = a; red[warp * 3 + 1] = b; red[warp * 3 + 2] = c; }
-    __syncthreads();
-    double ra = 0.0, rb = 0.0, rc = 0.0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) { ra += red[w * 3]; rb += red[w * 3 + 1]; rc += red[w * 3 + 2]; }
-    __syncthreads();
-    a = ra; b = rb; c = rc;
-}
-
-__device__ __forceinline__ void adam_vec(float* prm, float* m, float* v, const float* g, int cnt,
-                                         const A3rProblem& p, const A3rAdamStep& a) {
-    for (int k = 0; k < cnt; ++k)
-        adam_update(prm[k], m[k], v[k], g[k], p.adam_beta1, p.adam_beta2, p.adam_eps, a.step_size, a.bc2_sqrt);
-}
-
-// every frame's fp64 camera into shared memory; `focals` may point at a shared-memory copy of the shared focal
-// (one copy of this code, called twice; plain arguments so that the parameter block is not spilled to pass a reference)
-__device__ __noinline__ void fill_cameras(const float* im_poses, const float* focals, const float* im_pp, const int32_t* frame_hw,
-                                          int N, bool shared_focal, double focal_break, FrameD* fr) {
-    for (int n = threadIdx.x; n < N; n += K2_THREADS)
-        load_frame(im_poses, focals, im_pp, frame_hw, n, shared_focal, focal_break, fr[n]);
-    __syncthreads();
-}
-
-__global__ void __cluster_dims__(K2_CLUSTER, 1, 1) __launch_bounds__(K2_THREADS, 1)
-k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const uint32_t prepare_next, FrameD* const cam_scratch) {
-    extern __shared__ __align__(16) unsigned char k2_smem[];
-    // cameras: shared memory up to K2_MAX_FRAMES frames; beyond that a library-owned global scratch every CTA fills with the
-    // same values (identical writes; a CTA reads what it wrote itself after its own block barrier)
-    FrameD* fr = cam_scratch ? cam_scratch : reinterpret_cast<FrameD*>(k2_smem);
-    __shared__ double s_red[32];
-    __shared__ double s_sc[2];
-    __shared__ double s_mean;
-    __shared__ float s_foc[3];                 // the shared focal: parameter, m, v as they were when the kernel started
-    const int tid = threadIdx.x;
-    const int vt = blockIdx.x * K2_THREADS + tid, nvt = gridDim.x * K2_THREADS;      // the grid is one cluster
-    const int N = p.n_frames, E = p.n_edges;
-    const bool shared_focal = p.flags & A3R_F_SHARED_FOCAL;
-    const bool norm_scale = p.flags & A3R_F_NORM_PW_SCALE;
-    const bool flow_active = (mode & A3R_M_FLOW_ACTIVE) && (p.flags & A3R_F_HAS_FLOW) && p.flow_loss_weight > 0.f;
-    const bool apply = mode & A3R_M_APPLY_ADAM;
-    const double fb = (double)p.focal_break;
-    const double tsw = (double)p.temporal_smoothing_weight, tw = (double)p.translation_weight;
-
-    // ---------------- phase A: cameras, loss assembly + gate (reference optimizer.py:538-557), chains ----------------
-    k2_stamp(0);
-    if (shared_focal && tid == 0) { s_foc[0] = p.im_focals[0]; s_foc[1] = p.im_focals_m[0]; s_foc[2] = p.im_focals_v[0]; }
-    fill_cameras(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, N, shared_focal, fb, fr);
-    k2_stamp(1);
-    {
-        double l_align = 0, l_temp = 0, l_prior = 0;
-        if (p.depth_regularize_weight > 0.f)
-            for (int n = tid; n < N; n += K2_THREADS)
-                l_prior += prior_frame(p.prior_acc + (int64_t)n * PR_N, (double)p.frame_hw[2 * n] * p.frame_hw[2 * n + 1]).loss;
-        for (int gs = tid; gs < 2 * E; gs += K2_THREADS) l_align += p.acc_slot[(int64_t)gs * ACC_STRIDE + ACC_LOSS];
-        if (tsw > 0)
-            for (int n = tid; n < N - 1; n += K2_THREADS) l_temp += temporal_pair(fr[n + 1], fr[n], tsw, tw, nullptr);
-        double fs[4];
-        flow_sums_256(p, s_red, fs);
-        block_sum3_256(l_align, l_temp, l_prior, s_red);
-        l_prior /= (double)N;
-        if (tid == 0) {
-            LossScalars r = assemble_loss(l_align, l_temp, fs[0], fs[1], fs[2], fs[3], flow_active,
-                                          (double)p.flow_loss_weight, (double)p.flow_loss_thre, tsw);
-            s_sc[0] = r.sc_i; s_sc[1] = r.sc_j;
-            if (blockIdx.x == 0) {
-                r.loss += (double)p.depth_regularize_weight * l_prior;           // optimizer.py:554-557
-                p.scal[A3R_S_PRIOR] = l_prior;
-                p.scal[A3R_S_LOSS] = r.loss; p.scal[A3R_S_ALIGN] = l_align; p.scal[A3R_S_TEMPORAL] = l_temp;
-                p.scal[A3R_S_FLOW] = r.floss; p.scal[A3R_S_FLOW_DROPPED] = r.dropped;
-                p.scal[A3R_S_SC_I] = r.sc_i; p.scal[A3R_S_SC_J] = r.sc_j;
-                if (r.dropped != 0) p.scal[A3R_S_FLAG_STICKY] = 1.0;
-                if (p.loss_hist && adam.iter >= 0) p.loss_hist[adam.iter] = (float)r.loss;
-            }
-        }
-        __syncthreads();
-    }
-    k2_stamp(2);
-    //   chain items: [0,N) alignment part of frame n | [N, N+2E) flow chain of a slot | [.., +N-1) temporal pair | [.., +E) edge
-    //   (frame_grad, scal[S_GSUM] and scal[S_GPHI] are zero on entry: zeroed by the previous call's tail / the entry point)
-    {
-        const double sc_i = s_sc[0], sc_j = s_sc[1];
-        const int total = N + 2 * E + (N - 1) + E;
-        for (int it = vt; it < total; it += nvt) {
-            if (it < N) {
-                const int n = it;
-                double fg[FG_STRIDE];
-                frame_align_grad(fr[n], p.acc_frame + (int64_t)n * FACC_N, fg);
-                double* dst = p.frame_grad + (int64_t)n * FG_STRIDE;
-                for (int k = 0; k < 15; ++k) atomicAdd(&dst[k], fg[k]);
-            } else if (it < N + 2 * E) {
-                if (!(flow_active && (sc_i != 0 || sc_j != 0))) continue;
-                const int gs = it - N, e = gs >> 1, side = gs & 1;
-                const int i = p.edge_ij[2 * e], j = p.edge_ij[2 * e + 1];
-                const int sI = side ? j : i, tI = side ? i : j;
-                PairGrad g;
-                slot_flow_chain(fr[sI], fr[tI], p.acc_slot + (int64_t)gs * ACC_STRIDE, side ? sc_j : sc_i, g);
-                scatter_pair(g, p.frame_grad + (int64_t)sI * FG_STRIDE, p.frame_grad + (int64_t)tI * FG_STRIDE);
-            } else if (it < N + 2 * E + N - 1) {
-                if (!(tsw > 0)) continue;
-                const int n = it - N - 2 * E;
-                PairGrad g;
-                temporal_pair(fr[n + 1], fr[n], tsw, tw, &g);
-                scatter_pair(g, p.frame_grad + (int64_t)(n + 1) * FG_STRIDE, p.frame_grad + (int64_t)n * FG_STRIDE);
-            } else {
-                const int e = it - N - 2 * E - (N - 1);
-                const double* a0 = p.acc_slot + (int64_t)(2 * e) * ACC_STRIDE;
-                const double g = edge_logscale_grad(p.edge_par + EP_STRIDE * e, a0, a0 + ACC_STRIDE);
-                p.edge_scratch[e] = g;
-                atomicAdd(&p.scal[S_GSUM], g);
-            }
-        }
-    }
-    k2_stamp(3);
-    cluster_barrier();
-    k2_stamp(4);
-
-    // ---------------- phase B: gradients of the small parameters + torch.optim.Adam ----------------
-    //   items: [0,E) pairwise pose | [E, E+N) image pose
-    {
-        const double gmean = norm_scale ? p.scal[S_GSUM] / (double)E : 0.0;
-        for (int it = vt; it < E + N; it += nvt) {
-            if (it < E) {
-                const int e = it;
-                const double* a0 = p.acc_slot + (int64_t)(2 * e) * ACC_STRIDE;
-                float g[8], ga[2];
-                edge_pose_grad(p.pw_poses + 8 * e, p.edge_par + EP_STRIDE * e, a0, a0 + ACC_STRIDE, p.edge_scratch[e] - gmean,
-                               p.flags & A3R_F_TRAIN_ADAPTORS, norm_scale, (double)p.pw_break, g, ga);
-                for (int k = 0; k < 8; ++k) p.g_pw_poses[8 * e + k] = g[k];
-                p.g_pw_adaptors[2 * e] = ga[0]; p.g_pw_adaptors[2 * e + 1] = ga[1];
-                if (apply && (p.flags & A3R_F_TRAIN_PW_POSES)) adam_vec(p.pw_poses + 8 * e, p.pw_poses_m + 8 * e, p.pw_poses_v + 8 * e, g, 8, p, adam);
-                if (apply && (p.flags & A3R_F_TRAIN_ADAPTORS)) adam_vec(p.pw_adaptors + 2 * e, p.pw_adaptors_m + 2 * e, p.pw_adaptors_v + 2 * e, ga, 2, p, adam);
-            } else {
-                const int n = it - E;
-                float g[7], gpp[2];
-                double gphi;
-                frame_pose_grad(p.im_poses + 7 * n, fr[n], p.frame_grad + (int64_t)n * FG_STRIDE, fb, p.flags & A3R_F_TRAIN_PP, g, &gphi, gpp);
-                for (int k = 0; k < 7; ++k) p.g_im_poses[7 * n + k] = g[k];
-                p.g_im_pp[2 * n] = gpp[0]; p.g_im_pp[2 * n + 1] = gpp[1];
-                if (shared_focal) atomicAdd(&p.scal[S_GPHI], gphi);     // applied in phase C
-                else {
-                    float gf = (float)gphi;
-                    p.g_im_focals[n] = gf;
-                    if (apply && (p.flags & A3R_F_TRAIN_FOCALS)) adam_vec(p.im_focals + n, p.im_focals_m + n, p.im_focals_v + n, &gf, 1, p, adam);
-                }
-                if (apply && (p.flags & A3R_F_TRAIN_PP)) adam_vec(p.im_pp + 2 * n, p.im_pp_m + 2 * n, p.im_pp_v + 2 * n, gpp, 2, p, adam);
-                if (apply && (p.flags & A3R_F_TRAIN_IM_POSES)) adam_vec(p.im_poses + 7 * n, p.im_poses_m + 7 * n, p.im_poses_v + 7 * n, g, 7, p, adam);
-            }
-        }
-    }
-    k2_stamp(5);
-    cluster_barrier();
-    k2_stamp(6);
-
-    // ---------------- phase C: the shared focal, the parameter maps of the next iteration, zero the scratch ----------------
-    // Every CTA steps the shared focal from the values it saved in phase A (nobody has written them yet) and the complete
-    // sum of phase B: the same number on every CTA; CTA 0 stores it.
-    if (shared_focal && tid == 0) {
-        float gf = (float)p.scal[S_GPHI];
-        if (apply && (p.flags & A3R_F_TRAIN_FOCALS)) adam_vec(&s_foc[0], &s_foc[1], &s_foc[2], &gf, 1, p, adam);
-        if (blockIdx.x == 0) {
-            p.g_im_focals[0] = gf;
-            p.im_focals[0] = s_foc[0]; p.im_focals_m[0] = s_foc[1]; p.im_focals_v[0] = s_foc[2];
-        }
-    }
-    __syncthreads();
-    if (prepare_next) {       // reference base_opt.py:195-247, optimizer.py:398-428 of the updated parameters
-        const float* focals = shared_focal ? s_foc : p.im_focals;
-        fill_cameras(p.im_poses, focals, p.im_pp, p.frame_hw, N, shared_focal, fb, fr);
-        double part = 0.0;    // every CTA recomputes mean_e(log scale) in k_prepare's order -> the same number everywhere
-        for (int e = tid; e < E; e += K2_THREADS) part += (double)p.pw_poses[8 * e + 7];
-        part = block_sum(part, s_red);
-        if (tid == 0) s_mean = part / (double)E;
-        __syncthreads();
-        const double log_norm = norm_scale ? (log((double)p.base_scale) - s_mean) : 0.0;
-        for (int n = vt; n < N; n += nvt) derive_frame_par(fr[n], p.frame_par + FP_STRIDE * n);
-        for (int e = vt; e < E; e += nvt)
-            derive_edge_par(p.pw_poses + 8 * e, p.pw_adaptors + 2 * e, log_norm, norm_scale, (double)p.pw_break, p.edge_par + EP_STRIDE * e);
-        if (p.flags & A3R_F_HAS_FLOW) {
-            for (int gs = vt; gs < 2 * E; gs += nvt) {
-                const int e = gs >> 1, side = gs & 1;
-                const int i = p.edge_ij[2 * e], j = p.edge_ij[2 * e + 1];
-                derive_slot_par(fr[side ? j : i], fr[side ? i : j], p.slot_par + SP_STRIDE * gs);
-            }
-        }
-    }
-    for (int i = vt; i < N * FG_STRIDE; i += nvt) p.frame_grad[i] = 0.0;
-    if (vt == 0) { p.scal[S_GSUM] = 0.0; p.scal[S_GPHI] = 0.0; }
-    k2_stamp(7);
-}
-
-// ==========================================================================================
 // K3: Adam on the log-depth planes (or, without A3R_M_APPLY_ADAM, total depth gradient -> g_align)
 // ==========================================================================================
 template <bool FLOW>
 __global__ void __launch_bounds__(256, 4) k_update_depth(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam) {
     const int64_t total4 = (int64_t)p.n_local_frames * p.pix_stride / 4;
     const bool prior = p.depth_regularize_weight > 0.f;
-    // the flow normalisers and the gate, evaluated here exactly as K2 evaluates them: K3 starts right after the scan,
-    // beside K2, instead of waiting for K2's scalars
+    // the flow normalisers and the gate as K2 published them (K3 runs after K2 on the same stream)
     float sc_i = 0.f, sc_j = 0.f;
-    if (FLOW) {
-        __shared__ double s_red[32];
-        __shared__ float s_sc[2];
-        double fs[4];
-        flow_sums_256(p, s_red, fs);
-        if (threadIdx.x == 0) {
-            const LossScalars r = assemble_loss(0.0, 0.0, fs[0], fs[1], fs[2], fs[3], true, (double)p.flow_loss_weight,
-                                                (double)p.flow_loss_thre, 0.0);
-            s_sc[0] = (float)r.sc_i; s_sc[1] = (float)r.sc_j;
-        }
-        __syncthreads();
-        sc_i = s_sc[0]; sc_j = s_sc[1];
-    }
+    if (FLOW) { sc_i = (float)p.scal[A3R_S_SC_I]; sc_j = (float)p.scal[A3R_S_SC_J]; }
     const bool apply = mode & A3R_M_APPLY_ADAM;
     float4* ld = reinterpret_cast<float4*>(p.logdepth);
     float4* mm = reinterpret_cast<float4*>(p.logdepth_m);
@@ -690,6 +365,15 @@ static int check_problem(const A3rProblem* p) {
     if (p->pix_stride % 4 != 0) return a3r_fail(A3R_E_ARG, "pix_stride must be a multiple of 4");
     if (p->acc_frame != p->acc_slot + (int64_t)2 * p->n_edges * A3R_SLOT_ACC)
         return a3r_fail(A3R_E_ARG, "acc_frame must directly follow acc_slot");
+    {
+        const bool prior = p->depth_regularize_weight > 0.f;
+        if (prior && p->prior_acc != p->acc_frame + (int64_t)p->n_frames * A3R_FRAME_ACC)
+            return a3r_fail(A3R_E_ARG, "prior_acc must directly follow acc_frame");
+        if (p->acc_glob != p->acc_frame + (int64_t)p->n_frames * (A3R_FRAME_ACC + (prior ? A3R_PRIOR_ACC : 0)))
+            return a3r_fail(A3R_E_ARG, "acc_glob must close the accumulator block (after prior_acc / acc_frame)");
+    }
+    if (!p->pair_scratch || !p->cam_cache || !p->inc_begin || !p->inc_items || !p->sync_ctr || !p->frame_grad || !p->edge_scratch || !p->scal)
+        return a3r_fail(A3R_E_ARG, "a scratch buffer of the update step is NULL (pair_scratch, cam_cache, inc_begin, inc_items, sync_ctr, ...)");
     return A3R_OK;
 }
 
@@ -777,26 +461,39 @@ int a3r_pack_flow(const float* flow_src, int32_t n, int64_t P, const int32_t* ds
 int a3r_ga_prepare(const A3rProblem* p, uint32_t mode, void* stream) {
     (void)mode;
     if (int rc = check_problem(p)) return rc;
-    int work = 2 * p->n_edges > p->n_frames ? 2 * p->n_edges : p->n_frames;
-    int grid = (work + 255) / 256;
+    const int work = 3 * p->n_edges + p->n_frames;
+    int grid = (work + K2_THREADS - 1) / K2_THREADS;
     if (grid > 148) grid = 148;
-    k_prepare<<<grid, 256, 0, (cudaStream_t)stream>>>(*p);
+    k_prepare<<<grid, K2_THREADS, 0, (cudaStream_t)stream>>>(*p);
     A3R_CUDA(cudaGetLastError());
     return A3R_OK;
 }
 
-int a3r_ga_accumulate(const A3rProblem* p, uint32_t mode, void* stream) {
-    if (int rc = check_problem(p)) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
+// doubles in one accumulator block: acc_slot | acc_frame | prior_acc | acc_glob
+static int64_t acc_block_doubles(const A3rProblem* p) {
+    const bool prior = p->depth_regularize_weight > 0.f;
+    return (int64_t)2 * p->n_edges * A3R_SLOT_ACC + (int64_t)p->n_frames * (A3R_FRAME_ACC + (prior ? A3R_PRIOR_ACC : 0)) + A3R_GLOB_ACC;
+}
+
+// a copy of the descriptor whose accumulator pointers address `block`
+static A3rProblem with_block(const A3rProblem* p, double* block) {
+    A3rProblem q = *p;
+    const bool prior = p->depth_regularize_weight > 0.f;
+    q.acc_slot = block;
+    q.acc_frame = block + (int64_t)2 * p->n_edges * A3R_SLOT_ACC;
+    q.prior_acc = prior ? q.acc_frame + (int64_t)p->n_frames * A3R_FRAME_ACC : p->prior_acc;
+    q.acc_glob = q.acc_frame + (int64_t)p->n_frames * (A3R_FRAME_ACC + (prior ? A3R_PRIOR_ACC : 0));
+    return q;
+}
+
+// the scan proper; the accumulator block it adds into must be zero (zero_first: a memset ahead of it)
+static int accumulate(const A3rProblem* p, uint32_t mode, cudaStream_t st, bool zero_first) {
     const bool flow = (mode & A3R_M_FLOW_ACTIVE) && (p->flags & A3R_F_HAS_FLOW) && p->flow_loss_weight > 0.f;
     if (flow && (!p->flow || !p->static_mask)) return a3r_fail(A3R_E_ARG, "flow active but flow/static_mask planes are NULL");
     const bool prior = p->depth_regularize_weight > 0.f;
     if (prior && (!p->logdepth_init || !p->static_mask || !p->prior_acc))
         return a3r_fail(A3R_E_ARG, "depth_regularize_weight > 0 needs logdepth_init, static_mask and prior_acc");
-    if (prior && p->prior_acc != p->acc_frame + (int64_t)p->n_frames * A3R_FRAME_ACC)
-        return a3r_fail(A3R_E_ARG, "prior_acc must directly follow acc_frame");
-    const size_t acc_bytes = sizeof(double) * ((size_t)2 * p->n_edges * A3R_SLOT_ACC + (size_t)p->n_frames * (A3R_FRAME_ACC + (prior ? A3R_PRIOR_ACC : 0)));
-    A3R_CUDA(cudaMemsetAsync(p->acc_slot, 0, acc_bytes, st));
+    if (zero_first) A3R_CUDA(cudaMemsetAsync(p->acc_slot, 0, sizeof(double) * (size_t)acc_block_doubles(p), st));
     if (prior && p->n_local_frames > 0) {
         k_depth_prior<<<dim3(16, (unsigned)p->n_local_frames), 256, 0, st>>>(*p);
         A3R_CUDA(cudaGetLastError());
@@ -815,136 +512,82 @@ int a3r_ga_accumulate(const A3rProblem* p, uint32_t mode, void* stream) {
     return l2 ? launch_accumulate<false, true>(p, st) : launch_accumulate<false, false>(p, st);
 }
 
-// The depth-plane Adam step (K3, HBM-bound, ~38 us on C2) needs only the flow normalisers, which it evaluates itself from
-// the slot accumulators; K2 (latency-bound) never touches the depth planes.  They run side by side: K3 on a library-owned
-// auxiliary stream, forked right after the scan (or the exchange) and joined before the next scan.
-struct AuxLane {
-    cudaStream_t stream = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
-};
-static int aux_lane(AuxLane** out) {
-    static AuxLane lanes[64];
-    int dev = 0;
+int a3r_ga_accumulate(const A3rProblem* p, uint32_t mode, void* stream) {
+    if (int rc = check_problem(p)) return rc;
+    return accumulate(p, mode, (cudaStream_t)stream, true);
+}
+
+// K2: one launch, grid sized by the problem (every CTA resident: the kernel's grid barrier needs it)
+static int launch_small(const A3rProblem* p, uint32_t mode, const A3rAdamStep* adam, cudaStream_t st, bool prepare_next, const AccSrc& src) {
+    int dev = 0, sm = 148;
     A3R_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) return a3r_fail(A3R_E_ARG, "device index %d out of range", dev);
-    AuxLane& l = lanes[dev];
-    if (!l.stream) {
-        A3R_CUDA(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
-        A3R_CUDA(cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming));
-        A3R_CUDA(cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming));
-    }
-    *out = &l;
-    return A3R_OK;
-}
-
-// K2 reads frame_grad / scal[S_GSUM] / scal[S_GPHI] as zero and leaves them zero: once per entry point, before the first launch
-static int zero_small_scratch(const A3rProblem* p, cudaStream_t st) {
-    A3R_CUDA(cudaMemsetAsync(p->frame_grad, 0, sizeof(double) * FG_STRIDE * (size_t)p->n_frames, st));
-    A3R_CUDA(cudaMemsetAsync(p->scal + S_GSUM, 0, sizeof(double) * 2, st));
-    return A3R_OK;
-}
-
-// cameras of problems with more than K2_MAX_FRAMES frames: one lazily grown global scratch per device (never shrinks)
-struct CamScratch { void* ptr = nullptr; size_t bytes = 0; };
-static int camera_scratch(int dev, size_t bytes, void** out) {
-    static CamScratch scratch[64];
-    CamScratch& c = scratch[dev];
-    if (c.bytes < bytes) {
-        if (c.ptr) { A3R_CUDA(cudaDeviceSynchronize()); A3R_CUDA(cudaFree(c.ptr)); c.ptr = nullptr; c.bytes = 0; }
-        A3R_CUDA(cudaMalloc(&c.ptr, bytes));
-        c.bytes = bytes;
-    }
-    *out = c.ptr;
-    return A3R_OK;
-}
-
-static int launch_small(const A3rProblem* p, uint32_t mode, const A3rAdamStep* adam, cudaStream_t st, bool prepare_next) {
-    static bool attr_set[64] = {};
-    static int max_smem_frames = -1;
-    int dev = 0;
-    A3R_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) return a3r_fail(A3R_E_ARG, "device index %d out of range", dev);
-    if (!attr_set[dev]) {
-        A3R_CUDA(cudaFuncSetAttribute(k_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FrameD) * K2_MAX_FRAMES)));
-        attr_set[dev] = true;
-    }
-    if (max_smem_frames < 0) {        // A3R_K2_SMEM_FRAMES: lower the switch-over point (tests exercise the global-scratch path)
-        const char* e = getenv("A3R_K2_SMEM_FRAMES");
-        max_smem_frames = e ? atoi(e) : K2_MAX_FRAMES;
-        if (max_smem_frames > K2_MAX_FRAMES || max_smem_frames < 0) max_smem_frames = K2_MAX_FRAMES;
-    }
-    void* scratch = nullptr;
-    size_t smem = sizeof(FrameD) * (size_t)p->n_frames;
-    if (p->n_frames > max_smem_frames) {
-        if (int rc = camera_scratch(dev, sizeof(FrameD) * (size_t)p->n_frames, &scratch)) return rc;
-        smem = 0;
-    }
-    k_small<<<K2_CLUSTER, K2_THREADS, smem, st>>>(*p, mode, *adam, prepare_next ? 1u : 0u, static_cast<FrameD*>(scratch));
+    A3R_CUDA(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev));
+    const int64_t items = (int64_t)3 * p->n_edges + p->n_frames;
+    int grid = (int)((items + K2_THREADS - 1) / K2_THREADS);
+    if (grid < 8) grid = 8;
+    if (grid > sm) grid = sm;
+    k_small<<<grid, K2_THREADS, 0, st>>>(*p, mode, *adam, prepare_next ? 1u : 0u, src);
     A3R_CUDA(cudaGetLastError());
     return A3R_OK;
 }
 
-// update without the final join: *pending_join is set when K3 is still running on the auxiliary stream.
-// prepare_next: K2's tail writes the parameter maps of the updated parameters (the next iteration's k_prepare).
-static int update_forked(const A3rProblem* p, uint32_t mode, const A3rAdamStep* adam, cudaStream_t st, AuxLane* lane, bool* pending_join,
-                         bool prepare_next) {
-    *pending_join = false;
+// K3: Adam on the log-depth planes (or, without A3R_M_APPLY_ADAM, the total depth gradient), after K2 on the same stream
+static int launch_depth(const A3rProblem* p, uint32_t mode, const A3rAdamStep* adam, cudaStream_t st) {
     const bool apply = mode & A3R_M_APPLY_ADAM;
-    if (p->n_local_frames > 0 && (!apply || (p->flags & A3R_F_TRAIN_DEPTH))) {
-        A3R_CUDA(cudaEventRecord(lane->fork, st));
-        A3R_CUDA(cudaStreamWaitEvent(lane->stream, lane->fork, 0));
-        const bool flow = (mode & A3R_M_FLOW_ACTIVE) && (p->flags & A3R_F_HAS_FLOW) && p->flow_loss_weight > 0.f;
-        const int64_t total4 = (int64_t)p->n_local_frames * p->pix_stride / 4;
-        int64_t grid = (total4 + 255) / 256;
-        if (grid > 148 * 4) grid = 148 * 4;              // one resident wave (62 registers: 4 CTAs per SM)
-        if (flow) k_update_depth<true><<<(unsigned)grid, 256, 0, lane->stream>>>(*p, mode, *adam);
-        else k_update_depth<false><<<(unsigned)grid, 256, 0, lane->stream>>>(*p, mode, *adam);
-        A3R_CUDA(cudaGetLastError());
-        A3R_CUDA(cudaEventRecord(lane->join, lane->stream));
-        *pending_join = true;
-    }
-    if (int rc = launch_small(p, mode, adam, st, prepare_next)) return rc;
+    if (p->n_local_frames <= 0 || (apply && !(p->flags & A3R_F_TRAIN_DEPTH))) return A3R_OK;
+    const bool flow = (mode & A3R_M_FLOW_ACTIVE) && (p->flags & A3R_F_HAS_FLOW) && p->flow_loss_weight > 0.f;
+    const int64_t total4 = (int64_t)p->n_local_frames * p->pix_stride / 4;
+    int64_t grid = (total4 + 255) / 256;
+    if (grid > 148 * 4) grid = 148 * 4;              // one resident wave (62 registers: 4 CTAs per SM)
+    if (flow) k_update_depth<true><<<(unsigned)grid, 256, 0, st>>>(*p, mode, *adam);
+    else k_update_depth<false><<<(unsigned)grid, 256, 0, st>>>(*p, mode, *adam);
+    A3R_CUDA(cudaGetLastError());
     return A3R_OK;
+}
+
+static AccSrc local_source(const A3rProblem* q, double* zero_block) {
+    AccSrc src;
+    memset(&src, 0, sizeof(src));
+    src.world = 1;
+    src.base[0] = q->acc_slot;
+    src.zero_block = zero_block;
+    src.n_acc = acc_block_doubles(q);
+    return src;
 }
 
 int a3r_ga_update(const A3rProblem* p, uint32_t mode, const A3rAdamStep* adam, void* stream) {
     if (int rc = check_problem(p)) return rc;
     if (!adam) return a3r_fail(A3R_E_ARG, "adam is NULL");
     cudaStream_t st = (cudaStream_t)stream;
-    AuxLane* lane = nullptr;
-    if (int rc = aux_lane(&lane)) return rc;
-    bool pending = false;
-    if (int rc = zero_small_scratch(p, st)) return rc;
-    if (int rc = update_forked(p, mode, adam, st, lane, &pending, false)) return rc;
-    if (pending) A3R_CUDA(cudaStreamWaitEvent(st, lane->join, 0));      // everything is ordered in the caller's stream on return
-    return A3R_OK;
+    A3R_CUDA(cudaMemsetAsync(p->sync_ctr, 0, sizeof(uint32_t) * 4, st));
+    if (int rc = launch_small(p, mode, adam, st, false, local_source(p, nullptr))) return rc;
+    return launch_depth(p, mode, adam, st);
 }
 
 int a3r_ga_run(const A3rProblem* p, int32_t count, const uint32_t* modes, const A3rAdamStep* steps, void* stream) {
     if (count < 0 || !modes || !steps) return a3r_fail(A3R_E_ARG, "a3r_ga_run: bad arguments");
     if (int rc = check_problem(p)) return rc;
+    if (count == 0) return A3R_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    AuxLane* lane = nullptr;
-    if (int rc = aux_lane(&lane)) return rc;
-    bool pending = false;
-    if (int rc = zero_small_scratch(p, st)) return rc;
-    if (count > 0)
-        if (int rc = a3r_ga_prepare(p, modes[0], stream)) return rc;                 // later ones: the tail of K2
+    A3R_CUDA(cudaMemsetAsync(p->sync_ctr, 0, sizeof(uint32_t) * 4, st));
+    if (int rc = a3r_ga_prepare(p, modes[0], stream)) return rc;                     // later ones: the tail of K2
+    // two accumulator blocks alternate by iteration parity: K2 of iteration k zeroes the block iteration k+1 adds into
+    const size_t block_bytes = sizeof(double) * (size_t)acc_block_doubles(p);
+    double* block[2] = {p->acc_slot, p->acc_alt ? p->acc_alt : p->acc_slot};
+    A3R_CUDA(cudaMemsetAsync(block[0], 0, block_bytes, st));
+    if (p->acc_alt) A3R_CUDA(cudaMemsetAsync(block[1], 0, block_bytes, st));
     for (int32_t k = 0; k < count; ++k) {
-        if (pending) A3R_CUDA(cudaStreamWaitEvent(st, lane->join, 0));               // the scan reads the depth planes
-        if (int rc = a3r_ga_accumulate(p, modes[k], stream)) return rc;
-        if (int rc = update_forked(p, modes[k], &steps[k], st, lane, &pending, k + 1 < count)) return rc;
+        const A3rProblem q = with_block(p, block[k & 1]);
+        if (int rc = accumulate(&q, modes[k], st, !p->acc_alt && k > 0)) return rc;
+        if (int rc = launch_small(&q, modes[k], &steps[k], st, k + 1 < count, local_source(&q, p->acc_alt ? block[(k + 1) & 1] : nullptr))) return rc;
+        if (int rc = launch_depth(&q, modes[k], &steps[k], st)) return rc;
     }
-    if (pending) A3R_CUDA(cudaStreamWaitEvent(st, lane->join, 0));
     return A3R_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // multi-GPU exchange over peer memory
 // ------------------------------------------------------------------------------------------------------------
-constexpr size_t PEER_FLAG_STRIDE = 128;
-constexpr size_t PEER_HEADER = A3R_MAX_PEERS * PEER_FLAG_STRIDE;
-
 size_t a3r_peer_region_bytes(int64_t n_acc) { return PEER_HEADER + 2 * sizeof(double) * (size_t)n_acc; }
 
 int a3r_peer_alloc(int64_t n_acc, void** region, unsigned char handle[64]) {
@@ -970,91 +613,53 @@ int a3r_peer_open(const unsigned char handle[64], void** region) {
 int a3r_peer_close(void* region) { if (region) A3R_CUDA(cudaIpcCloseMemHandle(region)); return A3R_OK; }
 int a3r_peer_free(void* region) { if (region) A3R_CUDA(cudaFree(region)); return A3R_OK; }
 
-}  // extern "C"
-
-__device__ __forceinline__ void st_release_sys(uint32_t* q, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(q), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* q) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(q) : "memory");
-    return v;
-}
-__device__ __forceinline__ double ld_peer_f64(const double* q) {
-    double v;
-    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(q) : "memory");
-    return v;
-}
-
-// signal + wait + reduce in one launch (every CTA is resident: grid <= SM count)
-__global__ void __launch_bounds__(256) k_exchange(const A3rPeers peers, const uint32_t tag, double* __restrict__ out) {
-    const int W = peers.world, me = peers.rank;
-    if (blockIdx.x == 0 && threadIdx.x < W && (int)threadIdx.x != me) {
-        // the scan of this iteration completed before this kernel started (stream order): publish its sums
-        __threadfence_system();
-        uint32_t* flag = reinterpret_cast<uint32_t*>(static_cast<char*>(peers.base[threadIdx.x]) + (size_t)me * PEER_FLAG_STRIDE);
-        st_release_sys(flag, tag);
-    }
-    if (threadIdx.x < W && (int)threadIdx.x != me) {
-        const uint32_t* flag = reinterpret_cast<const uint32_t*>(static_cast<const char*>(peers.base[me]) + (size_t)threadIdx.x * PEER_FLAG_STRIDE);
-        uint32_t spins = 0;
-        while ((int32_t)(ld_acquire_sys(flag) - tag) < 0) {
-            if (++spins > (1u << 26)) __trap();          // a peer that never arrives must fail loudly, not hang the GPU
-            __nanosleep(64);
-        }
-    }
-    __syncthreads();
-    const size_t off = PEER_HEADER + (size_t)(tag & 1u) * sizeof(double) * (size_t)peers.n_acc;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < peers.n_acc; i += (int64_t)gridDim.x * blockDim.x) {
-        double s = 0.0;
-        for (int r = 0; r < W; ++r)                       // rank order: the same sum, bit for bit, on every rank
-            s += ld_peer_f64(reinterpret_cast<const double*>(static_cast<const char*>(peers.base[r]) + off) + i);
-        out[i] = s;
-    }
-}
-
-extern "C" {
-
 int a3r_ga_run_peers(const A3rProblem* p, const A3rPeers* peers, uint32_t tag0, int32_t count, const uint32_t* modes,
                      const A3rAdamStep* steps, void* stream) {
     if (count < 0 || !modes || !steps || !peers) return a3r_fail(A3R_E_ARG, "a3r_ga_run_peers: bad arguments");
     if (int rc = check_problem(p)) return rc;
     if (peers->world < 1 || peers->world > A3R_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world)
         return a3r_fail(A3R_E_ARG, "a3r_ga_run_peers: world %d rank %d", peers->world, peers->rank);
-    const bool prior = p->depth_regularize_weight > 0.f;
-    const int64_t n_acc = (int64_t)2 * p->n_edges * A3R_SLOT_ACC + (int64_t)p->n_frames * (A3R_FRAME_ACC + (prior ? A3R_PRIOR_ACC : 0));
+    const int64_t n_acc = acc_block_doubles(p);
     if (peers->n_acc != n_acc) return a3r_fail(A3R_E_ARG, "a3r_ga_run_peers: n_acc %lld != %lld", (long long)peers->n_acc, (long long)n_acc);
+    if (peers->win[0] != 0 || peers->win[peers->world] != p->n_frames)
+        return a3r_fail(A3R_E_ARG, "a3r_ga_run_peers: the frame windows must cover frames 0 .. %d", p->n_frames);
+    for (int r = 0; r < peers->world; ++r)
+        if (!peers->base[r] || peers->win[r] > peers->win[r + 1]) return a3r_fail(A3R_E_ARG, "a3r_ga_run_peers: bad region / window of rank %d", r);
+    if (count == 0) return A3R_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    AuxLane* lane = nullptr;
-    if (int rc = aux_lane(&lane)) return rc;
-    int sm = 148;
-    { int dev = 0; A3R_CUDA(cudaGetDevice(&dev)); A3R_CUDA(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev)); }
-    int grid = (int)((n_acc + 255) / 256);
-    if (grid > sm) grid = sm;
-    bool pending = false;
-    if (int rc = zero_small_scratch(p, st)) return rc;
+    A3R_CUDA(cudaMemsetAsync(p->sync_ctr, 0, sizeof(uint32_t) * 4, st));
+    if (int rc = a3r_ga_prepare(p, modes[0], stream)) return rc;                     // later ones: the tail of K2
+    auto block_of = [&](int r, uint32_t parity) {
+        return reinterpret_cast<double*>(static_cast<char*>(peers->base[r]) + PEER_HEADER) + (size_t)parity * (size_t)n_acc;
+    };
+    // Both blocks of this rank's region start from zero.  A peer may still be reading this rank's block of the previous
+    // call's last iteration (parity tag0 & 1): it is zeroed by this call's first K2 - which runs after the peers'
+    // flags of this call's first iteration - and only the block the first scan adds into is cleared here.
+    A3R_CUDA(cudaMemsetAsync(block_of(peers->rank, (tag0 + 1u) & 1u), 0, sizeof(double) * (size_t)n_acc, st));
     for (int32_t k = 0; k < count; ++k) {
         const uint32_t tag = tag0 + 1u + (uint32_t)k;
-        A3rProblem q = *p;                               // the scan adds into this rank's shared partial-sum buffer
-        double* part = reinterpret_cast<double*>(static_cast<char*>(peers->base[peers->rank]) + PEER_HEADER) + (size_t)(tag & 1u) * (size_t)n_acc;
-        q.acc_slot = part;
-        q.acc_frame = part + (int64_t)2 * p->n_edges * A3R_SLOT_ACC;
-        if (prior) q.prior_acc = q.acc_frame + (int64_t)p->n_frames * A3R_FRAME_ACC;
-        if (k == 0)
-            if (int rc = a3r_ga_prepare(p, modes[k], stream)) return rc;             // later ones: the tail of K2
-        if (pending) A3R_CUDA(cudaStreamWaitEvent(st, lane->join, 0));
-        if (int rc = a3r_ga_accumulate(&q, modes[k], stream)) return rc;
-        k_exchange<<<grid, 256, 0, st>>>(*peers, tag, p->acc_slot);
-        A3R_CUDA(cudaGetLastError());
-        if (int rc = update_forked(p, modes[k], &steps[k], st, lane, &pending, k + 1 < count)) return rc;
+        const A3rProblem q = with_block(p, block_of(peers->rank, tag & 1u));      // the scan adds into this rank's shared block
+        if (int rc = accumulate(&q, modes[k], st, false)) return rc;
+        AccSrc src;
+        memset(&src, 0, sizeof(src));
+        src.world = peers->world;
+        src.rank = peers->rank;
+        for (int r = 0; r <= peers->world; ++r) src.win[r] = peers->win[r];
+        for (int r = 0; r < peers->world; ++r) { src.base[r] = block_of(r, tag & 1u); src.region[r] = peers->base[r]; }
+        src.zero_block = block_of(peers->rank, (tag + 1u) & 1u);
+        src.n_acc = n_acc;
+        src.tag = tag;
+        if (int rc = launch_small(&q, modes[k], &steps[k], st, k + 1 < count, src)) return rc;
+        if (int rc = launch_depth(&q, modes[k], &steps[k], st)) return rc;
     }
-    if (pending) A3R_CUDA(cudaStreamWaitEvent(st, lane->join, 0));
     return A3R_OK;
 }
 
 // diagnostic: switch the K2 phase trace on / off and read the stamps of the last launch (nanoseconds of %globaltimer;
-// [cta][8]: start, cameras, loss + gate, chains, barrier 1, phase B, barrier 2, end).  Synchronises the device.
+// [cta 0..7][8]: start, gate, phase A1, barrier 1, phase A2, barrier 2, phase C, end).  Synchronises the device.
 int a3r_debug_k2_trace(int enable, unsigned long long* out) {
     A3R_CUDA(cudaDeviceSynchronize());
-    if (out) A3R_CUDA(cudaMemcpyFromSymbol(out, g_k2_trace, sizeof(unsigned long long) * K2_CLUSTER * 8));
+    if (out) A3R_CUDA(cudaMemcpyFromSymbol(out, g_k2_trace, sizeof(unsigned long long) * 8 * 8));
     A3R_CUDA(cudaMemcpyToSymbol(g_k2_trace_on, &enable, sizeof(int)));
     return A3R_OK;
 }

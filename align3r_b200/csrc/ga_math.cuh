@@ -17,6 +17,16 @@
 
 namespace a3r {
 
+// fp64 exp / expm1: ~100-instruction inline sequences on the device.  The small-parameter kernel is run-once,
+// latency-bound code whose instruction fetch matters: one out-of-line copy of each instead of two dozen inlined ones.
+#if defined(__CUDA_ARCH__)
+static __device__ __noinline__ double a3r_exp(double x) { return exp(x); }
+static __device__ __noinline__ double a3r_expm1(double x) { return expm1(x); }
+#else
+inline double a3r_exp(double x) { return exp(x); }
+inline double a3r_expm1(double x) { return expm1(x); }
+#endif
+
 // accumulator slots (A3R_SLOT_ACC = 28 per edge-side)
 enum : int {
     ACC_SG = 0,      // sum g                (3)
@@ -29,6 +39,9 @@ enum : int {
     ACC_N = 27,
     ACC_STRIDE = 28
 };
+// whole-problem sums the scan adds up beside the per-slot ones (A3R_GLOB_ACC = 8, 5 used): the gate and the loss need them
+// before anything else can start
+enum : int { GL_LOSS = 0, GL_FNUM_I = 1, GL_FCNT_I = 2, GL_FNUM_J = 3, GL_FCNT_J = 4 };
 // per-frame accumulators (A3R_FRAME_ACC = 12), in the CAMERA frame: with h = R^T gsum (gsum = sum over the
 // pixel's slots of dL/dz): sum h (3), sum h c^T (9).  The focal / principal-point gradients are single entries
 // of sum h c^T (no cancellation between separately rounded sums).
@@ -75,7 +88,7 @@ A3R_HD void quat_to_rot(const double q[4], double R[9]) {
 }
 
 A3R_HD double signed_expm1_d(double x) {   // reference commons.py:83-85
-    const double a = expm1(fabs(x));
+    const double a = a3r_expm1(fabs(x));
     return x > 0 ? a : (x < 0 ? -a : 0.0);
 }
 
@@ -104,7 +117,7 @@ A3R_HD void rot_grad_to_quat(const double G[9], const double qn[4], double inv_n
 }
 
 // d/dt~ of sign(t~) expm1(|t~|): exp(|t~|), and exactly 0 at t~ == 0 (torch.sign(0) = 0)
-A3R_HD double signed_expm1_grad(float tt) { return tt != 0.0f ? exp(fabs((double)tt)) : 0.0; }
+A3R_HD double signed_expm1_grad(float tt) { return tt != 0.0f ? a3r_exp(fabs((double)tt)) : 0.0; }
 
 A3R_HD void mat3_mul(const double A[9], const double B[9], double C[9]) {
     for (int r = 0; r < 3; ++r)
@@ -128,7 +141,7 @@ A3R_HD void load_frame(const float* im_poses, const float* im_focals, const floa
                        int n, bool shared_focal, double focal_break, FrameD& F) {
     pose_to_Rt(im_poses + 7 * n, F.qn, &F.inv_norm, F.R, F.t);
     const double phi = (double)im_focals[shared_focal ? 0 : n];
-    F.f = exp(phi / focal_break);                                    // reference optimizer.py:398-403
+    F.f = a3r_exp(phi / focal_break);                                    // reference optimizer.py:398-403
     F.cx = 0.5 * frame_hw[2 * n + 1] + 10.0 * (double)im_pp[2 * n];     // optimizer.py:76,415-416
     F.cy = 0.5 * frame_hw[2 * n] + 10.0 * (double)im_pp[2 * n + 1];
 }
@@ -173,14 +186,14 @@ A3R_HD void derive_frame_par(const FrameD& F, float* o) {
 A3R_HD void derive_edge_par(const float* pv, const float* adaptor, double log_norm, bool norm_scale, double pw_break, float* o) {
     double qn[4], inv_norm, R[9], t[3];
     pose_to_Rt(pv, qn, &inv_norm, R, t);
-    const double s = exp((double)pv[7] + log_norm);
+    const double s = a3r_exp((double)pv[7] + log_norm);
     double ad[3] = {(double)adaptor[0], (double)adaptor[0], (double)adaptor[1]};
     if (norm_scale) {
         const double m = (ad[0] + ad[1] + ad[2]) / 3.0;
         ad[0] -= m; ad[1] -= m; ad[2] -= m;
     }
     for (int c = 0; c < 3; ++c) {
-        const double a = exp(ad[c] / pw_break);
+        const double a = a3r_exp(ad[c] / pw_break);
         o[EP_A + c] = (float)a;
         for (int r = 0; r < 3; ++r) o[EP_M + r * 3 + c] = (float)(s * R[r * 3 + c] * a);
     }

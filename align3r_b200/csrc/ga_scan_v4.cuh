@@ -183,13 +183,21 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
 
     auto flush = [&]() {                        // this warp's share of a work frame is complete
         __syncwarp();
+        float gl_i = 0.f, gl_j = 0.f;           // lanes ACC_LOSS / ACC_FNUM / ACC_FCNT: the whole-problem sums (acc_glob), per side
         for (int s = 0; s < deg; ++s) {
             const uint32_t a = wb + V4_WACC + (s * V4_ROW + lane) * 4;
             if (lane < NV) {
                 const float v = lds32(a);
                 sts32(a, 0.f);
-                if (v != 0.f) atomicAdd(&p.acc_slot[(int64_t)p.lslot_gslot[s_begin + s] * ACC_STRIDE + lane], (double)v);
+                const int gs = p.lslot_gslot[s_begin + s];
+                if (v != 0.f) atomicAdd(&p.acc_slot[(int64_t)gs * ACC_STRIDE + lane], (double)v);
+                if (gs & 1) gl_j += v; else gl_i += v;
             }
+        }
+        if (lane == ACC_LOSS) atomicAdd(&p.acc_glob[GL_LOSS], (double)gl_i + (double)gl_j);
+        if (FLOW && (lane == ACC_FNUM || lane == ACC_FCNT)) {
+            atomicAdd(&p.acc_glob[GL_FNUM_I + (lane - ACC_FNUM)], (double)gl_i);
+            atomicAdd(&p.acc_glob[GL_FNUM_J + (lane - ACC_FNUM)], (double)gl_j);
         }
         if (lane < FACC_N) {
             const uint32_t a = wb + V4_WACC + (V4_SLOTS * V4_ROW + lane) * 4;

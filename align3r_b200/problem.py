@@ -94,14 +94,25 @@ class ProblemBuffers:
         self.g_flow_j = carve("g_flow_j", torch.float32, nl1, stride) if has_flow else self.g_align
         self.stage = carve("stage", torch.float32, self.stage_rows * stride * 4)
 
-        # fp64 reduction buffers: acc_slot and acc_frame are one contiguous allocation
-        n_acc = 2 * E * _lib.SLOT_ACC + N * _lib.FRAME_ACC
-        self.acc = zeros(n_acc + (N * _lib.PRIOR_ACC if has_prior else 0), dtype=torch.float64)    # what multi-GPU runs all-reduce
+        # fp64 reduction buffers: the accumulator block acc_slot | acc_frame | prior_acc | acc_glob is one contiguous
+        # allocation, twice (the loop alternates the two blocks by iteration parity; `acc` is block 0)
+        n_sf = 2 * E * _lib.SLOT_ACC + N * _lib.FRAME_ACC
+        n_pr = N * _lib.PRIOR_ACC if has_prior else 0
+        self.n_acc = n_sf + n_pr + _lib.GLOB_ACC
+        both = zeros(2 * self.n_acc, dtype=torch.float64)
+        self.acc = both[:self.n_acc]                       # what multi-GPU runs all-reduce
+        self.acc_alt = both[self.n_acc:]
         self.acc_slot = self.acc[: 2 * E * _lib.SLOT_ACC].view(2 * E, _lib.SLOT_ACC)
-        self.acc_frame = self.acc[2 * E * _lib.SLOT_ACC:n_acc].view(N, _lib.FRAME_ACC)
-        self.prior_acc = self.acc[n_acc:].view(N, _lib.PRIOR_ACC) if has_prior else None
+        self.acc_frame = self.acc[2 * E * _lib.SLOT_ACC:n_sf].view(N, _lib.FRAME_ACC)
+        self.prior_acc = self.acc[n_sf:n_sf + n_pr].view(N, _lib.PRIOR_ACC) if has_prior else None
+        self.acc_glob = self.acc[n_sf + n_pr:]
         self.frame_grad = zeros(N, 16, dtype=torch.float64)
         self.edge_scratch = zeros(E, dtype=torch.float64)
+        self.pair_scratch = zeros(2 * E + N, _lib.PAIR_ROW, dtype=torch.float64)
+        self.cam_cache = zeros(N, _lib.CAM_ROW, dtype=torch.float64)
+        inc_begin, inc_items = incidence_lists(plan.edges, N)
+        self.inc_begin, self.inc_items = i32(inc_begin), i32(inc_items)
+        self.sync_ctr = torch.zeros(4, dtype=torch.int32, device=dev)
         self.scal = zeros(_lib.SCAL, dtype=torch.float64)
         self.loss_hist = zeros(loss_hist_len)
         self._struct = None
@@ -181,6 +192,9 @@ class ProblemBuffers:
         p.frame_grad, p.edge_scratch, p.scal = P(self.frame_grad), P(self.edge_scratch), P(self.scal)
         p.loss_hist = P(self.loss_hist)
         p.logdepth_init, p.prior_acc = P(self.logdepth_init), P(self.prior_acc)
+        p.acc_glob, p.acc_alt = P(self.acc_glob), P(self.acc_alt)
+        p.pair_scratch, p.cam_cache = P(self.pair_scratch), P(self.cam_cache)
+        p.inc_begin, p.inc_items, p.sync_ctr = P(self.inc_begin), P(self.inc_items), P(self.sync_ctr)
         self._struct = p
         return p
 
@@ -193,6 +207,24 @@ class ProblemBuffers:
     def ensure_loss_hist(self, n: int):
         if self.loss_hist.numel() < n:
             self.loss_hist = torch.zeros(n, dtype=torch.float32, device=self.device)
+
+
+def incidence_lists(edges, n_frames):
+    """Per frame, the rows of A3rProblem.pair_scratch that carry a gradient contribution to its camera, as 2*row + part
+    (include/a3r_ga.h): flow slot gs = 2e+side contributes its source half to the frame it lives on and its target half to
+    the pair's other frame; temporal pair n (row 2E+n) its source half to frame n+1 and its target half to frame n.
+    Ascending row order inside a frame: the gather of the update kernel sums in this fixed order."""
+    edges = np.asarray(edges, dtype=np.int64).reshape(-1, 2)
+    E = len(edges)
+    rows = np.arange(2 * E, dtype=np.int64)
+    src = edges[rows >> 1, rows & 1]
+    tgt = edges[rows >> 1, 1 - (rows & 1)]
+    frame = np.concatenate([src, tgt, np.arange(1, n_frames), np.arange(0, n_frames - 1)])
+    code = np.concatenate([2 * rows, 2 * rows + 1, 2 * (2 * E + np.arange(n_frames - 1)), 2 * (2 * E + np.arange(n_frames - 1)) + 1])
+    order = np.lexsort((code, frame))
+    begin = np.zeros(n_frames + 1, dtype=np.int64)
+    np.add.at(begin, frame + 1, 1)
+    return np.cumsum(begin).astype(np.int32), code[order].astype(np.int32)
 
 
 def adam_schedule(lrs, start_step: int = 0, betas=(0.9, 0.9), first_iter: int = 0):

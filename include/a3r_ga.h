@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define A3R_ABI_VERSION 6
+#define A3R_ABI_VERSION 7
 
 /* error codes */
 #define A3R_OK 0
@@ -62,6 +62,8 @@ extern "C" {
 #define A3R_SLOT_ACC 28
 #define A3R_FRAME_ACC 12
 #define A3R_PRIOR_ACC 4      /* per frame: sum d, sum w, sum w d, sum w d^2 of the depth prior (d = log-depth - its initial value) */
+#define A3R_GLOB_ACC 8       /* whole-problem sums the scan adds up beside the per-slot ones: alignment loss, flow numerator and
+                                per-channel mask count of side i, the same of side j (5 used) */
 #define A3R_SCAL 16
 
 /* layout of A3rProblem.scal (fp64[A3R_SCAL]) after a3r_ga_update */
@@ -133,18 +135,34 @@ typedef struct A3rProblem {
     float *logdepth, *logdepth_m, *logdepth_v;   /* [n_local_frames][pix_stride] */
     float *g_align, *g_flow_i, *g_flow_j;        /* [n_local_frames][pix_stride] per-pixel gradient planes */
 
-    /* ---- reduction buffers (fp64).  Multi-GPU: all-reduce(sum) acc_slot..acc_frame between
-     *      a3r_ga_accumulate and a3r_ga_update; they are contiguous: acc_frame = acc_slot + 2E*28 ---- */
+    /* ---- reduction buffers (fp64): ONE contiguous "accumulator block"
+     *      acc_slot [2E][28] | acc_frame [N][12] | prior_acc [N][4] (only with the depth prior) | acc_glob [8].
+     *      Multi-GPU: all-reduce(sum) the block between a3r_ga_accumulate and a3r_ga_update (or a3r_ga_run_peers) ---- */
     double *acc_slot;                 /* [2E][A3R_SLOT_ACC] */
     double *acc_frame;                /* [N][A3R_FRAME_ACC] */
-    double *frame_grad;               /* [N][16] scratch of a3r_ga_update */
-    double *edge_scratch;             /* [E] scratch of a3r_ga_update */
+    double *frame_grad;               /* [N][16] scratch of a3r_ga_update (per-frame focal gradient, temporal pair loss) */
+    double *edge_scratch;             /* [E] scratch of a3r_ga_update (d loss / d log-scale of every pair) */
     double *scal;                     /* [A3R_SCAL] */
     float *loss_hist;                 /* [>= niter] loss of every iteration, or NULL */
 
     /* ---- depth prior (reference optimizer.py:546-552, goem_opt.py:15-36), only read when depth_regularize_weight > 0 ---- */
     const float *logdepth_init;       /* [n_local_frames][pix_stride] log(clamp(initial depth, 1e-6)) */
     double *prior_acc;                /* [N][A3R_PRIOR_ACC], directly after acc_frame (rides on the same all-reduce) */
+
+    /* ---- added with ABI 7 ---- */
+    double *acc_glob;                 /* [A3R_GLOB_ACC] last part of the accumulator block (after prior_acc / acc_frame) */
+    double *acc_alt;                  /* a second accumulator block of the same layout, or NULL.  With it a3r_ga_run
+                                         alternates the two by iteration parity: the update kernel of iteration k zeroes the
+                                         block iteration k+1 accumulates into (no memset between the kernels) */
+    double *pair_scratch;             /* [2E + N][32] scratch of a3r_ga_update: the gradient contribution of every flow slot /
+                                         temporal pair to its source frame ([0,16)) and to its target frame ([16,32)) */
+    double *cam_cache;                /* [N][20] fp64 cameras (R 9, t 3, f, cx, cy, unit quaternion 4, 1/|q|) of the CURRENT
+                                         parameters: written by a3r_ga_prepare and by the update kernel for the next iteration */
+    const int32_t *inc_begin;         /* [N+1] incidence lists: rows of pair_scratch that touch frame n ... */
+    const int32_t *inc_items;         /* ... as 2*row + part (part 0: the row's source half, 1: its target half).  Row gs < 2E:
+                                         flow slot gs (source = the frame it lives on, target = the pair's other frame);
+                                         row 2E + n: temporal pair (source n+1, target n) */
+    uint32_t *sync_ctr;               /* [4] zero-initialised counters of the update kernel's grid barrier */
 } A3rProblem;
 
 /* Adam scalars of one step, computed on the host in double like torch/optim/adam.py:457-547 */
@@ -238,6 +256,7 @@ typedef struct A3rPeers {
     int32_t world, rank;
     int64_t n_acc;                          /* doubles in the accumulator block */
     void *base[A3R_MAX_PEERS];              /* every rank's region mapped into this process (base[rank] = own) */
+    int32_t win[A3R_MAX_PEERS + 1];         /* frame windows: rank r owns frames win[r] <= n < win[r+1] */
 } A3rPeers;
 size_t a3r_peer_region_bytes(int64_t n_acc);
 /* own region: cudaMalloc + zero + cudaIpcGetMemHandle (64-byte handle to hand to the other ranks) */

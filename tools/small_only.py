@@ -38,6 +38,6 @@ global_alignment_loop(net, lr=0.01, niter=a.iters, schedule="linear")
 lib.a3r_debug_k2_trace(0, buf)
 rows = [[buf[c * 8 + k] for k in range(8)] for c in range(8)]
 t0 = min(r[0] for r in rows)
-print("K2 phase trace (us since the first CTA started): start cameras loss+gate chains | barrier1 | phaseB | barrier2 | end")
+print("K2 phase trace (us since the first CTA started): start | gate | phase A1 | barrier 1 | phase A2 | barrier 2 | phase C | end")
 for c, r in enumerate(rows):
     print(f"  cta {c}: " + "  ".join(f"{(x - t0) / 1e3:7.2f}" for x in r))
