@@ -377,9 +377,12 @@ static int check_problem(const A3rProblem* p) {
     return A3R_OK;
 }
 
+// fold: the scan's tile prologue applies the previous iteration's depth Adam step (prev_adam, prev_flow); NULL: plain scan
 template <bool FLOW, bool L2D>
-static int launch_accumulate(const A3rProblem* p, cudaStream_t st) {
+static int launch_accumulate(const A3rProblem* p, cudaStream_t st, const A3rAdamStep* prev_adam, bool prev_flow) {
+    const A3rAdamStep none = {0.f, 1.f, -1, 0};
     if (scan_variant() == 1) {
+        if (prev_adam) return a3r_fail(A3R_E_UNSUPPORTED, "the v1 scan has no folded depth step");
         const size_t smem = sizeof(double) * K1_WARPS * K1_MAXS * ACC_STRIDE + sizeof(K1Shared);
         static bool configured = false;   // per template instantiation
         if (!configured) {
@@ -397,15 +400,27 @@ static int launch_accumulate(const A3rProblem* p, cudaStream_t st) {
         const bool tma = forced == 1;      // measured on C2: per-lane cp.async 0.760 / 0.474 ms (flow / align), TMA 0.843 / 0.533 ms
         static bool configured = false;
         if (!configured) {
-            A3R_CUDA(cudaFuncSetAttribute(k_accumulate_v4<FLOW, L2D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V4_SMEM));
-            A3R_CUDA(cudaFuncSetAttribute(k_accumulate_v4<FLOW, L2D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V4_SMEM));
+            A3R_CUDA(cudaFuncSetAttribute(k_accumulate_v4<FLOW, L2D, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V4_SMEM));
+            A3R_CUDA(cudaFuncSetAttribute(k_accumulate_v4<FLOW, L2D, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V4_SMEM));
+            A3R_CUDA(cudaFuncSetAttribute(k_accumulate_v4<FLOW, L2D, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V4_SMEM));
             configured = true;
         }
-        if (tma) k_accumulate_v4<FLOW, L2D, true><<<p->n_ctas / V4_WARPS, V4_THREADS, V4_SMEM, st>>>(*p);
-        else k_accumulate_v4<FLOW, L2D, false><<<p->n_ctas / V4_WARPS, V4_THREADS, V4_SMEM, st>>>(*p);
+        const unsigned grid = p->n_ctas / V4_WARPS;
+        if (prev_adam) k_accumulate_v4<FLOW, L2D, false, true><<<grid, V4_THREADS, V4_SMEM, st>>>(*p, *prev_adam, prev_flow ? 1u : 0u);
+        else if (tma) k_accumulate_v4<FLOW, L2D, true, false><<<grid, V4_THREADS, V4_SMEM, st>>>(*p, none, 0u);
+        else k_accumulate_v4<FLOW, L2D, false, false><<<grid, V4_THREADS, V4_SMEM, st>>>(*p, none, 0u);
     }
     A3R_CUDA(cudaGetLastError());
     return A3R_OK;
+}
+
+// the depth step of an iteration can ride in the NEXT scan's tile prologue when every pixel belongs to exactly one warp
+// (no split work frames), the depth planes are trained, the depth prior is off and the product scan (v4, cp.async) runs
+static bool depth_step_folds(const A3rProblem* p) {
+    static const bool off = [] { const char* e = getenv("A3R_FOLD_DEPTH"); return e && e[0] == '0'; }();
+    static const bool tma = [] { const char* e = getenv("A3R_V4_COPY"); return e && e[0] == 't'; }();
+    return !off && !tma && scan_variant() != 1 && p->n_work_frames == p->n_local_frames && (p->flags & A3R_F_TRAIN_DEPTH) &&
+           !(p->depth_regularize_weight > 0.f) && p->n_tiles > 0;
 }
 
 extern "C" {
@@ -487,7 +502,8 @@ static A3rProblem with_block(const A3rProblem* p, double* block) {
 }
 
 // the scan proper; the accumulator block it adds into must be zero (zero_first: a memset ahead of it)
-static int accumulate(const A3rProblem* p, uint32_t mode, cudaStream_t st, bool zero_first) {
+static int accumulate(const A3rProblem* p, uint32_t mode, cudaStream_t st, bool zero_first, const A3rAdamStep* prev_adam = nullptr,
+                      bool prev_flow = false) {
     const bool flow = (mode & A3R_M_FLOW_ACTIVE) && (p->flags & A3R_F_HAS_FLOW) && p->flow_loss_weight > 0.f;
     if (flow && (!p->flow || !p->static_mask)) return a3r_fail(A3R_E_ARG, "flow active but flow/static_mask planes are NULL");
     const bool prior = p->depth_regularize_weight > 0.f;
@@ -508,8 +524,12 @@ static int accumulate(const A3rProblem* p, uint32_t mode, cudaStream_t st, bool 
     }
     if (p->n_tiles == 0) return A3R_OK;
     const bool l2 = p->flags & A3R_F_DIST_L2;
-    if (flow) return l2 ? launch_accumulate<true, true>(p, st) : launch_accumulate<true, false>(p, st);
-    return l2 ? launch_accumulate<false, true>(p, st) : launch_accumulate<false, false>(p, st);
+    if (flow) return l2 ? launch_accumulate<true, true>(p, st, prev_adam, prev_flow) : launch_accumulate<true, false>(p, st, prev_adam, prev_flow);
+    return l2 ? launch_accumulate<false, true>(p, st, prev_adam, prev_flow) : launch_accumulate<false, false>(p, st, prev_adam, prev_flow);
+}
+
+static bool flow_on(const A3rProblem* p, uint32_t mode) {
+    return (mode & A3R_M_FLOW_ACTIVE) && (p->flags & A3R_F_HAS_FLOW) && p->flow_loss_weight > 0.f;
 }
 
 int a3r_ga_accumulate(const A3rProblem* p, uint32_t mode, void* stream) {
@@ -576,11 +596,16 @@ int a3r_ga_run(const A3rProblem* p, int32_t count, const uint32_t* modes, const 
     double* block[2] = {p->acc_slot, p->acc_alt ? p->acc_alt : p->acc_slot};
     A3R_CUDA(cudaMemsetAsync(block[0], 0, block_bytes, st));
     if (p->acc_alt) A3R_CUDA(cudaMemsetAsync(block[1], 0, block_bytes, st));
+    // the depth Adam step of iteration k rides in the tile prologue of scan k+1 (the last one runs stand-alone)
+    bool pending_depth = false;
     for (int32_t k = 0; k < count; ++k) {
         const A3rProblem q = with_block(p, block[k & 1]);
-        if (int rc = accumulate(&q, modes[k], st, !p->acc_alt && k > 0)) return rc;
+        const bool fold = pending_depth;
+        if (int rc = accumulate(&q, modes[k], st, !p->acc_alt && k > 0, fold ? &steps[k - 1] : nullptr, fold && flow_on(p, modes[k - 1]))) return rc;
         if (int rc = launch_small(&q, modes[k], &steps[k], st, k + 1 < count, local_source(&q, p->acc_alt ? block[(k + 1) & 1] : nullptr))) return rc;
-        if (int rc = launch_depth(&q, modes[k], &steps[k], st)) return rc;
+        pending_depth = (modes[k] & A3R_M_APPLY_ADAM) && k + 1 < count && (modes[k + 1] & A3R_M_APPLY_ADAM) && depth_step_folds(p);
+        if (!pending_depth)
+            if (int rc = launch_depth(&q, modes[k], &steps[k], st)) return rc;
     }
     return A3R_OK;
 }
@@ -636,10 +661,12 @@ int a3r_ga_run_peers(const A3rProblem* p, const A3rPeers* peers, uint32_t tag0, 
     // call's last iteration (parity tag0 & 1): it is zeroed by this call's first K2 - which runs after the peers'
     // flags of this call's first iteration - and only the block the first scan adds into is cleared here.
     A3R_CUDA(cudaMemsetAsync(block_of(peers->rank, (tag0 + 1u) & 1u), 0, sizeof(double) * (size_t)n_acc, st));
+    bool pending_depth = false;
     for (int32_t k = 0; k < count; ++k) {
         const uint32_t tag = tag0 + 1u + (uint32_t)k;
         const A3rProblem q = with_block(p, block_of(peers->rank, tag & 1u));      // the scan adds into this rank's shared block
-        if (int rc = accumulate(&q, modes[k], st, false)) return rc;
+        const bool fold = pending_depth;
+        if (int rc = accumulate(&q, modes[k], st, false, fold ? &steps[k - 1] : nullptr, fold && flow_on(p, modes[k - 1]))) return rc;
         AccSrc src;
         memset(&src, 0, sizeof(src));
         src.world = peers->world;
@@ -650,7 +677,9 @@ int a3r_ga_run_peers(const A3rProblem* p, const A3rPeers* peers, uint32_t tag0, 
         src.n_acc = n_acc;
         src.tag = tag;
         if (int rc = launch_small(&q, modes[k], &steps[k], st, k + 1 < count, src)) return rc;
-        if (int rc = launch_depth(&q, modes[k], &steps[k], st)) return rc;
+        pending_depth = (modes[k] & A3R_M_APPLY_ADAM) && k + 1 < count && (modes[k + 1] & A3R_M_APPLY_ADAM) && depth_step_folds(p);
+        if (!pending_depth)
+            if (int rc = launch_depth(&q, modes[k], &steps[k], st)) return rc;
     }
     return A3R_OK;
 }

@@ -105,8 +105,15 @@ __device__ __forceinline__ float2 transpose_reduce(uint32_t tr_s, int lane, cons
     return t0;
 }
 
-template <bool FLOW, bool L2D, bool TMA>
-__global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProblem p) {
+// ADAM: the tile prologue first applies the PREVIOUS iteration's Adam step to the tile's log-depths (reference
+// base_opt.py:581 for the depth parameter; the stand-alone K3 otherwise): the six planes it needs (log-depth, m, v, and the
+// three parked gradient planes = 24 B per pixel = exactly one 3 KB ring chunk per tile) ride through the warp's cp.async
+// ring as a pseudo-slot ahead of the tile's first real slot, so their DRAM latency is hidden behind the previous tile's
+// last slots like any other chunk's.  prev_adam / prev_flow: the Adam scalars and the flow state of that iteration; the
+// flow normalisers and the gate are read from scal, where that iteration's K2 left them.
+template <bool FLOW, bool L2D, bool TMA, bool ADAM>
+__global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProblem p, const A3rAdamStep prev_adam, const uint32_t prev_flow) {
+    static_assert(!(TMA && ADAM), "the folded depth step rides on the per-lane cp.async ring");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gw = blockIdx.x * V4_WARPS + warp;                 // this warp's range in the plan ("CTA" = warp here)
@@ -134,9 +141,12 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
 #if A3R_V4_EVICT_FIRST
     const uint64_t stream_policy = l2_policy_evict_first();      // predw / flow are read once per scan
 #endif
-    // ---- copy cursor: next chunk = (l_tile, l_s) at pixel offset l_off of the slot-major planes ----
+    // ---- copy cursor: next chunk = (l_tile, l_s) at pixel offset l_off of the slot-major planes; with ADAM every tile
+    //      starts with the pseudo-slot l_s = -1 (the tile's six per-frame planes at pixel offset l_pix) ----
     int l_tile = t0, l_wf = 0, l_wf_end = -1, l_s = 0, l_deg = 1;
-    int64_t l_off = 0;
+    int64_t l_off = 0, l_pix = 0;
+    float sc_i = 0.f, sc_j = 0.f;
+    if (ADAM && prev_flow) { sc_i = (float)p.scal[A3R_S_SC_I]; sc_j = (float)p.scal[A3R_S_SC_J]; }
     auto issue = [&](uint32_t stage_off) {      // stage_off = stage * (V4_T * 16)
         if (l_tile < t1) {
             if (l_tile >= l_wf_end) {
@@ -144,9 +154,25 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
                 l_wf_end = p.wf_tile_begin[l_wf + 1];
                 const int sb = p.wf_slot_begin[l_wf];
                 l_deg = p.wf_slot_begin[l_wf + 1] - sb;
-                l_off = (int64_t)sb * stride + (int64_t)(l_tile - p.wf_tile_begin[l_wf]) * V4_T;
-                l_s = 0;
+                const int64_t in_frame = (int64_t)(l_tile - p.wf_tile_begin[l_wf]) * V4_T;
+                l_off = (int64_t)sb * stride + in_frame;
+                if (ADAM) l_pix = (int64_t)p.wf_lframe[l_wf] * stride + in_frame;
+                l_s = ADAM ? -1 : 0;
             }
+            if (ADAM && l_s < 0) {              // lane L copies pixels 4L .. 4L+3 of every plane (16 B each)
+                const uint32_t xd = wb + V4_XW + stage_off + lane * 16;
+                const int64_t po = l_pix + 4 * lane;
+                cp_async16(xd, p.logdepth + po);
+                cp_async16(xd + 512, p.logdepth_m + po);
+                cp_async16(xd + 1024, p.logdepth_v + po);
+                cp_async16(xd + 1536, p.g_align + po);
+                if (prev_flow) {
+                    const uint32_t fd = wb + V4_FL + (stage_off >> 1) + lane * 16;
+                    cp_async16(fd, p.g_flow_i + po);
+                    cp_async16(fd + 512, p.g_flow_j + po);
+                }
+                l_s = 0;
+            } else {
             if (TMA) {
                 if (lane == 0) {
                     const uint32_t bar = wb + V4_BAR + (stage_off >> 8);
@@ -168,8 +194,9 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
 #endif
                 }
             }
-            if (++l_s >= l_deg) { l_s = 0; ++l_tile; l_off += V4_T - (int64_t)(l_deg - 1) * stride; }
+            if (++l_s >= l_deg) { l_s = ADAM ? -1 : 0; ++l_tile; l_off += V4_T - (int64_t)(l_deg - 1) * stride; if (ADAM) l_pix += V4_T; }
             else l_off += stride;
+            }
         }
         if (!TMA) cp_async_commit();   // one group per chunk slot, empty past the end: uniform wait_group accounting
     };
@@ -254,6 +281,35 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
         const int p0 = (tile - tile0) * V4_T;
         const int64_t pix_base = (int64_t)lf * stride + p0;
 
+        // ---- the previous iteration's Adam step on this tile's log-depths (the pseudo-slot of the ring) ----
+        float ldv[V4_PPL];
+        if (ADAM) {
+            cp_async_wait<V4_STAGES - 1>();       // this lane's copies of the pseudo-slot have landed (it reads only its own)
+            const uint32_t xa = wb + V4_XW + stage_off + lane * 16;
+            float4 l = lds128(xa), m = lds128(xa + 512), v = lds128(xa + 1024), g = lds128(xa + 1536);
+            if (prev_flow) {
+                const uint32_t fa = wb + V4_FL + (stage_off >> 1) + lane * 16;
+                const float4 a = lds128(fa), b = lds128(fa + 512);
+                g.x += sc_i * a.x + sc_j * b.x; g.y += sc_i * a.y + sc_j * b.y;
+                g.z += sc_i * a.z + sc_j * b.z; g.w += sc_i * a.w + sc_j * b.w;
+            }
+            adam_update(l.x, m.x, v.x, g.x, p.adam_beta1, p.adam_beta2, p.adam_eps, prev_adam.step_size, prev_adam.bc2_sqrt);
+            adam_update(l.y, m.y, v.y, g.y, p.adam_beta1, p.adam_beta2, p.adam_eps, prev_adam.step_size, prev_adam.bc2_sqrt);
+            adam_update(l.z, m.z, v.z, g.z, p.adam_beta1, p.adam_beta2, p.adam_eps, prev_adam.step_size, prev_adam.bc2_sqrt);
+            adam_update(l.w, m.w, v.w, g.w, p.adam_beta1, p.adam_beta2, p.adam_eps, prev_adam.step_size, prev_adam.bc2_sqrt);
+            const int64_t po = pix_base + 4 * lane;
+            *reinterpret_cast<float4*>(p.logdepth + po) = l;
+            *reinterpret_cast<float4*>(p.logdepth_m + po) = m;
+            *reinterpret_cast<float4*>(p.logdepth_v + po) = v;
+            sts128(xa, l.x, l.y, l.z, l.w);       // the main loop owns pixels lane, lane + 32, ...: hand the new values over
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < V4_PPL; ++j) ldv[j] = lds32(wb + V4_XW + stage_off + (j * 32 + lane) * 4);
+            __syncwarp();                         // every lane has read before the stage is refilled
+            issue(stage_off);
+            stage_off = stage_off == (V4_STAGES - 1) * (V4_T * 16) ? 0u : stage_off + V4_T * 16;
+        }
+
         // ---- per-pixel state (4 pixels per lane) ----
         float zx[V4_PPL], zy[V4_PPL], zz[V4_PPL], pu[V4_PPL], pv[V4_PPL], sdisp[V4_PPL], dep[V4_PPL];
         float gsx[V4_PPL], gsy[V4_PPL], gsz[V4_PPL];
@@ -269,7 +325,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
             for (int j = 0; j < V4_PPL; ++j) {
                 const int pl = j * 32 + lane, pix = p0 + pl;
                 const bool valid = pix < P;
-                const float ld = valid ? p.logdepth[pix_base + pl] : 0.f;
+                const float ld = valid ? (ADAM ? ldv[j] : p.logdepth[pix_base + pl]) : 0.f;
                 bool stat = false;
                 if (FLOW) stat = valid && p.static_mask[pix_base + pl] != 0;
                 int u, v;

@@ -65,22 +65,16 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* q) {
 }
 // accumulators: written by another kernel (the scan's fp64 atomics land in L2), possibly by another GPU
 __device__ __forceinline__ double ld_acc(const double* q, bool sys) {
-    double v;
-    if (sys) asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(q) : "memory");
-    else asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(q) : "memory");
-    return v;
+    if (sys) {
+        double v;
+        asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(q) : "memory");
+        return v;
+    }
+    return __ldcg(q);
 }
-// scratch written by other CTAs of this launch before the last grid barrier
-__device__ __forceinline__ double ld_cg(const double* q) {
-    double v;
-    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(q) : "memory");
-    return v;
-}
-__device__ __forceinline__ float ld_cg(const float* q) {
-    float v;
-    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(q) : "memory");
-    return v;
-}
+// scratch written by other CTAs of this launch before the last grid barrier (L2 loads; the barrier's acquire orders them)
+__device__ __forceinline__ double ld_cg(const double* q) { return __ldcg(q); }
+__device__ __forceinline__ float ld_cg(const float* q) { return __ldcg(q); }
 
 // diagnostic phase trace (a3r_debug_k2_trace): globaltimer stamps of thread 0 of the first 8 CTAs at the phase boundaries
 __device__ unsigned long long g_k2_trace[8 * 8];
@@ -95,12 +89,10 @@ __device__ __forceinline__ void k2_stamp(int slot) {
 
 // grid barrier: every CTA of the launch is resident (grid <= SM count, nothing runs beside it)
 __device__ __forceinline__ void grid_barrier(uint32_t* ctr, uint32_t target) {
-    __syncthreads();
+    __syncthreads();                           // the CTA's writes precede thread 0's release (bar.sync is morally strong)
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(ctr, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");      // arrive: no round trip
         while (ld_acquire_gpu(ctr) < target) {}
-        __threadfence();
     }
     __syncthreads();
 }
@@ -202,6 +194,7 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
     __shared__ double s_mean;
     __shared__ float s_foc[3];                 // the shared focal: parameter, m, v as they were when the kernel started
     __shared__ double s_fg[K2_WARPS * FG_STRIDE];
+    __shared__ double s_tr[K2_WARPS * 32 * FG_STRIDE];            // 32 KB: the frame gather's transpose buffers
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x;
     const int vt = blockIdx.x * K2_THREADS + tid, nvt = G * K2_THREADS;
@@ -327,23 +320,36 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
             p.g_pw_poses[8 * e + 7] = g7;
             if (apply && (p.flags & A3R_F_TRAIN_PW_POSES)) adam_vec(p.pw_poses + 8 * e + 7, p.pw_poses_m + 8 * e + 7, p.pw_poses_v + 8 * e + 7, &g7, 1, p, adam);
         }
-        // frames: a warp gathers the rows of the frame's incidence list - lane j owns column j and walks the rows in list
-        // order (a fixed order: reproducible sums; ~40 independent loads per lane, no shuffles) - lane 0 finishes the camera
+        // frames: a warp gathers the rows of the frame's incidence list.  Lane L takes rows L, L+32, ... (all loads of
+        // all lanes in flight at once), the 32 x 15 partial sums cross the warp through shared memory, lane j adds column
+        // j in lane order: a fixed order, reproducible sums, no shuffles; lane 0 finishes the camera.
         const int gw = blockIdx.x * K2_WARPS + warp, nw = G * K2_WARPS;
+        double* my_tr = s_tr + warp * (32 * FG_STRIDE);
         double* my_fg = s_fg + warp * FG_STRIDE;
 #pragma unroll 1
         for (int n = gw; n < N; n += nw) {
             const int b = p.inc_begin[n], c = p.inc_begin[n + 1];
-            double col = 0.0;
-            if (lane < 15) {
-#pragma unroll 4
-                for (int k = b; k < c; ++k) {
-                    const int code = p.inc_items[k], row = code >> 1;
-                    if (row < 2 * E ? !chains : !(tsw > 0)) continue;
-                    col += ld_cg(p.pair_scratch + (int64_t)row * PS_STRIDE + (code & 1) * 16 + lane);
+            double part[15];
+#pragma unroll
+            for (int j = 0; j < 15; ++j) part[j] = 0.0;
+#pragma unroll 1
+            for (int k = b + lane; k < c; k += 32) {
+                const int code = p.inc_items[k], row = code >> 1;
+                if (row < 2 * E ? chains : (tsw > 0)) {
+                    const double* q = p.pair_scratch + (int64_t)row * PS_STRIDE + (code & 1) * 16;
+#pragma unroll
+                    for (int j = 0; j < 15; ++j) part[j] += ld_cg(q + j);
                 }
             }
-            if (lane < FG_STRIDE) my_fg[lane] = col;
+#pragma unroll
+            for (int j = 0; j < 15; ++j) my_tr[lane * FG_STRIDE + j] = part[j];
+            __syncwarp();
+            if (lane < 15) {
+                double col = 0.0;
+#pragma unroll
+                for (int l = 0; l < 32; ++l) col += my_tr[l * FG_STRIDE + lane];
+                my_fg[lane] = col;
+            }
             __syncwarp();
             if (lane == 0) {
                 FrameD F;
