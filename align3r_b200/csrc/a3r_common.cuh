@@ -16,6 +16,28 @@ int a3r_fail(int code, const char* fmt, ...);
     } while (0)
 
 #if defined(__CUDACC__)
+// Programmatic dependent launch: a kernel launched with the attribute may start while its predecessor in the stream is
+// still running; pdl_wait() returns once the predecessor has completed and its memory is visible (a no-op for a normal
+// launch), pdl_trigger() lets the successor's CTAs be scheduled from here on.  Every kernel launched with the attribute
+// calls pdl_wait() before it touches anything its predecessors wrote.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll

@@ -377,10 +377,16 @@ static int check_problem(const A3rProblem* p) {
     return A3R_OK;
 }
 
+static bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("A3R_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 // fold: the scan's tile prologue applies the previous iteration's depth Adam step (prev_adam, prev_flow); NULL: plain scan
 template <bool FLOW, bool L2D>
 static int launch_accumulate(const A3rProblem* p, cudaStream_t st, const A3rAdamStep* prev_adam, bool prev_flow) {
     const A3rAdamStep none = {0.f, 1.f, -1, 0};
+    const bool pdl = pdl_enabled();
     if (scan_variant() == 1) {
         if (prev_adam) return a3r_fail(A3R_E_UNSUPPORTED, "the v1 scan has no folded depth step");
         const size_t smem = sizeof(double) * K1_WARPS * K1_MAXS * ACC_STRIDE + sizeof(K1Shared);
@@ -406,9 +412,9 @@ static int launch_accumulate(const A3rProblem* p, cudaStream_t st, const A3rAdam
             configured = true;
         }
         const unsigned grid = p->n_ctas / V4_WARPS;
-        if (prev_adam) k_accumulate_v4<FLOW, L2D, false, true><<<grid, V4_THREADS, V4_SMEM, st>>>(*p, *prev_adam, prev_flow ? 1u : 0u);
+        if (prev_adam) A3R_CUDA(launch_ex(k_accumulate_v4<FLOW, L2D, false, true>, dim3(grid), dim3(V4_THREADS), V4_SMEM, st, pdl, *p, *prev_adam, prev_flow ? 1u : 0u));
         else if (tma) k_accumulate_v4<FLOW, L2D, true, false><<<grid, V4_THREADS, V4_SMEM, st>>>(*p, none, 0u);
-        else k_accumulate_v4<FLOW, L2D, false, false><<<grid, V4_THREADS, V4_SMEM, st>>>(*p, none, 0u);
+        else A3R_CUDA(launch_ex(k_accumulate_v4<FLOW, L2D, false, false>, dim3(grid), dim3(V4_THREADS), V4_SMEM, st, pdl, *p, none, 0u));
     }
     A3R_CUDA(cudaGetLastError());
     return A3R_OK;
@@ -546,8 +552,7 @@ static int launch_small(const A3rProblem* p, uint32_t mode, const A3rAdamStep* a
     int grid = (int)((items + K2_THREADS - 1) / K2_THREADS);
     if (grid < 8) grid = 8;
     if (grid > sm) grid = sm;
-    k_small<<<grid, K2_THREADS, 0, st>>>(*p, mode, *adam, prepare_next ? 1u : 0u, src);
-    A3R_CUDA(cudaGetLastError());
+    A3R_CUDA(launch_ex(k_small, dim3(grid), dim3(K2_THREADS), 0, st, pdl_enabled(), *p, mode, *adam, prepare_next ? 1u : 0u, src));
     return A3R_OK;
 }
 

@@ -145,8 +145,6 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
     //      starts with the pseudo-slot l_s = -1 (the tile's six per-frame planes at pixel offset l_pix) ----
     int l_tile = t0, l_wf = 0, l_wf_end = -1, l_s = 0, l_deg = 1;
     int64_t l_off = 0, l_pix = 0;
-    float sc_i = 0.f, sc_j = 0.f;
-    if (ADAM && prev_flow) { sc_i = (float)p.scal[A3R_S_SC_I]; sc_j = (float)p.scal[A3R_S_SC_J]; }
     auto issue = [&](uint32_t stage_off) {      // stage_off = stage * (V4_T * 16)
         if (l_tile < t1) {
             if (l_tile >= l_wf_end) {
@@ -202,6 +200,12 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
     };
 #pragma unroll
     for (int k = 0; k < V4_STAGES; ++k) issue(k * (V4_T * 16));
+    // Everything above reads only what no kernel of this iteration writes (the plan, the packed inputs and - ADAM - the
+    // per-pixel planes the previous SCAN left): with a programmatic launch it overlaps the tail of K2.  From here on the
+    // kernel reads K2's results (parameter maps, flow normalisers) and adds into the accumulator block K2 zeroed.
+    pdl_wait();
+    float sc_i = 0.f, sc_j = 0.f;
+    if (ADAM && prev_flow) { sc_i = (float)p.scal[A3R_S_SC_I]; sc_j = (float)p.scal[A3R_S_SC_J]; }
 
     // ---- compute cursor ----
     int cw = 0, cw_end = -1, lf = 0, n = 0, P = 0, W = 1, deg = 0, n_i = 0, s_begin = 0, accum = 0, tile0 = 0;

@@ -92,7 +92,11 @@ __device__ __forceinline__ void grid_barrier(uint32_t* ctr, uint32_t target) {
     __syncthreads();                           // the CTA's writes precede thread 0's release (bar.sync is morally strong)
     if (threadIdx.x == 0) {
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");      // arrive: no round trip
-        while (ld_acquire_gpu(ctr) < target) {}
+        uint32_t seen;
+        do {        // poll at L2 without an L1 invalidation per probe (ld.acquire costs one); acquire once, on the way out
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+        } while (seen < target);
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
     __syncthreads();
 }
@@ -121,22 +125,17 @@ __device__ __noinline__ void nl_load_frame(const float* im_poses, const float* i
                                            int n, bool shared_focal, double focal_break, FrameD* F) {
     load_frame(im_poses, im_focals, im_pp, frame_hw, n, shared_focal, focal_break, *F);
 }
-__device__ __noinline__ void nl_slot_flow_chain(const FrameD* S, const FrameD* T, const double* acc, double sc, PairGrad* o) {
-    slot_flow_chain(*S, *T, acc, sc, *o);
-}
-__device__ __noinline__ double nl_temporal_pair(const FrameD* S, const FrameD* T, double tsw, double tw, PairGrad* o) {
-    return temporal_pair(*S, *T, tsw, tw, o);
-}
 __device__ __noinline__ void nl_derive_slot_par(const FrameD* S, const FrameD* T, float* o) { derive_slot_par(*S, *T, o); }
 
-// torch.optim.Adam on `cnt` consecutive entries: ONE copy of the IEEE sqrt / division sequences (a rolled loop)
-__device__ __noinline__ void nl_adam(float* prm, float* m, float* v, const float* g, int cnt, float b1, float b2, float eps,
-                                     float step_size, float bc2_sqrt) {
-#pragma unroll 1
-    for (int k = 0; k < cnt; ++k) adam_update(prm[k], m[k], v[k], g[k], b1, b2, eps, step_size, bc2_sqrt);
+// torch.optim.Adam on ONE entry (every caller spreads the entries of a parameter over threads: no serial loops of
+// dependent load -> sqrt -> divide -> store round trips)
+__device__ __noinline__ void adam_one(float* prm, float* m, float* v, float g, float b1, float b2, float eps, float step_size, float bc2_sqrt) {
+    float pv = *prm, mv = *m, vv = *v;
+    adam_update(pv, mv, vv, g, b1, b2, eps, step_size, bc2_sqrt);
+    *prm = pv; *m = mv; *v = vv;
 }
-__device__ __forceinline__ void adam_vec(float* prm, float* m, float* v, const float* g, int cnt, const A3rProblem& p, const A3rAdamStep& a) {
-    nl_adam(prm, m, v, g, cnt, p.adam_beta1, p.adam_beta2, p.adam_eps, a.step_size, a.bc2_sqrt);
+__device__ __forceinline__ void adam_entry(float* prm, float* m, float* v, float g, const A3rProblem& p, const A3rAdamStep& a) {
+    adam_one(prm, m, v, g, p.adam_beta1, p.adam_beta2, p.adam_eps, a.step_size, a.bc2_sqrt);
 }
 
 // parameter maps of the current parameters (k_prepare, and the tail of K2 for the next iteration): items
@@ -212,6 +211,8 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
     const int64_t off_prior = off_frame + (int64_t)N * FACC_N;
     const int64_t off_glob = off_prior + (prior ? (int64_t)N * PR_N : 0);
 
+    pdl_wait();             // launched while the scan was still running: from here on its sums are complete and visible
+    pdl_trigger();          // the next scan's CTAs may take the idle SMs and prefetch their first tiles (they wait for this grid)
     k2_stamp(0);
     // ---------------- exchange: publish "my sums of this iteration are complete", wait for the peers' ----------------
     if (sys) {
@@ -266,7 +267,7 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
 #pragma unroll
                 for (int k = ACC_GA; k < ACC_GB + 3; ++k) row[k] = ld_acc(a + k, sys);
                 PairGrad g;
-                nl_slot_flow_chain(&S, &T, row, side ? sc_j : sc_i, &g);
+                slot_flow_chain(S, T, row, side ? sc_j : sc_i, g);
                 double* o = p.pair_scratch + (int64_t)gs * PS_STRIDE;
 #pragma unroll
                 for (int k = 0; k < 15; ++k) { o[k] = g.s[k]; o[16 + k] = g.t[k]; }
@@ -282,17 +283,15 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
                 p.edge_scratch[e] = edge_logscale_grad(ep, a0, a1);
                 float g[8], ga[2];
                 edge_pose_grad(p.pw_poses + 8 * e, ep, a0, a1, 0.0, p.flags & A3R_F_TRAIN_ADAPTORS, norm_scale, (double)p.pw_break, g, ga);
-                for (int k = 0; k < 7; ++k) p.g_pw_poses[8 * e + k] = g[k];
+                for (int k = 0; k < 7; ++k) p.g_pw_poses[8 * e + k] = g[k];       // Adam: phase A2, one thread per entry
                 p.g_pw_adaptors[2 * e] = ga[0]; p.g_pw_adaptors[2 * e + 1] = ga[1];
-                if (apply && (p.flags & A3R_F_TRAIN_PW_POSES)) adam_vec(p.pw_poses + 8 * e, p.pw_poses_m + 8 * e, p.pw_poses_v + 8 * e, g, 7, p, adam);
-                if (apply && (p.flags & A3R_F_TRAIN_ADAPTORS)) adam_vec(p.pw_adaptors + 2 * e, p.pw_adaptors_m + 2 * e, p.pw_adaptors_v + 2 * e, ga, 2, p, adam);
             } else {                                             // temporal pair (S = n+1, T = n)
                 const int n = it - nS - E;
                 FrameD S, T;
                 cam_load(p.cam_cache, n + 1, S);
                 cam_load(p.cam_cache, n, T);
                 PairGrad g;
-                const double l = nl_temporal_pair(&S, &T, tsw, tw, &g);
+                const double l = temporal_pair(S, T, tsw, tw, &g);
                 p.frame_grad[(int64_t)n * FG_STRIDE + 15] = l;
                 double* o = p.pair_scratch + (int64_t)(2 * E + n) * PS_STRIDE;
 #pragma unroll
@@ -314,11 +313,24 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
         if (tid == 0) s_mean = part / (double)E;
         __syncthreads();
         const double gmean = norm_scale ? s_mean : 0.0;
+        // the pair parameters, one thread per entry: entries 0-6 of a pair carry the gradient phase A1 wrote, entry 7
+        // (log-scale) G_e - mean G
 #pragma unroll 1
-        for (int e = vt; e < E; e += nvt) {
-            float g7 = (float)(ld_cg(p.edge_scratch + e) - gmean);
-            p.g_pw_poses[8 * e + 7] = g7;
-            if (apply && (p.flags & A3R_F_TRAIN_PW_POSES)) adam_vec(p.pw_poses + 8 * e + 7, p.pw_poses_m + 8 * e + 7, p.pw_poses_v + 8 * e + 7, &g7, 1, p, adam);
+        for (int idx = vt; idx < 8 * E; idx += nvt) {
+            const int e = idx >> 3, k = idx & 7;
+            float g;
+            if (k == 7) {
+                g = (float)(ld_cg(p.edge_scratch + e) - gmean);
+                p.g_pw_poses[idx] = g;
+            } else {
+                g = ld_cg(p.g_pw_poses + idx);
+            }
+            if (apply && (p.flags & A3R_F_TRAIN_PW_POSES)) adam_entry(p.pw_poses + idx, p.pw_poses_m + idx, p.pw_poses_v + idx, g, p, adam);
+        }
+        if (apply && (p.flags & A3R_F_TRAIN_ADAPTORS)) {
+#pragma unroll 1
+            for (int idx = vt; idx < 2 * E; idx += nvt)
+                adam_entry(p.pw_adaptors + idx, p.pw_adaptors_m + idx, p.pw_adaptors_v + idx, ld_cg(p.g_pw_adaptors + idx), p, adam);
         }
         // frames: a warp gathers the rows of the frame's incidence list.  Lane L takes rows L, L+32, ... (all loads of
         // all lanes in flight at once), the 32 x 15 partial sums cross the warp through shared memory, lane j adds column
@@ -369,13 +381,21 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
                 for (int k = 0; k < 7; ++k) p.g_im_poses[7 * n + k] = g[k];
                 p.g_im_pp[2 * n] = gpp[0]; p.g_im_pp[2 * n + 1] = gpp[1];
                 if (shared_focal) p.frame_grad[(int64_t)n * FG_STRIDE + FG_F] = gphi;      // summed in phase C
-                else {
-                    float gf = (float)gphi;
-                    p.g_im_focals[n] = gf;
-                    if (apply && (p.flags & A3R_F_TRAIN_FOCALS)) adam_vec(p.im_focals + n, p.im_focals_m + n, p.im_focals_v + n, &gf, 1, p, adam);
+                else p.g_im_focals[n] = (float)gphi;
+                float* hand = reinterpret_cast<float*>(my_fg);        // hand the 10 gradients to the lanes that step them
+                for (int k = 0; k < 7; ++k) hand[k] = g[k];
+                hand[7] = gpp[0]; hand[8] = gpp[1]; hand[9] = (float)gphi;
+            }
+            __syncwarp();
+            if (apply && lane < 10) {        // lanes 0-6: pose entries, 7-8: principal point, 9: per-frame focal
+                const float gk = reinterpret_cast<const float*>(my_fg)[lane];
+                if (lane < 7) {
+                    if (p.flags & A3R_F_TRAIN_IM_POSES) adam_entry(p.im_poses + 7 * n + lane, p.im_poses_m + 7 * n + lane, p.im_poses_v + 7 * n + lane, gk, p, adam);
+                } else if (lane < 9) {
+                    if (p.flags & A3R_F_TRAIN_PP) adam_entry(p.im_pp + 2 * n + lane - 7, p.im_pp_m + 2 * n + lane - 7, p.im_pp_v + 2 * n + lane - 7, gk, p, adam);
+                } else if (!shared_focal && (p.flags & A3R_F_TRAIN_FOCALS)) {
+                    adam_entry(p.im_focals + n, p.im_focals_m + n, p.im_focals_v + n, gk, p, adam);
                 }
-                if (apply && (p.flags & A3R_F_TRAIN_PP)) adam_vec(p.im_pp + 2 * n, p.im_pp_m + 2 * n, p.im_pp_v + 2 * n, gpp, 2, p, adam);
-                if (apply && (p.flags & A3R_F_TRAIN_IM_POSES)) adam_vec(p.im_poses + 7 * n, p.im_poses_m + 7 * n, p.im_poses_v + 7 * n, g, 7, p, adam);
             }
             __syncwarp();
         }
@@ -393,7 +413,7 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
         part = block_sum(part, s_red);
         if (tid == 0) {
             float gf = (float)part;
-            if (apply && (p.flags & A3R_F_TRAIN_FOCALS)) adam_vec(&s_foc[0], &s_foc[1], &s_foc[2], &gf, 1, p, adam);
+            if (apply && (p.flags & A3R_F_TRAIN_FOCALS)) adam_entry(&s_foc[0], &s_foc[1], &s_foc[2], gf, p, adam);
             if (blockIdx.x == 0) {
                 p.g_im_focals[0] = gf;
                 p.im_focals[0] = s_foc[0]; p.im_focals_m[0] = s_foc[1]; p.im_focals_v[0] = s_foc[2];
