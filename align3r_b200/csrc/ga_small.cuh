@@ -341,6 +341,15 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
 #pragma unroll 1
         for (int n = gw; n < N; n += nw) {
             const int b = p.inc_begin[n], c = p.inc_begin[n + 1];
+            // lane 0's inputs for the end of the item, requested now: their L2 round trips overlap the gather's
+            FrameD F;
+            double af[FACC_N];
+            if (lane == 0) {
+                cam_load(p.cam_cache, n, F);
+                const double* qa = src.base[sys ? owner_of(src, n) : 0] + off_frame + (int64_t)n * FACC_N;
+#pragma unroll
+                for (int k = 0; k < FACC_N; ++k) af[k] = ld_acc(qa + k, sys);
+            }
             double part[15];
 #pragma unroll
             for (int j = 0; j < 15; ++j) part[j] = 0.0;
@@ -364,12 +373,7 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
             }
             __syncwarp();
             if (lane == 0) {
-                FrameD F;
-                cam_load(p.cam_cache, n, F);
-                const double* qa = src.base[sys ? owner_of(src, n) : 0] + off_frame + (int64_t)n * FACC_N;
-                double af[FACC_N], fa[FG_STRIDE];
-#pragma unroll
-                for (int k = 0; k < FACC_N; ++k) af[k] = ld_acc(qa + k, sys);
+                double fa[FG_STRIDE];
                 frame_align_grad(F, af, fa);
                 double fg[FG_STRIDE];
 #pragma unroll

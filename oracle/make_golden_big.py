@@ -33,17 +33,18 @@ import ga_oracle as go                                     # noqa: E402
 from align3r_b200.synth import make_scene, near_solution_params, CANONICAL_KW   # noqa: E402
 from make_golden import checksum, load_params, teacher_forced                    # noqa: E402
 
-STRIDE = 97                      # co-prime with the image width: the sample walks over rows and columns
+STRIDES = {"c2": 389, "f200": 1553}      # ~19 000 depth-gradient samples per case; co-prime with the image width: the sample
+                                         # walks over rows and columns
 TRAIN = ("pw_poses", "im_depthmaps", "im_poses", "im_focals")
 CASES = {"c2": dict(n_frames=50, H=288, W=512, scene_graph="swin-5-noncyclic", seed=0, with_flow=True),
          "f200": dict(n_frames=200, H=288, W=512, scene_graph="swin-5-noncyclic", seed=0, with_flow=True)}
 
 
-def pack_grads(grads):
+def pack_grads(grads, stride):
     """Small gradients in full; the depth gradient as a strided sample + per-frame moments."""
     out = {k: grads[k].detach().clone() for k in TRAIN if k != "im_depthmaps"}
     gd = grads["im_depthmaps"].detach()
-    out["depth_sample"] = gd.reshape(-1)[::STRIDE].clone()
+    out["depth_sample"] = gd.reshape(-1)[::stride].clone()
     out["depth_frame_sum"] = gd.double().sum(dim=1)
     out["depth_frame_sq"] = gd.double().square().sum(dim=1)
     out["depth_norm"] = float(gd.double().norm())
@@ -66,6 +67,7 @@ def main():
     which = [a for a in sys.argv[1:] if a in CASES] or list(CASES)
     for name in which:
         recipe = CASES[name]
+        STRIDE = STRIDES[name]
         t0 = time.time()
         scene = make_scene(**recipe, workers=os.cpu_count() or 1)
         kw = dict(CANONICAL_KW, num_total_iter=300)
@@ -79,7 +81,7 @@ def main():
             for dt, key in ((torch.float64, "tf64"), (torch.float32, "tf32_oracle")):
                 t0 = time.time()
                 loss, grads, info = go.chunked_loss_and_grads(prob.to(dt), {k: v.to(dt) for k, v in params.items()}, epoch, chunk=40)
-                out[f"{key}_{tag}"] = dict(epoch=epoch, loss=float(loss), grads=pack_grads(grads), flow_dropped=info["flow_dropped"],
+                out[f"{key}_{tag}"] = dict(epoch=epoch, loss=float(loss), grads=pack_grads(grads, STRIDE), flow_dropped=info["flow_dropped"],
                                            flow_loss=info["flow_loss"])
                 print(name, key, tag, "loss", float(loss), f"{time.time() - t0:.0f} s", flush=True)
                 if dt == torch.float64:
@@ -95,7 +97,7 @@ def main():
                 t0 = time.time()
                 ref.flow_loss_flag = False
                 loss, grads, flag = teacher_forced(ref, epoch)
-                rec = dict(epoch=epoch, loss=float(loss), grads=pack_grads(grads), flow_dropped=flag)
+                rec = dict(epoch=epoch, loss=float(loss), grads=pack_grads(grads, STRIDE), flow_dropped=flag)
                 o64, o32 = out[f"tf64_{tag}"], out[f"tf32_oracle_{tag}"]
                 # the reference's own fp32 error against the arbiter, and the oracle's fp32 evaluation against the reference's
                 rec["err_vs_fp64"] = {k: rel(rec["grads"][k], o64["grads"][k]) for k in ("pw_poses", "im_poses", "im_focals")}
