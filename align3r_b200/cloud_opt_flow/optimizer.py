@@ -31,6 +31,26 @@ from . import init_im_poses as init_fun
 
 _TRAIN_ORDER = ("pw_poses", "im_depthmaps", "im_poses", "im_focals")   # reference base_opt.py:514 order
 
+# exchange regions of frame-window sharded runs (a3r_peer_alloc + the peers' CUDA-IPC mappings), cached per
+# (device, world, rank, accumulator-block size, group): see PointCloudOptimizer._setup_peers
+_PEER_REGIONS = {}
+
+
+def free_peer_regions():
+    """Releases every cached peer-exchange region of this process.  COLLECTIVE on sharded runs (every rank calls it, with no
+    alignment in flight): a barrier makes sure no peer still reads a region before it is unmapped and freed."""
+    import torch.distributed as dist
+    for key in list(_PEER_REGIONS):
+        e = _PEER_REGIONS.pop(key)
+        torch.cuda.synchronize(e['device'])
+        if dist.is_available() and dist.is_initialized():
+            dist.barrier(group=e['group'])
+        with torch.cuda.device(e['device']):
+            for ptr in e['opened']:
+                e['lib'].a3r_peer_close(ptr)
+            if e['region'].value:
+                e['lib'].a3r_peer_free(e['region'])
+
 
 def _row_hw(rows, r):
     """(H, W) of row r of a stack of pointmaps: one (E,H,W,3) array-like (a tensor, or rows drawn on demand) or a list of
@@ -223,7 +243,7 @@ class PointCloudOptimizer(nn.Module):
         ph.mark('enqueue-pred')
         self._injected_flow = flow
         self._uploads_ready = None
-        self._peers, self._peers_tried = None, False
+        self._peers, self._peers_tried, self._peer_entry = None, False, None
         self._prior_ready = False
         if want_flow:
             self.flow_ij, self.flow_ji, valid_i, valid_j = self.get_flow(sintel_ckpt)
@@ -915,10 +935,13 @@ class PointCloudOptimizer(nn.Module):
             dist.all_reduce(self._bufs.acc, op=dist.ReduceOp.SUM, group=self._shard.get('group'))
 
     def _setup_peers(self):
-        """Frame-window sharded runs on one node: map every rank's partial-sum region (CUDA IPC over NVLink) so that the
-        per-iteration exchange is one kernel of ours (a3r_ga_run_peers) instead of a library all-reduce between launches.
-        Returns the A3rPeers descriptor, or None when the NCCL path is to be used (A3R_EXCHANGE=nccl, more ranks than
-        A3R_MAX_PEERS, or peer mapping unavailable on some rank - all ranks take the same decision)."""
+        """Frame-window sharded runs on one node: map every rank's accumulator region (CUDA IPC over NVLink) so that the
+        per-iteration exchange happens inside our own update kernel (a3r_ga_run_peers: every value is read from the one rank
+        that owns it) instead of a library all-reduce between launches.  Returns the A3rPeers descriptor, or None when the
+        NCCL path is to be used (A3R_EXCHANGE=nccl, more ranks than A3R_MAX_PEERS, or peer mapping unavailable on some rank -
+        all ranks take the same decision).  Regions and mappings are cached per (device, world, rank, block size) and
+        outlive the optimiser: the clips of a hierarchical run, or consecutive jobs of one process, pay the cudaMalloc + IPC
+        handshake (milliseconds) once - ``free_peer_regions()`` releases them."""
         if self._peers is not None or self._peers_tried:
             return self._peers
         self._peers_tried = True
@@ -929,69 +952,57 @@ class PointCloudOptimizer(nn.Module):
             return None
         want = os.environ.get("A3R_EXCHANGE", "peer") != "nccl" and world <= _lib.MAX_PEERS
         n_acc = int(self._bufs.n_acc)
-        region, handle, ok = C.c_void_p(), C.create_string_buffer(64), want
-        with torch.cuda.device(self._device):
-            if want and self._lib.a3r_peer_alloc(n_acc, C.byref(region), handle) != 0:
-                ok = False
-            handles = [None] * world
-            dist.all_gather_object(handles, (bool(ok), bytes(handle.raw)), group=group)
-            ok = all(h[0] for h in handles)
-            peers = _lib.A3rPeers()
-            peers.world, peers.rank, peers.n_acc = world, rank, n_acc
-            for r, (lo, hi) in enumerate(self._windows):
-                peers.win[r], peers.win[r + 1] = lo, hi
-            opened = []
-            if ok:
-                for r in range(world):
-                    if r == rank:
-                        peers.base[r] = region.value
-                        continue
-                    ptr = C.c_void_p()
-                    if self._lib.a3r_peer_open(handles[r][1], C.byref(ptr)) != 0:
-                        ok = False
-                        break
-                    opened.append(ptr)
-                    peers.base[r] = ptr.value
-            flag = torch.tensor([1 if ok else 0], device=self._device)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-            if int(flag.item()) == 0:                       # some rank cannot map its peers: everybody uses NCCL
-                for ptr in opened:
-                    self._lib.a3r_peer_close(ptr)
-                if region.value:
-                    self._lib.a3r_peer_free(region)
-                return None
-        self._peers, self._peer_region, self._peer_opened, self._peer_tag = peers, region, opened, 0
-        return peers
+        key = (self._device.index, world, rank, n_acc, id(group))
+        entry = _PEER_REGIONS.get(key)
+        if entry is None:
+            region, handle, ok = C.c_void_p(), C.create_string_buffer(64), want
+            with torch.cuda.device(self._device):
+                if want and self._lib.a3r_peer_alloc(n_acc, C.byref(region), handle) != 0:
+                    ok = False
+                handles = [None] * world
+                dist.all_gather_object(handles, (bool(ok), bytes(handle.raw)), group=group)
+                ok = all(h[0] for h in handles)
+                peers = _lib.A3rPeers()
+                peers.world, peers.rank, peers.n_acc = world, rank, n_acc
+                opened = []
+                if ok:
+                    for r in range(world):
+                        if r == rank:
+                            peers.base[r] = region.value
+                            continue
+                        ptr = C.c_void_p()
+                        if self._lib.a3r_peer_open(handles[r][1], C.byref(ptr)) != 0:
+                            ok = False
+                            break
+                        opened.append(ptr)
+                        peers.base[r] = ptr.value
+                flag = torch.tensor([1 if ok else 0], device=self._device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+                if int(flag.item()) == 0:                       # some rank cannot map its peers: everybody uses NCCL
+                    for ptr in opened:
+                        self._lib.a3r_peer_close(ptr)
+                    if region.value:
+                        self._lib.a3r_peer_free(region)
+                    return None
+            entry = dict(peers=peers, region=region, opened=opened, tag=0, group=group, device=self._device, lib=self._lib)
+            _PEER_REGIONS[key] = entry
+        for r, (lo, hi) in enumerate(self._windows):
+            entry['peers'].win[r], entry['peers'].win[r + 1] = lo, hi
+        self._peers, self._peer_entry = entry['peers'], entry
+        return self._peers
+
+    @property
+    def _peer_tag(self):
+        return self._peer_entry['tag']
+
+    @_peer_tag.setter
+    def _peer_tag(self, v):
+        self._peer_entry['tag'] = int(v)
 
     def close(self):
-        """Releases what a frame-window sharded run holds outside torch's allocator: the CUDA-IPC mappings of the peers'
-        exchange regions and this rank's own region (a3r_peer_alloc).  Collective on sharded problems (every rank calls it:
-        a barrier makes sure no peer still reads the region); a no-op otherwise.  The optimiser stays usable - the next
-        sharded loop maps the peers again."""
-        if getattr(self, '_peers', None) is None:
-            return
-        import torch.distributed as dist
-        torch.cuda.synchronize(self._device)
-        if dist.is_available() and dist.is_initialized():
-            dist.barrier(group=self._shard.get('group'))
-        with torch.cuda.device(self._device):
-            for ptr in self._peer_opened:
-                self._lib.a3r_peer_close(ptr)
-            if self._peer_region.value:
-                self._lib.a3r_peer_free(self._peer_region)
-        self._peers, self._peers_tried, self._peer_opened = None, False, []
-
-    def __del__(self):
-        # not collective: only this process's mappings of the peers' regions are dropped here; the own region is released
-        # by close() (a peer may still be reading it)
-        try:
-            if getattr(self, '_peers', None) is not None:
-                with torch.cuda.device(self._device):
-                    for ptr in self._peer_opened:
-                        self._lib.a3r_peer_close(ptr)
-                self._peer_opened = []
-        except Exception:
-            pass
+        """Detaches the optimiser from the cached peer-exchange region of a frame-window sharded run (the region itself
+        stays mapped for the next optimiser of this process - ``free_peer_regions()`` releases it).  Not collective."""
+        self._peers, self._peers_tried, self._peer_entry = None, False, None
 
     def _phase_accumulate(self, mode):
         """parameter maps + fused forward/backward scan over this device's pixel-slots."""

@@ -559,6 +559,8 @@ def run_ours(args, cfg, name):
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
+        from align3r_b200.cloud_opt_flow.optimizer import free_peer_regions
+        free_peer_regions()
         dist.barrier()
         dist.destroy_process_group()
 

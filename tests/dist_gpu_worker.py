@@ -65,6 +65,8 @@ def readout(net, scene, prob, rank, world, lo, hi):
     gathered = [None] * world
     dist.all_gather_object(gathered, (lo, hi, conf, rows_i, vi[rows_i].cpu(), rows_j, vj[rows_j].cpu()))
     net.close()
+    from align3r_b200.cloud_opt_flow.optimizer import free_peer_regions
+    free_peer_regions()
     if rank == 0:
         torch.save(dict(parts=gathered), sys.argv[2])
     dist.barrier()
