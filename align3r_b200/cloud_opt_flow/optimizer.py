@@ -222,6 +222,9 @@ class PointCloudOptimizer(nn.Module):
             n_ctas = self._lib.a3r_max_ctas(device.index)
         if n_ctas <= 0:
             _lib.check(n_ctas, "a3r_max_ctas")
+        import os
+        if os.environ.get("A3R_PLAN_CTAS"):       # diagnostic: another partition of the tiles (tools/partition_sensitivity.py)
+            n_ctas = int(os.environ["A3R_PLAN_CTAS"])
         self._plan = build_plan(self.edges, self.imshapes, self._lib.a3r_tile_pixels(), self._lib.a3r_max_slots(),
                                 n_ctas, frame_range)
         plan = self._plan

@@ -337,16 +337,22 @@ A3R_HD void edge_pose_grad(const float* pv, const float* ep, const double* a0, c
     }
 }
 
-// gradient of one image pose vector (7), its log-focal and principal point from its frame_grad row
-A3R_HD void frame_pose_grad(const float* pv, const FrameD& F, const double* fg, double focal_break, bool train_pp,
-                            float g[7], double* gphi, float gpp[2]) {
+// gradient of one image pose vector (7), its log-focal and principal point from its frame_grad row;
+// ex[k] = signed_expm1_grad(pv[4 + k]) (the caller may have evaluated the three exponentials ahead of time)
+A3R_HD void frame_pose_grad_pre(const FrameD& F, const double* fg, double focal_break, bool train_pp, const double ex[3],
+                                float g[7], double* gphi, float gpp[2]) {
     double gq[4];
     rot_grad_to_quat(fg + FG_R, F.qn, F.inv_norm, gq);
     for (int k = 0; k < 4; ++k) g[k] = (float)gq[k];
-    for (int k = 0; k < 3; ++k) g[4 + k] = (float)(fg[FG_T + k] * signed_expm1_grad(pv[4 + k]));
+    for (int k = 0; k < 3; ++k) g[4 + k] = (float)(fg[FG_T + k] * ex[k]);
     *gphi = fg[FG_F] * F.f / focal_break;                       // f = exp(phi / focal_break)
     gpp[0] = train_pp ? (float)(10.0 * fg[FG_CX]) : 0.f;         // pp = (W/2,H/2) + 10 im_pp
     gpp[1] = train_pp ? (float)(10.0 * fg[FG_CY]) : 0.f;
+}
+A3R_HD void frame_pose_grad(const float* pv, const FrameD& F, const double* fg, double focal_break, bool train_pp,
+                            float g[7], double* gphi, float gpp[2]) {
+    const double ex[3] = {signed_expm1_grad(pv[4]), signed_expm1_grad(pv[5]), signed_expm1_grad(pv[6])};
+    frame_pose_grad_pre(F, fg, focal_break, train_pp, ex, g, gphi, gpp);
 }
 
 // loss assembly + gate (reference optimizer.py:536-557)

@@ -306,49 +306,39 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
     // ---------------- phase A2 ----------------
     {
         // d loss / d log s_e = G_e - mean_e G (base_opt.py:230-241): the mean in one fixed order on every CTA
-        double part = 0.0;
+        double gsum = 0.0;
         if (norm_scale)
-            for (int e = tid; e < E; e += K2_THREADS) part += ld_cg(p.edge_scratch + e);
-        part = block_sum(part, s_red);
-        if (tid == 0) s_mean = part / (double)E;
-        __syncthreads();
-        const double gmean = norm_scale ? s_mean : 0.0;
-        // the pair parameters, one thread per entry: entries 0-6 of a pair carry the gradient phase A1 wrote, entry 7
-        // (log-scale) G_e - mean G
-#pragma unroll 1
-        for (int idx = vt; idx < 8 * E; idx += nvt) {
-            const int e = idx >> 3, k = idx & 7;
-            float g;
-            if (k == 7) {
-                g = (float)(ld_cg(p.edge_scratch + e) - gmean);
-                p.g_pw_poses[idx] = g;
-            } else {
-                g = ld_cg(p.g_pw_poses + idx);
-            }
-            if (apply && (p.flags & A3R_F_TRAIN_PW_POSES)) adam_entry(p.pw_poses + idx, p.pw_poses_m + idx, p.pw_poses_v + idx, g, p, adam);
-        }
-        if (apply && (p.flags & A3R_F_TRAIN_ADAPTORS)) {
-#pragma unroll 1
-            for (int idx = vt; idx < 2 * E; idx += nvt)
-                adam_entry(p.pw_adaptors + idx, p.pw_adaptors_m + idx, p.pw_adaptors_v + idx, ld_cg(p.g_pw_adaptors + idx), p, adam);
-        }
-        // frames: a warp gathers the rows of the frame's incidence list.  Lane L takes rows L, L+32, ... (all loads of
-        // all lanes in flight at once), the 32 x 15 partial sums cross the warp through shared memory, lane j adds column
-        // j in lane order: a fixed order, reproducible sums, no shuffles; lane 0 finishes the camera.
+            for (int e = tid; e < E; e += K2_THREADS) gsum += ld_cg(p.edge_scratch + e);
+        gsum = block_sum(gsum, s_red);
+        const double gmean = norm_scale ? gsum / (double)E : 0.0;
+
+        // frames (the longest dependent chain of the phase): a warp gathers the rows of the frame's incidence list.  Lane L
+        // takes rows L, L+32, ... (all loads of all lanes in flight at once), the 32 x 15 partial sums cross the warp
+        // through shared memory, lane j adds column j in lane order: a fixed order, reproducible sums, no shuffles; lane 0
+        // finishes the camera, lanes 0-9 step the frame's ten parameter entries.
         const int gw = blockIdx.x * K2_WARPS + warp, nw = G * K2_WARPS;
         double* my_tr = s_tr + warp * (32 * FG_STRIDE);
         double* my_fg = s_fg + warp * FG_STRIDE;
 #pragma unroll 1
         for (int n = gw; n < N; n += nw) {
             const int b = p.inc_begin[n], c = p.inc_begin[n + 1];
-            // lane 0's inputs for the end of the item, requested now: their L2 round trips overlap the gather's
+            // everything the end of the item needs is requested now: the L2 round trips overlap the gather's
             FrameD F;
-            double af[FACC_N];
+            double af[FACC_N], ex[3];
+            float* e_prm = nullptr; float* e_m = nullptr; float* e_v = nullptr;       // this lane's parameter entry (lanes 0-9)
+            float e_p = 0.f, e_mm = 0.f, e_vv = 0.f;
+            if (apply && lane < 10) {
+                if (lane < 7) { if (p.flags & A3R_F_TRAIN_IM_POSES) { e_prm = p.im_poses + 7 * n + lane; e_m = p.im_poses_m + 7 * n + lane; e_v = p.im_poses_v + 7 * n + lane; } }
+                else if (lane < 9) { if (p.flags & A3R_F_TRAIN_PP) { e_prm = p.im_pp + 2 * n + lane - 7; e_m = p.im_pp_m + 2 * n + lane - 7; e_v = p.im_pp_v + 2 * n + lane - 7; } }
+                else if (!shared_focal && (p.flags & A3R_F_TRAIN_FOCALS)) { e_prm = p.im_focals + n; e_m = p.im_focals_m + n; e_v = p.im_focals_v + n; }
+                if (e_prm) { e_p = *e_prm; e_mm = *e_m; e_vv = *e_v; }
+            }
             if (lane == 0) {
                 cam_load(p.cam_cache, n, F);
                 const double* qa = src.base[sys ? owner_of(src, n) : 0] + off_frame + (int64_t)n * FACC_N;
 #pragma unroll
                 for (int k = 0; k < FACC_N; ++k) af[k] = ld_acc(qa + k, sys);
+                for (int k = 0; k < 3; ++k) ex[k] = signed_expm1_grad(p.im_poses[7 * n + 4 + k]);
             }
             double part[15];
 #pragma unroll
@@ -381,7 +371,7 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
                 fg[15] = 0.0;
                 float g[7], gpp[2];
                 double gphi;
-                frame_pose_grad(p.im_poses + 7 * n, F, fg, fb, p.flags & A3R_F_TRAIN_PP, g, &gphi, gpp);
+                frame_pose_grad_pre(F, fg, fb, p.flags & A3R_F_TRAIN_PP, ex, g, &gphi, gpp);
                 for (int k = 0; k < 7; ++k) p.g_im_poses[7 * n + k] = g[k];
                 p.g_im_pp[2 * n] = gpp[0]; p.g_im_pp[2 * n + 1] = gpp[1];
                 if (shared_focal) p.frame_grad[(int64_t)n * FG_STRIDE + FG_F] = gphi;      // summed in phase C
@@ -391,17 +381,44 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
                 hand[7] = gpp[0]; hand[8] = gpp[1]; hand[9] = (float)gphi;
             }
             __syncwarp();
-            if (apply && lane < 10) {        // lanes 0-6: pose entries, 7-8: principal point, 9: per-frame focal
-                const float gk = reinterpret_cast<const float*>(my_fg)[lane];
-                if (lane < 7) {
-                    if (p.flags & A3R_F_TRAIN_IM_POSES) adam_entry(p.im_poses + 7 * n + lane, p.im_poses_m + 7 * n + lane, p.im_poses_v + 7 * n + lane, gk, p, adam);
-                } else if (lane < 9) {
-                    if (p.flags & A3R_F_TRAIN_PP) adam_entry(p.im_pp + 2 * n + lane - 7, p.im_pp_m + 2 * n + lane - 7, p.im_pp_v + 2 * n + lane - 7, gk, p, adam);
-                } else if (!shared_focal && (p.flags & A3R_F_TRAIN_FOCALS)) {
-                    adam_entry(p.im_focals + n, p.im_focals_m + n, p.im_focals_v + n, gk, p, adam);
-                }
+            if (e_prm) {                     // lanes 0-6: pose entries, 7-8: principal point, 9: per-frame focal
+                adam_update(e_p, e_mm, e_vv, reinterpret_cast<const float*>(my_fg)[lane], p.adam_beta1, p.adam_beta2, p.adam_eps,
+                            adam.step_size, adam.bc2_sqrt);
+                *e_prm = e_p; *e_m = e_mm; *e_v = e_vv;
             }
             __syncwarp();
+        }
+
+        // the pair parameters, one thread per entry (four entries of a thread in flight at once): entries 0-6 of a pair
+        // carry the gradient phase A1 wrote, entry 7 (log-scale) G_e - mean G
+        const bool step_pw = apply && (p.flags & A3R_F_TRAIN_PW_POSES);
+#pragma unroll 1
+        for (int base = vt; base < 8 * E; base += 4 * nvt) {
+            float g[4], pv[4], mv[4], vv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * nvt;
+                if (idx < 8 * E) {
+                    g[u] = (idx & 7) == 7 ? (float)(ld_cg(p.edge_scratch + (idx >> 3)) - gmean) : ld_cg(p.g_pw_poses + idx);
+                    if (step_pw) { pv[u] = p.pw_poses[idx]; mv[u] = p.pw_poses_m[idx]; vv[u] = p.pw_poses_v[idx]; }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * nvt;
+                if (idx < 8 * E) {
+                    if ((idx & 7) == 7) p.g_pw_poses[idx] = g[u];
+                    if (step_pw) {
+                        adam_update(pv[u], mv[u], vv[u], g[u], p.adam_beta1, p.adam_beta2, p.adam_eps, adam.step_size, adam.bc2_sqrt);
+                        p.pw_poses[idx] = pv[u]; p.pw_poses_m[idx] = mv[u]; p.pw_poses_v[idx] = vv[u];
+                    }
+                }
+            }
+        }
+        if (apply && (p.flags & A3R_F_TRAIN_ADAPTORS)) {
+#pragma unroll 1
+            for (int idx = vt; idx < 2 * E; idx += nvt)
+                adam_entry(p.pw_adaptors + idx, p.pw_adaptors_m + idx, p.pw_adaptors_v + idx, ld_cg(p.g_pw_adaptors + idx), p, adam);
         }
     }
     k2_stamp(4);
