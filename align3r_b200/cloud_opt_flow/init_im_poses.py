@@ -468,44 +468,64 @@ def init_from_pts3d(self, T, src, edge_reg, im_focals, im_poses):
 def init_from_known_poses(self, niter_PnP=10, min_conf_thr=3):
     """init='known_poses' - reference init_im_poses.py:44-85.  Pairwise poses: RANSAC-PnP pose of the second view of
     every pair (on the host, as in the reference) aligned with the two known cameras; depth maps: the best-scoring
-    pred_i of every frame, rescaled.  Single-device only (an edge's two sides may live on different frame windows)."""
-    if self._shard is not None and int(self._shard['world']) > 1:
-        raise NotImplementedError("init='known_poses' on a frame-window sharded problem")
+    pred_i of every frame, rescaled.  Frame-window shards: the rank owning a pair's FIRST frame solves the pair (its mask and
+    its depth candidate live there); the pair's pred_j plane is fetched from the neighbour when the pair straddles a window
+    boundary, and the E pose rows are summed across ranks."""
     from concurrent.futures import ThreadPoolExecutor
-    import os as _os
     from scipy.spatial.transform import Rotation
     E = self.n_edges
+    sharded = self._shard is not None and int(self._shard['world']) > 1
     known = self.get_im_poses().detach().cpu().double().numpy()
     focals = self.get_focals().detach().cpu().numpy().reshape(self.n_imgs, -1).mean(axis=1)
     pps = self.get_principal_points().detach().cpu().numpy()
+    mine = [e for e in range(E) if (2 * e) in self._lslot]                  # pairs whose first frame lives here
+    remote = {}
+    if sharded:
+        remote = self._fetch_remote_planes(self._bufs.predw, [2 * e + 1 for e in mine if (2 * e + 1) not in self._lslot])
     jobs = []
-    for e, (i, j) in enumerate(self.edges):
+    for e in mine:
+        i, j = self.edges[e]
         i_j = edge_str(i, j)
         conf = self.conf_i[i_j].cpu()
         msk = conf > min(min_conf_thr, float(conf.min()) - 0.1)
-        jobs.append((e, self.pred_j[i_j].cpu().numpy(), msk.numpy(), float(focals[i]), tuple(pps[i]), float(conf.mean())))
+        if (2 * e + 1) in self._lslot:
+            pts = self.pred_j[i_j].cpu().numpy()
+        else:
+            h, w = self.imshapes[j]
+            pts = remote[2 * e + 1][:h * w, :3].reshape(h, w, 3).cpu().numpy()
+        jobs.append((e, pts, msk.numpy(), float(focals[i]), tuple(pps[i]), float(conf.mean())))
 
     def _solve(job):
         e, pts, msk, f, pp, _ = job
         return e, fast_pnp(pts, f, msk, pp=pp, niter_PnP=niter_PnP)
 
-    pw = np.zeros((E, 8), dtype=np.float32)
+    pw = np.zeros((E, 9), dtype=np.float64)              # 8 pose entries + "solved" flag
     best = {}
-    with ThreadPoolExecutor(max_workers=host_workers(len(jobs), self._shard)) as pool:
-        results = dict(pool.map(_solve, jobs))
-    for e, (i, j) in enumerate(self.edges):
+    results = {}
+    if jobs:
+        with ThreadPoolExecutor(max_workers=host_workers(len(jobs), self._shard)) as pool:
+            results = dict(pool.map(_solve, jobs))
+    failed = [edge_str(*self.edges[e]) for e in mine if results[e] is None]
+    for job in jobs:
+        e = job[0]
+        i, j = self.edges[e]
         res = results[e]
         if res is None:
-            raise RuntimeError(f"init='known_poses': PnP failed on pair {edge_str(i, j)} (the reference fails here too)")
+            continue
         s, R, t = align_multiple_poses(np.stack((np.eye(4), res[1])), known[[i, j]])
         pw[e, 0:4] = Rotation.from_matrix(R).as_quat().astype(np.float32)                       # _set_pose, base_opt.py:221
         pw[e, 4:7] = signed_log1p(torch.from_numpy((t / s).astype(np.float32))).numpy()
         pw[e, 7] = np.float32(np.log(s))
-        score = jobs[e][5]
+        pw[e, 8] = 1.0
+        score = job[5]
         if score > best.get(i, (0,))[0]:
             best[i] = (score, e, s)
+    pw = _allreduce_np(self, pw)
+    if failed or not np.all(pw[:, 8] == 1.0):
+        bad = failed or [edge_str(*self.edges[e]) for e in np.nonzero(pw[:, 8] != 1.0)[0]]
+        raise RuntimeError(f"init='known_poses': PnP failed on pair(s) {bad} (the reference fails here too)")
     if self.pw_poses.requires_grad:
-        self.pw_poses.data.copy_(torch.from_numpy(pw).to(self.device))
+        self.pw_poses.data.copy_(torch.from_numpy(pw[:, :8].astype(np.float32)).to(self.device))
     for n in range(self.n_imgs):
         if n in best:
             _, e, scale = best[n]

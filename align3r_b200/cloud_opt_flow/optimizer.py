@@ -319,6 +319,15 @@ class PointCloudOptimizer(nn.Module):
                 r = self._row_of_edge[e]
                 camera_poses[self.edges[e][0]] = view1['camera_pose'][r]
                 camera_poses[self.edges[e][1]] = view2['camera_pose'][r]
+            if shard is not None and int(shard['world']) > 1:
+                # a rank was handed the rows of its own edges only: every frame's pose from the rank(s) that saw it
+                acc = np.zeros((self.n_imgs, 17))
+                for e in rows:
+                    for n in self.edges[e]:
+                        acc[n, :16] = torch.as_tensor(camera_poses[n]).double().reshape(-1).numpy()
+                        acc[n, 16] = 1.0
+                acc = init_fun._allreduce_np(self, acc)
+                camera_poses = [torch.from_numpy(acc[n, :16] / max(acc[n, 16], 1.0)).float().reshape(4, 4) for n in range(self.n_imgs)]
             self.camera_poses = camera_poses
         self.img_pathes = None
         if 'instance' in view1 and 'instance' in view2:

@@ -35,6 +35,8 @@ def main():
                          shard=dict(world=world, rank=rank, group=None), edge_rows=rows, **kw)
     if len(sys.argv) > 3 and sys.argv[3] == "readout":
         return readout(net, scene, prob, rank, world, lo, hi)
+    if len(sys.argv) > 3 and sys.argv[3] == "known_poses":
+        return known_poses(net, fx, prob, rank, world, lo, hi)
     loss = net.compute_global_alignment(init="mst", niter=fx["niter"], schedule="linear", lr=0.01)
     # replicated parameters must be bit-identical on every rank
     small = torch.cat([net.pw_poses.detach().flatten(), net.im_poses.detach().flatten(), net.im_focals.detach().flatten()])
@@ -48,6 +50,19 @@ def main():
     if rank == 0:
         torch.save(dict(parts=gathered, im_poses=net.get_im_poses().detach().cpu(), focals=net.get_focals().detach().cpu(),
                         exchange="peer" if net._peers is not None else "nccl"), sys.argv[2])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def known_poses(net, fx, prob, rank, world, lo, hi):
+    """init='known_poses' on frame windows (every rank is handed all cameras here, as a caller holding the trajectory would)."""
+    net.camera_poses = [p for p in fx["known_c2w"]]
+    net.compute_global_alignment(init="known_poses", niter=0)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (lo, hi, net.im_depthmaps.detach()[:, :prob.P].cpu(), net.get_pw_poses().detach().cpu(),
+                                      net.get_im_poses().detach().cpu()))
+    if rank == 0:
+        torch.save(dict(parts=gathered), sys.argv[2])
     dist.barrier()
     dist.destroy_process_group()
 

@@ -102,3 +102,27 @@ def test_sharded_readouts_equal_the_single_device_ones(cuda_device, tmp_path):
         seen_i |= set(rows_i)
         seen_j |= set(rows_j)
     assert seen_i == set(range(prob.n_edges)) and seen_j == set(range(prob.n_edges))
+
+
+def test_sharded_known_poses_initialisation(cuda_device, tmp_path):
+    """init='known_poses' (reference init_im_poses.py:44-85) on frame windows: the rank owning a pair's first frame solves it,
+    pred_j planes of boundary pairs are fetched from the neighbour - same result as the real reference's fixture."""
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    from tests.helpers import go
+    out = str(tmp_path / "res.pt")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "dist_gpu_worker.py"), "small_known_poses", out, "known_poses"]
+    subprocess.run(cmd, check=True, timeout=600, cwd=ROOT, env=dict(os.environ))
+    res = torch.load(out, weights_only=False)
+    fx, scene, prob = golden_case("small_known_poses")
+    ref = fx["known_poses"]["params"]
+    parts = sorted(res["parts"], key=lambda t: t[0])
+    prob.norm_pw_scale = False
+    T_ref = go.pw_pose_matrices(prob, ref["pw_poses"])
+    for p in parts:                                            # replicated on every rank
+        assert float((p[3] - T_ref).abs().max()) < 2e-3
+        assert float((p[4] - fx["known_c2w"]).abs().max()) < 1e-5
+    depth = torch.cat([p[2] for p in parts])
+    assert float((depth - ref["im_depthmaps"]).abs().median()) < 1e-5
