@@ -77,6 +77,7 @@ _SIGNATURES = {
     "a3r_pack_flow": (C.c_int, [_vp, _i32, _i64, _vp, _i64, _vp, _vp]),
     "a3r_ga_prepare": (C.c_int, [C.POINTER(A3rProblem), _u32, _vp]),
     "a3r_ga_accumulate": (C.c_int, [C.POINTER(A3rProblem), _u32, _vp]),
+    "a3r_ga_accumulate_folded": (C.c_int, [C.POINTER(A3rProblem), _u32, C.POINTER(A3rAdamStep), _u32, _vp]),
     "a3r_ga_update": (C.c_int, [C.POINTER(A3rProblem), _u32, C.POINTER(A3rAdamStep), _vp]),
     "a3r_ga_run": (C.c_int, [C.POINTER(A3rProblem), _i32, C.POINTER(_u32), C.POINTER(A3rAdamStep), _vp]),
     "a3r_ga_unproject": (C.c_int, [C.POINTER(A3rProblem), _vp, _vp]),

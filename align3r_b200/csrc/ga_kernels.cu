@@ -543,6 +543,14 @@ int a3r_ga_accumulate(const A3rProblem* p, uint32_t mode, void* stream) {
     return accumulate(p, mode, (cudaStream_t)stream, true);
 }
 
+int a3r_ga_accumulate_folded(const A3rProblem* p, uint32_t mode, const A3rAdamStep* prev_adam, uint32_t prev_mode, void* stream) {
+    if (int rc = check_problem(p)) return rc;
+    if (!prev_adam) return a3r_fail(A3R_E_ARG, "prev_adam is NULL");
+    if (!depth_step_folds(p)) return a3r_fail(A3R_E_UNSUPPORTED, "the depth step does not fold on this problem (split work frames, depth "
+                                              "prior, frozen depth maps, A3R_FOLD_DEPTH=0 or a non-default scan)");
+    return accumulate(p, mode, (cudaStream_t)stream, true, prev_adam, flow_on(p, prev_mode));
+}
+
 // K2: one launch, grid sized by the problem (every CTA resident: the kernel's grid barrier needs it)
 static int launch_small(const A3rProblem* p, uint32_t mode, const A3rAdamStep* adam, cudaStream_t st, bool prepare_next, const AccSrc& src) {
     int dev = 0, sm = 148;

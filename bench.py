@@ -489,29 +489,44 @@ def run_ours(args, cfg, name):
     ms = sorted(loops)[len(loops) // 2]
     n_flow = sum(1 for it in range(K) if net._flow_active(it))
 
-    # ---------------- roofline of the dominant kernel: the accumulate scan, timed alone ----------------
+    # ---------------- roofline of the dominant kernel, timed alone ----------------
+    # The loop's dominant kernel is the scan WITH the previous iteration's depth Adam step folded into its tile prologue
+    # (every iteration but the first): it moves the whole iteration's algorithmic bytes (48 B per pixel-slot +
+    # 25 B per pixel with flow) plus the parked gradient planes, which are overhead, not algorithmic.  The plain scan (the
+    # first iteration of a loop, and forward()) is reported beside it.
     b = net._bufs
     st = b.struct(net._trainable())
     stream = net._stream()
     roof = {}
     reps = 20
-    for label, mode in (("flow", _lib.M_FLOW_ACTIVE), ("align", 0)):
+    prev = adam_schedule([0.0], start_step=10, first_iter=-1)          # lr 0: the repeated depth steps leave the planes alone
+    folds = True
+    for label, mode, folded in (("flow", _lib.M_FLOW_ACTIVE, True), ("align", 0, True), ("flow_plain", _lib.M_FLOW_ACTIVE, False),
+                                ("align_plain", 0, False)):
+        def launch():
+            if folded and folds:
+                return net._lib.a3r_ga_accumulate_folded(C.byref(st), mode, prev, mode, stream)
+            return net._lib.a3r_ga_accumulate(C.byref(st), mode, stream)
         _lib.check(net._lib.a3r_ga_prepare(C.byref(st), mode, stream))
+        if folded and net._lib.a3r_ga_accumulate_folded(C.byref(st), mode, prev, mode, stream) != 0:
+            folds = False                               # (split work frames / frozen depth: the loop runs the plain scan + K3)
         for _ in range(3):
-            _lib.check(net._lib.a3r_ga_accumulate(C.byref(st), mode, stream))
+            _lib.check(launch())
         barrier()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record(torch.cuda.current_stream(dev))
         for _ in range(reps):
-            _lib.check(net._lib.a3r_ga_accumulate(C.byref(st), mode, stream))
+            _lib.check(launch())
         a1.record(torch.cuda.current_stream(dev))
         torch.cuda.synchronize(dev)
         roof[label] = a0.elapsed_time(a1) / reps
-    # per-rank share of the scan (pixel-slots are what a launch processes)
+    # per-rank share (pixel-slots are what a launch processes)
     local_ps = net._plan.pixel_slots()
     nl = net._plan.n_local_frames
-    k1_bytes_flow = local_ps * 24 + nl * P * 5
-    k1_bytes_align = local_ps * 16 + nl * P * 4
+    adam_b = 24 if folds else 0
+    k1_bytes_flow = local_ps * 24 + nl * P * (5 + adam_b)
+    k1_bytes_align = local_ps * 16 + nl * P * (4 + adam_b)
+    plain_bytes_flow, plain_bytes_align = local_ps * 24 + nl * P * 5, local_ps * 16 + nl * P * 4
     peak, peak_src = measured_peak()
     ach = k1_bytes_flow / (roof["flow"] * 1e-3) / 1e9
     traffic = recorded_traffic()
@@ -536,16 +551,21 @@ def run_ours(args, cfg, name):
                             "note": "K-step loops from the restored MST initialisation; value = K / median"},
             "synth": {"where": "device rows" if device_synth else "host, pinned", "seconds": t_synth},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": (traffic or {}).get("accumulate_flow_bytes_per_launch") if world == 1 and name == "c2" else None,
+                         "traffic": (traffic or {}).get("accumulate_folded_flow_bytes_per_launch" if folds else "accumulate_flow_bytes_per_launch")
+                         if world == 1 and name == "c2" else None,
                          "traffic_source": "recorded: profiles/traffic.json (ncu --set full of this kernel on this workload), not measured in this run",
-                         "kernel": "k_accumulate (flow active), timed alone over %d launches" % reps,
+                         "kernel": ("k_accumulate_v4<flow, fold> = the scan with the previous iteration's depth Adam step in its tile prologue"
+                                    if folds else "k_accumulate (flow active)") + ", timed alone over %d launches" % reps,
                          "ms_per_launch": roof["flow"], "algorithmic_bytes_per_launch": k1_bytes_flow, "peak_source": peak_src,
                          "align_only": {"ms_per_launch": roof["align"], "achieved": k1_bytes_align / (roof["align"] * 1e-3) / 1e9,
-                                        "frac": k1_bytes_align / (roof["align"] * 1e-3) / 1e9 / peak}},
+                                        "frac": k1_bytes_align / (roof["align"] * 1e-3) / 1e9 / peak},
+                         "plain_scan": {"what": "the scan without the folded depth step (first iteration of a loop, forward())",
+                                        "flow": {"ms_per_launch": roof["flow_plain"], "frac": plain_bytes_flow / (roof["flow_plain"] * 1e-3) / 1e9 / peak},
+                                        "align_only": {"ms_per_launch": roof["align_plain"], "frac": plain_bytes_align / (roof["align_plain"] * 1e-3) / 1e9 / peak}}},
             "roofline_iteration": {"bytes_per_iteration": blended_bytes, "achieved": blended_bytes / world / (ms / K * 1e-3) / 1e9,
                                    "frac": blended_bytes / (ms / K * 1e-3) / 1e9 / peak / world,
                                    "note": "whole iteration (all kernels), SURVEY 8(d) bytes, per GPU"},
-            "gpu_launches": (3 if world == 1 else 4) * K + 1,      # scan + K2 + K3 (+ exchange) per iteration, one k_prepare
+            "gpu_launches": len(loops) * (2 * K + 2),      # per K-step loop: K scans + K update kernels + one k_prepare + the last depth step
             "clocks": clocks,
         }
         if e2e is not None:

@@ -200,6 +200,11 @@ int a3r_ga_prepare(const A3rProblem *p, uint32_t mode, void *stream);
 /* fused forward + backward over all local pixel-slots: reference optimizer.py:500-544 and its autograd
  * backward.  Zeroes then fills acc_slot/acc_frame, writes g_align/g_flow_i/g_flow_j. */
 int a3r_ga_accumulate(const A3rProblem *p, uint32_t mode, void *stream);
+/* The scan as a3r_ga_run launches it from the second iteration on: the tile prologue first applies the PREVIOUS iteration's
+ * Adam step to the log-depth planes (prev_adam, prev_mode: that iteration's step scalars and mode; the flow normalisers are
+ * read from scal, where that iteration's a3r_ga_update left them), then scans.  Exposed for measurements and tests (the loop
+ * entry points drive it themselves); A3R_E_UNSUPPORTED when the depth step does not fold on this problem. */
+int a3r_ga_accumulate_folded(const A3rProblem *p, uint32_t mode, const A3rAdamStep *prev_adam, uint32_t prev_mode, void *stream);
 /* loss assembly + gate (optimizer.py:538-557), temporal term (:559-572), parameter-chain gradients,
  * torch.optim.Adam step (base_opt.py:524,581) on the small parameters and on the depth planes. */
 int a3r_ga_update(const A3rProblem *p, uint32_t mode, const A3rAdamStep *adam, void *stream);

@@ -17,6 +17,7 @@ ap.add_argument("--mode", default="both")
 ap.add_argument("--workload", default="c2")
 ap.add_argument("--world", type=int, default=1, help="time the scan of ONE frame-window shard of `world` (rank-emulated on this GPU)")
 ap.add_argument("--rank", type=int, default=0)
+ap.add_argument("--folded", action="store_true", help="the scan as the loop runs it: the previous iteration's depth Adam step in the tile prologue")
 ap.add_argument("--recipe", action="store_true", help="device-drawn inputs (only this shard's edges) + parameters by recipe "
                 "(synth.near_solution_params) instead of host inputs + MST initialisation: the 1000-frame workload")
 a = ap.parse_args()
@@ -59,17 +60,25 @@ if a.world > 1:        # one shard of a `world`-way frame-window partition, with
 st = net._bufs.struct(net._trainable())
 stream = net._stream()
 ps, nl, P = net._plan.pixel_slots(), net._plan.n_local_frames, H * W
-for label, mode, nbytes in (("flow", _lib.M_FLOW_ACTIVE, ps * 24 + nl * P * 5), ("align", 0, ps * 16 + nl * P * 4)):
+from align3r_b200.problem import adam_schedule
+prev = adam_schedule([0.0], start_step=10, first_iter=-1)       # lr 0: repeated depth steps leave the planes alone
+extra = 24 if a.folded else 0
+for label, mode, nbytes in (("flow", _lib.M_FLOW_ACTIVE, ps * 24 + nl * P * (5 + extra)), ("align", 0, ps * 16 + nl * P * (4 + extra))):
     if a.mode not in ("both", label):
         continue
+
+    def launch():
+        if a.folded:
+            return net._lib.a3r_ga_accumulate_folded(C.byref(st), mode, prev, mode, stream)
+        return net._lib.a3r_ga_accumulate(C.byref(st), mode, stream)
     _lib.check(net._lib.a3r_ga_prepare(C.byref(st), mode, stream))
     for _ in range(3):
-        _lib.check(net._lib.a3r_ga_accumulate(C.byref(st), mode, stream))
+        _lib.check(launch())
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.reps):
-        _lib.check(net._lib.a3r_ga_accumulate(C.byref(st), mode, stream))
+        _lib.check(launch())
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.reps
