@@ -36,8 +36,13 @@
 
 namespace a3r {
 
-constexpr int V4_T = 128;                     // pixels per tile
-constexpr int V4_PPL = V4_T / 32;             // 4 per lane
+#ifndef A3R_V4_TILE
+#define A3R_V4_TILE 128
+#endif
+constexpr int V4_T = A3R_V4_TILE;             // pixels per tile (128: 4 per lane; 256: 8 per lane - needs A3R_V4_WARPS <= 8)
+constexpr int V4_PPL = V4_T / 32;             // pixels per lane
+static_assert(V4_T == 128 || V4_T == 192 || V4_T == 256, "tile of 128, 192 or 256 pixels");
+constexpr uint32_t V4_PLANE = V4_T * 4;       // bytes of one per-frame plane's share of a tile (folded depth step)
 #ifndef A3R_V4_WARPS
 #define A3R_V4_WARPS 16
 #endif
@@ -157,23 +162,27 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
                 if (ADAM) l_pix = (int64_t)p.wf_lframe[l_wf] * stride + in_frame;
                 l_s = ADAM ? -1 : 0;
             }
-            if (ADAM && l_s < 0) {              // lane L copies pixels 4L .. 4L+3 of every plane (16 B each)
-                const uint32_t xd = wb + V4_XW + stage_off + lane * 16;
-                const int64_t po = l_pix + 4 * lane;
-                cp_async16(xd, p.logdepth + po);
-                cp_async16(xd + 512, p.logdepth_m + po);
-                cp_async16(xd + 1024, p.logdepth_v + po);
-                cp_async16(xd + 1536, p.g_align + po);
-                if (prev_flow) {
-                    const uint32_t fd = wb + V4_FL + (stage_off >> 1) + lane * 16;
-                    cp_async16(fd, p.g_flow_i + po);
-                    cp_async16(fd + 512, p.g_flow_j + po);
+            if (ADAM && l_s < 0) {              // lane L copies pixels 4L .. 4L+3 (+128 ...) of every plane (16 B each)
+#pragma unroll
+                for (int h = 0; h < (V4_T + 127) / 128; ++h) {
+                    if (4 * lane + h * 128 >= V4_T) break;
+                    const uint32_t xd = wb + V4_XW + stage_off + lane * 16 + h * 512;
+                    const int64_t po = l_pix + 4 * lane + h * 128;
+                    cp_async16(xd, p.logdepth + po);
+                    cp_async16(xd + V4_PLANE, p.logdepth_m + po);
+                    cp_async16(xd + 2 * V4_PLANE, p.logdepth_v + po);
+                    cp_async16(xd + 3 * V4_PLANE, p.g_align + po);
+                    if (prev_flow) {
+                        const uint32_t fd = wb + V4_FL + (stage_off >> 1) + lane * 16 + h * 512;
+                        cp_async16(fd, p.g_flow_i + po);
+                        cp_async16(fd + V4_PLANE, p.g_flow_j + po);
+                    }
                 }
                 l_s = 0;
             } else {
             if (TMA) {
                 if (lane == 0) {
-                    const uint32_t bar = wb + V4_BAR + (stage_off >> 8);
+                    const uint32_t bar = wb + V4_BAR + (stage_off / (V4_T * 16)) * 8;
                     mbar_expect_tx_a(bar, kBytes);
                     tma_load_1d_a(wb + V4_XW + stage_off, xw_g + l_off, V4_T * 16, bar);
                     if (FLOW) tma_load_1d_a(wb + V4_FL + (stage_off >> 1), fl_g + l_off, V4_T * 8, bar);
@@ -289,23 +298,27 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
         float ldv[V4_PPL];
         if (ADAM) {
             cp_async_wait<V4_STAGES - 1>();       // this lane's copies of the pseudo-slot have landed (it reads only its own)
-            const uint32_t xa = wb + V4_XW + stage_off + lane * 16;
-            float4 l = lds128(xa), m = lds128(xa + 512), v = lds128(xa + 1024), g = lds128(xa + 1536);
-            if (prev_flow) {
-                const uint32_t fa = wb + V4_FL + (stage_off >> 1) + lane * 16;
-                const float4 a = lds128(fa), b = lds128(fa + 512);
-                g.x += sc_i * a.x + sc_j * b.x; g.y += sc_i * a.y + sc_j * b.y;
-                g.z += sc_i * a.z + sc_j * b.z; g.w += sc_i * a.w + sc_j * b.w;
+#pragma unroll
+            for (int h = 0; h < (V4_T + 127) / 128; ++h) {
+                if (4 * lane + h * 128 >= V4_T) break;
+                const uint32_t xa = wb + V4_XW + stage_off + lane * 16 + h * 512;
+                float4 l = lds128(xa), m = lds128(xa + V4_PLANE), v = lds128(xa + 2 * V4_PLANE), g = lds128(xa + 3 * V4_PLANE);
+                if (prev_flow) {
+                    const uint32_t fa = wb + V4_FL + (stage_off >> 1) + lane * 16 + h * 512;
+                    const float4 a = lds128(fa), b = lds128(fa + V4_PLANE);
+                    g.x += sc_i * a.x + sc_j * b.x; g.y += sc_i * a.y + sc_j * b.y;
+                    g.z += sc_i * a.z + sc_j * b.z; g.w += sc_i * a.w + sc_j * b.w;
+                }
+                adam_update(l.x, m.x, v.x, g.x, p.adam_beta1, p.adam_beta2, p.adam_eps, prev_adam.step_size, prev_adam.bc2_sqrt);
+                adam_update(l.y, m.y, v.y, g.y, p.adam_beta1, p.adam_beta2, p.adam_eps, prev_adam.step_size, prev_adam.bc2_sqrt);
+                adam_update(l.z, m.z, v.z, g.z, p.adam_beta1, p.adam_beta2, p.adam_eps, prev_adam.step_size, prev_adam.bc2_sqrt);
+                adam_update(l.w, m.w, v.w, g.w, p.adam_beta1, p.adam_beta2, p.adam_eps, prev_adam.step_size, prev_adam.bc2_sqrt);
+                const int64_t po = pix_base + 4 * lane + h * 128;
+                *reinterpret_cast<float4*>(p.logdepth + po) = l;
+                *reinterpret_cast<float4*>(p.logdepth_m + po) = m;
+                *reinterpret_cast<float4*>(p.logdepth_v + po) = v;
+                sts128(xa, l.x, l.y, l.z, l.w);   // the main loop owns pixels lane, lane + 32, ...: hand the new values over
             }
-            adam_update(l.x, m.x, v.x, g.x, p.adam_beta1, p.adam_beta2, p.adam_eps, prev_adam.step_size, prev_adam.bc2_sqrt);
-            adam_update(l.y, m.y, v.y, g.y, p.adam_beta1, p.adam_beta2, p.adam_eps, prev_adam.step_size, prev_adam.bc2_sqrt);
-            adam_update(l.z, m.z, v.z, g.z, p.adam_beta1, p.adam_beta2, p.adam_eps, prev_adam.step_size, prev_adam.bc2_sqrt);
-            adam_update(l.w, m.w, v.w, g.w, p.adam_beta1, p.adam_beta2, p.adam_eps, prev_adam.step_size, prev_adam.bc2_sqrt);
-            const int64_t po = pix_base + 4 * lane;
-            *reinterpret_cast<float4*>(p.logdepth + po) = l;
-            *reinterpret_cast<float4*>(p.logdepth_m + po) = m;
-            *reinterpret_cast<float4*>(p.logdepth_v + po) = v;
-            sts128(xa, l.x, l.y, l.z, l.w);       // the main loop owns pixels lane, lane + 32, ...: hand the new values over
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < V4_PPL; ++j) ldv[j] = lds32(wb + V4_XW + stage_off + (j * 32 + lane) * 4);
@@ -352,8 +365,8 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
         for (int s = s_lo; s < s_hi; ++s) {
             const uint32_t tab = wb + V4_STAB + s * (V4_ROW * 4);
             if (TMA) {
-                mbar_wait_a(wb + V4_BAR + (stage_off >> 8), (phase >> (stage_off >> 11)) & 1);
-                phase ^= 1u << (stage_off >> 11);
+                mbar_wait_a(wb + V4_BAR + (stage_off / (V4_T * 16)) * 8, (phase >> (stage_off / (V4_T * 16))) & 1);
+                phase ^= 1u << (stage_off / (V4_T * 16));
             } else {
                 cp_async_wait<V4_STAGES - 1>();       // this lane's copies of the oldest chunk have landed
             }

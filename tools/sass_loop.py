@@ -2,7 +2,7 @@
     python tools/sass_loop.py k_accumulate_v4ILb1ELb0ELb1 [--list]
 """
 import collections, re, subprocess, sys, os
-lib = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "align3r_b200", "lib", "liba3r_ga.so")
+lib = os.environ.get("A3R_LIB") or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "align3r_b200", "lib", "liba3r_ga.so")
 pat = sys.argv[1]
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout.splitlines()
 ins, on = [], False
