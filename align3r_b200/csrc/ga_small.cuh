@@ -92,9 +92,10 @@ __device__ __forceinline__ void grid_barrier(uint32_t* ctr, uint32_t target) {
     __syncthreads();                           // the CTA's writes precede thread 0's release (bar.sync is morally strong)
     if (threadIdx.x == 0) {
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");      // arrive: no round trip
-        uint32_t seen;
+        uint32_t seen, spins = 0;
         do {        // poll at L2 without an L1 invalidation per probe (ld.acquire costs one); acquire once, on the way out
             asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+            if (++spins > (1u << 27)) __trap();      // a CTA that never arrives (the grid is not co-resident) must fail loudly, not hang
         } while (seen < target);
         asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
