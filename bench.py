@@ -43,6 +43,9 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--long-video", default="auto", choices=["auto", "on", "off"],
+                    help="attach a long_video sub-record (the 1000-frame workload c5, device-drawn inputs, 40 iterations) to the line; "
+                         "auto: on 8 GPUs with the default workload")
     ap.add_argument("--synth", default="auto", choices=["auto", "host", "device"],
                     help="where the synthetic pair predictions are drawn: host (pinned memory, the default workload) or "
                          "device (rows drawn on the GPU while they are packed: the 1000-frame workload; no e2e leg)")
@@ -570,10 +573,22 @@ def run_ours(args, cfg, name):
         }
         if e2e is not None:
             line["e2e"] = e2e
+    # ---------------- long video (BASELINE configs[4]) beside it: the north star's scaling target ----------------
+    want_long = args.long_video == "on" or (args.long_video == "auto" and world == 8 and name == "c2")
+    if want_long:
+        del net
+        scene = None
+        torch.cuda.empty_cache()
+        lv = long_video_record(args, world, rank, dev, barrier)
+        if rank == 0:
+            line["long_video"] = lv
+        net = None
     # ---------------- CPU baseline beside it (rank 0, N = 1 only) ----------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        del net
+        net = None
         torch.cuda.empty_cache()
+        if scene is None:
+            scene = make_scene(n, H, W, graph, seed=args.seed, with_flow=True, workers=os.cpu_count() or 1)
         cb = reference_rate(cfg, args.cpu_budget, 5, 1, args.seed, scene=scene)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     if rank == 0:
@@ -583,6 +598,70 @@ def run_ours(args, cfg, name):
         free_peer_regions()
         dist.barrier()
         dist.destroy_process_group()
+
+
+def long_video_record(args, world, rank, dev, barrier, steps=40, warmup=3):
+    """The 1000-frame workload (BASELINE configs[4], c5) on the same ranks: device-drawn inputs, MST initialisation,
+    `steps` iterations of the canonical loop timed like the main line (CUDA events, barrier on both sides, max over ranks)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from align3r_b200.cloud_opt_flow import GlobalAlignerMode, global_aligner
+    from align3r_b200.cloud_opt_flow.optimizer import global_alignment_loop
+    from align3r_b200.plan import frame_costs, partition_frames
+    from align3r_b200.synth import CANONICAL_KW, CONFIGS, make_edge_list, make_scene_device
+    n, H, W, graph = CONFIGS["c5"]
+    all_edges = make_edge_list(n, graph)
+    rows, shard = None, None
+    if world > 1:
+        lo, hi = partition_frames(frame_costs(np.asarray(all_edges, dtype=np.int32), np.asarray([(H, W)] * n, dtype=np.int32)), world)[rank]
+        rows = [e for e, (i, j) in enumerate(all_edges) if lo <= i < hi or lo <= j < hi]
+        shard = dict(world=world, rank=rank, group=None)
+    t0 = time.perf_counter()
+    scene = make_scene_device(n, H, W, graph, seed=args.seed, device=dev, edges=None if rows is None else [all_edges[e] for e in rows])
+    out = scene.output
+    if rows is not None:
+        out = dict(out, view1=dict(out["view1"], idx=[i for i, _ in all_edges]), view2=dict(out["view2"], idx=[j for _, j in all_edges]))
+    net = global_aligner(out, dev, mode=GlobalAlignerMode.PointCloudOptimizer, flow=(scene.flow_ij, scene.flow_ji), shard=shard,
+                         edge_rows=rows, **dict(CANONICAL_KW, num_total_iter=steps))
+    net.verbose = False
+    net.compute_global_alignment(init="mst", niter=0)
+    snap = {k: getattr(net, k).detach().clone() for k in ("pw_poses", "im_depthmaps", "im_poses", "im_focals")}
+    net.num_total_iter = 2 * warmup
+    global_alignment_loop(net, lr=0.01, niter=2 * warmup, schedule="linear")
+    net.num_total_iter = steps
+    with torch.no_grad():
+        for k, v in snap.items():
+            getattr(net, k).data.copy_(v)
+    net.flow_loss_flag = False
+    torch.cuda.synchronize(dev)
+    t_setup = time.perf_counter() - t0
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(torch.cuda.current_stream(dev))
+    final = global_alignment_loop(net, lr=0.01, niter=steps, schedule="linear")
+    e1.record(torch.cuda.current_stream(dev))
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt)
+    E, P = len(all_edges), H * W
+    n_flow = sum(1 for it in range(steps) if net._flow_active(it))
+    it_f, _ = algorithmic_bytes(E, n, P, True)
+    it_a, _ = algorithmic_bytes(E, n, P, False)
+    blended = (n_flow * it_f + (steps - n_flow) * it_a) / steps
+    peak, _ = measured_peak()
+    rec = {"workload": workload_name("c5", CONFIGS["c5"]), "value": steps / (ms * 1e-3), "unit": "iterations/s", "n_gpus": world,
+           "steps": steps, "warmup": 2 * warmup, "ms_per_step": ms / steps, "pixel_edges_per_sec": E * P * steps / (ms * 1e-3),
+           "final_loss": final, "loss_hist_head": [float(x) for x in net._bufs.loss_hist[:min(steps, 12)].cpu()],
+           "roofline_iteration_frac_per_gpu": blended / (ms / steps * 1e-3) / 1e9 / peak / world,
+           "setup_seconds": t_setup, "synth": "rows drawn on the GPUs while they are packed (no host copy, no e2e leg)",
+           "one_gpu_recorded": {"value": 59.4, "source": "profiles/r02_c5_lines.jsonl (same workload and protocol on one B200, round 2)"}}
+    del net
+    torch.cuda.empty_cache()
+    return rec
 
 
 def main():

@@ -192,3 +192,45 @@ def test_self_estimated_masks_match_reference(tag):
     assert torch.equal(cams["K_i"], fx["cams"]["K_i"]) and torch.equal(cams["K_j"], fx["cams"]["K_j"])
     assert float((cams["P_i"][:, :3, :3] - fx["cams"]["R_i"]).abs().max()) < 1e-6
     assert float((cams["P_j"][:, :3, 3:] - fx["cams"]["T_j"]).abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize("shared_focal", [True, False])
+def test_chunked_evaluation_equals_the_plain_oracle(shared_focal):
+    """ga_oracle.chunked_loss_and_grads (the fp64 arbiter of the full-size fixtures, whose autograd graph would not fit in
+    memory un-chunked): the same loss and gradients as loss_and_grads - 1e-12 in fp64, fp32 rounding in fp32 - with the flow
+    term on, off, and dropped by the gate."""
+    import torch
+    from align3r_b200.synth import CANONICAL_KW, make_scene
+    sc = make_scene(9, 32, 48, "swin-3-noncyclic", seed=2)
+    for over, epoch in ((dict(), 9999), (dict(), 0), (dict(flow_loss_thre=0.05), 9999)):
+        kw = dict(CANONICAL_KW, num_total_iter=10, shared_focal=shared_focal, **over)
+        prob = go.problem_from_output(sc.output, sc.flow_ij, sc.flow_ji, **kw)
+        params, _ = go.mst_init(prob)
+        for dt, tol in ((torch.float64, 1e-12), (torch.float32, 2e-6)):
+            pr, pp = prob.to(dt), {k: v.to(dt) for k, v in params.items()}
+            l0, g0, i0 = go.loss_and_grads(pr, pp, epoch)
+            l1, g1, i1 = go.chunked_loss_and_grads(pr, pp, epoch, chunk=7)
+            assert i0["flow_dropped"] == i1["flow_dropped"] and i0["flow_active"] == i1["flow_active"]
+            assert abs(float(l0) - float(l1)) <= tol * abs(float(l0))
+            for k in g0:
+                assert float((g0[k].double() - g1[k].double()).norm()) <= tol * float(g0[k].double().norm()) + 1e-300, (k, dt)
+        if over:
+            assert i1["flow_dropped"]
+
+
+def test_full_size_fixture_records_the_reference_at_full_size():
+    """tests/golden/c2_teacher_forced.pt (oracle/make_golden_big.py): the REAL reference's fp32 evaluation of BASELINE
+    configs[1] at full size agrees with the chunked oracle - loss to 1e-6, gradients to the reference's own fp32 noise -
+    which is what makes the chunked fp64 evaluation a legitimate arbiter at that size."""
+    from tests.helpers import load_golden
+    fx = load_golden("c2_teacher_forced")
+    assert fx["recipe"]["n_frames"] == 50 and (fx["recipe"]["H"], fx["recipe"]["W"]) == (288, 512) and len(fx["edges"]) == 470
+    for tag in ("flow", "pre_flow"):
+        ref, o32, o64 = fx[f"tf32_{tag}"], fx[f"tf32_oracle_{tag}"], fx[f"tf64_{tag}"]
+        assert abs(ref["loss"] - o64["loss"]) <= 1e-6 * o64["loss"]
+        agree = ref["oracle32_vs_reference32"]
+        assert agree["loss"] <= 2e-7 and agree["pw_poses"] <= 1e-6 and agree["im_depthmaps"] <= 2e-6
+        assert agree["im_poses"] <= 1e-5 and agree["im_focals"] <= 5e-5
+        for k in ("pw_poses", "im_poses", "im_depthmaps"):         # the reference's own fp32 error against the arbiter
+            assert 1e-7 < ref["err_vs_fp64"][k] < 1e-4
+    assert fx["mst_init"]["pw_poses"].shape == (470, 8) and abs(fx["mst_init"]["loss_pre_flow"] - 0.0433117) < 1e-6
