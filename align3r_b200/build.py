@@ -33,7 +33,7 @@ def build(force=False, verbose=False):
     cmd = [nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
            "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(HERE, "csrc"),
            "-o", out] + [os.path.join(HERE, "csrc", f) for f in SOURCES]
-    for macro in ("A3R_V4_WARPS", "A3R_V4_SLOTS", "A3R_V4_STAGES", "A3R_V4_EVICT_FIRST", "A3R_V4_TILE"):      # tuning knobs of the scan kernel (csrc/ga_scan_v4.cuh)
+    for macro in ("A3R_V4_WARPS", "A3R_V4_SLOTS", "A3R_V4_STAGES", "A3R_V4_EVICT_FIRST", "A3R_V4_TILE", "A3R_V4_NOFLUSH"):      # tuning knobs of the scan kernel (csrc/ga_scan_v4.cuh)
         if os.environ.get(macro):
             cmd.append(f"-D{macro}={os.environ[macro]}")
     if verbose:

@@ -123,9 +123,13 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gw = blockIdx.x * V4_WARPS + warp;                 // this warp's range in the plan ("CTA" = warp here)
     const int t0 = p.cta_tile_begin[gw], t1 = p.cta_tile_begin[gw + 1];
-    if (t0 >= t1) return;
     constexpr int NV = FLOW ? ACC_N : ACC_GA;
     constexpr int NQ = (NV + 3) / 4;
+    // the LAST work frame of every warp is flushed by the CTA together (below): what each warp ends on
+    __shared__ int s_last[V4_WARPS][4];          // work frame (-1: none), global frame, first local slot, slot count
+    int f_cw = -1, f_n = 0, f_sbegin = 0, f_deg = 0;
+    do {
+    if (t0 >= t1) break;
     const float thre_eff = flow_thre_eff(p.pxl_thre);
     const float4* xw_g = reinterpret_cast<const float4*>(p.predw);
     const float2* fl_g = reinterpret_cast<const float2*>(p.flow);
@@ -223,6 +227,9 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
 
     auto flush = [&]() {                        // this warp's share of a work frame is complete
         __syncwarp();
+#ifdef A3R_V4_NOFLUSH                          // diagnostic build: what the flush atomics cost (results are wrong)
+        return;
+#endif
         float gl_i = 0.f, gl_j = 0.f;           // lanes ACC_LOSS / ACC_FNUM / ACC_FCNT: the whole-problem sums (acc_glob), per side
         for (int s = 0; s < deg; ++s) {
             const uint32_t a = wb + V4_WACC + (s * V4_ROW + lane) * 4;
@@ -470,7 +477,48 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
             __syncwarp();
         }
     }
-    flush();
+    f_cw = cw; f_n = n; f_sbegin = s_begin; f_deg = deg;
+    } while (0);
+
+    // ---- final flush, per CTA: the 16 warps of a CTA walk adjacent tile ranges, so most of them end on the same work
+    //      frame - the first warp of every such group adds the group's running sums (fixed warp order, fp64) and issues ONE
+    //      atomic per value instead of one per warp (2 M fp64 atomics per scan on C2 otherwise, all landing at the kernel's
+    //      end on a few thousand addresses: 17 us of 720; 7 us of 112 on a 1/8 shard) ----
+#ifndef A3R_V4_NOFLUSH
+    if (lane == 0) { s_last[warp][0] = f_cw; s_last[warp][1] = f_n; s_last[warp][2] = f_sbegin; s_last[warp][3] = f_deg; }
+    __syncthreads();
+    if (f_cw >= 0) {
+        bool leader = true;
+        for (int w = 0; w < warp; ++w) leader = leader && s_last[w][0] != f_cw;
+        if (leader) {
+            unsigned members = 0;
+            for (int w = warp; w < V4_WARPS; ++w) members |= (s_last[w][0] == f_cw) ? (1u << w) : 0u;
+            const uint32_t base = smem_u32(smem_raw) + V4_WACC + lane * 4;
+            double gl_i = 0.0, gl_j = 0.0;          // lanes ACC_LOSS / ACC_FNUM / ACC_FCNT: whole-problem sums (acc_glob), per side
+            for (int s = 0; s < f_deg; ++s) {
+                if (lane < NV) {
+                    double v = 0.0;
+                    for (int w = warp; w < V4_WARPS; ++w)
+                        if (members >> w & 1u) v += (double)lds32(base + w * V4_WARP_BYTES + s * (V4_ROW * 4));
+                    const int gs = p.lslot_gslot[f_sbegin + s];
+                    if (v != 0.0) atomicAdd(&p.acc_slot[(int64_t)gs * ACC_STRIDE + lane], v);
+                    if (gs & 1) gl_j += v; else gl_i += v;
+                }
+            }
+            if (lane == ACC_LOSS) atomicAdd(&p.acc_glob[GL_LOSS], gl_i + gl_j);
+            if (FLOW && (lane == ACC_FNUM || lane == ACC_FCNT)) {
+                atomicAdd(&p.acc_glob[GL_FNUM_I + (lane - ACC_FNUM)], gl_i);
+                atomicAdd(&p.acc_glob[GL_FNUM_J + (lane - ACC_FNUM)], gl_j);
+            }
+            if (lane < FACC_N) {
+                double v = 0.0;
+                for (int w = warp; w < V4_WARPS; ++w)
+                    if (members >> w & 1u) v += (double)lds32(base + w * V4_WARP_BYTES + V4_SLOTS * (V4_ROW * 4));
+                atomicAdd(&p.acc_frame[(int64_t)f_n * FACC_N + lane], v);
+            }
+        }
+    }
+#endif
 }
 
 }  // namespace a3r
