@@ -481,41 +481,40 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
     } while (0);
 
     // ---- final flush, per CTA: the 16 warps of a CTA walk adjacent tile ranges, so most of them end on the same work
-    //      frame - the first warp of every such group adds the group's running sums (fixed warp order, fp64) and issues ONE
+    //      frame - such a group adds its members' running sums in shared memory (fixed warp order, fp64) and issues ONE
     //      atomic per value instead of one per warp (2 M fp64 atomics per scan on C2 otherwise, all landing at the kernel's
     //      end on a few thousand addresses: 17 us of 720; 7 us of 112 on a 1/8 shard) ----
 #ifndef A3R_V4_NOFLUSH
     if (lane == 0) { s_last[warp][0] = f_cw; s_last[warp][1] = f_n; s_last[warp][2] = f_sbegin; s_last[warp][3] = f_deg; }
     __syncthreads();
     if (f_cw >= 0) {
-        bool leader = true;
-        for (int w = 0; w < warp; ++w) leader = leader && s_last[w][0] != f_cw;
-        if (leader) {
-            unsigned members = 0;
-            for (int w = warp; w < V4_WARPS; ++w) members |= (s_last[w][0] == f_cw) ? (1u << w) : 0u;
-            const uint32_t base = smem_u32(smem_raw) + V4_WACC + lane * 4;
-            double gl_i = 0.0, gl_j = 0.0;          // lanes ACC_LOSS / ACC_FNUM / ACC_FCNT: whole-problem sums (acc_glob), per side
-            for (int s = 0; s < f_deg; ++s) {
-                if (lane < NV) {
-                    double v = 0.0;
-                    for (int w = warp; w < V4_WARPS; ++w)
-                        if (members >> w & 1u) v += (double)lds32(base + w * V4_WARP_BYTES + s * (V4_ROW * 4));
-                    const int gs = p.lslot_gslot[f_sbegin + s];
-                    if (v != 0.0) atomicAdd(&p.acc_slot[(int64_t)gs * ACC_STRIDE + lane], v);
-                    if (gs & 1) gl_j += v; else gl_i += v;
-                }
-            }
-            if (lane == ACC_LOSS) atomicAdd(&p.acc_glob[GL_LOSS], gl_i + gl_j);
-            if (FLOW && (lane == ACC_FNUM || lane == ACC_FCNT)) {
-                atomicAdd(&p.acc_glob[GL_FNUM_I + (lane - ACC_FNUM)], gl_i);
-                atomicAdd(&p.acc_glob[GL_FNUM_J + (lane - ACC_FNUM)], gl_j);
-            }
-            if (lane < FACC_N) {
+        // the group = the warps of this CTA that end on work frame f_cw; its members share the frame's slots out among
+        // themselves (slot s goes to member s mod size), so the flush is as parallel as the per-warp one it replaces
+        unsigned members = 0;
+        for (int w = 0; w < V4_WARPS; ++w) members |= (s_last[w][0] == f_cw) ? (1u << w) : 0u;
+        const int size = __popc(members), rank = __popc(members & ((1u << warp) - 1u));
+        const uint32_t base = smem_u32(smem_raw) + V4_WACC + lane * 4;
+        double gl_i = 0.0, gl_j = 0.0;              // lanes ACC_LOSS / ACC_FNUM / ACC_FCNT: whole-problem sums (acc_glob), per side
+        for (int s = rank; s < f_deg; s += size) {
+            if (lane < NV) {
                 double v = 0.0;
-                for (int w = warp; w < V4_WARPS; ++w)
-                    if (members >> w & 1u) v += (double)lds32(base + w * V4_WARP_BYTES + V4_SLOTS * (V4_ROW * 4));
-                atomicAdd(&p.acc_frame[(int64_t)f_n * FACC_N + lane], v);
+                for (int w = 0; w < V4_WARPS; ++w)      // fixed warp order: reproducible sums
+                    if (members >> w & 1u) v += (double)lds32(base + w * V4_WARP_BYTES + s * (V4_ROW * 4));
+                const int gs = p.lslot_gslot[f_sbegin + s];
+                if (v != 0.0) atomicAdd(&p.acc_slot[(int64_t)gs * ACC_STRIDE + lane], v);
+                if (gs & 1) gl_j += v; else gl_i += v;
             }
+        }
+        if (lane == ACC_LOSS && gl_i + gl_j != 0.0) atomicAdd(&p.acc_glob[GL_LOSS], gl_i + gl_j);
+        if (FLOW && (lane == ACC_FNUM || lane == ACC_FCNT)) {
+            if (gl_i != 0.0) atomicAdd(&p.acc_glob[GL_FNUM_I + (lane - ACC_FNUM)], gl_i);
+            if (gl_j != 0.0) atomicAdd(&p.acc_glob[GL_FNUM_J + (lane - ACC_FNUM)], gl_j);
+        }
+        if (rank == size - 1 && lane < FACC_N) {      // the frame row: the member with the fewest slots
+            double v = 0.0;
+            for (int w = 0; w < V4_WARPS; ++w)
+                if (members >> w & 1u) v += (double)lds32(base + w * V4_WARP_BYTES + V4_SLOTS * (V4_ROW * 4));
+            atomicAdd(&p.acc_frame[(int64_t)f_n * FACC_N + lane], v);
         }
     }
 #endif
