@@ -9,8 +9,10 @@
          the arbiter is the oracle's edge-chunked evaluation in fp64 (``ga_oracle.chunked_loss_and_grads``: equal to the
          un-chunked oracle to 1e-16 in fp64 / 1e-7 in fp32, tests/test_oracle_golden.py; checked here against the real
          reference's fp32 result at full size, the agreement is stored in the fixture).
-``f200`` a 200-frame 288x512 swin-5 sub-scene of the long-video workload (1990 directed edges, 293 M pixel-edges): the
+``f200`` a 200-frame 288x512 swin-5 sub-scene of the long-video workload (1970 directed edges, 290 M pixel-edges): the
          edge-chunked oracle in fp32 and fp64 (the reference's graph would need > 100 GB).
+``c3``, ``c4``  BASELINE configs[2] and [3] at full size (90 frames 288x512 with per-frame-coherent noise; 110 frames 384x512):
+         the edge-chunked oracle in fp32 and fp64.
 
 Stored per case: loss, every small gradient in full, and of the depth gradient (N x 147456 floats) a strided sample plus
 per-frame sums / sums of squares; the recipe regenerates inputs and parameters bit for bit (input checksum included).
@@ -33,11 +35,14 @@ import ga_oracle as go                                     # noqa: E402
 from align3r_b200.synth import make_scene, near_solution_params, CANONICAL_KW   # noqa: E402
 from make_golden import checksum, load_params, teacher_forced                    # noqa: E402
 
-STRIDES = {"c2": 389, "f200": 1553}      # ~19 000 depth-gradient samples per case; co-prime with the image width: the sample
+STRIDES = {"c2": 389, "f200": 1553, "c3": 701, "c4": 1151}      # ~19 000 depth-gradient samples per case; co-prime with the image width: the sample
                                          # walks over rows and columns
 TRAIN = ("pw_poses", "im_depthmaps", "im_poses", "im_focals")
 CASES = {"c2": dict(n_frames=50, H=288, W=512, scene_graph="swin-5-noncyclic", seed=0, with_flow=True),
-         "f200": dict(n_frames=200, H=288, W=512, scene_graph="swin-5-noncyclic", seed=0, with_flow=True)}
+         "f200": dict(n_frames=200, H=288, W=512, scene_graph="swin-5-noncyclic", seed=0, with_flow=True),
+         # BASELINE configs[2] (DAVIS-shaped, per-frame-coherent "Depth-Pro-conditioned" pointmap noise) and configs[3] (Bonn/TUM-shaped)
+         "c3": dict(n_frames=90, H=288, W=512, scene_graph="swin-5-noncyclic", seed=2, with_flow=True, frame_noise=0.02, pixel_noise=0.003),
+         "c4": dict(n_frames=110, H=384, W=512, scene_graph="swin-5-noncyclic", seed=2, with_flow=True)}
 
 
 def pack_grads(grads, stride):

@@ -991,11 +991,11 @@ def full_size_rows(fx, net, P, tag):
     return rows, bool(net.flow_loss_flag) == bool(g64["flow_dropped"])
 
 
-@pytest.mark.parametrize("name", ["c2", "f200"])
+@pytest.mark.parametrize("name", ["c2", "f200", "c3", "c4"])
 def test_full_size_teacher_forced(cuda_device, name):
     """BASELINE configs[1] at full size (c2: 50 frames 288x512, 470 edges) against the REAL reference's fp32 forward +
-    autograd and the fp64 arbiter, and a 200-frame 288x512 sub-scene of the long-video workload (1990 edges) against the
-    edge-chunked oracle: loss 2e-6; small gradients by the arbiter criterion (tests/helpers.py::grad_close); per-pixel depth
+    autograd and the fp64 arbiter; a 200-frame 288x512 sub-scene of the long-video workload (1970 edges), configs[2] (c3: 90
+    frames, per-frame-coherent pointmap noise) and configs[3] (c4: 110 frames 384x512) against the edge-chunked oracle: loss 2e-6; small gradients by the arbiter criterion (tests/helpers.py::grad_close); per-pixel depth
     gradients within 1e-5 relative of the fp64 gradients (the north star's figure) on a 19 000-pixel strided sample, the
     per-frame sums and the norm of the whole plane."""
     fx, scene, net, P = full_size_case(name, cuda_device)

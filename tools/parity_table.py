@@ -37,7 +37,7 @@ for name in T.CASES:
             ok, err, ref = grad_close(k, mine[k], g32["grads"][k], g64["grads"][k])
             print(f"| | | {k} | {err:.1e} | {ref:.1e} | {err / max(ref, 1e-30):.2f} |")
     del net
-for name in ("c2", "f200"):
+for name in ("c2", "f200", "c3", "c4"):
     fx, scene, net, P = T.full_size_case(name, "cuda")
     for tag in ("pre_flow", "flow"):
         for k in ("pw_poses", "im_depthmaps", "im_poses", "im_focals"):
