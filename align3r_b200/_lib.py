@@ -105,6 +105,7 @@ _SIGNATURES = {
     "a3r_occ_masks": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp]),
     "a3r_motion_minmax": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "a3r_debug_k2_trace": (C.c_int, [C.c_int, _vp]),
+    "a3r_debug_timeline": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "a3r_motion_masks": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _vp, _vp, _vp]),
 }
 EXPORTS = tuple(_SIGNATURES)

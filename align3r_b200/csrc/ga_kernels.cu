@@ -706,6 +706,20 @@ int a3r_debug_k2_trace(int enable, unsigned long long* out) {
     return A3R_OK;
 }
 
+// diagnostic: the last 64 scan / update launches as CTA 0 saw them: rows (kernel id 1 = scan, 2 = update; entry; return of the
+// programmatic-launch wait; exit) in %globaltimer nanoseconds, oldest first in out[0..n); returns n in *count.  Synchronises.
+int a3r_debug_timeline(unsigned long long* out, int* count) {
+    A3R_CUDA(cudaDeviceSynchronize());
+    unsigned long long ring[64 * 4];
+    unsigned int seq = 0;
+    A3R_CUDA(cudaMemcpyFromSymbol(ring, g_timeline, sizeof(ring)));
+    A3R_CUDA(cudaMemcpyFromSymbol(&seq, g_timeline_seq, sizeof(seq)));
+    const unsigned int n = seq < 64u ? seq : 64u;
+    for (unsigned int k = 0; k < n; ++k) memcpy(out + 4 * k, ring + 4 * ((seq - n + k) & 63u), 4 * sizeof(unsigned long long));
+    if (count) *count = (int)n;
+    return A3R_OK;
+}
+
 int a3r_ga_unproject(const A3rProblem* p, float* pts3d, void* stream) {
     if (int rc = check_problem(p)) return rc;
     if (!pts3d) return a3r_fail(A3R_E_ARG, "pts3d is NULL");

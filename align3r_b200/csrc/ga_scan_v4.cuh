@@ -33,6 +33,7 @@
 #include "ga_math.cuh"
 #include "a3r_common.cuh"
 #include "ptx_helpers.cuh"    // mbarrier, bulk copy, cp.async, raw shared-memory accesses
+#include "ga_small.cuh"       // (the diagnostic launch timeline lives there)
 
 namespace a3r {
 
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gw = blockIdx.x * V4_WARPS + warp;                 // this warp's range in the plan ("CTA" = warp here)
     const int t0 = p.cta_tile_begin[gw], t1 = p.cta_tile_begin[gw + 1];
+    const TimelineSlot tl = timeline_enter(1);
     constexpr int NV = FLOW ? ACC_N : ACC_GA;
     constexpr int NQ = (NV + 3) / 4;
     // the LAST work frame of every warp is flushed by the CTA together (below): what each warp ends on
@@ -217,6 +219,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
     // per-pixel planes the previous SCAN left): with a programmatic launch it overlaps the tail of K2.  From here on the
     // kernel reads K2's results (parameter maps, flow normalisers) and adds into the accumulator block K2 zeroed.
     pdl_wait();
+    timeline_mark(tl, 2);
     float sc_i = 0.f, sc_j = 0.f;
     if (ADAM && prev_flow) { sc_i = (float)p.scal[A3R_S_SC_I]; sc_j = (float)p.scal[A3R_S_SC_J]; }
 
@@ -518,6 +521,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
         }
     }
 #endif
+    timeline_mark(tl, 3);
 }
 
 }  // namespace a3r

@@ -87,6 +87,26 @@ __device__ __forceinline__ void k2_stamp(int slot) {
     }
 }
 
+// diagnostic launch timeline (a3r_debug_timeline): CTA 0 of every scan / update launch records (kernel id, entry, the moment
+// its programmatic-launch wait returned, exit) in a 64-entry ring
+__device__ unsigned long long g_timeline[64 * 4];
+__device__ unsigned int g_timeline_seq = 0;
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+struct TimelineSlot { unsigned long long* row; };
+__device__ __forceinline__ TimelineSlot timeline_enter(int kernel_id) {
+    TimelineSlot t{nullptr};
+    if (g_k2_trace_on && blockIdx.x == 0 && threadIdx.x == 0) {
+        t.row = g_timeline + (atomicAdd(&g_timeline_seq, 1u) & 63u) * 4;
+        t.row[0] = (unsigned long long)kernel_id; t.row[1] = global_ns(); t.row[2] = 0; t.row[3] = 0;
+    }
+    return t;
+}
+__device__ __forceinline__ void timeline_mark(const TimelineSlot& t, int k) { if (t.row) t.row[k] = global_ns(); }
+
 // grid barrier: every CTA of the launch is resident (grid <= SM count, nothing runs beside it)
 __device__ __forceinline__ void grid_barrier(uint32_t* ctr, uint32_t target) {
     __syncthreads();                           // the CTA's writes precede thread 0's release (bar.sync is morally strong)
@@ -212,7 +232,9 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
     const int64_t off_prior = off_frame + (int64_t)N * FACC_N;
     const int64_t off_glob = off_prior + (prior ? (int64_t)N * PR_N : 0);
 
+    const TimelineSlot tl = timeline_enter(2);
     pdl_wait();             // launched while the scan was still running: from here on its sums are complete and visible
+    timeline_mark(tl, 2);
     pdl_trigger();          // the next scan's CTAs may take the idle SMs and prefetch their first tiles (they wait for this grid)
     k2_stamp(0);
     // ---------------- exchange: publish "my sums of this iteration are complete", wait for the peers' ----------------
@@ -488,6 +510,7 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
         }
     }
     k2_stamp(7);
+    timeline_mark(tl, 3);
 }
 
 }  // namespace a3r

@@ -279,6 +279,10 @@ int a3r_ga_run_peers(const A3rProblem *p, const A3rPeers *peers, uint32_t tag0, 
  * the following launches; out (host, 64 entries, may be NULL) receives the %globaltimer stamps [cta][8] of the last
  * traced launch.  Synchronises the device. */
 int a3r_debug_k2_trace(int enable, unsigned long long *out);
+/* diagnostic: while the trace is enabled, CTA 0 of every scan (id 1) / update (id 2) launch records (id, entry, return of its
+ * programmatic-launch wait, exit) in %globaltimer ns; out (host, 64 x 4 entries) receives the last <= 64 launches oldest first,
+ * *count how many.  Synchronises the device. */
+int a3r_debug_timeline(unsigned long long *out, int *count);
 
 /* ---- read-out (reference optimizer.py:468-478 depth_to_pts3d) ----
  * world points [n_local_frames][pix_stride][3] from logdepth + frame_par (call a3r_ga_prepare first) */
