@@ -701,6 +701,10 @@ int a3r_ga_run_peers(const A3rProblem* p, const A3rPeers* peers, uint32_t tag0, 
 // [cta 0..7][8]: start, gate, phase A1, barrier 1, phase A2, barrier 2, phase C, end).  Synchronises the device.
 int a3r_debug_k2_trace(int enable, unsigned long long* out) {
     A3R_CUDA(cudaDeviceSynchronize());
+    {       // enable >= 2: stamp only the launch of iteration enable - 2 (a mid-loop launch also writes the next parameter maps)
+        const int it = enable >= 2 ? enable - 2 : -1;
+        A3R_CUDA(cudaMemcpyToSymbol(g_k2_trace_iter, &it, sizeof(int)));
+    }
     if (out) A3R_CUDA(cudaMemcpyFromSymbol(out, g_k2_trace, sizeof(unsigned long long) * 8 * 8));
     A3R_CUDA(cudaMemcpyToSymbol(g_k2_trace_on, &enable, sizeof(int)));
     return A3R_OK;

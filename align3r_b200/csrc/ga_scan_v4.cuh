@@ -220,6 +220,10 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
     // kernel reads K2's results (parameter maps, flow normalisers) and adds into the accumulator block K2 zeroed.
     pdl_wait();
     timeline_mark(tl, 2);
+    // From here on K2 of this iteration may be launched: its few CTAs take the first SMs this grid frees and block in their own
+    // pdl_wait until the whole scan has completed and flushed - the update kernel's launch latency (10 us between the scan's
+    // last exit and K2's first instruction otherwise, tools/timeline.py) disappears from the critical path.
+    pdl_trigger();
     float sc_i = 0.f, sc_j = 0.f;
     if (ADAM && prev_flow) { sc_i = (float)p.scal[A3R_S_SC_I]; sc_j = (float)p.scal[A3R_S_SC_J]; }
 

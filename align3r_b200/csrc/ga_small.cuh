@@ -79,8 +79,9 @@ __device__ __forceinline__ float ld_cg(const float* q) { return __ldcg(q); }
 // diagnostic phase trace (a3r_debug_k2_trace): globaltimer stamps of thread 0 of the first 8 CTAs at the phase boundaries
 __device__ unsigned long long g_k2_trace[8 * 8];
 __device__ int g_k2_trace_on = 0;
-__device__ __forceinline__ void k2_stamp(int slot) {
-    if (g_k2_trace_on && threadIdx.x == 0 && blockIdx.x < 8) {
+__device__ int g_k2_trace_iter = -1;           // >= 0: stamp only the launch of this iteration (A3rAdamStep.iter)
+__device__ __forceinline__ void k2_stamp(int slot, int iter = -1) {
+    if (g_k2_trace_on && threadIdx.x == 0 && blockIdx.x < 8 && (g_k2_trace_iter < 0 || g_k2_trace_iter == iter)) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         g_k2_trace[blockIdx.x * 8 + slot] = t;
@@ -236,7 +237,7 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
     pdl_wait();             // launched while the scan was still running: from here on its sums are complete and visible
     timeline_mark(tl, 2);
     pdl_trigger();          // the next scan's CTAs may take the idle SMs and prefetch their first tiles (they wait for this grid)
-    k2_stamp(0);
+    k2_stamp(0, adam.iter);
     // ---------------- exchange: publish "my sums of this iteration are complete", wait for the peers' ----------------
     if (sys) {
         if (blockIdx.x == 0 && tid < src.world && tid != src.rank) {
@@ -269,7 +270,7 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
     __syncthreads();
     const double sc_i = s_sc[0], sc_j = s_sc[1];
     const bool chains = flow_active && (sc_i != 0.0 || sc_j != 0.0);
-    k2_stamp(1);
+    k2_stamp(1, adam.iter);
 
     // ---------------- phase A1 ----------------
     {
@@ -322,9 +323,9 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
             }
         }
     }
-    k2_stamp(2);
+    k2_stamp(2, adam.iter);
     grid_barrier(p.sync_ctr, (uint32_t)G);
-    k2_stamp(3);
+    k2_stamp(3, adam.iter);
 
     // ---------------- phase A2 ----------------
     {
@@ -444,9 +445,9 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
                 adam_entry(p.pw_adaptors + idx, p.pw_adaptors_m + idx, p.pw_adaptors_v + idx, ld_cg(p.g_pw_adaptors + idx), p, adam);
         }
     }
-    k2_stamp(4);
+    k2_stamp(4, adam.iter);
     grid_barrier(p.sync_ctr, (uint32_t)(2 * G));
-    k2_stamp(5);
+    k2_stamp(5, adam.iter);
 
     // ---------------- phase C ----------------
     // the shared focal: every CTA sums the frames' contributions in one fixed order and steps its own copy of the
@@ -498,7 +499,7 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
         prepare_items(p, shared_focal ? s_foc : p.im_focals, vt, nvt, s_red, &s_mean);
     if (src.zero_block)
         for (int64_t i = vt; i < src.n_acc; i += nvt) src.zero_block[i] = 0.0;
-    k2_stamp(6);
+    k2_stamp(6, adam.iter);
     // the last CTA out re-arms the barrier counters for the next launch
     __syncthreads();
     if (tid == 0) {
@@ -509,7 +510,7 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
             __threadfence();
         }
     }
-    k2_stamp(7);
+    k2_stamp(7, adam.iter);
     timeline_mark(tl, 3);
 }
 

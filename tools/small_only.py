@@ -33,7 +33,7 @@ for rep in range(3):
 import ctypes as C
 lib = net._lib
 buf = (C.c_ulonglong * 64)()
-lib.a3r_debug_k2_trace(1, None)
+lib.a3r_debug_k2_trace(2 + a.iters // 2, None)          # a mid-loop launch (it also writes the next iteration's parameter maps)
 global_alignment_loop(net, lr=0.01, niter=a.iters, schedule="linear")
 lib.a3r_debug_k2_trace(0, buf)
 rows = [[buf[c * 8 + k] for k in range(8)] for c in range(8)]
