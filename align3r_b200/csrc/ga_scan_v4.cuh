@@ -220,10 +220,9 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
     // kernel reads K2's results (parameter maps, flow normalisers) and adds into the accumulator block K2 zeroed.
     pdl_wait();
     timeline_mark(tl, 2);
-    // From here on K2 of this iteration may be launched: its few CTAs take the first SMs this grid frees and block in their own
-    // pdl_wait until the whole scan has completed and flushed - the update kernel's launch latency (10 us between the scan's
-    // last exit and K2's first instruction otherwise, tools/timeline.py) disappears from the critical path.
-    pdl_trigger();
+    // (No early griddepcontrol.launch_dependents here: with it K2's CTAs are resident before the scan's last CTA exits and its
+    // launch latency disappears, but they land on the first SMs the scan frees - neighbours - and K2 itself runs 6-8 us longer:
+    // the iteration gets slower, 135 vs 128 us on a 7-frame shard, 808 vs 792 us on C2, tools/timeline.py.)
     float sc_i = 0.f, sc_j = 0.f;
     if (ADAM && prev_flow) { sc_i = (float)p.scal[A3R_S_SC_I]; sc_j = (float)p.scal[A3R_S_SC_J]; }
 
