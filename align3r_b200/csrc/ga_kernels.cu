@@ -560,7 +560,8 @@ static int launch_small(const A3rProblem* p, uint32_t mode, const A3rAdamStep* a
     int grid = (int)((items + K2_THREADS - 1) / K2_THREADS);
     if (grid < 8) grid = 8;
     if (grid > sm) grid = sm;
-    A3R_CUDA(launch_ex(k_small, dim3(grid), dim3(K2_THREADS), 0, st, pdl_enabled(), *p, mode, *adam, prepare_next ? 1u : 0u, src));
+    static const bool late = [] { const char* e = getenv("A3R_K2_TRIGGER"); return e && e[0] == 'l'; }();
+    A3R_CUDA(launch_ex(k_small, dim3(grid), dim3(K2_THREADS), 0, st, pdl_enabled(), *p, mode, *adam, (prepare_next ? 1u : 0u) | (late ? 2u : 0u), src));
     return A3R_OK;
 }
 

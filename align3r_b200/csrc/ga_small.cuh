@@ -30,6 +30,7 @@
 #include "ga_math.cuh"
 #include "a3r_common.cuh"
 #include "a3r_ga.h"
+#include <stddef.h>
 
 namespace a3r {
 
@@ -37,7 +38,7 @@ constexpr int K2_THREADS = 256;
 constexpr int K2_WARPS = K2_THREADS / 32;
 constexpr int PS_STRIDE = 32;                  // pair_scratch row: source half [0,16), target half [16,32)
 constexpr int CAM_STRIDE = 20;                 // FrameD as doubles
-static_assert(sizeof(FrameD) == CAM_STRIDE * sizeof(double), "cam_cache rows hold a FrameD");
+static_assert(sizeof(FrameD) == CAM_STRIDE * sizeof(double) && offsetof(FrameD, f) == 12 * sizeof(double), "cam_cache rows hold a FrameD");
 constexpr size_t PEER_FLAG_STRIDE = 128;
 constexpr size_t PEER_HEADER = A3R_MAX_PEERS * PEER_FLAG_STRIDE;
 
@@ -236,7 +237,7 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
     const TimelineSlot tl = timeline_enter(2);
     pdl_wait();             // launched while the scan was still running: from here on its sums are complete and visible
     timeline_mark(tl, 2);
-    pdl_trigger();          // the next scan's CTAs may take the idle SMs and prefetch their first tiles (they wait for this grid)
+    if (!(prepare_next & 2u)) pdl_trigger();   // the next scan's CTAs may take the idle SMs and prefetch their first tiles (they wait for this grid)
     k2_stamp(0, adam.iter);
     // ---------------- exchange: publish "my sums of this iteration are complete", wait for the peers' ----------------
     if (sys) {
@@ -411,6 +412,14 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
                 *e_prm = e_p; *e_m = e_mm; *e_v = e_vv;
             }
             __syncwarp();
+            // the camera of the frame's UPDATED parameters -> cam_cache (what the next iteration's chains and this launch's
+            // phase C read; the shared focal, only known after phase C's sum, is patched in there).  A1 is done with the old row.
+            if ((prepare_next & 1u) && lane == 0) {
+                FrameD F2;
+                load_frame(p.im_poses, p.im_focals, p.im_pp, p.frame_hw, n, shared_focal, fb, F2);
+                cam_store(p.cam_cache, n, F2);
+            }
+            __syncwarp();
         }
 
         // the pair parameters, one thread per entry (four entries of a thread in flight at once): entries 0-6 of a pair
@@ -448,6 +457,7 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
     k2_stamp(4, adam.iter);
     grid_barrier(p.sync_ctr, (uint32_t)(2 * G));
     k2_stamp(5, adam.iter);
+    if (prepare_next & 2u) pdl_trigger();      // (A3R_K2_TRIGGER=late: the next scan's prologue overlaps phase C only)
 
     // ---------------- phase C ----------------
     // the shared focal: every CTA sums the frames' contributions in one fixed order and steps its own copy of the
@@ -495,8 +505,42 @@ k_small(const A3rProblem p, const uint32_t mode, const A3rAdamStep adam, const u
         }
         __syncthreads();
     }
-    if (prepare_next)       // reference base_opt.py:195-247, optimizer.py:398-428 of the updated parameters
-        prepare_items(p, shared_focal ? s_foc : p.im_focals, vt, nvt, s_red, &s_mean);
+    if (prepare_next & 1u) {        // reference base_opt.py:195-247, optimizer.py:398-428 of the updated parameters
+        // (k_prepare's job, from the cameras phase A2 cached: no quaternion / expm1 is evaluated again)
+        double part = 0.0;
+        for (int e = tid; e < E; e += K2_THREADS) part += (double)ld_cg(p.pw_poses + 8 * e + 7);
+        part = block_sum(part, s_red);
+        if (tid == 0) { s_mean = part / (double)E; s_gl[7] = shared_focal ? a3r_exp((double)s_foc[0] / fb) : 0.0; }
+        __syncthreads();
+        const double log_norm = norm_scale ? (log((double)p.base_scale) - s_mean) : 0.0;
+        const double f_shared = s_gl[7];
+        const int nS = (p.flags & A3R_F_HAS_FLOW) ? 2 * E : 0;
+        const int total = nS + E + N;
+#pragma unroll 1
+        for (int it = vt; it < total; it += nvt) {
+            if (it < nS) {
+                const int gs = it, e = gs >> 1, side = gs & 1;
+                const int i = p.edge_ij[2 * e], j = p.edge_ij[2 * e + 1];
+                FrameD S, T;
+                cam_load(p.cam_cache, side ? j : i, S);
+                cam_load(p.cam_cache, side ? i : j, T);
+                if (shared_focal) { S.f = f_shared; T.f = f_shared; }
+                nl_derive_slot_par(&S, &T, p.slot_par + SP_STRIDE * gs);
+            } else if (it < nS + E) {
+                const int e = it - nS;
+                derive_edge_par(p.pw_poses + 8 * e, p.pw_adaptors + 2 * e, log_norm, norm_scale, (double)p.pw_break, p.edge_par + EP_STRIDE * e);
+            } else {
+                const int n = it - nS - E;
+                FrameD F;
+                cam_load(p.cam_cache, n, F);
+                if (shared_focal) {
+                    F.f = f_shared;
+                    p.cam_cache[(int64_t)n * CAM_STRIDE + 12] = f_shared;       // FrameD::f (the other fields are final since A2)
+                }
+                derive_frame_par(F, p.frame_par + FP_STRIDE * n);
+            }
+        }
+    }
     if (src.zero_block)
         for (int64_t i = vt; i < src.n_acc; i += nvt) src.zero_block[i] = 0.0;
     k2_stamp(6, adam.iter);
