@@ -72,6 +72,7 @@ _SIGNATURES = {
     "a3r_tile_pixels": (C.c_int, []),
     "a3r_max_slots": (C.c_int, []),
     "a3r_max_ctas": (C.c_int, [C.c_int]),
+    "a3r_scan_align_warps": (C.c_int, []),
     "a3r_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "a3r_pack_pred": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "a3r_pack_flow": (C.c_int, [_vp, _i32, _i64, _vp, _i64, _vp, _vp]),

@@ -226,7 +226,7 @@ class PointCloudOptimizer(nn.Module):
         if os.environ.get("A3R_PLAN_CTAS"):       # diagnostic: another partition of the tiles (tools/partition_sensitivity.py)
             n_ctas = int(os.environ["A3R_PLAN_CTAS"])
         self._plan = build_plan(self.edges, self.imshapes, self._lib.a3r_tile_pixels(), self._lib.a3r_max_slots(),
-                                n_ctas, frame_range)
+                                n_ctas, frame_range, align_warps=self._lib.a3r_scan_align_warps())
         plan = self._plan
         self._lslot = plan.local_slot_of()
         self._lframe = plan.local_frame_of()

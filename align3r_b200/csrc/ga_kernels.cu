@@ -10,6 +10,7 @@
 #include "ga_math.cuh"
 #include "a3r_common.cuh"
 #include "ga_scan_v4.cuh"
+#include "ga_scan_v5.cuh"
 #include "ga_small.cuh"     // K0 (parameter maps) and K2 (loss, gate, chains, small Adam, exchange)
 #include <stdlib.h>
 
@@ -349,12 +350,14 @@ __global__ void __launch_bounds__(256) k_pack_flow(const float* __restrict__ src
 static int scan_variant() {
     static int v = [] {
         const char* e = getenv("A3R_SCAN");
-        return (e && e[0] == 'v' && e[1] == '1') ? 1 : 4;
+        if (e && e[0] == 'v' && e[1] == '1') return 1;
+        if (e && e[0] == 'v' && e[1] == '5') return 5;
+        return 4;
     }();
     return v;
 }
-static int scan_tile() { return scan_variant() == 1 ? K1_TILE : V4_T; }
-static int scan_slots() { return scan_variant() == 1 ? K1_MAXS : V4_SLOTS; }
+static int scan_tile() { const int v = scan_variant(); return v == 1 ? K1_TILE : v == 5 ? V5_T : V4_T; }
+static int scan_slots() { const int v = scan_variant(); return v == 1 ? K1_MAXS : v == 5 ? V5_SLOTS : V4_SLOTS; }
 
 static int check_problem(const A3rProblem* p) {
     if (!p) return a3r_fail(A3R_E_ARG, "problem is NULL");
@@ -387,7 +390,17 @@ template <bool FLOW, bool L2D>
 static int launch_accumulate(const A3rProblem* p, cudaStream_t st, const A3rAdamStep* prev_adam, bool prev_flow) {
     const A3rAdamStep none = {0.f, 1.f, -1, 0};
     const bool pdl = pdl_enabled();
-    if (scan_variant() == 1) {
+    if (scan_variant() == 5) {
+        if (prev_adam) return a3r_fail(A3R_E_UNSUPPORTED, "the v5 scan has no folded depth step");
+        if (p->n_ctas % V5_WARPS != 0) return a3r_fail(A3R_E_ARG, "n_ctas must be a multiple of %d for the v5 scan", V5_WARPS);
+        constexpr size_t smem = FLOW ? V5_SMEM_FLOW : V5_SMEM_ALIGN;
+        static bool configured = false;
+        if (!configured) {
+            A3R_CUDA(cudaFuncSetAttribute(k_accumulate_v5<FLOW, L2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = true;
+        }
+        A3R_CUDA(launch_ex(k_accumulate_v5<FLOW, L2D>, dim3(p->n_ctas / V5_WARPS), dim3(V5_THREADS), smem, st, pdl, *p));
+    } else if (scan_variant() == 1) {
         if (prev_adam) return a3r_fail(A3R_E_UNSUPPORTED, "the v1 scan has no folded depth step");
         const size_t smem = sizeof(double) * K1_WARPS * K1_MAXS * ACC_STRIDE + sizeof(K1Shared);
         static bool configured = false;   // per template instantiation
@@ -425,7 +438,7 @@ static int launch_accumulate(const A3rProblem* p, cudaStream_t st, const A3rAdam
 static bool depth_step_folds(const A3rProblem* p) {
     static const bool off = [] { const char* e = getenv("A3R_FOLD_DEPTH"); return e && e[0] == '0'; }();
     static const bool tma = [] { const char* e = getenv("A3R_V4_COPY"); return e && e[0] == 't'; }();
-    return !off && !tma && scan_variant() != 1 && p->n_work_frames == p->n_local_frames && (p->flags & A3R_F_TRAIN_DEPTH) &&
+    return !off && !tma && scan_variant() == 4 && p->n_work_frames == p->n_local_frames && (p->flags & A3R_F_TRAIN_DEPTH) &&
            !(p->depth_regularize_weight > 0.f) && p->n_tiles > 0;
 }
 
@@ -448,12 +461,15 @@ int a3r_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
     return A3R_OK;
 }
 
+/* v5 scan: align warps per CTA when the flow term is on (cta_tile_begin then holds three partitions, ga_scan_v5.cuh); 0 otherwise */
+int a3r_scan_align_warps(void) { return scan_variant() == 5 ? V5_NA : 0; }
+
 int a3r_max_ctas(int device) {
     int sm = 0;
     if (a3r_device_info(device, &sm, nullptr, nullptr) != A3R_OK) return A3R_E_CUDA;
     // v1: 2 resident CTAs per SM; v4: every warp has its own range of the plan
     const int v = scan_variant();
-    return v == 1 ? sm * 2 : sm * V4_WARPS;
+    return v == 1 ? sm * 2 : v == 5 ? sm * V5_WARPS : sm * V4_WARPS;
 }
 
 int a3r_pack_pred(const float* pts, const float* conf, int32_t n, int64_t P, const int32_t* dst_slot,

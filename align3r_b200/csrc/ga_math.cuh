@@ -454,6 +454,8 @@ A3R_HD void align_px(const SlotConst& c, float X0, float X1, float X2, float w, 
 A3R_HD float flow_thre_eff(float pxl_thre) { return pxl_thre > 0.0f ? pxl_thre : INFINITY; }
 
 // Returns gf0 + g_q . b (gf0: the running d loss / d disp of this pixel, so that the dot product folds into FMAs).
+// BASE: index of acc[0] in the accumulator row (0: a whole row; ACC_GA: an array that holds only the 14 flow sums).
+template <int BASE = 0>
 A3R_HD float flow_px(const SlotConst& c, const PixState& s, float fu, float fv, float thre_eff, bool stat, float* acc,
                      float gf0 = 0.0f) {
     const float qx = fmaf(c.A[0], s.u, fmaf(c.A[1], s.v, fmaf(s.disp, c.b[0], c.A[2])));
@@ -469,18 +471,18 @@ A3R_HD float flow_px(const SlotConst& c, const PixState& s, float fu, float fv, 
     const float rv = mv * fmaf(-0.5f, mv, av);
     const bool pu = stat && ru < thre_eff;                            // per_pixel_mask (NaN residuals are out)
     const bool pv = stat && rv < thre_eff;
-    if (pu) { acc[ACC_FNUM] += ru; acc[ACC_FCNT] += 1.0f; }
-    if (pv) { acc[ACC_FNUM] += rv; acc[ACC_FCNT] += 1.0f; }
+    if (pu) { acc[ACC_FNUM - BASE] += ru; acc[ACC_FCNT - BASE] += 1.0f; }
+    if (pv) { acc[ACC_FNUM - BASE] += rv; acc[ACC_FCNT - BASE] += 1.0f; }
     const float geu = pu ? copysignf(mu, eu) : 0.0f;
     const float gev = pv ? copysignf(mv, ev) : 0.0f;
     const float gqx = geu * inv, gqy = gev * inv;
     const float gqz = -fmaf(gqx, up, gqy * vp);
-    acc[ACC_GA + 0] = fmaf(gqx, s.u, acc[ACC_GA + 0]); acc[ACC_GA + 1] = fmaf(gqx, s.v, acc[ACC_GA + 1]); acc[ACC_GA + 2] += gqx;
-    acc[ACC_GA + 3] = fmaf(gqy, s.u, acc[ACC_GA + 3]); acc[ACC_GA + 4] = fmaf(gqy, s.v, acc[ACC_GA + 4]); acc[ACC_GA + 5] += gqy;
-    acc[ACC_GA + 6] = fmaf(gqz, s.u, acc[ACC_GA + 6]); acc[ACC_GA + 7] = fmaf(gqz, s.v, acc[ACC_GA + 7]); acc[ACC_GA + 8] += gqz;
-    acc[ACC_GB + 0] = fmaf(s.disp, gqx, acc[ACC_GB + 0]);
-    acc[ACC_GB + 1] = fmaf(s.disp, gqy, acc[ACC_GB + 1]);
-    acc[ACC_GB + 2] = fmaf(s.disp, gqz, acc[ACC_GB + 2]);
+    acc[ACC_GA - BASE + 0] = fmaf(gqx, s.u, acc[ACC_GA - BASE + 0]); acc[ACC_GA - BASE + 1] = fmaf(gqx, s.v, acc[ACC_GA - BASE + 1]); acc[ACC_GA - BASE + 2] += gqx;
+    acc[ACC_GA - BASE + 3] = fmaf(gqy, s.u, acc[ACC_GA - BASE + 3]); acc[ACC_GA - BASE + 4] = fmaf(gqy, s.v, acc[ACC_GA - BASE + 4]); acc[ACC_GA - BASE + 5] += gqy;
+    acc[ACC_GA - BASE + 6] = fmaf(gqz, s.u, acc[ACC_GA - BASE + 6]); acc[ACC_GA - BASE + 7] = fmaf(gqz, s.v, acc[ACC_GA - BASE + 7]); acc[ACC_GA - BASE + 8] += gqz;
+    acc[ACC_GB - BASE + 0] = fmaf(s.disp, gqx, acc[ACC_GB - BASE + 0]);
+    acc[ACC_GB - BASE + 1] = fmaf(s.disp, gqy, acc[ACC_GB - BASE + 1]);
+    acc[ACC_GB - BASE + 2] = fmaf(s.disp, gqz, acc[ACC_GB - BASE + 2]);
     return fmaf(gqx, c.b[0], fmaf(gqy, c.b[1], fmaf(gqz, c.b[2], gf0)));
 }
 

@@ -111,7 +111,10 @@ def frame_costs(edges: np.ndarray, frame_hw: np.ndarray) -> np.ndarray:
     return (slots_per_frame(edges, len(frame_hw)) + 2.0) * areas
 
 
-def build_plan(edges, frame_hw, tile_pixels: int, max_slots: int, n_ctas: int, frame_range=None) -> ShardPlan:
+def build_plan(edges, frame_hw, tile_pixels: int, max_slots: int, n_ctas: int, frame_range=None, align_warps: int = 0) -> ShardPlan:
+    """``align_warps`` > 0 (class-specialised scan, include/a3r_ga.h a3r_scan_align_warps): cta_tile_begin holds three
+    partitions of the tile list behind each other - n_ctas ranges (every warp an align warp: flow term off), then
+    align_warps/16 * n_ctas ranges (the align warps of a flow-on launch), then the rest (its flow warps)."""
     edges = np.asarray(edges, dtype=np.int32).reshape(-1, 2)
     frame_hw = np.asarray(frame_hw, dtype=np.int32).reshape(-1, 2)
     N, E = len(frame_hw), len(edges)
@@ -152,17 +155,25 @@ def build_plan(edges, frame_hw, tile_pixels: int, max_slots: int, n_ctas: int, f
 
     # balanced contiguous tile ranges: cost of a tile ~ slots of its work frame + per-pixel overhead
     n_ctas = max(1, int(n_ctas))
-    if n_tiles > 0:
-        deg = np.diff(np.asarray(wf_slot_begin)).astype(np.float64) + 2.0
-        ntile_wf = np.diff(wf_tile_begin)
-        cost = np.repeat(deg, ntile_wf)
-        pref = np.concatenate(([0.0], np.cumsum(cost)))
-        targets = pref[-1] * np.arange(n_ctas + 1) / n_ctas
-        cta = np.searchsorted(pref, targets, side="left")
-        cta[0], cta[-1] = 0, n_tiles
-        cta = np.maximum.accumulate(cta)
+
+    def partition(parts):
+        if n_tiles > 0:
+            deg = np.diff(np.asarray(wf_slot_begin)).astype(np.float64) + 2.0
+            ntile_wf = np.diff(wf_tile_begin)
+            cost = np.repeat(deg, ntile_wf)
+            pref = np.concatenate(([0.0], np.cumsum(cost)))
+            targets = pref[-1] * np.arange(parts + 1) / parts
+            c = np.searchsorted(pref, targets, side="left")
+            c[0], c[-1] = 0, n_tiles
+            return np.maximum.accumulate(c)
+        return np.zeros(parts + 1, dtype=np.int64)
+
+    if align_warps > 0:
+        assert n_ctas % 16 == 0 and 0 < align_warps < 16
+        S = n_ctas // 16
+        cta = np.concatenate([partition(n_ctas), partition(align_warps * S), partition((16 - align_warps) * S)])
     else:
-        cta = np.zeros(n_ctas + 1, dtype=np.int64)
+        cta = partition(n_ctas)
 
     return ShardPlan(
         n_frames=N, n_edges=E, edges=edges, frame_hw=frame_hw, pix_stride=pix_stride,

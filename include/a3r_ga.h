@@ -179,6 +179,10 @@ const char *a3r_last_error(void);
 int a3r_tile_pixels(void);              /* pixels per tile the accumulate kernel was built for */
 int a3r_max_slots(void);                /* most slots one work frame may hold */
 int a3r_max_ctas(int device);           /* recommended n_ctas = SM count * resident CTAs per SM */
+int a3r_scan_align_warps(void);         /* 0, or (class-specialised scan, A3R_SCAN=v5) the number NA of align warps among a CTA's
+                                           16: cta_tile_begin then holds three partitions of the tile list behind each other -
+                                           n_ctas + 1 ranges for all-align launches, NA/16 n_ctas + 1 for the align warps and
+                                           (16-NA)/16 n_ctas + 1 for the flow warps of flow-on launches */
 int a3r_device_info(int device, int *sm_count, int *cc_major, int *cc_minor);
 
 /* ---- one-off packing (replaces the ParameterStack buffers of reference optimizer.py:80-92,
