@@ -435,6 +435,28 @@ def test_scan_v1_cross_checks_v4(cuda_device, tmp_path):
         assert rel_err(mine[k], v1["grads"][k]) <= 2e-5, (k, rel_err(mine[k], v1["grads"][k]))
 
 
+def test_scan_v5_cross_checks_v4(cuda_device, tmp_path):
+    """A3R_SCAN=v5 (csrc/ga_scan_v5.cuh: class-specialised warps - align warps and flow warps walk the tiles separately, 8
+    pixels per lane, three partitions of the tile list) against the product scan: same loss and gradients, flow term on."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "v5.pt")
+    snippet = _V1_SNIPPET.replace("== 1024          # the v1 kernel's tile", "== 256           # the v5 kernel's tile")
+    subprocess.run([sys.executable, "-c", snippet.format(root=root, out=out)], check=True, timeout=600,
+                   env=dict(os.environ, A3R_SCAN="v5"), cwd=root)
+    v5 = torch.load(out, weights_only=False)
+    fx, scene, prob = golden_case("small_flow")
+    net = build(scene, fx["kw"])
+    set_params(net, fx["init_params"])
+    loss = net(epoch=fx["tf32_flow"]["epoch"])
+    loss.backward()
+    assert abs(float(loss.detach()) - v5["loss"]) <= 1e-6 * abs(v5["loss"])
+    mine = grads_of(net, prob.P)
+    for k in mine:
+        assert rel_err(mine[k], v5["grads"][k]) <= 2e-5, (k, rel_err(mine[k], v5["grads"][k]))
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # clean_pointcloud (SURVEY.md 8(a) row G2) against the fixture the real reference produced
 # ---------------------------------------------------------------------------------------------------------------
