@@ -12,7 +12,7 @@ ABI_VERSION = 7
 # A3rProblem.flags
 F_SHARED_FOCAL, F_NORM_PW_SCALE, F_DIST_L2 = 1 << 0, 1 << 1, 1 << 2
 F_TRAIN_PW_POSES, F_TRAIN_DEPTH, F_TRAIN_IM_POSES, F_TRAIN_FOCALS = 1 << 3, 1 << 4, 1 << 5, 1 << 6
-F_TRAIN_PP, F_TRAIN_ADAPTORS, F_HAS_FLOW = 1 << 7, 1 << 8, 1 << 9
+F_TRAIN_PP, F_TRAIN_ADAPTORS, F_HAS_FLOW, F_ROW_TILES = 1 << 7, 1 << 8, 1 << 9, 1 << 10
 # mode bits
 M_FLOW_ACTIVE, M_APPLY_ADAM = 1 << 0, 1 << 1
 SLOT_ACC, FRAME_ACC, PRIOR_ACC, GLOB_ACC, SCAL = 28, 12, 4, 8, 16

@@ -422,10 +422,19 @@ static int launch_accumulate(const A3rProblem* p, cudaStream_t st, const A3rAdam
             A3R_CUDA(cudaFuncSetAttribute(k_accumulate_v4<FLOW, L2D, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V4_SMEM));
             A3R_CUDA(cudaFuncSetAttribute(k_accumulate_v4<FLOW, L2D, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V4_SMEM));
             A3R_CUDA(cudaFuncSetAttribute(k_accumulate_v4<FLOW, L2D, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V4_SMEM));
+            if (FLOW) {
+                A3R_CUDA(cudaFuncSetAttribute(k_accumulate_v4<FLOW, L2D, false, false, FLOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V4_SMEM));
+                A3R_CUDA(cudaFuncSetAttribute(k_accumulate_v4<FLOW, L2D, false, true, FLOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V4_SMEM));
+            }
             configured = true;
         }
         const unsigned grid = p->n_ctas / V4_WARPS;
-        if (prev_adam) A3R_CUDA(launch_ex(k_accumulate_v4<FLOW, L2D, false, true>, dim3(grid), dim3(V4_THREADS), V4_SMEM, st, pdl, *p, *prev_adam, prev_flow ? 1u : 0u));
+        // row tiles (every frame's width a multiple of the tile): the flow arithmetic with v as a per-tile constant
+        static const bool rowt_off = [] { const char* e = getenv("A3R_V4_ROWT"); return e && e[0] == '0'; }();
+        const bool rowt = FLOW && !tma && !rowt_off && (p->flags & A3R_F_ROW_TILES);
+        if (rowt && prev_adam) A3R_CUDA(launch_ex(k_accumulate_v4<FLOW, L2D, false, true, FLOW>, dim3(grid), dim3(V4_THREADS), V4_SMEM, st, pdl, *p, *prev_adam, prev_flow ? 1u : 0u));
+        else if (rowt) A3R_CUDA(launch_ex(k_accumulate_v4<FLOW, L2D, false, false, FLOW>, dim3(grid), dim3(V4_THREADS), V4_SMEM, st, pdl, *p, none, 0u));
+        else if (prev_adam) A3R_CUDA(launch_ex(k_accumulate_v4<FLOW, L2D, false, true>, dim3(grid), dim3(V4_THREADS), V4_SMEM, st, pdl, *p, *prev_adam, prev_flow ? 1u : 0u));
         else if (tma) k_accumulate_v4<FLOW, L2D, true, false><<<grid, V4_THREADS, V4_SMEM, st>>>(*p, none, 0u);
         else A3R_CUDA(launch_ex(k_accumulate_v4<FLOW, L2D, false, false>, dim3(grid), dim3(V4_THREADS), V4_SMEM, st, pdl, *p, none, 0u));
     }

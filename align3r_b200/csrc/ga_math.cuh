@@ -76,6 +76,18 @@ A3R_HD float fast_rcp(float x) {
 #endif
 }
 
+// sign(e) min(|e|, 1) = d smooth_l1(e) / d e in one instruction (FMNMX.XORSIGN.ABS: the sign of the result is the xor of the
+// operands' signs); its magnitude is the min(|e|, 1) of the loss's min form
+A3R_HD float clamp_unit_signed(float e) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(r) : "f"(e), "f"(1.0f));
+    return r;
+#else
+    return copysignf(fminf(fabsf(e), 1.0f), e);
+#endif
+}
+
 // ------------------------------------------------------------------------------------------
 // parameter maps (fp64 in, rounded to fp32 by the caller)
 // ------------------------------------------------------------------------------------------
@@ -421,7 +433,8 @@ struct SlotConst {
 };
 
 // alignment residual of one pixel-slot: updates acc[ACC_SG..ACC_LOSS], returns the pixel-slot's g = dL/dz
-template <bool L2DIST>
+// FIRST: the chunk's first pixel - the sums START with its terms (acc is not read: no adds onto freshly zeroed registers)
+template <bool L2DIST, bool FIRST = false>
 A3R_HD void align_px(const SlotConst& c, float X0, float X1, float X2, float w, const PixState& s,
                      float* acc, float& gx, float& gy, float& gz) {
     const float w2 = w * c.wn;
@@ -429,17 +442,26 @@ A3R_HD void align_px(const SlotConst& c, float X0, float X1, float X2, float w, 
     rx = fmaf(c.nM[0], X0, fmaf(c.nM[1], X1, fmaf(c.nM[2], X2, rx)));
     ry = fmaf(c.nM[3], X0, fmaf(c.nM[4], X1, fmaf(c.nM[5], X2, ry)));
     rz = fmaf(c.nM[6], X0, fmaf(c.nM[7], X1, fmaf(c.nM[8], X2, rz)));
-    const float r2 = fmaf(rx, rx, fmaf(ry, ry, rz * rz));
+    // 'l1': the 1e-30 keeps rsqrt finite at rho = 0 (zero (sub)gradient there, as torch.norm) without a clamp of its own;
+    // it is below half an ulp of r2 unless rz^2 < 1e-23
+    const float r2 = fmaf(rx, rx, fmaf(ry, ry, L2DIST ? rz * rz : fmaf(rz, rz, 1e-30f)));
     float k;
     if (L2DIST) {                     // reference commons.py:67-68
-        acc[ACC_LOSS] = fmaf(w2, r2, acc[ACC_LOSS]);
+        acc[ACC_LOSS] = FIRST ? w2 * r2 : fmaf(w2, r2, acc[ACC_LOSS]);
         k = 2.0f * w2;
     } else {                          // reference commons.py:71-72 ('l1' = un-squared L2 norm)
-        const float inv = fast_rsqrt(fmaxf(r2, 1e-30f));      // rho = 0 -> zero (sub)gradient, as torch.norm
+        const float inv = fast_rsqrt(r2);
         k = w2 * inv;
-        acc[ACC_LOSS] = fmaf(k, r2, acc[ACC_LOSS]);             // w rho = (w / rho) rho^2
+        acc[ACC_LOSS] = FIRST ? k * r2 : fmaf(k, r2, acc[ACC_LOSS]);     // w rho = (w / rho) rho^2
     }
     gx = k * rx; gy = k * ry; gz = k * rz;
+    if (FIRST) {
+        acc[ACC_SG + 0] = gx; acc[ACC_SG + 1] = gy; acc[ACC_SG + 2] = gz;
+        acc[ACC_SGX + 0] = gx * X0; acc[ACC_SGX + 1] = gx * X1; acc[ACC_SGX + 2] = gx * X2;
+        acc[ACC_SGX + 3] = gy * X0; acc[ACC_SGX + 4] = gy * X1; acc[ACC_SGX + 5] = gy * X2;
+        acc[ACC_SGX + 6] = gz * X0; acc[ACC_SGX + 7] = gz * X1; acc[ACC_SGX + 8] = gz * X2;
+        return;
+    }
     acc[ACC_SG + 0] += gx; acc[ACC_SG + 1] += gy; acc[ACC_SG + 2] += gz;
     acc[ACC_SGX + 0] = fmaf(gx, X0, acc[ACC_SGX + 0]); acc[ACC_SGX + 1] = fmaf(gx, X1, acc[ACC_SGX + 1]); acc[ACC_SGX + 2] = fmaf(gx, X2, acc[ACC_SGX + 2]);
     acc[ACC_SGX + 3] = fmaf(gy, X0, acc[ACC_SGX + 3]); acc[ACC_SGX + 4] = fmaf(gy, X1, acc[ACC_SGX + 4]); acc[ACC_SGX + 5] = fmaf(gy, X2, acc[ACC_SGX + 5]);
@@ -466,15 +488,16 @@ A3R_HD float flow_px(const SlotConst& c, const PixState& s, float fu, float fv, 
     const float eu = (up - s.u) - fu, ev = (vp - s.v) - fv;
     // smooth L1, beta = 1, in min form: m = min(|e|, 1); loss = m (|e| - m/2); d loss / d e = sign(e) m
     const float au = fabsf(eu), av = fabsf(ev);
-    const float mu = fminf(au, 1.0f), mv = fminf(av, 1.0f);
+    const float su = clamp_unit_signed(eu), sv = clamp_unit_signed(ev);
+    const float mu = fabsf(su), mv = fabsf(sv);
     const float ru = mu * fmaf(-0.5f, mu, au);
     const float rv = mv * fmaf(-0.5f, mv, av);
     const bool pu = stat && ru < thre_eff;                            // per_pixel_mask (NaN residuals are out)
     const bool pv = stat && rv < thre_eff;
     if (pu) { acc[ACC_FNUM - BASE] += ru; acc[ACC_FCNT - BASE] += 1.0f; }
     if (pv) { acc[ACC_FNUM - BASE] += rv; acc[ACC_FCNT - BASE] += 1.0f; }
-    const float geu = pu ? copysignf(mu, eu) : 0.0f;
-    const float gev = pv ? copysignf(mv, ev) : 0.0f;
+    const float geu = pu ? su : 0.0f;
+    const float gev = pv ? sv : 0.0f;
     const float gqx = geu * inv, gqy = gev * inv;
     const float gqz = -fmaf(gqx, up, gqy * vp);
     acc[ACC_GA - BASE + 0] = fmaf(gqx, s.u, acc[ACC_GA - BASE + 0]); acc[ACC_GA - BASE + 1] = fmaf(gqx, s.v, acc[ACC_GA - BASE + 1]); acc[ACC_GA - BASE + 2] += gqx;
@@ -484,6 +507,76 @@ A3R_HD float flow_px(const SlotConst& c, const PixState& s, float fu, float fv, 
     acc[ACC_GB - BASE + 1] = fmaf(s.disp, gqy, acc[ACC_GB - BASE + 1]);
     acc[ACC_GB - BASE + 2] = fmaf(s.disp, gqz, acc[ACC_GB - BASE + 2]);
     return fmaf(gqx, c.b[0], fmaf(gqy, c.b[1], fmaf(gqz, c.b[2], gf0)));
+}
+
+// The same pixel-slot as the product scan (ga_scan_v4.cuh) evaluates it.  Differences to flow_px, all of them in what is
+// folded where, none in the function computed:
+//   * c.A[8] already carries the + 1e-6 of the projection's denominator (added when the slot table is staged);
+//   * the static mask comes as the pixel's own threshold thre_pix = static ? thre_eff : -1 (residuals are >= 0);
+//   * ROWT (every tile lies in one image row: v is the same for all pixels of a (tile, slot) chunk): c.A[2], c.A[5], c.A[8]
+//     hold the row constants A[3r+1] v + A[3r+2], and the v-column of sum g_q (u,v,1)^T is NOT accumulated here - the
+//     caller sets it to v * sum g_q once per chunk (flow_row_finish).
+// FIRST: as in align_px - the chunk's first pixel starts the sums.
+template <int BASE, bool ROWT, bool FIRST = false>
+A3R_HD float flow_px_scan(const SlotConst& c, float u, float v, float disp, float fu, float fv, float thre_pix, float* acc,
+                          float gf0) {
+    float qx, qy, qz;
+    if (ROWT) {
+        qx = fmaf(c.A[0], u, fmaf(disp, c.b[0], c.A[2]));
+        qy = fmaf(c.A[3], u, fmaf(disp, c.b[1], c.A[5]));
+        qz = fmaf(c.A[6], u, fmaf(disp, c.b[2], c.A[8]));
+    } else {
+        qx = fmaf(c.A[0], u, fmaf(c.A[1], v, fmaf(disp, c.b[0], c.A[2])));
+        qy = fmaf(c.A[3], u, fmaf(c.A[4], v, fmaf(disp, c.b[1], c.A[5])));
+        qz = fmaf(c.A[6], u, fmaf(c.A[7], v, fmaf(disp, c.b[2], c.A[8])));
+    }
+    const float inv = fast_rcp(qz);
+    const float up = qx * inv, vp = qy * inv;
+    const float eu = (up - u) - fu, ev = (vp - v) - fv;
+    const float au = fabsf(eu), av = fabsf(ev);
+    const float su = clamp_unit_signed(eu), sv = clamp_unit_signed(ev);
+    const float mu = fabsf(su), mv = fabsf(sv);
+    const float ru = mu * fmaf(-0.5f, mu, au);
+    const float rv = mv * fmaf(-0.5f, mv, av);
+    const bool pu = ru < thre_pix;                                    // per_pixel_mask (NaN residuals are out)
+    const bool pv = rv < thre_pix;
+    if (FIRST) { acc[ACC_FNUM - BASE] = pu ? ru : 0.0f; acc[ACC_FCNT - BASE] = pu ? 1.0f : 0.0f; }
+    else if (pu) { acc[ACC_FNUM - BASE] += ru; acc[ACC_FCNT - BASE] += 1.0f; }
+    if (pv) { acc[ACC_FNUM - BASE] += rv; acc[ACC_FCNT - BASE] += 1.0f; }
+    const float geu = pu ? su : 0.0f;
+    const float gev = pv ? sv : 0.0f;
+    const float gqx = geu * inv, gqy = gev * inv;
+    const float gqz = -fmaf(gqx, up, gqy * vp);
+    if (FIRST) {
+        acc[ACC_GA - BASE + 0] = gqx * u; acc[ACC_GA - BASE + 2] = gqx;
+        acc[ACC_GA - BASE + 3] = gqy * u; acc[ACC_GA - BASE + 5] = gqy;
+        acc[ACC_GA - BASE + 6] = gqz * u; acc[ACC_GA - BASE + 8] = gqz;
+        if (!ROWT) { acc[ACC_GA - BASE + 1] = gqx * v; acc[ACC_GA - BASE + 4] = gqy * v; acc[ACC_GA - BASE + 7] = gqz * v; }
+        acc[ACC_GB - BASE + 0] = disp * gqx; acc[ACC_GB - BASE + 1] = disp * gqy; acc[ACC_GB - BASE + 2] = disp * gqz;
+        return fmaf(gqx, c.b[0], fmaf(gqy, c.b[1], fmaf(gqz, c.b[2], gf0)));
+    }
+    acc[ACC_GA - BASE + 0] = fmaf(gqx, u, acc[ACC_GA - BASE + 0]); acc[ACC_GA - BASE + 2] += gqx;
+    acc[ACC_GA - BASE + 3] = fmaf(gqy, u, acc[ACC_GA - BASE + 3]); acc[ACC_GA - BASE + 5] += gqy;
+    acc[ACC_GA - BASE + 6] = fmaf(gqz, u, acc[ACC_GA - BASE + 6]); acc[ACC_GA - BASE + 8] += gqz;
+    if (!ROWT) {
+        acc[ACC_GA - BASE + 1] = fmaf(gqx, v, acc[ACC_GA - BASE + 1]);
+        acc[ACC_GA - BASE + 4] = fmaf(gqy, v, acc[ACC_GA - BASE + 4]);
+        acc[ACC_GA - BASE + 7] = fmaf(gqz, v, acc[ACC_GA - BASE + 7]);
+    }
+    acc[ACC_GB - BASE + 0] = fmaf(disp, gqx, acc[ACC_GB - BASE + 0]);
+    acc[ACC_GB - BASE + 1] = fmaf(disp, gqy, acc[ACC_GB - BASE + 1]);
+    acc[ACC_GB - BASE + 2] = fmaf(disp, gqz, acc[ACC_GB - BASE + 2]);
+    return fmaf(gqx, c.b[0], fmaf(gqy, c.b[1], fmaf(gqz, c.b[2], gf0)));
+}
+// ROWT: the row constants of a chunk, and the v-column once the chunk's pixels are in
+A3R_HD void flow_row_begin(SlotConst& c, float v) {
+    c.A[2] = fmaf(c.A[1], v, c.A[2]); c.A[5] = fmaf(c.A[4], v, c.A[5]); c.A[8] = fmaf(c.A[7], v, c.A[8]);
+}
+template <int BASE>
+A3R_HD void flow_row_finish(float v, float* acc) {
+    acc[ACC_GA - BASE + 1] = v * acc[ACC_GA - BASE + 2];
+    acc[ACC_GA - BASE + 4] = v * acc[ACC_GA - BASE + 5];
+    acc[ACC_GA - BASE + 7] = v * acc[ACC_GA - BASE + 8];
 }
 
 // ------------------------------------------------------------------------------------------

@@ -74,7 +74,7 @@ constexpr uint32_t V4_WARP_BYTES = ((V4_BAR + V4_STAGES * 8 + 127) / 128) * 128;
 constexpr size_t V4_SMEM = (size_t)V4_WARP_BYTES * V4_WARPS;
 static_assert(V4_SMEM <= 232448, "v4 scan: shared memory of one CTA exceeds the 227 KB opt-in limit");
 
-// slot table row: q0..q2 = -M (9), s t (3); q3..q5 = A (9), b (3); q6 = 1/area, side, global slot, -
+// slot table row: q0..q2 = -M (9), s t (3); q3..q5 = A (9), b (3); q6 = 1/area, side (not read by the scan: the class loop knows both)
 __device__ __forceinline__ void sts64(uint32_t a, float x, float y) {
     asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a), "f"(x), "f"(y) : "memory");
 }
@@ -97,9 +97,9 @@ __device__ __forceinline__ float2 transpose_reduce(uint32_t tr_s, int lane, cons
     for (int q = 0; q < NQ; ++q) sts128(row + q * 16, a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
     __syncwarp();
     const uint32_t col = tr_s + (lane >> 4) * (16 * V4_ROW * 4) + (lane & 15) * 8;
-    float2 t0 = make_float2(0.f, 0.f), t1 = t0;
+    float2 t0 = lds64(col), t1 = lds64(col + V4_ROW * 4);          // (the sums start with the first rows: no 0 + x)
 #pragma unroll
-    for (int r = 0; r < 16; r += 2) {
+    for (int r = 2; r < 16; r += 2) {
         const float2 x0 = lds64(col + r * (V4_ROW * 4));
         const float2 x1 = lds64(col + (r + 1) * (V4_ROW * 4));
         t0.x += x0.x; t0.y += x0.y;
@@ -117,11 +117,15 @@ __device__ __forceinline__ float2 transpose_reduce(uint32_t tr_s, int lane, cons
 // ring as a pseudo-slot ahead of the tile's first real slot, so their DRAM latency is hidden behind the previous tile's
 // last slots like any other chunk's.  prev_adam / prev_flow: the Adam scalars and the flow state of that iteration; the
 // flow normalisers and the gate are read from scal, where that iteration's K2 left them.
-template <bool FLOW, bool L2D, bool TMA, bool ADAM>
+// ROWT: the caller promises (A3R_F_ROW_TILES; checked per work frame) that every frame's width is a multiple of the tile, so a
+// tile lies in one image row: v is a per-tile constant, no pixel of a tile is out of the frame (ga_math.cuh: flow_px_scan).
+template <bool FLOW, bool L2D, bool TMA, bool ADAM, bool ROWT = false>
 __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProblem p, const A3rAdamStep prev_adam, const uint32_t prev_flow) {
     static_assert(!(TMA && ADAM), "the folded depth step rides on the per-lane cp.async ring");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    int lane = tid & 31;
+    asm volatile("" : "+r"(lane));           // opaque: a register, not an S2R (25 cycles) wherever an address needs it
     const int gw = blockIdx.x * V4_WARPS + warp;                 // this warp's range in the plan ("CTA" = warp here)
     const int t0 = p.cta_tile_begin[gw], t1 = p.cta_tile_begin[gw + 1];
     const TimelineSlot tl = timeline_enter(1);
@@ -137,7 +141,8 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
     const float2* fl_g = reinterpret_cast<const float2*>(p.flow);
     const int64_t stride = p.pix_stride;
 
-    const uint32_t wb = smem_u32(smem_raw) + warp * V4_WARP_BYTES;         // the warp's private block
+    uint32_t wb = smem_u32(smem_raw) + warp * V4_WARP_BYTES;               // the warp's private block
+    asm volatile("" : "+r"(wb));             // opaque: kept in a register instead of re-derived from %tid in every chunk
     constexpr uint32_t kBytes = V4_T * 16 + (FLOW ? V4_T * 8 : 0);
 
     if (TMA && lane == 0) {
@@ -152,28 +157,60 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
 #if A3R_V4_EVICT_FIRST
     const uint64_t stream_policy = l2_policy_evict_first();      // predw / flow are read once per scan
 #endif
-    // ---- copy cursor: next chunk = (l_tile, l_s) at pixel offset l_off of the slot-major planes; with ADAM every tile
-    //      starts with the pseudo-slot l_s = -1 (the tile's six per-frame planes at pixel offset l_pix) ----
-    int l_tile = t0, l_wf = 0, l_wf_end = -1, l_s = 0, l_deg = 1;
+    // ---- copy cursor: l_left real slots of tile l_tile are still to be copied, the next one from pixel offset l_off of the
+    //      slot-major planes; with ADAM every tile starts with the pseudo-slot (the tile's six per-frame planes at pixel offset
+    //      l_pix).  Both offsets carry the lane (l_off + lane, l_pix + 4 lane).  The common case - the next slot of the same
+    //      tile - is one test, the copies and two additions. ----
+    int l_tile = t0 - 1, l_wf = 0, l_wf_end = -1, l_left = 0, l_deg = 0;
     int64_t l_off = 0, l_pix = 0;
+    auto copy_chunk = [&](uint32_t stage_off) {
+        if (TMA) {
+            if (lane == 0) {
+                const uint32_t bar = wb + V4_BAR + (stage_off / (V4_T * 16)) * 8;
+                mbar_expect_tx_a(bar, kBytes);
+                tma_load_1d_a(wb + V4_XW + stage_off, xw_g + l_off, V4_T * 16, bar);        // (lane 0: l_off is the chunk's)
+                if (FLOW) tma_load_1d_a(wb + V4_FL + (stage_off >> 1), fl_g + l_off, V4_T * 8, bar);
+            }
+        } else {
+            const uint32_t xd = wb + V4_XW + stage_off + lane * 16;
+            const uint32_t fd = wb + V4_FL + (stage_off >> 1) + lane * 8;
+#pragma unroll
+            for (int j = 0; j < V4_PPL; ++j) {
+#if A3R_V4_EVICT_FIRST
+                cp_async16_hint(xd + j * 512, xw_g + l_off + j * 32, stream_policy);
+                if (FLOW) cp_async8_hint(fd + j * 256, fl_g + l_off + j * 32, stream_policy);
+#else
+                cp_async16(xd + j * 512, xw_g + l_off + j * 32);
+                if (FLOW) cp_async8(fd + j * 256, fl_g + l_off + j * 32);
+#endif
+            }
+        }
+        l_off += stride;
+        --l_left;
+    };
     auto issue = [&](uint32_t stage_off) {      // stage_off = stage * (V4_T * 16)
-        if (l_tile < t1) {
+        if (l_left > 0) copy_chunk(stage_off);
+        else if (l_tile + 1 < t1) {             // the next tile
+            ++l_tile;
             if (l_tile >= l_wf_end) {
                 while (l_tile >= p.wf_tile_begin[l_wf + 1]) ++l_wf;
                 l_wf_end = p.wf_tile_begin[l_wf + 1];
                 const int sb = p.wf_slot_begin[l_wf];
                 l_deg = p.wf_slot_begin[l_wf + 1] - sb;
                 const int64_t in_frame = (int64_t)(l_tile - p.wf_tile_begin[l_wf]) * V4_T;
-                l_off = (int64_t)sb * stride + in_frame;
-                if (ADAM) l_pix = (int64_t)p.wf_lframe[l_wf] * stride + in_frame;
-                l_s = ADAM ? -1 : 0;
+                l_off = (int64_t)sb * stride + in_frame + lane;
+                if (ADAM) l_pix = (int64_t)p.wf_lframe[l_wf] * stride + in_frame + 4 * lane;
+            } else {
+                l_off += V4_T - (int64_t)l_deg * stride;
+                if (ADAM) l_pix += V4_T;
             }
-            if (ADAM && l_s < 0) {              // lane L copies pixels 4L .. 4L+3 (+128 ...) of every plane (16 B each)
+            l_left = l_deg;
+            if (ADAM) {                         // lane L copies pixels 4L .. 4L+3 (+128 ...) of every plane (16 B each)
 #pragma unroll
                 for (int h = 0; h < (V4_T + 127) / 128; ++h) {
                     if (4 * lane + h * 128 >= V4_T) break;
                     const uint32_t xd = wb + V4_XW + stage_off + lane * 16 + h * 512;
-                    const int64_t po = l_pix + 4 * lane + h * 128;
+                    const int64_t po = l_pix + h * 128;
                     cp_async16(xd, p.logdepth + po);
                     cp_async16(xd + V4_PLANE, p.logdepth_m + po);
                     cp_async16(xd + 2 * V4_PLANE, p.logdepth_v + po);
@@ -184,32 +221,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
                         cp_async16(fd + V4_PLANE, p.g_flow_j + po);
                     }
                 }
-                l_s = 0;
-            } else {
-            if (TMA) {
-                if (lane == 0) {
-                    const uint32_t bar = wb + V4_BAR + (stage_off / (V4_T * 16)) * 8;
-                    mbar_expect_tx_a(bar, kBytes);
-                    tma_load_1d_a(wb + V4_XW + stage_off, xw_g + l_off, V4_T * 16, bar);
-                    if (FLOW) tma_load_1d_a(wb + V4_FL + (stage_off >> 1), fl_g + l_off, V4_T * 8, bar);
-                }
-            } else {
-                const uint32_t xd = wb + V4_XW + stage_off + lane * 16;
-                const uint32_t fd = wb + V4_FL + (stage_off >> 1) + lane * 8;
-#pragma unroll
-                for (int j = 0; j < V4_PPL; ++j) {
-#if A3R_V4_EVICT_FIRST
-                    cp_async16_hint(xd + j * 512, xw_g + l_off + lane + j * 32, stream_policy);
-                    if (FLOW) cp_async8_hint(fd + j * 256, fl_g + l_off + lane + j * 32, stream_policy);
-#else
-                    cp_async16(xd + j * 512, xw_g + l_off + lane + j * 32);
-                    if (FLOW) cp_async8(fd + j * 256, fl_g + l_off + lane + j * 32);
-#endif
-                }
-            }
-            if (++l_s >= l_deg) { l_s = ADAM ? -1 : 0; ++l_tile; l_off += V4_T - (int64_t)(l_deg - 1) * stride; if (ADAM) l_pix += V4_T; }
-            else l_off += stride;
-            }
+            } else copy_chunk(stage_off);
         }
         if (!TMA) cp_async_commit();   // one group per chunk slot, empty past the end: uniform wait_group accounting
     };
@@ -271,6 +283,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
             n = p.lframe_id[lf];
             W = p.frame_hw[2 * n + 1];
             P = p.frame_hw[2 * n] * W;
+            if (ROWT && (W % V4_T) != 0) __trap();               // the caller's promise behind A3R_F_ROW_TILES
             invW = 1.0f / (float)W;
             s_begin = p.wf_slot_begin[cw];
             deg = p.wf_slot_begin[cw + 1] - s_begin;
@@ -290,6 +303,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
                     if (q < 2) { v4.y = -v4.y; v4.z = -v4.z; v4.w = -v4.w; }
                 } else if (q < 6) {
                     if (FLOW) v4 = __ldg(reinterpret_cast<const float4*>(p.slot_par + SP_STRIDE * gs) + (q - 3));
+                    if (FLOW && ROWT && q == 5) v4.x += 1e-6f;    // A[8] + the 1e-6 of the projection's denominator (flow_px_scan)
                 } else {
                     v4.x = (gs & 1) ? p.inv_area_j : p.inv_area_i;
                     v4.y = (gs & 1) ? 1.0f : 0.0f;
@@ -300,7 +314,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
                 const bool is_i = lane < deg && (p.lslot_gslot[s_begin + (lane < deg ? lane : 0)] & 1) == 0;
                 const unsigned mi = __ballot_sync(0xffffffffu, is_i);
                 n_i = __popc(mi);
-                if (FLOW && mi != (n_i >= 32 ? 0xffffffffu : (1u << n_i) - 1u)) __trap();   // plan contract: side-i slots first
+                if (mi != (n_i >= 32 ? 0xffffffffu : (1u << n_i) - 1u)) __trap();   // plan contract: side-i slots first
             }
             __syncwarp();
         }
@@ -341,7 +355,10 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
         }
 
         // ---- per-pixel state (4 pixels per lane) ----
-        float zx[V4_PPL], zy[V4_PPL], zz[V4_PPL], pu[V4_PPL], pv[V4_PPL], sdisp[V4_PPL], dep[V4_PPL];
+        // ROWT: v is the tile's constant, the static mask is the pixel's own flow threshold (thre_eff where static, -1
+        // elsewhere); general form: the mask is the sign of disp (the arithmetic of flow_px, as the v1 / v5 scans use it)
+        float zx[V4_PPL], zy[V4_PPL], zz[V4_PPL], pu[V4_PPL], pv[ROWT ? 1 : V4_PPL], disp[V4_PPL], dep[V4_PPL];
+        float thr[ROWT ? V4_PPL : 1];
         float gsx[V4_PPL], gsy[V4_PPL], gsz[V4_PPL];
         float gf[V4_PPL];                        // d loss / d disp of the flow class (side i, then side j) being walked
         {
@@ -351,19 +368,23 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
                 const float4 v4 = lds128(wb + V4_FP + k * 16);
                 fpr[4 * k] = v4.x; fpr[4 * k + 1] = v4.y; fpr[4 * k + 2] = v4.z; fpr[4 * k + 3] = v4.w;
             }
+            int u0 = 0, v0 = 0;
+            if (ROWT) pix_to_uv(p0 + lane, W, invW, u0, v0);
 #pragma unroll
             for (int j = 0; j < V4_PPL; ++j) {
                 const int pl = j * 32 + lane, pix = p0 + pl;
-                const bool valid = pix < P;
+                const bool valid = ROWT || pix < P;
                 const float ld = valid ? (ADAM ? ldv[j] : p.logdepth[pix_base + pl]) : 0.f;
                 bool stat = false;
                 if (FLOW) stat = valid && p.static_mask[pix_base + pl] != 0;
                 int u, v;
-                pix_to_uv(pix, W, invW, u, v);
+                if (ROWT) { u = u0 + 32 * j; v = v0; }
+                else pix_to_uv(pix, W, invW, u, v);
                 PixState s;
                 pixel_state(fpr, ld, u, v, s);
-                zx[j] = s.zx; zy[j] = s.zy; zz[j] = s.zz; pu[j] = s.u; pv[j] = s.v; dep[j] = s.cz;
-                sdisp[j] = stat ? s.disp : -s.disp;
+                zx[j] = s.zx; zy[j] = s.zy; zz[j] = s.zz; pu[j] = s.u; pv[ROWT ? 0 : j] = s.v; dep[j] = s.cz;
+                if (ROWT) { disp[j] = s.disp; thr[j] = stat ? thre_eff : -1.0f; }
+                else disp[j] = stat ? s.disp : -s.disp;
                 gsx[j] = gsy[j] = gsz[j] = gf[j] = 0.f;
             }
         }
@@ -372,8 +393,9 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
         //      slot table is staged).  The two flow classes are normalised by different global counts that are only
         //      known after the scan, so each class parks its own per-pixel plane as soon as it is complete. ----
 #pragma unroll 1
-        for (int cls = 0; cls < (FLOW ? 2 : 1); ++cls) {
-        const int s_lo = (FLOW && cls) ? n_i : 0, s_hi = (FLOW && !cls) ? n_i : deg;
+        for (int cls = 0; cls < 2; ++cls) {
+        const int s_lo = cls ? n_i : 0, s_hi = cls ? deg : n_i;
+        const float wn = cls ? p.inv_area_j : p.inv_area_i;     // 1 / total area of the class (warp-uniform: not a table load)
 #pragma unroll 1
         for (int s = s_lo; s < s_hi; ++s) {
             const uint32_t tab = wb + V4_STAB + s * (V4_ROW * 4);
@@ -388,21 +410,21 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
             for (int k = 0; k < 4 * NQ; ++k) acc[k] = 0.f;
             const uint32_t xa = wb + V4_XW + stage_off + lane * 16;
             const uint32_t fa = wb + V4_FL + (stage_off >> 1) + lane * 8;
-            const float4 q6 = lds128(tab + 96);
             {
                 SlotConst c;
                 const float4 q0 = lds128(tab), q1 = lds128(tab + 16), q2 = lds128(tab + 32);
                 c.nM[0] = q0.x; c.nM[1] = q0.y; c.nM[2] = q0.z; c.nM[3] = q0.w;
                 c.nM[4] = q1.x; c.nM[5] = q1.y; c.nM[6] = q1.z; c.nM[7] = q1.w;
                 c.nM[8] = q2.x; c.st[0] = q2.y; c.st[1] = q2.z; c.st[2] = q2.w;
-                c.wn = q6.x;
+                c.wn = wn;
 #pragma unroll
                 for (int j = 0; j < V4_PPL; ++j) {
                     const float4 X = lds128(xa + j * 512);
                     PixState st;
                     st.zx = zx[j]; st.zy = zy[j]; st.zz = zz[j];
                     float gx, gy, gz;
-                    align_px<L2D>(c, X.x, X.y, X.z, X.w, st, acc, gx, gy, gz);
+                    if (j == 0) align_px<L2D, true>(c, X.x, X.y, X.z, X.w, st, acc, gx, gy, gz);
+                    else align_px<L2D>(c, X.x, X.y, X.z, X.w, st, acc, gx, gy, gz);
                     gsx[j] += gx; gsy[j] += gy; gsz[j] += gz;
                 }
             }
@@ -412,13 +434,19 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
                 c.A[0] = q3.x; c.A[1] = q3.y; c.A[2] = q3.z; c.A[3] = q3.w;
                 c.A[4] = q4.x; c.A[5] = q4.y; c.A[6] = q4.z; c.A[7] = q4.w;
                 c.A[8] = q5.x; c.b[0] = q5.y; c.b[1] = q5.z; c.b[2] = q5.w;
+                if (ROWT) flow_row_begin(c, pv[0]);
 #pragma unroll
                 for (int j = 0; j < V4_PPL; ++j) {
                     const float2 F = lds64(fa + j * 256);
-                    PixState st;
-                    st.u = pu[j]; st.v = pv[j]; st.disp = fabsf(sdisp[j]);
-                    gf[j] = flow_px(c, st, F.x, F.y, thre_eff, sdisp[j] > 0.f, acc, gf[j]);
+                    if (ROWT && j == 0) gf[j] = flow_px_scan<0, true, true>(c, pu[j], pv[0], disp[j], F.x, F.y, thr[j], acc, gf[j]);
+                    else if (ROWT) gf[j] = flow_px_scan<0, true>(c, pu[j], pv[0], disp[j], F.x, F.y, thr[j], acc, gf[j]);
+                    else {
+                        PixState st;
+                        st.u = pu[j]; st.v = pv[ROWT ? 0 : j]; st.disp = fabsf(disp[j]);
+                        gf[j] = flow_px(c, st, F.x, F.y, thre_eff, disp[j] > 0.f, acc, gf[j]);
+                    }
                 }
+                if (ROWT) flow_row_finish<0>(pv[0], acc);
             }
             // the chunk is consumed: refill its stage (LDGSTS: a lane only ever reads what it copied itself)
             if (TMA) __syncwarp();
@@ -440,9 +468,8 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
 #pragma unroll
             for (int j = 0; j < V4_PPL; ++j) {
                 const int pl = j * 32 + lane;
-                if (p0 + pl < P) {
-                    const float disp = fabsf(sdisp[j]);
-                    const float v = gf[j] * (-dep[j] * disp * disp);
+                if (ROWT || p0 + pl < P) {
+                    const float v = gf[j] * (-dep[j] * disp[j] * disp[j]);      // (general form: the sign squares away)
                     if (accum) atomicAdd(&plane[pix_base + pl], v); else plane[pix_base + pl] = v;
                 }
                 gf[j] = 0.f;
@@ -464,11 +491,11 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
 #pragma unroll
             for (int j = 0; j < V4_PPL; ++j) {
                 const int pl = j * 32 + lane, pix = p0 + pl;
-                if (pix >= P) continue;
+                if (!ROWT && pix >= P) continue;
                 PixState s;
                 const float d = dep[j];
                 s.cx = d * (pu[j] - fpr[FP_CX]) * fpr[FP_INVF];
-                s.cy = d * (pv[j] - fpr[FP_CY]) * fpr[FP_INVF];
+                s.cy = d * (pv[ROWT ? 0 : j] - fpr[FP_CY]) * fpr[FP_INVF];
                 s.cz = d;
                 const float ga = pixel_epilogue(fpr, s, gsx[j], gsy[j], gsz[j], facc);
                 const int64_t o = pix_base + pl;

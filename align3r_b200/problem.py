@@ -149,6 +149,9 @@ class ProblemBuffers:
             f |= _lib.F_DIST_L2
         if self.has_flow:
             f |= _lib.F_HAS_FLOW
+        pl = self.plan
+        if pl.n_local_frames > 0 and all(int(pl.frame_hw[n, 1]) % pl.tile_pixels == 0 for n in pl.lframe_id.tolist()):
+            f |= _lib.F_ROW_TILES      # every tile lies in one image row: the scan specialised for it (csrc/ga_scan_v4.cuh)
         for name, bit in (("pw_poses", _lib.F_TRAIN_PW_POSES), ("im_depthmaps", _lib.F_TRAIN_DEPTH),
                           ("im_poses", _lib.F_TRAIN_IM_POSES), ("im_focals", _lib.F_TRAIN_FOCALS),
                           ("im_pp", _lib.F_TRAIN_PP), ("pw_adaptors", _lib.F_TRAIN_ADAPTORS)):

@@ -53,6 +53,9 @@ extern "C" {
 #define A3R_F_TRAIN_PP       (1u << 7)  /* optimize_pp (optimizer.py:63-64) */
 #define A3R_F_TRAIN_ADAPTORS (1u << 8)  /* allow_pw_adaptors (base_opt.py:113-114) */
 #define A3R_F_HAS_FLOW       (1u << 9)  /* flow planes + dynamic masks are present */
+#define A3R_F_ROW_TILES      (1u << 10) /* the caller's promise that every local frame's width is a multiple of tile_pixels (a tile
+                                           lies in one image row): selects the scan specialised for it; the kernel traps on a frame
+                                           that breaks the promise */
 
 /* a3r_ga_* `mode` argument */
 #define A3R_M_FLOW_ACTIVE (1u << 0)     /* epoch >= num_total_iter*flow_loss_start_epoch (optimizer.py:520) */

@@ -74,6 +74,8 @@ def emul_lib():
     lib.emul_prepare.argtypes = [C.POINTER(_lib.A3rProblem)]
     lib.emul_accumulate.argtypes = [C.POINTER(_lib.A3rProblem), C.c_uint32]
     lib.emul_update.argtypes = [C.POINTER(_lib.A3rProblem), C.c_uint32, C.POINTER(_lib.A3rAdamStep)]
+    lib.emul_set_flow_form.argtypes = [C.c_int]
+    lib.emul_set_flow_form.restype = None
     _EMUL = lib
     return lib
 
@@ -123,9 +125,11 @@ def cpu_problem(prob: go.OracleProblem, params: dict, trainable=None, n_ctas=3, 
     return bufs
 
 
-def emul_eval(bufs: ProblemBuffers, flow_active: bool, apply=False, lr=0.01, step=0, trainable=None):
-    """One evaluation through the emulator.  Returns (loss, grads dict, scal tensor)."""
+def emul_eval(bufs: ProblemBuffers, flow_active: bool, apply=False, lr=0.01, step=0, trainable=None, flow_form=0):
+    """One evaluation through the emulator.  Returns (loss, grads dict, scal tensor).  flow_form: which form of the flow
+    pixel-slot (ga_math.cuh) - 0 flow_px, 1 flow_px_scan (the product scan), 2 its row-tile form."""
     lib = emul_lib()
+    lib.emul_set_flow_form(int(flow_form))
     trainable = trainable or TRAIN_ALL
     st = bufs.struct(trainable)
     mode = (_lib.M_FLOW_ACTIVE if flow_active else 0) | (_lib.M_APPLY_ADAM if apply else 0)

@@ -45,6 +45,11 @@ extern "C" int emul_prepare(const A3rProblem* p) {
     return 0;
 }
 
+// which form of the flow pixel-slot emul_accumulate evaluates: 0 = flow_px (the v1 / v5 cross-check scans), 1 = flow_px_scan
+// (the product scan's general form), 2 = its row-tile form (v as the chunk's constant; a "chunk" here is one pixel)
+static int g_flow_form = 0;
+extern "C" void emul_set_flow_form(int form) { g_flow_form = form; }
+
 extern "C" int emul_accumulate(const A3rProblem* p, uint32_t mode) {
     const int E = p->n_edges, N = p->n_frames;
     const bool flow = flow_on(p, mode), l2 = p->flags & A3R_F_DIST_L2;
@@ -86,7 +91,19 @@ extern "C" int emul_accumulate(const A3rProblem* p, uint32_t mode) {
                 gsx += gx; gsy += gy; gsz += gz;
                 if (flow) {         // evaluated for every pixel, masked branch-free like the kernels
                     const float* f = p->flow + ((int64_t)s * p->pix_stride + pix) * 2;
-                    const float gd = flow_px(c, st, f[0], f[1], flow_thre_eff(p->pxl_thre), stat, acc);
+                    const float thre_eff = flow_thre_eff(p->pxl_thre);
+                    float gd;
+                    if (g_flow_form == 0) gd = flow_px(c, st, f[0], f[1], thre_eff, stat, acc);
+                    else {
+                        c.A[8] += 1e-6f;                       // as the product scan stages its slot table
+                        const float thre_pix = stat ? thre_eff : -1.0f;
+                        if (g_flow_form == 1) gd = flow_px_scan<0, false>(c, st.u, st.v, st.disp, f[0], f[1], thre_pix, acc, 0.0f);
+                        else {
+                            flow_row_begin(c, st.v);
+                            gd = flow_px_scan<0, true>(c, st.u, st.v, st.disp, f[0], f[1], thre_pix, acc, 0.0f);
+                            flow_row_finish<0>(st.v, acc);
+                        }
+                    }
                     if (gs & 1) gfj += gd; else gfi += gd;
                 }
                 double* a = p->acc_slot + (int64_t)gs * ACC_STRIDE;

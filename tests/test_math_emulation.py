@@ -19,13 +19,14 @@ def _grads_ok(mine, g32, g64, P):
 
 
 @pytest.mark.parametrize("name", CASES)
-@pytest.mark.parametrize("tag", ["pre_flow", "flow"])
-def test_loss_and_gradients_match_reference_fixtures(name, tag):
+@pytest.mark.parametrize("tag,flow_form", [("pre_flow", 0), ("flow", 0), ("flow", 1), ("flow", 2)])
+def test_loss_and_gradients_match_reference_fixtures(name, tag, flow_form):
+    """flow_form 1 / 2: the flow pixel-slot as the product scan evaluates it (flow_px_scan, general and row-tile form)."""
     fx, scene, prob = golden_case(name)
     g32, g64 = fx[f"tf32_{tag}"], fx[f"tf64_{tag}"]
     flow_active = prob.flow_loss_weight > 0 and g32["epoch"] >= prob.num_total_iter * prob.flow_loss_start_epoch
     bufs = cpu_problem(prob, fx["init_params"])
-    loss, grads, scal = emul_eval(bufs, flow_active)
+    loss, grads, scal = emul_eval(bufs, flow_active, flow_form=flow_form)
     assert abs(loss - float(g64["loss"])) <= 1e-6 * abs(float(g64["loss"]))
     assert bool(scal[4]) == g32["flow_dropped"]
     _grads_ok(grads, g32["grads"], g64["grads"], prob.P)
