@@ -209,6 +209,25 @@ class PointCloudOptimizer(nn.Module):
         self.total_area_j = sum(im_areas[j] for i, j in self.edges)
 
         ph = Phases('construct')
+        # ---------------- parameters (reference base_opt.py:112-114, optimizer.py:54-75) ----------------
+        # drawn on the CPU in the reference's order so that a seeded run starts from the same values - on a worker thread
+        # (torch.randn releases the GIL: 7.4 M normal deviates on the 50-frame workload, ~40 ms) while this thread plans,
+        # allocates, queues the uploads and sets up the rest; joined below, before the first parameter is written
+        nfoc = 1 if shared_focal else self.n_imgs
+        drawn = {}
+
+        def _draw():
+            try:
+                pw = rand_pose((self.n_edges, 1 + self.POSE_DIM))
+                depth0 = [torch.randn(H, W) / 10 - 3 for H, W in self.imshapes]
+                im = torch.stack([rand_pose(self.POSE_DIM) for _ in range(self.n_imgs)])
+                drawn.update(pw_poses=pw.float().contiguous(), depth0=depth0, im_poses=im.float().contiguous())
+            except BaseException as exc:           # re-raised by the constructor's thread
+                drawn['error'] = exc
+
+        import threading
+        draw_thread = threading.Thread(target=_draw, name='a3r-rand-params')
+        draw_thread.start()
         # ---------------- plan + shard ----------------
         self._shard = shard
         frame_range = None
@@ -241,6 +260,24 @@ class PointCloudOptimizer(nn.Module):
         self._conf_sum = torch.zeros(max(plan.n_local_slots, 1), dtype=torch.float64, device=device)
         self._im_conf_plane = torch.zeros(max(plan.n_local_frames, 1), plan.pix_stride, device=device)
         ph.mark('alloc')
+        # the parameter tensors exist from here on; the three random ones are filled when the worker is done (below).  Small
+        # pageable uploads are synchronous - issued after the big copies they would wait for all of them: they go first
+        im_focals = torch.tensor([[focal_break * np.log(max(H, W))] for H, W in self.imshapes[:nfoc]], dtype=torch.float32)
+        self.pw_poses = nn.Parameter(torch.empty((self.n_edges, 1 + self.POSE_DIM), device=device))
+        self.pw_adaptors = nn.Parameter(torch.zeros((self.n_edges, 2), device=device))
+        self.pw_adaptors.requires_grad_(allow_pw_adaptors)
+        self.im_depthmaps = nn.Parameter(torch.empty((plan.n_local_frames, plan.pix_stride), device=device))   # log-depth
+        self.im_poses = nn.Parameter(torch.empty((self.n_imgs, self.POSE_DIM), device=device))
+        self.im_focals = nn.Parameter(im_focals.to(device))
+        self.im_pp = nn.Parameter(torch.zeros((self.n_imgs, 2), device=device))
+        self.im_pp.requires_grad_(optimize_pp)
+        self.register_buffer('_pp', torch.tensor([(w / 2, h / 2) for h, w in self.imshapes], device=device))
+        self.register_buffer('_ei', torch.tensor([i for i, j in self.edges], device=device))
+        self.register_buffer('_ej', torch.tensor([j for i, j in self.edges], device=device))
+        self._bufs.attach_params(dict(pw_poses=self.pw_poses.data, pw_adaptors=self.pw_adaptors.data,
+                                      im_depthmaps=self.im_depthmaps.data, im_poses=self.im_poses.data,
+                                      im_focals=self.im_focals.data.view(-1), im_pp=self.im_pp.data))
+        ph.mark('attach')
         self._dest = None
         self._pack_predictions(pred1_pts, pred2_pts, pred1_conf, pred2_conf, pack_chunk)
         ph.mark('enqueue-pred')
@@ -260,41 +297,12 @@ class PointCloudOptimizer(nn.Module):
                 self._pack_flow(masks=False)      # asynchronous from pinned host memory; the masks follow below
 
         ph.mark('enqueue-flow')
-        # ---------------- parameters (reference base_opt.py:112-114, optimizer.py:54-75) ----------------
-        # drawn on the CPU in the reference's order so that a seeded run starts from the same values (the copies above
-        # are in flight meanwhile)
-        pw_poses = rand_pose((self.n_edges, 1 + self.POSE_DIM))
-        depth0 = [torch.randn(H, W) / 10 - 3 for H, W in self.imshapes]
-        im_poses = torch.stack([rand_pose(self.POSE_DIM) for _ in range(self.n_imgs)])
-        nfoc = 1 if shared_focal else self.n_imgs
-        im_focals = torch.tensor([[focal_break * np.log(max(H, W))] for H, W in self.imshapes[:nfoc]], dtype=torch.float32)
-        depth_local = torch.zeros(plan.n_local_frames, plan.pix_stride)
-        for k, n in enumerate(plan.lframe_id.tolist()):
-            depth_local[k, :im_areas[n]] = depth0[n].reshape(-1)
-        del depth0
-        self.pw_poses = nn.Parameter(pw_poses.float().to(device).contiguous())
-        self.pw_adaptors = nn.Parameter(torch.zeros((self.n_edges, 2), device=device))
-        self.pw_adaptors.requires_grad_(allow_pw_adaptors)
-        ph.mark('rand-params')
-        self.im_depthmaps = nn.Parameter(depth_local.to(device))          # (local frames, pix_stride) log-depth
-        ph.mark('depth-upload')
-        self.im_poses = nn.Parameter(im_poses.float().to(device).contiguous())
-        self.im_focals = nn.Parameter(im_focals.to(device))
-        self.im_pp = nn.Parameter(torch.zeros((self.n_imgs, 2), device=device))
-        self.im_pp.requires_grad_(optimize_pp)
-        self.register_buffer('_pp', torch.tensor([(w / 2, h / 2) for h, w in self.imshapes], device=device))
-        self.register_buffer('_ei', torch.tensor([i for i, j in self.edges], device=device))
-        self.register_buffer('_ej', torch.tensor([j for i, j in self.edges], device=device))
-        self._bufs.attach_params(dict(pw_poses=self.pw_poses.data, pw_adaptors=self.pw_adaptors.data,
-                                      im_depthmaps=self.im_depthmaps.data, im_poses=self.im_poses.data,
-                                      im_focals=self.im_focals.data.view(-1), im_pp=self.im_pp.data))
         self.im_conf = [self._im_conf_plane[k, :im_areas[n]].view(self.imshapes[n]) for k, n in enumerate(plan.lframe_id.tolist())]
         init_plane = self._im_conf_plane.clone()
         self.init_conf_maps = [init_plane[k, :im_areas[n]].view(self.imshapes[n]) for k, n in enumerate(plan.lframe_id.tolist())]
         self.pred_i, self.pred_j = _SlotDict(self, 0, "pts"), _SlotDict(self, 1, "pts")
         self.conf_i, self.conf_j = _SlotDict(self, 0, "conf"), _SlotDict(self, 1, "conf")
 
-        ph.mark('attach')
         # ---------------- optional per-frame extras (reference base_opt.py:118-157) ----------------
         self.imgs = None
         if 'img' in view1 and 'img' in view2:
@@ -359,6 +367,20 @@ class PointCloudOptimizer(nn.Module):
                                  "view1/view2 (the reference fails with torch.stack(None) here, optimizer.py:549)")
             self._upload_masks()
         ph.mark('extras+masks')
+        # ---------------- the random initial parameters ----------------
+        draw_thread.join()
+        if 'error' in drawn:
+            raise drawn['error']
+        ph.mark('rand-params (join)')
+        depth_local = torch.zeros(plan.n_local_frames, plan.pix_stride)
+        for k, n in enumerate(plan.lframe_id.tolist()):
+            depth_local[k, :im_areas[n]] = drawn['depth0'][n].reshape(-1)
+        with torch.no_grad():
+            self.pw_poses.data.copy_(drawn['pw_poses'])
+            self.im_poses.data.copy_(drawn['im_poses'])
+            self.im_depthmaps.data.copy_(depth_local)     # (queues behind the prediction uploads of this stream)
+        del drawn, depth_local
+        ph.mark('param-upload')
         ph.done()
         self._adam_step = 0
         self._eval_version = 0
@@ -483,13 +505,20 @@ class PointCloudOptimizer(nn.Module):
         b, plan = self._bufs, self._plan
         masks = self.sam2_dynamic_masks if self.sam2_dynamic_masks is not None else self.dynamic_masks
         lfr = plan.lframe_id.tolist()
+        # through pinned memory, asynchronously: a pageable upload is synchronous - on the side stream it would hold the
+        # constructor until the flow planes queued ahead of it have landed (the caching host allocator keeps the pinned
+        # block until the copy has run)
+        def up(t):
+            t = t.contiguous()
+            return (t if t.is_cuda else t.pin_memory()).to(self._device, non_blocking=True)
+
         if len(lfr) and len({tuple(torch.as_tensor(masks[n]).shape) for n in lfr}) == 1:      # one upload for all frames
             m = torch.stack([torch.as_tensor(masks[n]).bool().reshape(-1) for n in lfr])
-            b.static_mask[:, :m.shape[1]] = (~m).to(torch.uint8).to(self._device)
+            b.static_mask[:, :m.shape[1]] = up((~m).to(torch.uint8))
             return
         for k, n in enumerate(lfr):
-            m = torch.as_tensor(masks[n]).to(self._device).bool().reshape(-1)
-            b.static_mask[k, :m.numel()] = (~m).to(torch.uint8)
+            m = torch.as_tensor(masks[n]).bool().reshape(-1)
+            b.static_mask[k, :m.numel()] = up((~m).to(torch.uint8))
 
     def get_motion_mask_from_pairs(self, view1, view2, pred1, pred2):
         """reference optimizer.py:156-235 (``use_self_mask=True``): see cloud_opt_flow/motion_mask.py."""
