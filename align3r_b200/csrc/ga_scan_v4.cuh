@@ -323,6 +323,13 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
 
         // ---- the previous iteration's Adam step on this tile's log-depths (the pseudo-slot of the ring) ----
         float ldv[V4_PPL];
+        // the tile's static-mask bytes: loaded ahead of the depth step, whose arithmetic covers their latency
+        uint8_t smask[V4_PPL];
+        if (FLOW) {
+#pragma unroll
+            for (int j = 0; j < V4_PPL; ++j)
+                smask[j] = (ROWT || p0 + j * 32 + lane < P) ? p.static_mask[pix_base + j * 32 + lane] : (uint8_t)0;
+        }
         if (ADAM) {
             cp_async_wait<V4_STAGES - 1>();       // this lane's copies of the pseudo-slot have landed (it reads only its own)
 #pragma unroll
@@ -376,7 +383,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_accumulate_v4(const A3rProble
                 const bool valid = ROWT || pix < P;
                 const float ld = valid ? (ADAM ? ldv[j] : p.logdepth[pix_base + pl]) : 0.f;
                 bool stat = false;
-                if (FLOW) stat = valid && p.static_mask[pix_base + pl] != 0;
+                if (FLOW) stat = smask[j] != 0;
                 int u, v;
                 if (ROWT) { u = u0 + 32 * j; v = v0; }
                 else pix_to_uv(pix, W, invW, u, v);

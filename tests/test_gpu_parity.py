@@ -777,18 +777,33 @@ def test_graft_entry_smoke(cuda_device):
 _K2_SCRATCH_SNIPPET = """
 import sys, torch
 sys.path.insert(0, {root!r})
-from tests.test_gpu_parity import build, set_params
-from tests.helpers import golden_case
-fx, scene, prob = golden_case("small_flow")
-net = build(scene, fx["kw"])
-set_params(net, fx["init_params"])
-loss = net.compute_global_alignment(init=None, niter=fx["niter"], schedule="linear", lr=0.01)
-torch.save(dict(loss=loss, hist=net._bufs.loss_hist[:fx["niter"]].cpu(), im_poses=net.im_poses.detach().cpu(),
+from tests.test_gpu_parity import loop_case
+net, niter = loop_case({case!r})
+loss = net.compute_global_alignment(init=None, niter=niter, schedule="linear", lr=0.01)
+torch.save(dict(loss=loss, hist=net._bufs.loss_hist[:niter].cpu(), im_poses=net.im_poses.detach().cpu(),
                 pw_poses=net.pw_poses.detach().cpu(), depth=net.im_depthmaps.detach().cpu()), {out!r})
 """
 
 
-def test_loop_organisation_changes_no_bit(cuda_device, tmp_path):
+def loop_case(case):
+    """'small': the 48x64 reference fixture (general form of the scan); 'rowtile': a 128-pixel-wide scene (the row-tile scan)."""
+    if case == "small":
+        fx, scene, prob = golden_case("small_flow")
+        net = build(scene, fx["kw"])
+        set_params(net, fx["init_params"])
+        return net, fx["niter"]
+    scene = make_scene(6, 24, 128, "swin-2-noncyclic", seed=21, with_flow=True)
+    kw = dict(CANONICAL_KW, num_total_iter=16)
+    prob = go.problem_from_output(scene.output, scene.flow_ij, scene.flow_ji, **kw)
+    params, _ = go.mst_init(prob)
+    net = build(scene, kw)
+    net.verbose = False
+    set_params(net, params)
+    return net, 16
+
+
+@pytest.mark.parametrize("case", ["small", "rowtile"])
+def test_loop_organisation_changes_no_bit(cuda_device, tmp_path, case):
     """The loop's organisation is invisible in the results: the depth Adam step folded into the next scan's tile prologue
     (vs the stand-alone K3 kernel, A3R_FOLD_DEPTH=0) and programmatic dependent launches (vs plain stream order, A3R_PDL=0)
     - both switched off in a separate process - give the same loss history and the same parameters, bit for bit."""
@@ -796,16 +811,60 @@ def test_loop_organisation_changes_no_bit(cuda_device, tmp_path):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = str(tmp_path / "plain.pt")
-    subprocess.run([sys.executable, "-c", _K2_SCRATCH_SNIPPET.format(root=root, out=out)], check=True, timeout=600,
+    subprocess.run([sys.executable, "-c", _K2_SCRATCH_SNIPPET.format(root=root, out=out, case=case)], check=True, timeout=600,
                    env=dict(os.environ, A3R_FOLD_DEPTH="0", A3R_PDL="0"), cwd=root)
     alt = torch.load(out, weights_only=False)
-    fx, scene, prob = golden_case("small_flow")
-    net = build(scene, fx["kw"])
-    set_params(net, fx["init_params"])
-    loss = net.compute_global_alignment(init=None, niter=fx["niter"], schedule="linear", lr=0.01)
-    assert torch.equal(net._bufs.loss_hist[:fx["niter"]].cpu(), alt["hist"]) and loss == alt["loss"]
+    net, niter = loop_case(case)
+    loss = net.compute_global_alignment(init=None, niter=niter, schedule="linear", lr=0.01)
+    assert torch.equal(net._bufs.loss_hist[:niter].cpu(), alt["hist"]) and loss == alt["loss"]
     assert torch.equal(net.im_poses.detach().cpu(), alt["im_poses"]) and torch.equal(net.pw_poses.detach().cpu(), alt["pw_poses"])
     assert torch.equal(net.im_depthmaps.detach().cpu(), alt["depth"])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the row-tile specialisation of the scan (widths that are multiples of the 128-pixel tile: the configuration the benchmark
+# runs) against the general form of the same kernel and against the oracle
+# ---------------------------------------------------------------------------------------------------------------
+_ROWT_SNIPPET = """
+import sys, torch
+sys.path.insert(0, {root!r})
+from tests.test_gpu_parity import build, grads_of, set_params
+from tests.helpers import make_scene, CANONICAL_KW, go
+scene = make_scene(6, 24, 128, "swin-2-noncyclic", seed=21, with_flow=True)
+kw = dict(CANONICAL_KW, num_total_iter=12)
+prob = go.problem_from_output(scene.output, scene.flow_ij, scene.flow_ji, **kw)
+params, _ = go.mst_init(prob)
+net = build(scene, kw)
+net.verbose = False
+set_params(net, params)
+loss = net(epoch=9999)
+loss.backward()
+g = grads_of(net, prob.P)
+run = net.compute_global_alignment(init=None, niter=12, schedule="linear", lr=0.01)
+torch.save(dict(loss=float(loss.detach()), grads=g, run=run, flags=int(net._bufs.flags(net._trainable()))), {out!r})
+"""
+
+
+def test_row_tile_scan_against_general_form(cuda_device, tmp_path):
+    """W = 128: every tile lies in one image row, the product runs the row-tile scan (A3R_F_ROW_TILES; against the oracle:
+    test_medium_scene_against_live_oracle and the full-size fixtures).  The same scene through the general form of the kernel
+    (A3R_V4_ROWT=0, separate process): same loss (1e-6), same gradients (2e-5: fp32 summation order), and a 12-iteration
+    run that ends on the same loss (1e-4)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for tag, env in (("general", dict(A3R_V4_ROWT="0")), ("rowtile", {})):
+        out = str(tmp_path / f"{tag}.pt")
+        subprocess.run([sys.executable, "-c", _ROWT_SNIPPET.format(root=root, out=out)], check=True, timeout=600,
+                       env=dict(os.environ, **env), cwd=root)
+        res[tag] = torch.load(out, weights_only=False)
+    a, b = res["rowtile"], res["general"]
+    assert a["flags"] & _lib.F_ROW_TILES
+    assert abs(a["loss"] - b["loss"]) <= 1e-6 * abs(b["loss"])
+    for k in a["grads"]:
+        assert rel_err(a["grads"][k], b["grads"][k]) <= 2e-5, (k, rel_err(a["grads"][k], b["grads"][k]))
+    assert abs(a["run"] - b["run"]) <= 1e-4 * abs(b["run"]), (a["run"], b["run"])
 
 
 # ---------------------------------------------------------------------------------------------------------------
