@@ -667,7 +667,7 @@ def long_video_record(args, world, rank, dev, barrier, steps=40, warmup=3):
            "final_loss": final, "loss_hist_head": [float(x) for x in net._bufs.loss_hist[:min(steps, 12)].cpu()],
            "roofline_iteration_frac_per_gpu": blended / (ms / steps * 1e-3) / 1e9 / peak / world,
            "setup_seconds": t_setup, "synth": "rows drawn on the GPUs while they are packed (no host copy, no e2e leg)",
-           "one_gpu_recorded": {"value": 59.4, "source": "profiles/r02_c5_lines.jsonl (same workload and protocol on one B200, round 2)"}}
+           "one_gpu_recorded": {"value": 66.2, "source": "profiles/r02_c5_lines.jsonl (same workload and protocol on one B200, round 2, box power-capped at 1635 MHz)"}}
     del net
     torch.cuda.empty_cache()
     return rec
