@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -218,16 +219,22 @@ class PointCloudOptimizer(nn.Module):
 
         def _draw():
             try:
+                # draws only: an elementwise op on a 147 k-element tensor would open an OpenMP team of its own for this thread
+                # (libgomp keeps one pool per master thread), whose spinning threads starve the ranks of a sharded job
                 pw = rand_pose((self.n_edges, 1 + self.POSE_DIM))
-                depth0 = [torch.randn(H, W) / 10 - 3 for H, W in self.imshapes]
-                im = torch.stack([rand_pose(self.POSE_DIM) for _ in range(self.n_imgs)])
-                drawn.update(pw_poses=pw.float().contiguous(), depth0=depth0, im_poses=im.float().contiguous())
+                depth0 = [torch.randn(H, W) for H, W in self.imshapes]
+                im = [rand_pose(self.POSE_DIM) for _ in range(self.n_imgs)]
+                drawn.update(pw_poses=pw, depth0=depth0, im_poses=im)
             except BaseException as exc:           # re-raised by the constructor's thread
                 drawn['error'] = exc
 
         import threading
         draw_thread = threading.Thread(target=_draw, name='a3r-rand-params')
-        draw_thread.start()
+        if os.environ.get("A3R_DRAW_THREAD", "1") == "0":      # diagnostic: draw here, on the constructor's thread
+            _draw()
+            draw_thread = None
+        else:
+            draw_thread.start()
         # ---------------- plan + shard ----------------
         self._shard = shard
         frame_range = None
@@ -241,7 +248,6 @@ class PointCloudOptimizer(nn.Module):
             n_ctas = self._lib.a3r_max_ctas(device.index)
         if n_ctas <= 0:
             _lib.check(n_ctas, "a3r_max_ctas")
-        import os
         if os.environ.get("A3R_PLAN_CTAS"):       # diagnostic: another partition of the tiles (tools/partition_sensitivity.py)
             n_ctas = int(os.environ["A3R_PLAN_CTAS"])
         self._plan = build_plan(self.edges, self.imshapes, self._lib.a3r_tile_pixels(), self._lib.a3r_max_slots(),
@@ -346,6 +352,7 @@ class PointCloudOptimizer(nn.Module):
                 img_pathes[self.edges[e][1]] = view2['instance'][r]
             self.img_pathes = img_pathes
 
+        ph.mark('extras')
         # ---------------- flow term inputs (reference optimizer.py:104-116) ----------------
         self.sam2_dynamic_masks = None
         if want_flow:
@@ -366,18 +373,19 @@ class PointCloudOptimizer(nn.Module):
                 raise ValueError("depth_regularize_weight > 0 weighs pixels by 1 + dynamic_mask: put 'dynamic_mask' into "
                                  "view1/view2 (the reference fails with torch.stack(None) here, optimizer.py:549)")
             self._upload_masks()
-        ph.mark('extras+masks')
+        ph.mark('masks')
         # ---------------- the random initial parameters ----------------
-        draw_thread.join()
+        if draw_thread is not None:
+            draw_thread.join()
         if 'error' in drawn:
             raise drawn['error']
         ph.mark('rand-params (join)')
         depth_local = torch.zeros(plan.n_local_frames, plan.pix_stride)
         for k, n in enumerate(plan.lframe_id.tolist()):
-            depth_local[k, :im_areas[n]] = drawn['depth0'][n].reshape(-1)
+            depth_local[k, :im_areas[n]] = drawn['depth0'][n].reshape(-1) / 10 - 3        # reference optimizer.py:54
         with torch.no_grad():
-            self.pw_poses.data.copy_(drawn['pw_poses'])
-            self.im_poses.data.copy_(drawn['im_poses'])
+            self.pw_poses.data.copy_(drawn['pw_poses'].float())
+            self.im_poses.data.copy_(torch.stack(drawn['im_poses']).float())
             self.im_depthmaps.data.copy_(depth_local)     # (queues behind the prediction uploads of this stream)
         del drawn, depth_local
         ph.mark('param-upload')
@@ -485,18 +493,20 @@ class PointCloudOptimizer(nn.Module):
             for side, fl in enumerate((self.flow_ij, self.flow_ji)):
                 todo = [(e, r) for e, r in sorted(self._row_of_edge.items()) if (2 * e + side) in self._lslot]
                 slots_all, _ = self._dest_tables(side)
-                for k in range(0, len(todo), chunk):
-                    part = todo[k:k + chunk]
-                    rows = [r for _, r in part]
-                    if rows == list(range(rows[0], rows[0] + len(rows))):
-                        src = fl[rows[0]:rows[0] + len(rows)]
-                    else:
-                        src = fl[rows]
-                    d = b.stage[:len(rows) * 2 * P].view(len(rows), 2, P)
-                    d.copy_(src.reshape(len(rows), 2, P), non_blocking=True)
-                    slots = slots_all[k:k + len(part)]
-                    _lib.check(self._lib.a3r_pack_flow(_lib.ptr(d), len(rows), P, _lib.ptr(slots), plan.pix_stride,
+                k = 0
+                while k < len(todo):
+                    # one upload per run of consecutive rows (a frame-window shard packs a subset of its rows on side j):
+                    # slices of the caller's pinned tensor copy asynchronously, a gathered copy would be pageable
+                    r0 = todo[k][1]
+                    m = 1
+                    while k + m < len(todo) and m < chunk and todo[k + m][1] == r0 + m:
+                        m += 1
+                    d = b.stage[:m * 2 * P].view(m, 2, P)
+                    d.copy_(fl[r0:r0 + m].reshape(m, 2, P), non_blocking=True)
+                    slots = slots_all[k:k + m]
+                    _lib.check(self._lib.a3r_pack_flow(_lib.ptr(d), m, P, _lib.ptr(slots), plan.pix_stride,
                                                        _lib.ptr(b.flow), self._stream()), "a3r_pack_flow")
+                    k += m
             if masks:
                 self._upload_masks()
 
@@ -986,7 +996,6 @@ class PointCloudOptimizer(nn.Module):
         if self._peers is not None or self._peers_tried:
             return self._peers
         self._peers_tried = True
-        import os
         import torch.distributed as dist
         world, rank, group = int(self._shard['world']), int(self._shard['rank']), self._shard.get('group')
         if not (dist.is_available() and dist.is_initialized()):
