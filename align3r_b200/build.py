@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SOURCES = ["a3r_common.cu", "ga_kernels.cu", "ga_handle.cu", "mst_kernels.cu", "motion_kernels.cu"]
-HEADERS = ["a3r_common.cuh", "ga_math.cuh", "ptx_helpers.cuh", "ga_scan_v4.cuh", "ga_small.cuh"]
+HEADERS = ["a3r_common.cuh", "ga_math.cuh", "ptx_helpers.cuh", "ga_scan_v4.cuh", "ga_scan_v5.cuh", "ga_small.cuh"]
 
 
 def lib_path():
