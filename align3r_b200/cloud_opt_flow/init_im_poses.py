@@ -363,7 +363,8 @@ def init_minimum_spanning_tree(self, save_score_path=None, save_score_only=False
             pts = (Xn[:, 0:1] * A[:, 0] + Xn[:, 1:2] * A[:, 1] + Xn[:, 2:3] * A[:, 2] + t32).reshape(h, w, 3)
             return n, fast_pnp(pts, im_focals[n], msk.numpy(), niter_PnP=niter_PnP)
 
-        with ThreadPoolExecutor(max_workers=host_workers(len(jobs), self._shard)) as pool:
+        unposed = sum(1 for n in range(N) if im_poses[n] is None)          # the same number on every rank (the tree is global)
+        with ThreadPoolExecutor(max_workers=host_workers(len(jobs), self._shard, total_jobs=unposed)) as pool:
             for n, res in pool.map(_solve, jobs):
                 if res:
                     pnp[n, 0] = 1

@@ -139,5 +139,11 @@ def test_host_pool_is_shared_between_ranks(monkeypatch):
     cores = os.cpu_count() or 1
     assert host_workers(1000) == cores and host_workers(3) == min(3, cores)
     assert host_workers(1000, dict(world=8, rank=0)) == max(1, cores // 8)
+    # a rank that knows the jobs of all ranks takes its share of the cores: 3 of 12 jobs on 16 cores are 3 threads, not 16 // 8
+    monkeypatch.setattr(os, "cpu_count", lambda: 16)
+    assert host_workers(3, dict(world=8, rank=0), total_jobs=12) == 3
+    assert host_workers(1, dict(world=8, rank=0), total_jobs=12) == 1
+    assert host_workers(12, None, total_jobs=12) == 12
+    assert host_workers(40, dict(world=8, rank=0), total_jobs=320) == 2
     monkeypatch.setenv("A3R_HOST_THREADS", "2")
     assert host_workers(1000, dict(world=8, rank=0)) == 2
