@@ -251,6 +251,34 @@ def test_split_work_frames_complete_graph(cuda_device):
         assert rel_err(mine[k].reshape(g64[k].shape), g64[k]) < 5e-4, k
 
 
+def test_split_work_frames_with_flow_on_row_tiles(cuda_device):
+    """The same with the flow term on and 128-pixel-wide frames: a complete graph over 12 frames puts 22 slots on every frame
+    (> a3r_max_slots()), so the row-tile scan runs on split work frames (atomic per-pixel gradient planes, the stand-alone
+    depth Adam kernel instead of the folded step).  Loss and gradients against the fp64 oracle, then 8 iterations against the
+    oracle's own 8."""
+    scene = make_scene(12, 8, 128, "complete", seed=4, with_flow=True)
+    kw = dict(CANONICAL_KW, num_total_iter=8, flow_loss_thre=0)
+    prob = go.problem_from_output(scene.output, scene.flow_ij, scene.flow_ji, **kw)
+    params, _ = go.mst_init(prob)
+    net = build(scene, kw)
+    net.verbose = False
+    assert net._plan.n_work_frames == 2 * prob.n_imgs and net._bufs.flags(net._trainable()) & _lib.F_ROW_TILES
+    set_params(net, params)
+    loss = net(epoch=9999)
+    loss.backward()
+    p64 = {k: v.double() for k, v in params.items()}
+    loss64, g64, _ = go.loss_and_grads(prob.to(torch.float64), p64, 9999)
+    _, g32, _ = go.loss_and_grads(prob, params, 9999)
+    assert abs(float(loss.detach()) - float(loss64)) <= 2e-6 * abs(float(loss64))
+    mine = grads_of(net, prob.P)
+    for k in mine:
+        ok, err, ref = grad_close(k, mine[k].reshape(g64[k].shape), g32[k], g64[k])
+        assert ok, (k, err, ref)
+    run = net.compute_global_alignment(init=None, niter=8, schedule="linear", lr=0.01)
+    _, losses, _ = go.run_alignment(prob, params, niter=8, schedule="linear", lr=0.01)
+    assert abs(run - losses[-1]) <= 1e-4 * abs(losses[-1]), (run, losses[-1])
+
+
 def test_rank_emulated_frame_window_sharding(cuda_device):
     """Two frame-window shards driven from one process on one GPU (their accumulator blocks summed in-process
     instead of by NCCL) take exactly the steps of the unsharded problem."""
