@@ -380,6 +380,19 @@ static int check_problem(const A3rProblem* p) {
     return A3R_OK;
 }
 
+// cudaFuncSetAttribute acts on the CURRENT device's copy of a kernel: a process that drives several GPUs (rank-emulated runs,
+// a caller with one problem per device) must opt every device in, once - one flag per (template instantiation, device)
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool need() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+        if (done[dev]) return false;
+        done[dev] = true;
+        return true;
+    }
+};
+
 static bool pdl_enabled() {
     static const bool on = [] { const char* e = getenv("A3R_PDL"); return !(e && e[0] == '0'); }();
     return on;
@@ -394,20 +407,16 @@ static int launch_accumulate(const A3rProblem* p, cudaStream_t st, const A3rAdam
         if (prev_adam) return a3r_fail(A3R_E_UNSUPPORTED, "the v5 scan has no folded depth step");
         if (p->n_ctas % V5_WARPS != 0) return a3r_fail(A3R_E_ARG, "n_ctas must be a multiple of %d for the v5 scan", V5_WARPS);
         constexpr size_t smem = FLOW ? V5_SMEM_FLOW : V5_SMEM_ALIGN;
-        static bool configured = false;
-        if (!configured) {
+        static PerDeviceOnce configured;
+        if (configured.need())
             A3R_CUDA(cudaFuncSetAttribute(k_accumulate_v5<FLOW, L2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = true;
-        }
         A3R_CUDA(launch_ex(k_accumulate_v5<FLOW, L2D>, dim3(p->n_ctas / V5_WARPS), dim3(V5_THREADS), smem, st, pdl, *p));
     } else if (scan_variant() == 1) {
         if (prev_adam) return a3r_fail(A3R_E_UNSUPPORTED, "the v1 scan has no folded depth step");
         const size_t smem = sizeof(double) * K1_WARPS * K1_MAXS * ACC_STRIDE + sizeof(K1Shared);
-        static bool configured = false;   // per template instantiation
-        if (!configured) {
+        static PerDeviceOnce configured;   // per template instantiation
+        if (configured.need())
             A3R_CUDA(cudaFuncSetAttribute(k_accumulate_v1<FLOW, L2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = true;
-        }
         k_accumulate_v1<FLOW, L2D><<<p->n_ctas, K1_THREADS, smem, st>>>(*p);
     } else {
         if (p->n_ctas % V4_WARPS != 0) return a3r_fail(A3R_E_ARG, "n_ctas must be a multiple of %d for the v4 scan", V4_WARPS);
@@ -417,8 +426,8 @@ static int launch_accumulate(const A3rProblem* p, cudaStream_t st, const A3rAdam
             return (!e || !e[0]) ? 0 : (e[0] == 't' ? 1 : 2);
         }();
         const bool tma = forced == 1;      // measured on C2: per-lane cp.async 0.760 / 0.474 ms (flow / align), TMA 0.843 / 0.533 ms
-        static bool configured = false;
-        if (!configured) {
+        static PerDeviceOnce configured;
+        if (configured.need()) {
             A3R_CUDA(cudaFuncSetAttribute(k_accumulate_v4<FLOW, L2D, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V4_SMEM));
             A3R_CUDA(cudaFuncSetAttribute(k_accumulate_v4<FLOW, L2D, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V4_SMEM));
             A3R_CUDA(cudaFuncSetAttribute(k_accumulate_v4<FLOW, L2D, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V4_SMEM));
@@ -426,7 +435,6 @@ static int launch_accumulate(const A3rProblem* p, cudaStream_t st, const A3rAdam
                 A3R_CUDA(cudaFuncSetAttribute(k_accumulate_v4<FLOW, L2D, false, false, FLOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V4_SMEM));
                 A3R_CUDA(cudaFuncSetAttribute(k_accumulate_v4<FLOW, L2D, false, true, FLOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V4_SMEM));
             }
-            configured = true;
         }
         const unsigned grid = p->n_ctas / V4_WARPS;
         // row tiles (every frame's width a multiple of the tile): the flow arithmetic with v as a per-tile constant

@@ -6,11 +6,15 @@
 // computed (per-lane cp.async - a lane only ever reads what it copied itself, completion is cp.async.wait_group; or TMA
 // bulk copies issued by an elected lane, completion on the warp's own mbarriers).  No cross-warp hand-off exists.
 //
-// Measured on C2 (B200, profiles/): 16 warps x 2 stages x 127 registers: 0.721 ms flow-active (71 % of the measured
-// HBM peak), 0.424 ms align-only (81 %); 12 warps x 3 stages x 149 registers: 0.766 / 0.473 ms; 13 and 14 warps are
-// slower than 12 (uneven warps per scheduler); TMA copies 0.843 / 0.533 ms (elect + uniform-register issue sequence
-// and try_wait loop per chunk).  The kernel is bound by instruction issue, not by HBM: warps per scheduler matter
-// more than prefetch depth.
+// Measured on C2 (B200, profiles/): 16 warps x 2 stages x 127 registers.  Round 1 / first half of round 2: 0.721 ms
+// flow-active (71 % of the measured HBM peak), 0.424 ms align-only (81 %); 12 warps x 3 stages x 149 registers: 0.766 /
+// 0.473 ms; 13 and 14 warps are slower than 12 (uneven warps per scheduler); TMA copies 0.843 / 0.533 ms (elect +
+// uniform-register issue sequence and try_wait loop per chunk).  The kernel is bound by instruction issue first: warps per
+// scheduler matter more than prefetch depth, and every instruction taken out of the chunk loop comes back as time - the
+// row-tile form (ROWT below) with the leaner loop runs 0.618 ms flow-active (83 %), 0.633 ms with the folded depth step
+// (85 % of its 3.54 GB), at 420 executed instructions per (tile, slot) pass instead of 488; issue slots, the shared-memory
+// pipe (the 27-column transpose is half of its wavefronts) and DRAM now sit within ten points of each other
+// (profiles/r02b_scan_rowtile_ncu_full.txt).
 //
 // History (git log, profiles/r01_scan_v{1,2,3,3c}_*): v1 = thread owns pixels, shuffle reduction (33 % of the HBM roofline);
 // v2 = warp owns slot + pixel warps + TMA producer with mbarrier hand-offs (37 %: hand-off latency); v3 = this
