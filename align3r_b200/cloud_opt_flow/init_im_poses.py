@@ -184,14 +184,16 @@ def _pixel_grid(H, W):
     return np.mgrid[:W, :H].T.astype(np.float32)
 
 
-def fast_pnp(pts3d, focal, msk, pp=None, niter_PnP=10):
-    """RANSAC-PnP on the host, reference init_im_poses.py:473-513.  Returns (focal, cam2world 4x4) or None."""
+def fast_pnp(pts3d, focal, msk, pp=None, niter_PnP=10, device=None):
+    """RANSAC-PnP, reference init_im_poses.py:473-513.  Returns (focal, cam2world 4x4) or None.  With a CUDA ``device`` the
+    re-projection test of every hypothesis runs there (pnp_ransac.py: the same inlier sets and pose as cv2.solvePnPRansac,
+    which is what runs without a device)."""
     import cv2
+    from . import pnp_ransac
     if msk.sum() < 4:
         return None
     H, W, THREE = pts3d.shape
     assert THREE == 3
-    pixels = _pixel_grid(H, W)
     if focal is None:
         S = max(W, H)
         tentative_focals = np.geomspace(S / 2, S * 3, 21)
@@ -202,11 +204,9 @@ def fast_pnp(pts3d, focal, msk, pp=None, niter_PnP=10):
     best = (0,)
     for f in tentative_focals:
         K = np.float32([(f, 0, pp[0]), (0, f, pp[1]), (0, 0, 1)])
-        success, R, T, inliers = cv2.solvePnPRansac(pts3d[msk], pixels[msk], K, None, iterationsCount=niter_PnP,
-                                                    reprojectionError=5, flags=cv2.SOLVEPNP_SQPNP)
+        success, R, T, score = pnp_ransac.solve(pts3d, msk, K, device, iterations=niter_PnP, reproj=5, flags=cv2.SOLVEPNP_SQPNP)
         if not success:
             continue
-        score = len(inliers)
         if success and score > best[0]:
             best = score, R, T, f
     if not best[0]:
@@ -361,7 +361,7 @@ def init_minimum_spanning_tree(self, save_score_path=None, save_score_only=False
             A, t32, Xn = (s * R).astype(np.float32), tt.astype(np.float32), X.numpy()
             # plain ufuncs (no BLAS: a threaded GEMM inside every worker would oversubscribe the host)
             pts = (Xn[:, 0:1] * A[:, 0] + Xn[:, 1:2] * A[:, 1] + Xn[:, 2:3] * A[:, 2] + t32).reshape(h, w, 3)
-            return n, fast_pnp(pts, im_focals[n], msk.numpy(), niter_PnP=niter_PnP)
+            return n, fast_pnp(pts, im_focals[n], msk.numpy(), niter_PnP=niter_PnP, device=self.device)
 
         unposed = sum(1 for n in range(N) if im_poses[n] is None)          # the same number on every rank (the tree is global)
         with ThreadPoolExecutor(max_workers=host_workers(len(jobs), self._shard, total_jobs=unposed)) as pool:
@@ -498,7 +498,7 @@ def init_from_known_poses(self, niter_PnP=10, min_conf_thr=3):
 
     def _solve(job):
         e, pts, msk, f, pp, _ = job
-        return e, fast_pnp(pts, f, msk, pp=pp, niter_PnP=niter_PnP)
+        return e, fast_pnp(pts, f, msk, pp=pp, niter_PnP=niter_PnP, device=self.device)
 
     pw = np.zeros((E, 9), dtype=np.float64)              # 8 pose entries + "solved" flag
     best = {}

@@ -26,13 +26,14 @@ def _pixel_grid(H, W):
     return np.mgrid[:W, :H].T.astype(np.float32)
 
 
-def _pair_pnp(pts3d, msk, focal, H, W):
-    """pair_viewer.py:44-60: cam-to-world of the image whose points ``pts3d`` are expressed in the other image's frame."""
+def _pair_pnp(pts3d, msk, focal, H, W, device=None):
+    """pair_viewer.py:44-60: cam-to-world of the image whose points ``pts3d`` are expressed in the other image's frame
+    (cv2.solvePnPRansac, or its device-assisted equal: pnp_ransac.py)."""
     import cv2
+    from . import pnp_ransac
     K = np.float32([(focal, 0, W / 2), (0, focal, H / 2), (0, 0, 1)])
     try:
-        success, R, T, inliers = cv2.solvePnPRansac(pts3d[msk], _pixel_grid(H, W)[msk], K, None, iterationsCount=100,
-                                                    reprojectionError=5, flags=cv2.SOLVEPNP_SQPNP)
+        success, R, T, _ = pnp_ransac.solve(pts3d, msk, K, device, iterations=100, reproj=5, flags=cv2.SOLVEPNP_SQPNP)
         assert success
         R = cv2.Rodrigues(R)[0]                                        # world to cam
         pose = np.linalg.inv(np.r_[np.c_[R, T], [(0, 0, 0, 1)]])       # cam to world
@@ -84,7 +85,8 @@ def get_motion_mask_from_pairs(self, view1, view2, pred1, pred2):
 
         def _solve(job):
             k, first, r, conf, focal = job
-            return k, first, _pair_pnp(_row(pts2, r).reshape(H, W, 3), conf.reshape(H, W) > PAIR_MIN_CONF_THR, float(focal), H, W)
+            return k, first, _pair_pnp(_row(pts2, r).reshape(H, W, 3), conf.reshape(H, W) > PAIR_MIN_CONF_THR, float(focal), H, W,
+                                       device=self.device)
 
         with ThreadPoolExecutor(max_workers=host_workers(len(jobs), self._shard)) as pool:
             for k, first, pose in pool.map(_solve, jobs):

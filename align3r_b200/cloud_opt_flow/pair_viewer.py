@@ -42,13 +42,13 @@ class PairViewer(PointCloudOptimizer):
             # the point cloud is expressed in camera 0; image 1 is posed from its points in that frame, pred_j['0_1']
             H, W = H1W1
             msk = np.maximum(_row(conf2, r01), _row(conf1, r10)).reshape(H, W) > self.min_conf_thr
-            rel = _pair_pnp(_row(pts2, r01).reshape(H, W, 3), msk, self.focals_px[1], H, W)
+            rel = _pair_pnp(_row(pts2, r01).reshape(H, W, 3), msk, self.focals_px[1], H, W, device=self.device)
             poses = [eye, rel]
             depth_src = {0: (2 * e01, eye), 1: (2 * e01 + 1, np.linalg.inv(rel))}
         else:
             H, W = H0W0
             msk = np.maximum(_row(conf1, r01), _row(conf2, r10)).reshape(H, W) > self.min_conf_thr
-            rel = _pair_pnp(_row(pts2, r10).reshape(H, W, 3), msk, self.focals_px[0], H, W)
+            rel = _pair_pnp(_row(pts2, r10).reshape(H, W, 3), msk, self.focals_px[0], H, W, device=self.device)
             poses = [rel, eye]
             depth_src = {0: (2 * e10 + 1, np.linalg.inv(rel)), 1: (2 * e10, eye)}
         for p in (self.pw_poses, self.pw_adaptors, self.im_depthmaps, self.im_poses, self.im_focals, self.im_pp):

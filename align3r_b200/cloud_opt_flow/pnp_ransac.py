@@ -1,0 +1,251 @@
+"""RANSAC-PnP with the hypothesis tests on the GPU - what ``cv2.solvePnPRansac`` computes, not an approximation of it.
+
+The reference poses the frames its spanning tree cannot reach (``init_im_poses.py:272-279``), the second views of
+``init='known_poses'`` (``:44-85``) and the two-view cameras of the self-estimated masks (``optimizer.py:156-235`` through
+``pair_viewer.py``) with ``cv2.solvePnPRansac(..., iterationsCount=10, reprojectionError=5, flags=SOLVEPNP_SQPNP)`` on all
+confident pixels of a frame: ~45 ms per call on a 288x512 frame, the largest single item of an end-to-end job on a B200
+(12 calls on the 50-frame workload, one per pair - 235 - for the masks).  OpenCV's routine (``calib3d/src/solvepnp.cpp``,
+``ptsetreg.cpp``) is, in order:
+
+1. a RANSAC loop with OpenCV's own generator (``cv::RNG`` seeded with ``(uint64)-1``): five distinct point indices,
+   an EPnP pose of the five points, the squared re-projection error of EVERY point under that pose, the inlier count; the
+   best hypothesis so far shortens the loop (``RANSACUpdateNumIters``);
+2. the pose re-fitted to all inliers of the best hypothesis with the requested solver (SQPNP).
+
+Step 1's re-projection of every point for every hypothesis is the time (~8 ms each).  Here the sampling (a port of
+``cv::RNG`` and of ``getSubset``), the loop control and the loop shortening are restated in Python, the five-point EPnP
+solves and the final refit ARE OpenCV's (``cv2.solvePnP``), and the per-hypothesis inlier test runs on the device
+(``a3r_pnp_inliers``: OpenCV's arithmetic operation by operation - fp64 without FMA contraction, fp32 projection, fp32
+squared error).  The inlier sets, and with them the refit, are identical to ``cv2.solvePnPRansac``'s: checked against it
+on the CPU (``tests/test_pnp_ransac.py``: the same loop with the inlier test in numpy), on the GPU
+(``tests/test_gpu_parity.py::test_device_ransac_pnp_equals_opencv``) and ONCE PER PROCESS on the first real solve
+(``_self_check``): on any difference the process falls back to ``cv2.solvePnPRansac`` for good and says so.
+``A3R_FAST_PNP=0`` switches the device path off.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+import warnings
+
+import numpy as np
+
+_MODEL_POINTS = 5           # solvepnp.cpp: every solver but P3P / AP3P draws five points and fits them with EPnP
+
+
+class CvRNG:
+    """``cv::RNG`` (multiply-with-carry, ``core/operations.hpp``): ``next()`` and ``uniform(int, int)``."""
+
+    def __init__(self, state: int = 0xFFFFFFFFFFFFFFFF):
+        self.state = state & 0xFFFFFFFFFFFFFFFF
+
+    def next(self) -> int:
+        s = self.state
+        s = ((s & 0xFFFFFFFF) * 4164903690 + (s >> 32)) & 0xFFFFFFFFFFFFFFFF
+        self.state = s
+        return s & 0xFFFFFFFF
+
+    def uniform(self, a: int, b: int) -> int:
+        return a if a == b else int(self.next() % (b - a) + a)
+
+
+def draw_subset(rng: CvRNG, count: int, model_points: int = _MODEL_POINTS):
+    """``RANSACPointSetRegistrator::getSubset`` (ptsetreg.cpp): distinct indices, redrawn on repetition (the PnP callback
+    accepts every subset)."""
+    idx = []
+    for _ in range(model_points):
+        k = rng.uniform(0, count)
+        while k in idx:
+            k = rng.uniform(0, count)
+        idx.append(k)
+    return idx
+
+
+def update_num_iters(p: float, ep: float, model_points: int, max_iters: int) -> int:
+    """``cv::RANSACUpdateNumIters`` (ptsetreg.cpp)."""
+    p = min(max(p, 0.0), 1.0)
+    ep = min(max(ep, 0.0), 1.0)
+    tiny = float(np.finfo(np.float64).tiny)
+    num = max(1.0 - p, tiny)
+    denom = 1.0 - (1.0 - ep) ** model_points
+    if denom < tiny:
+        return 0
+    num, denom = float(np.log(num)), float(np.log(denom))
+    if denom >= 0 or -num >= max_iters * (-denom):
+        return max_iters
+    return int(np.rint(num / denom))          # cvRound: to nearest, ties to even
+
+
+def ransac_loop(obj, img, K, count_inliers, iterations=10, confidence=0.99, on_best=None):
+    """The loop of ``RANSACPointSetRegistrator::run`` for the PnP callback.  ``obj[idx]`` (5,3) / ``img[idx]`` (5,2) fp32: rows of
+    the list of points handed to the solver, in its order; ``count_inliers(rvec, tvec) -> (count, token)`` tests one hypothesis
+    on all points; ``on_best(token)``: the hypothesis just became the best one (its token must stay valid).
+    Returns ``(token of the best hypothesis, its (rvec, tvec))`` or ``(None, None)``."""
+    import cv2
+    count = len(obj)
+    rng = CvRNG()
+    niters = max(int(iterations), 1)
+    best, best_model, max_good = None, None, 0
+    it = 0
+    while it < niters:
+        idx = draw_subset(rng, count)
+        it += 1
+        ok, rvec, tvec = cv2.solvePnP(obj[idx], img[idx], K, None, flags=cv2.SOLVEPNP_EPNP)
+        if not ok:
+            continue
+        good, token = count_inliers(rvec, tvec)
+        if good > max(max_good, _MODEL_POINTS - 1):
+            best, best_model, max_good = token, (rvec.copy(), tvec.copy()), good
+            if on_best is not None:
+                on_best(token)
+            niters = update_num_iters(confidence, (count - good) / count, _MODEL_POINTS, niters)
+    return best, best_model
+
+
+def refit(obj_in, img_in, K, best_model, flags):
+    """solvepnp.cpp after the loop: the requested solver on the inliers (as doubles); the loop's model if it fails."""
+    import cv2
+    ok, rvec, tvec = cv2.solvePnP(np.ascontiguousarray(obj_in, dtype=np.float64), np.ascontiguousarray(img_in, dtype=np.float64),
+                                  K, None, flags=flags)
+    if not ok:
+        rvec, tvec = best_model
+    return rvec, tvec
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+_state = {"enabled": os.environ.get("A3R_FAST_PNP", "1") != "0", "checked": False}
+_lock = threading.Lock()
+
+
+def enabled() -> bool:
+    return _state["enabled"]
+
+
+def solve_pnp_ransac_device(pts3d, msk, K, device, iterations=10, reproj=5.0, confidence=0.99, flags=None):
+    """``cv2.solvePnPRansac(pts3d[msk], pixels[msk], K, None, iterationsCount, reprojectionError, flags)`` for the points of
+    one frame: ``pts3d`` (H,W,3) fp32 host array, ``msk`` (H,W) bool, pixel (u, v) observed at (u, v).  Returns
+    ``(success, rvec, tvec, n_inliers)``."""
+    import cv2
+    import torch
+    from .. import _lib
+    if flags is None:
+        flags = cv2.SOLVEPNP_SQPNP
+    H, W, _ = pts3d.shape
+    P = H * W
+    flat = np.ascontiguousarray(pts3d, dtype=np.float32).reshape(P, 3)
+    mflat = np.ascontiguousarray(msk, dtype=bool).reshape(P)
+    sel = np.flatnonzero(mflat)                              # position in the solver's list -> pixel
+    count = int(sel.size)
+    if count <= _MODEL_POINTS:                               # (OpenCV's special cases: not what a frame of pixels is)
+        ok, rvec, tvec, inl = cv2.solvePnPRansac(flat[sel], _pixels(sel, W), K, None, iterationsCount=iterations,
+                                                 reprojectionError=reproj, flags=flags)
+        return ok, rvec, tvec, (0 if inl is None else len(inl))
+    lib = _lib.load()
+    dev = torch.device(device)
+    K64 = np.asarray(K, dtype=np.float64)
+    with torch.cuda.device(dev):
+        d_pts = torch.from_numpy(flat).to(dev)
+        d_msk = torch.from_numpy(mflat.view(np.uint8)).to(dev)
+        d_flags = [torch.empty(P, dtype=torch.uint8, device=dev) for _ in range(2)]      # best so far / the one being tested
+        d_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        hyp = (C.c_double * 17)()
+        hyp[12], hyp[13], hyp[14], hyp[15], hyp[16] = K64[0, 0], K64[1, 1], K64[0, 2], K64[1, 2], float(reproj) * float(reproj)
+        cur = [0]
+
+        def count_inliers(rvec, tvec):
+            R = cv2.Rodrigues(rvec)[0]
+            for k in range(9):
+                hyp[k] = float(R.flat[k])
+            for k in range(3):
+                hyp[9 + k] = float(tvec.flat[k])
+            buf = d_flags[cur[0]]
+            _lib.check(lib.a3r_pnp_inliers(_lib.ptr(d_pts), _lib.ptr(d_msk), W, P, hyp, _lib.ptr(buf), _lib.ptr(d_count), stream),
+                       "a3r_pnp_inliers")
+            return int(d_count.item()), cur[0]
+
+        def on_best(token):
+            cur[0] = 1 - token                               # keep the best flags, test the next hypothesis in the other buffer
+
+        # the sampled points come from the host copy (five rows per hypothesis)
+        obj_list, img_list = _Lazy(flat, sel), _LazyPix(sel, W)
+        best, best_model = ransac_loop(obj_list, img_list, K, count_inliers, iterations, confidence, on_best=on_best)
+        if best is None:
+            return False, None, None, 0
+        inl = torch.nonzero(d_flags[best], as_tuple=False).flatten()          # pixel order = the solver's order
+        obj_in = d_pts.index_select(0, inl).cpu().numpy()
+        pix = inl.cpu().numpy()
+    img_in = _pixels(pix, W)
+    rvec, tvec = refit(obj_in, img_in, K, best_model, flags)
+    return True, rvec, tvec, int(pix.size)
+
+
+def _pixels(pix, W):
+    out = np.empty((pix.size, 2), dtype=np.float32)
+    out[:, 0] = pix % W
+    out[:, 1] = pix // W
+    return out
+
+
+class _Lazy:
+    """rows of the solver's point list without materialising it: list position -> pixel -> point"""
+
+    def __init__(self, flat, sel):
+        self.flat, self.sel = flat, sel
+
+    def __len__(self):
+        return int(self.sel.size)
+
+    def __getitem__(self, idx):
+        return self.flat[self.sel[idx]]
+
+
+class _LazyPix:
+    def __init__(self, sel, W):
+        self.sel, self.W = sel, W
+
+    def __getitem__(self, idx):
+        return _pixels(self.sel[idx], self.W)
+
+
+def solve(pts3d, msk, K, device, iterations=10, reproj=5.0, flags=None):
+    """The call sites' entry: the device path when it is on and has passed its self-check, ``cv2.solvePnPRansac`` otherwise.
+    Returns ``(success, rvec, tvec, n_inliers)``."""
+    import cv2
+    if flags is None:
+        flags = cv2.SOLVEPNP_SQPNP
+    if device is not None and _state["enabled"]:
+        if not _state["checked"]:
+            with _lock:
+                if not _state["checked"]:
+                    _self_check(pts3d, msk, K, device, iterations, reproj, flags)
+        if _state["enabled"]:
+            return solve_pnp_ransac_device(pts3d, msk, K, device, iterations, reproj, flags=flags)
+    H, W, _ = pts3d.shape
+    sel = np.flatnonzero(np.asarray(msk).reshape(-1))
+    ok, rvec, tvec, inl = cv2.solvePnPRansac(np.ascontiguousarray(pts3d, dtype=np.float32).reshape(-1, 3)[sel], _pixels(sel, W), K, None,
+                                             iterationsCount=iterations, reprojectionError=reproj, flags=flags)
+    return ok, rvec, tvec, (0 if inl is None else len(inl))
+
+
+def _self_check(pts3d, msk, K, device, iterations, reproj, flags):
+    """Once per process, on the first real solve: the device path against cv2.solvePnPRansac on the same points.  Anything but
+    the same success flag, inlier count and pose (bit for bit) switches the device path off for the process."""
+    import cv2
+    H, W, _ = pts3d.shape
+    sel = np.flatnonzero(np.asarray(msk).reshape(-1))
+    ref = cv2.solvePnPRansac(np.ascontiguousarray(pts3d, dtype=np.float32).reshape(-1, 3)[sel], _pixels(sel, W), K, None,
+                             iterationsCount=iterations, reprojectionError=reproj, flags=flags)
+    try:
+        got = solve_pnp_ransac_device(pts3d, msk, K, device, iterations, reproj, flags=flags)
+        same = bool(ref[0]) == bool(got[0]) and (not ref[0] or (len(ref[3]) == got[3] and np.array_equal(ref[1], got[1])
+                                                                and np.array_equal(ref[2], got[2])))
+    except Exception as exc:          # noqa: BLE001 - any failure of the fast path means: do not use it
+        same = False
+        warnings.warn(f"align3r_b200: device RANSAC-PnP raised {exc!r}; falling back to cv2.solvePnPRansac")
+    if not same:
+        warnings.warn("align3r_b200: device RANSAC-PnP does not reproduce cv2.solvePnPRansac on this installation "
+                      "(another OpenCV build?); falling back to cv2.solvePnPRansac for this process")
+        _state["enabled"] = False
+    _state["checked"] = True

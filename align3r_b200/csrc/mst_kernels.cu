@@ -205,6 +205,40 @@ __global__ void __launch_bounds__(256) k_init_depth(const float* __restrict__ pr
     }
 }
 
+
+// ---- RANSAC-PnP: the O(points) half of one hypothesis test ----------------------------------------------------------
+// cv::solvePnPRansac (reference init_im_poses.py:498: the frames the spanning tree leaves without a pose; two-view cameras of
+// the self-estimated masks; init='known_poses') spends its time re-projecting ALL points for every hypothesis
+// (PnPRansacCallback::computeError -> projectPoints, ~8 ms per hypothesis on 147 k points).  The sampling, the 5-point EPnP
+// solves and the final SQPNP refit stay on the host, in OpenCV's own routines (cloud_opt_flow/pnp_ransac.py); this kernel is
+// the inlier test of one hypothesis, operation by operation what OpenCV computes - fp64 products and sums in its order with
+// no contraction into FMAs, the projection rounded to fp32, the squared error in fp32, compared against the squared
+// threshold in fp64 - so that the inlier sets (and with them the refit) are the ones cv::solvePnPRansac finds.
+struct PnpHyp { double R[9], t[3], fx, fy, cx, cy, thr2; };
+
+__global__ void __launch_bounds__(256) k_pnp_inliers(const float* __restrict__ pts, const uint8_t* __restrict__ mask, int W,
+                                                     int64_t P, const PnpHyp h, uint8_t* __restrict__ flags,
+                                                     int* __restrict__ count) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool in = false;
+    if (p < P && mask[p]) {
+        const double X = (double)pts[3 * p], Y = (double)pts[3 * p + 1], Z = (double)pts[3 * p + 2];
+        const double x = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(h.R[0], X), __dmul_rn(h.R[1], Y)), __dmul_rn(h.R[2], Z)), h.t[0]);
+        const double y = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(h.R[3], X), __dmul_rn(h.R[4], Y)), __dmul_rn(h.R[5], Z)), h.t[1]);
+        const double z = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(h.R[6], X), __dmul_rn(h.R[7], Y)), __dmul_rn(h.R[8], Z)), h.t[2]);
+        const double iz = z != 0.0 ? __ddiv_rn(1.0, z) : 1.0;
+        const float pu = __double2float_rn(__dadd_rn(__dmul_rn(__dmul_rn(x, iz), h.fx), h.cx));
+        const float pv = __double2float_rn(__dadd_rn(__dmul_rn(__dmul_rn(y, iz), h.fy), h.cy));
+        const int v = (int)(p / W), u = (int)(p - (int64_t)v * W);
+        const float dx = __fsub_rn((float)u, pu), dy = __fsub_rn((float)v, pv);
+        const float err = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        in = (double)err <= h.thr2;
+    }
+    if (p < P) flags[p] = in ? 1 : 0;
+    const int n = __syncthreads_count(in);
+    if (threadIdx.x == 0 && n) atomicAdd(count, n);
+}
+
 }  // namespace
 
 // confidence clean-up of frame i against all other frames (reference base_opt.py:587-623)
@@ -294,6 +328,21 @@ int a3r_init_depth(const float* predw, int64_t pix_stride, const int32_t* src, c
     if (n_local_frames <= 0) return A3R_OK;
     if (!predw || !src || !npix || !rows || !logdepth) return a3r_fail(A3R_E_ARG, "a3r_init_depth: NULL pointer");
     k_init_depth<<<dim3(64, n_local_frames), 256, 0, (cudaStream_t)stream>>>(predw, pix_stride, src, npix, rows, logdepth);
+    A3R_CUDA(cudaGetLastError());
+    return A3R_OK;
+}
+
+int a3r_pnp_inliers(const float* pts, const uint8_t* mask, int32_t W, int64_t P, const double* hyp, uint8_t* flags,
+                    int32_t* count, void* stream) {
+    if (P <= 0) return A3R_OK;
+    if (!pts || !mask || !hyp || !flags || !count || W <= 0) return a3r_fail(A3R_E_ARG, "a3r_pnp_inliers: NULL pointer or W <= 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    PnpHyp h;
+    for (int k = 0; k < 9; ++k) h.R[k] = hyp[k];
+    for (int k = 0; k < 3; ++k) h.t[k] = hyp[9 + k];
+    h.fx = hyp[12]; h.fy = hyp[13]; h.cx = hyp[14]; h.cy = hyp[15]; h.thr2 = hyp[16];
+    A3R_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t), st));
+    k_pnp_inliers<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(pts, mask, W, P, h, flags, count);
     A3R_CUDA(cudaGetLastError());
     return A3R_OK;
 }

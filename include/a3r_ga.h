@@ -357,6 +357,15 @@ int a3r_weiszfeld_focal_batched(const float *predw, int64_t pix_stride, const in
 int a3r_init_depth(const float *predw, int64_t pix_stride, const int32_t *src, const int32_t *npix,
                    const double *rows, int32_t n_local_frames, float *logdepth, void *stream);
 
+/* The inlier test of ONE RANSAC-PnP hypothesis over all points (reference init_im_poses.py:498 -> cv::solvePnPRansac, whose
+ * PnPRansacCallback::computeError re-projects every point for every hypothesis on the host).  pts [P][3] fp32 world points of
+ * a frame (pixel p = v * W + u is observed at (u, v)), mask [P] bytes (the points handed to the solver), hyp = 17 HOST doubles:
+ * world-to-camera R (9, row-major), t (3), fx, fy, cx, cy, squared re-projection threshold.  Writes flags [P] (1 = masked-in
+ * inlier) and *count (device int32).  Operation by operation OpenCV's arithmetic (fp64 without FMA contraction, projection
+ * rounded to fp32, fp32 squared error, fp64 comparison): the inlier sets are cv::solvePnPRansac's. */
+int a3r_pnp_inliers(const float *pts, const uint8_t *mask, int32_t W, int64_t P, const double *hyp, uint8_t *flags,
+                    int32_t *count, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -279,6 +279,30 @@ def test_split_work_frames_with_flow_on_row_tiles(cuda_device):
     assert abs(run - losses[-1]) <= 1e-4 * abs(losses[-1]), (run, losses[-1])
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_device_ransac_pnp_equals_opencv(cuda_device, seed):
+    """cloud_opt_flow/pnp_ransac.py: the RANSAC-PnP whose per-hypothesis inlier test runs on the GPU (a3r_pnp_inliers) returns
+    what cv2.solvePnPRansac returns on the same points - the same number of inliers, rvec and tvec bit for bit - at the sizes
+    and iteration limits of its three call sites (init_im_poses.py:498: 10 iterations; pair_viewer.py:52: 100)."""
+    import cv2
+    from align3r_b200.cloud_opt_flow import pnp_ransac as pr
+    from tests.test_pnp_ransac import scene as pnp_scene
+    H, W = ((288, 512), (96, 160), (48, 64))[seed % 3]
+    X, msk, K = pnp_scene(H, W, 0.01 * (1 + seed % 3), 0.06 * (seed % 5), 100 + seed)
+    iterations = 10 if seed % 2 == 0 else 100
+    pix = np.mgrid[:W, :H].T.astype(np.float32)
+    ok, rvec, tvec, inl = cv2.solvePnPRansac(X[msk], pix[msk], K, None, iterationsCount=iterations, reprojectionError=5,
+                                             flags=cv2.SOLVEPNP_SQPNP)
+    ok2, rvec2, tvec2, n2 = pr.solve_pnp_ransac_device(X, msk, K, "cuda", iterations=iterations, reproj=5.0)
+    assert bool(ok) == bool(ok2)
+    if ok:
+        assert n2 == len(inl)
+        assert np.array_equal(rvec, rvec2) and np.array_equal(tvec, tvec2)
+    # the call sites' entry runs the device path (its once-per-process self-check has passed)
+    ok3, rvec3, tvec3, n3 = pr.solve(X, msk, K, "cuda", iterations=iterations, reproj=5)
+    assert pr.enabled() and bool(ok3) == bool(ok) and (not ok or (n3 == len(inl) and np.array_equal(rvec, rvec3)))
+
+
 def test_rank_emulated_frame_window_sharding(cuda_device):
     """Two frame-window shards driven from one process on one GPU (their accumulator blocks summed in-process
     instead of by NCCL) take exactly the steps of the unsharded problem."""
