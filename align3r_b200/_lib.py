@@ -104,6 +104,8 @@ _SIGNATURES = {
     "a3r_weiszfeld_focal_batched": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp]),
     "a3r_init_depth": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, _vp, _vp]),
     "a3r_pnp_inliers": (C.c_int, [_vp, _vp, _i32, _i64, C.POINTER(C.c_double), _vp, _vp, _vp]),
+    "a3r_similarity_points": (C.c_int, [_vp, _i64, C.POINTER(C.c_float), _vp, _vp]),
+    "a3r_pnp_gather": (C.c_int, [_vp, _vp, C.POINTER(C.c_int32), _i32, _vp, _vp]),
     "a3r_occ_masks": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp]),
     "a3r_motion_minmax": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "a3r_debug_k2_trace": (C.c_int, [C.c_int, _vp]),

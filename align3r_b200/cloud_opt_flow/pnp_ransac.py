@@ -114,71 +114,12 @@ def refit(obj_in, img_in, K, best_model, flags):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-_state = {"enabled": os.environ.get("A3R_FAST_PNP", "1") != "0", "checked": False}
+_state = {"enabled": os.environ.get("A3R_FAST_PNP", "1") != "0", "checked": False, "checked_plane": False}
 _lock = threading.Lock()
 
 
 def enabled() -> bool:
     return _state["enabled"]
-
-
-def solve_pnp_ransac_device(pts3d, msk, K, device, iterations=10, reproj=5.0, confidence=0.99, flags=None):
-    """``cv2.solvePnPRansac(pts3d[msk], pixels[msk], K, None, iterationsCount, reprojectionError, flags)`` for the points of
-    one frame: ``pts3d`` (H,W,3) fp32 host array, ``msk`` (H,W) bool, pixel (u, v) observed at (u, v).  Returns
-    ``(success, rvec, tvec, n_inliers)``."""
-    import cv2
-    import torch
-    from .. import _lib
-    if flags is None:
-        flags = cv2.SOLVEPNP_SQPNP
-    H, W, _ = pts3d.shape
-    P = H * W
-    flat = np.ascontiguousarray(pts3d, dtype=np.float32).reshape(P, 3)
-    mflat = np.ascontiguousarray(msk, dtype=bool).reshape(P)
-    sel = np.flatnonzero(mflat)                              # position in the solver's list -> pixel
-    count = int(sel.size)
-    if count <= _MODEL_POINTS:                               # (OpenCV's special cases: not what a frame of pixels is)
-        ok, rvec, tvec, inl = cv2.solvePnPRansac(flat[sel], _pixels(sel, W), K, None, iterationsCount=iterations,
-                                                 reprojectionError=reproj, flags=flags)
-        return ok, rvec, tvec, (0 if inl is None else len(inl))
-    lib = _lib.load()
-    dev = torch.device(device)
-    K64 = np.asarray(K, dtype=np.float64)
-    with torch.cuda.device(dev):
-        d_pts = torch.from_numpy(flat).to(dev)
-        d_msk = torch.from_numpy(mflat.view(np.uint8)).to(dev)
-        d_flags = [torch.empty(P, dtype=torch.uint8, device=dev) for _ in range(2)]      # best so far / the one being tested
-        d_count = torch.zeros(1, dtype=torch.int32, device=dev)
-        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        hyp = (C.c_double * 17)()
-        hyp[12], hyp[13], hyp[14], hyp[15], hyp[16] = K64[0, 0], K64[1, 1], K64[0, 2], K64[1, 2], float(reproj) * float(reproj)
-        cur = [0]
-
-        def count_inliers(rvec, tvec):
-            R = cv2.Rodrigues(rvec)[0]
-            for k in range(9):
-                hyp[k] = float(R.flat[k])
-            for k in range(3):
-                hyp[9 + k] = float(tvec.flat[k])
-            buf = d_flags[cur[0]]
-            _lib.check(lib.a3r_pnp_inliers(_lib.ptr(d_pts), _lib.ptr(d_msk), W, P, hyp, _lib.ptr(buf), _lib.ptr(d_count), stream),
-                       "a3r_pnp_inliers")
-            return int(d_count.item()), cur[0]
-
-        def on_best(token):
-            cur[0] = 1 - token                               # keep the best flags, test the next hypothesis in the other buffer
-
-        # the sampled points come from the host copy (five rows per hypothesis)
-        obj_list, img_list = _Lazy(flat, sel), _LazyPix(sel, W)
-        best, best_model = ransac_loop(obj_list, img_list, K, count_inliers, iterations, confidence, on_best=on_best)
-        if best is None:
-            return False, None, None, 0
-        inl = torch.nonzero(d_flags[best], as_tuple=False).flatten()          # pixel order = the solver's order
-        obj_in = d_pts.index_select(0, inl).cpu().numpy()
-        pix = inl.cpu().numpy()
-    img_in = _pixels(pix, W)
-    rvec, tvec = refit(obj_in, img_in, K, best_model, flags)
-    return True, rvec, tvec, int(pix.size)
 
 
 def _pixels(pix, W):
@@ -209,19 +150,189 @@ class _LazyPix:
         return _pixels(self.sel[idx], self.W)
 
 
+class HostFrame:
+    """The points of one frame handed over as host arrays (``pts3d`` (H,W,3) fp32, ``msk`` (H,W) bool): uploaded once, the
+    sampled rows of a hypothesis come from the host copy."""
+
+    def __init__(self, pts3d, msk, device):
+        import torch
+        self.H, self.W, _ = pts3d.shape
+        self.P = self.H * self.W
+        self.flat = np.ascontiguousarray(pts3d, dtype=np.float32).reshape(self.P, 3)
+        mflat = np.ascontiguousarray(msk, dtype=bool).reshape(self.P)
+        self.sel = np.flatnonzero(mflat)                     # position in the solver's list -> pixel
+        self.count = int(self.sel.size)
+        self.dev = torch.device(device)
+        self._mflat = mflat
+        self.d_pts = self.d_msk = None
+
+    def upload(self):
+        import torch
+        if self.d_pts is None:
+            self.d_pts = torch.from_numpy(self.flat).to(self.dev)
+            self.d_msk = torch.from_numpy(self._mflat.view(np.uint8)).to(self.dev)
+
+    def rows(self):
+        return _Lazy(self.flat, self.sel), _LazyPix(self.sel, self.W)
+
+    def host_lists(self):
+        return self.flat[self.sel], _pixels(self.sel, self.W)
+
+
+class PlaneFrame:
+    """The points of one frame taken from a raw slot plane that already lives on the device (``plane`` (P,4) fp32: X Y Z w) and
+    the similarity that makes them world points (``A32`` (3,3), ``t32`` (3,) fp32: pts = X A[:,0] + Y A[:,1] + Z A[:,2] + t, the
+    expression init_im_poses.py evaluates in numpy - a3r_similarity_points rounds every operation as numpy does), ``msk`` (P,)
+    bool on the device.  Nothing is uploaded: host-to-device copies, however small, queue behind the flow planes still in flight
+    from the constructor; the sampled rows of a hypothesis come back through a3r_pnp_gather (indices as kernel arguments)."""
+
+    def __init__(self, plane, A32, t32, msk, H, W):
+        import torch
+        from .. import _lib
+        self.H, self.W, self.P = H, W, H * W
+        self.dev = plane.device
+        self._plane, self._A, self._t = plane, np.ascontiguousarray(A32, dtype=np.float32), np.ascontiguousarray(t32, dtype=np.float32)
+        lib = _lib.load()
+        with torch.cuda.device(self.dev):
+            st = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+            self.d_pts = torch.empty((self.P, 3), dtype=torch.float32, device=self.dev)
+            sim = (C.c_float * 12)(*([float(v) for v in self._A.reshape(-1)] + [float(v) for v in self._t.reshape(-1)]))
+            assert plane.is_contiguous() and plane.dtype == torch.float32 and tuple(plane.shape) == (self.P, 4)
+            _lib.check(lib.a3r_similarity_points(_lib.ptr(plane), self.P, sim, _lib.ptr(self.d_pts), st), "a3r_similarity_points")
+            self.d_msk = msk.reshape(self.P).to(torch.uint8)
+            self.d_sel = torch.nonzero(self.d_msk, as_tuple=False).flatten()        # int64, ascending = the solver's order
+            self.count = int(self.d_sel.numel())
+            self._out = torch.empty((8, 4), dtype=torch.float32, device=self.dev)
+        self._lib, self._cache = lib, (None, None)
+
+    def upload(self):
+        pass
+
+    def _gather(self, idx):
+        import torch
+        from .. import _lib
+        key = tuple(idx)
+        if self._cache[0] != key:
+            arr = (C.c_int32 * len(idx))(*[int(k) for k in idx])
+            with torch.cuda.device(self.dev):
+                st = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+                _lib.check(self._lib.a3r_pnp_gather(_lib.ptr(self.d_pts), _lib.ptr(self.d_sel), arr, len(idx), _lib.ptr(self._out), st),
+                           "a3r_pnp_gather")
+                rows = self._out[:len(idx)].cpu().numpy()
+            self._cache = (key, (np.ascontiguousarray(rows[:, :3]), _pixels(rows[:, 3].astype(np.int64), self.W)))
+        return self._cache[1]
+
+    def rows(self):
+        frame = self
+
+        class _Obj:
+            def __len__(self):
+                return frame.count
+
+            def __getitem__(self, idx):
+                return frame._gather(idx)[0]
+
+        class _Img:
+            def __getitem__(self, idx):
+                return frame._gather(idx)[1]
+
+        return _Obj(), _Img()
+
+    def host_lists(self):
+        """(self-check only) the solver's lists as the host path builds them: numpy's transform of the downloaded plane."""
+        Xn = self._plane.cpu().numpy()
+        A, t32 = self._A, self._t
+        pts = (Xn[:, 0:1] * A[:, 0] + Xn[:, 1:2] * A[:, 1] + Xn[:, 2:3] * A[:, 2] + t32)
+        sel = np.flatnonzero(self.d_msk.cpu().numpy())
+        return np.ascontiguousarray(pts[sel], dtype=np.float32), _pixels(sel, self.W)
+
+
+def run_on_frame(frame, K, iterations=10, reproj=5.0, confidence=0.99, flags=None):
+    """``cv2.solvePnPRansac(points[msk], pixels[msk], K, None, iterationsCount, reprojectionError, flags)`` on a prepared frame
+    (HostFrame / PlaneFrame).  Returns ``(success, rvec, tvec, n_inliers)``."""
+    import cv2
+    import torch
+    from .. import _lib
+    if flags is None:
+        flags = cv2.SOLVEPNP_SQPNP
+    if frame.count <= _MODEL_POINTS:                         # (OpenCV's special cases: not what a frame of pixels is)
+        obj, img = frame.host_lists()
+        ok, rvec, tvec, inl = cv2.solvePnPRansac(obj, img, K, None, iterationsCount=iterations, reprojectionError=reproj, flags=flags)
+        return ok, rvec, tvec, (0 if inl is None else len(inl))
+    lib = _lib.load()
+    dev, P, W = frame.dev, frame.P, frame.W
+    K64 = np.asarray(K, dtype=np.float64)
+    frame.upload()
+    with torch.cuda.device(dev):
+        d_flags = [torch.empty(P, dtype=torch.uint8, device=dev) for _ in range(2)]      # best so far / the one being tested
+        d_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        hyp = (C.c_double * 17)()
+        hyp[12], hyp[13], hyp[14], hyp[15], hyp[16] = K64[0, 0], K64[1, 1], K64[0, 2], K64[1, 2], float(reproj) * float(reproj)
+        cur = [0]
+
+        def count_inliers(rvec, tvec):
+            R = cv2.Rodrigues(rvec)[0]
+            for k in range(9):
+                hyp[k] = float(R.flat[k])
+            for k in range(3):
+                hyp[9 + k] = float(tvec.flat[k])
+            buf = d_flags[cur[0]]
+            _lib.check(lib.a3r_pnp_inliers(_lib.ptr(frame.d_pts), _lib.ptr(frame.d_msk), W, P, hyp, _lib.ptr(buf), _lib.ptr(d_count),
+                                           stream), "a3r_pnp_inliers")
+            return int(d_count.item()), cur[0]
+
+        def on_best(token):
+            cur[0] = 1 - token                               # keep the best flags, test the next hypothesis in the other buffer
+
+        obj_rows, img_rows = frame.rows()
+        best, best_model = ransac_loop(obj_rows, img_rows, K, count_inliers, iterations, confidence, on_best=on_best)
+        if best is None:
+            return False, None, None, 0
+        inl = torch.nonzero(d_flags[best], as_tuple=False).flatten()          # pixel order = the solver's order
+        obj_in = frame.d_pts.index_select(0, inl).cpu().numpy()
+        pix = inl.cpu().numpy()
+    rvec, tvec = refit(obj_in, _pixels(pix, W), K, best_model, flags)
+    return True, rvec, tvec, int(pix.size)
+
+
+def solve_pnp_ransac_device(pts3d, msk, K, device, iterations=10, reproj=5.0, confidence=0.99, flags=None):
+    """The device-assisted solve on host arrays: ``pts3d`` (H,W,3) fp32, ``msk`` (H,W) bool, pixel (u, v) observed at (u, v)."""
+    return run_on_frame(HostFrame(pts3d, msk, device), K, iterations, reproj, confidence, flags)
+
+
+def _reference(frame, K, iterations, reproj, flags):
+    import cv2
+    obj, img = frame.host_lists()
+    ok, rvec, tvec, inl = cv2.solvePnPRansac(obj, img, K, None, iterationsCount=iterations, reprojectionError=reproj, flags=flags)
+    return ok, rvec, tvec, (0 if inl is None else len(inl))
+
+
+def solve_frame(frame, K, iterations=10, reproj=5.0, flags=None):
+    """The call sites' entry for a prepared frame: the device-assisted loop once it has passed its self-check (one per frame
+    kind and process), ``cv2.solvePnPRansac`` on the frame's host lists otherwise."""
+    import cv2
+    if flags is None:
+        flags = cv2.SOLVEPNP_SQPNP
+    key = "checked_plane" if isinstance(frame, PlaneFrame) else "checked"
+    if _state["enabled"]:
+        if not _state[key]:
+            with _lock:
+                if not _state[key]:
+                    _self_check(frame, K, iterations, reproj, flags, key)
+        if _state["enabled"]:
+            return run_on_frame(frame, K, iterations, reproj, flags=flags)
+    return _reference(frame, K, iterations, reproj, flags)
+
+
 def solve(pts3d, msk, K, device, iterations=10, reproj=5.0, flags=None):
-    """The call sites' entry: the device path when it is on and has passed its self-check, ``cv2.solvePnPRansac`` otherwise.
+    """Host arrays in: the device-assisted loop when a device is given and the path is on, ``cv2.solvePnPRansac`` otherwise.
     Returns ``(success, rvec, tvec, n_inliers)``."""
     import cv2
     if flags is None:
         flags = cv2.SOLVEPNP_SQPNP
     if device is not None and _state["enabled"]:
-        if not _state["checked"]:
-            with _lock:
-                if not _state["checked"]:
-                    _self_check(pts3d, msk, K, device, iterations, reproj, flags)
-        if _state["enabled"]:
-            return solve_pnp_ransac_device(pts3d, msk, K, device, iterations, reproj, flags=flags)
+        return solve_frame(HostFrame(pts3d, msk, device), K, iterations, reproj, flags)
     H, W, _ = pts3d.shape
     sel = np.flatnonzero(np.asarray(msk).reshape(-1))
     ok, rvec, tvec, inl = cv2.solvePnPRansac(np.ascontiguousarray(pts3d, dtype=np.float32).reshape(-1, 3)[sel], _pixels(sel, W), K, None,
@@ -229,17 +340,13 @@ def solve(pts3d, msk, K, device, iterations=10, reproj=5.0, flags=None):
     return ok, rvec, tvec, (0 if inl is None else len(inl))
 
 
-def _self_check(pts3d, msk, K, device, iterations, reproj, flags):
-    """Once per process, on the first real solve: the device path against cv2.solvePnPRansac on the same points.  Anything but
-    the same success flag, inlier count and pose (bit for bit) switches the device path off for the process."""
-    import cv2
-    H, W, _ = pts3d.shape
-    sel = np.flatnonzero(np.asarray(msk).reshape(-1))
-    ref = cv2.solvePnPRansac(np.ascontiguousarray(pts3d, dtype=np.float32).reshape(-1, 3)[sel], _pixels(sel, W), K, None,
-                             iterationsCount=iterations, reprojectionError=reproj, flags=flags)
+def _self_check(frame, K, iterations, reproj, flags, key):
+    """Once per process and frame kind, on the first real solve: the device-assisted loop against cv2.solvePnPRansac on the same
+    points.  Anything but the same success flag, inlier count and pose (bit for bit) switches the device path off for the process."""
+    ref = _reference(frame, K, iterations, reproj, flags)
     try:
-        got = solve_pnp_ransac_device(pts3d, msk, K, device, iterations, reproj, flags=flags)
-        same = bool(ref[0]) == bool(got[0]) and (not ref[0] or (len(ref[3]) == got[3] and np.array_equal(ref[1], got[1])
+        got = run_on_frame(frame, K, iterations, reproj, flags=flags)
+        same = bool(ref[0]) == bool(got[0]) and (not ref[0] or (ref[3] == got[3] and np.array_equal(ref[1], got[1])
                                                                 and np.array_equal(ref[2], got[2])))
     except Exception as exc:          # noqa: BLE001 - any failure of the fast path means: do not use it
         same = False
@@ -248,4 +355,4 @@ def _self_check(pts3d, msk, K, device, iterations, reproj, flags):
         warnings.warn("align3r_b200: device RANSAC-PnP does not reproduce cv2.solvePnPRansac on this installation "
                       "(another OpenCV build?); falling back to cv2.solvePnPRansac for this process")
         _state["enabled"] = False
-    _state["checked"] = True
+    _state[key] = True

@@ -239,6 +239,32 @@ __global__ void __launch_bounds__(256) k_pnp_inliers(const float* __restrict__ p
     if (threadIdx.x == 0 && n) atomicAdd(count, n);
 }
 
+// world points of a frame from its raw slot plane: pts = X * A[:,0] + Y * A[:,1] + Z * A[:,2] + t in fp32, every product and sum
+// rounded on its own, in the order numpy evaluates the same expression on the host (init_im_poses.py: the similarity of the
+// spanning tree applied next to the PnP call that consumes it) - the RANSAC-PnP sees the same fp32 points either way
+struct SimF { float A[9], t[3]; };
+__global__ void __launch_bounds__(256) k_similarity_points(const float4* __restrict__ plane, int64_t P, const SimF s,
+                                                           float* __restrict__ out) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const float4 x = plane[p];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        out[3 * p + c] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(x.x, s.A[3 * c]), __fmul_rn(x.y, s.A[3 * c + 1])),
+                                             __fmul_rn(x.z, s.A[3 * c + 2])), s.t[c]);
+}
+
+// the sampled points of one hypothesis: row idx[k] of the solver's list = pixel sel[idx[k]] -> (x, y, z, pixel)
+struct Idx8 { int32_t v[8]; };
+__global__ void k_pnp_gather(const float* __restrict__ pts, const int64_t* __restrict__ sel, const Idx8 idx, int n,
+                             float* __restrict__ out) {
+    const int k = threadIdx.x;
+    if (k >= n) return;
+    const int64_t pix = sel[idx.v[k]];
+    out[4 * k] = pts[3 * pix]; out[4 * k + 1] = pts[3 * pix + 1]; out[4 * k + 2] = pts[3 * pix + 2];
+    out[4 * k + 3] = (float)pix;           // < 2^24 (plan.py): exact
+}
+
 }  // namespace
 
 // confidence clean-up of frame i against all other frames (reference base_opt.py:587-623)
@@ -343,6 +369,27 @@ int a3r_pnp_inliers(const float* pts, const uint8_t* mask, int32_t W, int64_t P,
     h.fx = hyp[12]; h.fy = hyp[13]; h.cx = hyp[14]; h.cy = hyp[15]; h.thr2 = hyp[16];
     A3R_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t), st));
     k_pnp_inliers<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(pts, mask, W, P, h, flags, count);
+    A3R_CUDA(cudaGetLastError());
+    return A3R_OK;
+}
+
+int a3r_similarity_points(const float* plane, int64_t P, const float* sim, float* out, void* stream) {
+    if (P <= 0) return A3R_OK;
+    if (!plane || !sim || !out) return a3r_fail(A3R_E_ARG, "a3r_similarity_points: NULL pointer");
+    SimF s;
+    for (int k = 0; k < 9; ++k) s.A[k] = sim[k];
+    for (int k = 0; k < 3; ++k) s.t[k] = sim[9 + k];
+    k_similarity_points<<<(unsigned)((P + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(plane), P, s, out);
+    A3R_CUDA(cudaGetLastError());
+    return A3R_OK;
+}
+
+int a3r_pnp_gather(const float* pts, const int64_t* sel, const int32_t* idx, int32_t n, float* out, void* stream) {
+    if (n <= 0) return A3R_OK;
+    if (!pts || !sel || !idx || !out || n > 8) return a3r_fail(A3R_E_ARG, "a3r_pnp_gather: NULL pointer or more than 8 rows");
+    Idx8 v;
+    for (int k = 0; k < 8; ++k) v.v[k] = k < n ? idx[k] : 0;
+    k_pnp_gather<<<1, 32, 0, (cudaStream_t)stream>>>(pts, sel, v, n, out);
     A3R_CUDA(cudaGetLastError());
     return A3R_OK;
 }

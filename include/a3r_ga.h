@@ -366,6 +366,14 @@ int a3r_init_depth(const float *predw, int64_t pix_stride, const int32_t *src, c
 int a3r_pnp_inliers(const float *pts, const uint8_t *mask, int32_t W, int64_t P, const double *hyp, uint8_t *flags,
                     int32_t *count, void *stream);
 
+/* World points of a frame from a raw slot plane [P][4] (X Y Z w): out [P][3] = X * A[:,0] + Y * A[:,1] + Z * A[:,2] + t in fp32,
+ * every operation rounded on its own in numpy's order (the similarity of the spanning tree, reference init_im_poses.py:272-279
+ * applies it before fast_pnp).  sim = 12 HOST floats: A (9, row-major), t (3). */
+int a3r_similarity_points(const float *plane, int64_t P, const float *sim, float *out, void *stream);
+/* The n <= 8 sampled points of one RANSAC hypothesis: row idx[k] (HOST int32) of the solver's point list, whose k-th entry is
+ * pixel sel[k] (device int64, ascending), -> out [n][4] = x, y, z, pixel. */
+int a3r_pnp_gather(const float *pts, const int64_t *sel, const int32_t *idx, int32_t n, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

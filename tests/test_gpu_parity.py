@@ -301,6 +301,23 @@ def test_device_ransac_pnp_equals_opencv(cuda_device, seed):
     # the call sites' entry runs the device path (its once-per-process self-check has passed)
     ok3, rvec3, tvec3, n3 = pr.solve(X, msk, K, "cuda", iterations=iterations, reproj=5)
     assert pr.enabled() and bool(ok3) == bool(ok) and (not ok or (n3 == len(inl) and np.array_equal(rvec, rvec3)))
+    # the MST initialisation's form: a raw slot plane on the device + the similarity that makes its points world points
+    # (a3r_similarity_points with numpy's rounding, sampled rows through a3r_pnp_gather: no host-to-device copy at all)
+    r = np.random.default_rng(seed)
+    A = (cv2.Rodrigues(r.normal(0, 0.4, 3))[0] * (0.5 + r.random())).astype(np.float32)
+    t32 = r.normal(0, 1, 3).astype(np.float32)
+    Xn = X.reshape(-1, 3)
+    world = (Xn[:, 0:1] * A[:, 0] + Xn[:, 1:2] * A[:, 1] + Xn[:, 2:3] * A[:, 2] + t32)
+    plane = torch.zeros(H * W, 4, device="cuda")
+    plane[:, :3] = torch.from_numpy(Xn).cuda()
+    frame = pr.PlaneFrame(plane, A, t32, torch.from_numpy(msk).cuda(), H, W)
+    assert np.array_equal(frame.d_pts.cpu().numpy(), world)                      # bit for bit numpy's fp32 expression
+    ok4, rvec4, tvec4, inl4 = cv2.solvePnPRansac(world[msk.reshape(-1)], pix[msk], K, None, iterationsCount=iterations,
+                                                 reprojectionError=5, flags=cv2.SOLVEPNP_SQPNP)
+    ok5, rvec5, tvec5, n5 = pr.solve_frame(frame, K, iterations=iterations, reproj=5)
+    assert pr.enabled() and bool(ok4) == bool(ok5)
+    if ok4:
+        assert n5 == len(inl4) and np.array_equal(rvec4, rvec5) and np.array_equal(tvec4, tvec5)
 
 
 def test_rank_emulated_frame_window_sharding(cuda_device):
