@@ -184,16 +184,24 @@ def _pixel_grid(H, W):
     return np.mgrid[:W, :H].T.astype(np.float32)
 
 
-def fast_pnp(pts3d, focal, msk, pp=None, niter_PnP=10, device=None):
+def fast_pnp(pts3d, focal, msk, pp=None, niter_PnP=10, device=None, frame=None):
     """RANSAC-PnP, reference init_im_poses.py:473-513.  Returns (focal, cam2world 4x4) or None.  With a CUDA ``device`` the
     re-projection test of every hypothesis runs there (pnp_ransac.py: the same inlier sets and pose as cv2.solvePnPRansac,
-    which is what runs without a device)."""
+    which is what runs without a device); ``frame``: a pnp_ransac.PlaneFrame instead of the host arrays (points that already
+    live on the device)."""
     import cv2
     from . import pnp_ransac
-    if msk.sum() < 4:
-        return None
-    H, W, THREE = pts3d.shape
-    assert THREE == 3
+    if frame is None:
+        if msk.sum() < 4:
+            return None
+        H, W, THREE = pts3d.shape
+        assert THREE == 3
+        if device is not None and pnp_ransac.enabled():
+            frame = pnp_ransac.HostFrame(pts3d, msk, device)          # uploaded once for all tentative focals
+    else:
+        if frame.count < 4:
+            return None
+        H, W = frame.H, frame.W
     if focal is None:
         S = max(W, H)
         tentative_focals = np.geomspace(S / 2, S * 3, 21)
@@ -204,7 +212,10 @@ def fast_pnp(pts3d, focal, msk, pp=None, niter_PnP=10, device=None):
     best = (0,)
     for f in tentative_focals:
         K = np.float32([(f, 0, pp[0]), (0, f, pp[1]), (0, 0, 1)])
-        success, R, T, score = pnp_ransac.solve(pts3d, msk, K, device, iterations=niter_PnP, reproj=5, flags=cv2.SOLVEPNP_SQPNP)
+        if frame is not None:
+            success, R, T, score = pnp_ransac.solve_frame(frame, K, iterations=niter_PnP, reproj=5, flags=cv2.SOLVEPNP_SQPNP)
+        else:
+            success, R, T, score = pnp_ransac.solve(pts3d, msk, K, None, iterations=niter_PnP, reproj=5, flags=cv2.SOLVEPNP_SQPNP)
         if not success:
             continue
         if success and score > best[0]:
@@ -343,13 +354,17 @@ def init_minimum_spanning_tree(self, save_score_path=None, save_score_only=False
     # independent (cv2 seeds its RANSAC generator per call) and release the GIL: run them on a thread pool.
     pnp = np.zeros((N, 18))          # [solved, cam-to-world (16), focal the solve settled on]
     jobs = []
+    from . import pnp_ransac
+    on_device = pnp_ransac.enabled()     # the points stay where they are: plane + similarity + mask on the device (PlaneFrame)
     for n in range(N):
         if im_poses[n] is None and n in self._lframe:
             h, w = self.imshapes[n]
-            # the raw slot plane and the confidence map go to the host as they are; the similarity that makes the
-            # world pointmap of frame n is applied by the worker (numpy), next to the cv2 call that consumes it
-            X = self._bufs.predw[self._lslot[src[n]], :h * w].to('cpu', non_blocking=False)
-            msk = (self.im_conf[self._lframe[n]] > self.min_conf_thr).cpu()
+            X = self._bufs.predw[self._lslot[src[n]], :h * w]
+            msk = self.im_conf[self._lframe[n]] > self.min_conf_thr
+            if not on_device:
+                # the raw slot plane and the confidence map go to the host as they are; the similarity that makes the
+                # world pointmap of frame n is applied by the worker (numpy), next to the cv2 call that consumes it
+                X, msk = X.to('cpu', non_blocking=False), msk.cpu()
             jobs.append((n, X, msk, T[n], (h, w)))
     ph.mark(f'pnp-prep({len(jobs)})')
     if jobs:
@@ -358,10 +373,14 @@ def init_minimum_spanning_tree(self, save_score_path=None, save_score_only=False
 
         def _solve(job):
             n, X, msk, (s, R, tt), (h, w) = job
-            A, t32, Xn = (s * R).astype(np.float32), tt.astype(np.float32), X.numpy()
+            A, t32 = (s * R).astype(np.float32), tt.astype(np.float32)
+            if on_device:         # the same fp32 expression, evaluated by a3r_similarity_points with numpy's rounding
+                frame = pnp_ransac.PlaneFrame(X, A, t32, msk, h, w)
+                return n, fast_pnp(None, im_focals[n], None, niter_PnP=niter_PnP, frame=frame)
+            Xn = X.numpy()
             # plain ufuncs (no BLAS: a threaded GEMM inside every worker would oversubscribe the host)
             pts = (Xn[:, 0:1] * A[:, 0] + Xn[:, 1:2] * A[:, 1] + Xn[:, 2:3] * A[:, 2] + t32).reshape(h, w, 3)
-            return n, fast_pnp(pts, im_focals[n], msk.numpy(), niter_PnP=niter_PnP, device=self.device)
+            return n, fast_pnp(pts, im_focals[n], msk.numpy(), niter_PnP=niter_PnP)
 
         unposed = sum(1 for n in range(N) if im_poses[n] is None)          # the same number on every rank (the tree is global)
         with ThreadPoolExecutor(max_workers=host_workers(len(jobs), self._shard, total_jobs=unposed)) as pool:
