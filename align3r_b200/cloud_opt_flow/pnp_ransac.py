@@ -103,6 +103,39 @@ def ransac_loop(obj, img, K, count_inliers, iterations=10, confidence=0.99, on_b
     return best, best_model
 
 
+def ransac_loop_batched(rows, K, count, count_batch, iterations=10, confidence=0.99, batch=4):
+    """The same loop with the hypotheses tested ``batch`` at a time: OpenCV draws its samples from a generator of its own that no
+    result feeds back into, so the next ``batch`` subsets are known ahead; their rows are fetched together (``rows(list of
+    subsets) -> list of (obj (5,3), img (5,2))``), their EPnP poses solved, ``count_batch(list of (rvec, tvec)) -> counts`` tests them
+    in one go, and OpenCV's decisions are replayed on the counts in order - a hypothesis past the point where the loop would have
+    ended is ignored.  One device round trip per batch instead of two per hypothesis.  Returns the best ``(rvec, tvec)`` or None."""
+    import cv2
+    rng = CvRNG()
+    niters = max(int(iterations), 1)
+    best_model, max_good = None, 0
+    it = 0
+    while it < niters:
+        nb = min(int(batch), niters - it)
+        subsets = [draw_subset(rng, count) for _ in range(nb)]
+        models = []
+        for obj5, img5 in rows(subsets):
+            ok, rvec, tvec = cv2.solvePnP(obj5, img5, K, None, flags=cv2.SOLVEPNP_EPNP)
+            models.append((rvec, tvec) if ok else None)
+        live = [m for m in models if m is not None]
+        counts = iter(count_batch(live)) if live else iter(())
+        for m in models:
+            good = next(counts) if m is not None else None        # (keeps counts aligned with the live models)
+            if it >= niters:
+                continue
+            it += 1
+            if m is None:
+                continue
+            if good > max(max_good, _MODEL_POINTS - 1):
+                best_model, max_good = (m[0].copy(), m[1].copy()), int(good)
+                niters = update_num_iters(confidence, (count - good) / count, _MODEL_POINTS, niters)
+    return best_model
+
+
 def refit(obj_in, img_in, K, best_model, flags):
     """solvepnp.cpp after the loop: the requested solver on the inliers (as doubles); the loop's model if it fails."""
     import cv2
@@ -175,6 +208,9 @@ class HostFrame:
     def rows(self):
         return _Lazy(self.flat, self.sel), _LazyPix(self.sel, self.W)
 
+    def rows_batched(self, subsets):
+        return [(self.flat[self.sel[idx]], _pixels(self.sel[idx], self.W)) for idx in subsets]
+
     def host_lists(self):
         return self.flat[self.sel], _pixels(self.sel, self.W)
 
@@ -202,7 +238,7 @@ class PlaneFrame:
             self.d_msk = msk.reshape(self.P).to(torch.uint8)
             self.d_sel = torch.nonzero(self.d_msk, as_tuple=False).flatten()        # int64, ascending = the solver's order
             self.count = int(self.d_sel.numel())
-            self._out = torch.empty((8, 4), dtype=torch.float32, device=self.dev)
+            self._out = torch.empty((64, 4), dtype=torch.float32, device=self.dev)
         self._lib, self._cache = lib, (None, None)
 
     def upload(self):
@@ -238,6 +274,27 @@ class PlaneFrame:
 
         return _Obj(), _Img()
 
+    def rows_batched(self, subsets):
+        """the sampled rows of up to 12 hypotheses in one gather + one download"""
+        flat = [k for idx in subsets for k in idx]
+        rows = self._gather_flat(flat)
+        out = []
+        for j in range(len(subsets)):
+            r = rows[j * _MODEL_POINTS:(j + 1) * _MODEL_POINTS]
+            out.append((np.ascontiguousarray(r[:, :3]), _pixels(r[:, 3].astype(np.int64), self.W)))
+        return out
+
+    def _gather_flat(self, flat):
+        import torch
+        from .. import _lib
+        assert len(flat) <= 64
+        arr = (C.c_int32 * len(flat))(*[int(k) for k in flat])
+        with torch.cuda.device(self.dev):
+            st = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+            _lib.check(self._lib.a3r_pnp_gather(_lib.ptr(self.d_pts), _lib.ptr(self.d_sel), arr, len(flat), _lib.ptr(self._out), st),
+                       "a3r_pnp_gather")
+            return self._out[:len(flat)].cpu().numpy()
+
     def host_lists(self):
         """(self-check only) the solver's lists as the host path builds them: numpy's transform of the downloaded plane."""
         Xn = self._plane.cpu().numpy()
@@ -263,33 +320,33 @@ def run_on_frame(frame, K, iterations=10, reproj=5.0, confidence=0.99, flags=Non
     dev, P, W = frame.dev, frame.P, frame.W
     K64 = np.asarray(K, dtype=np.float64)
     frame.upload()
+    batch = 4 if int(iterations) <= 16 else 8
     with torch.cuda.device(dev):
-        d_flags = [torch.empty(P, dtype=torch.uint8, device=dev) for _ in range(2)]      # best so far / the one being tested
-        d_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        d_flags = torch.empty(P, dtype=torch.uint8, device=dev)
+        d_counts = torch.zeros(16, dtype=torch.int32, device=dev)
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         hyp = (C.c_double * 17)()
         hyp[12], hyp[13], hyp[14], hyp[15], hyp[16] = K64[0, 0], K64[1, 1], K64[0, 2], K64[1, 2], float(reproj) * float(reproj)
-        cur = [0]
 
-        def count_inliers(rvec, tvec):
-            R = cv2.Rodrigues(rvec)[0]
+        def launch(model, flags_ptr, j):
+            R = cv2.Rodrigues(model[0])[0]
             for k in range(9):
                 hyp[k] = float(R.flat[k])
             for k in range(3):
-                hyp[9 + k] = float(tvec.flat[k])
-            buf = d_flags[cur[0]]
-            _lib.check(lib.a3r_pnp_inliers(_lib.ptr(frame.d_pts), _lib.ptr(frame.d_msk), W, P, hyp, _lib.ptr(buf), _lib.ptr(d_count),
-                                           stream), "a3r_pnp_inliers")
-            return int(d_count.item()), cur[0]
+                hyp[9 + k] = float(model[1].flat[k])
+            _lib.check(lib.a3r_pnp_inliers(_lib.ptr(frame.d_pts), _lib.ptr(frame.d_msk), W, P, hyp, flags_ptr,
+                                           C.c_void_p(d_counts.data_ptr() + 4 * j), stream), "a3r_pnp_inliers")
 
-        def on_best(token):
-            cur[0] = 1 - token                               # keep the best flags, test the next hypothesis in the other buffer
+        def count_batch(models):                             # one launch per hypothesis, ONE download for the batch
+            for j, m in enumerate(models):
+                launch(m, None, j)
+            return d_counts[:len(models)].cpu().tolist()
 
-        obj_rows, img_rows = frame.rows()
-        best, best_model = ransac_loop(obj_rows, img_rows, K, count_inliers, iterations, confidence, on_best=on_best)
-        if best is None:
+        best_model = ransac_loop_batched(frame.rows_batched, K, frame.count, count_batch, iterations, confidence, batch=batch)
+        if best_model is None:
             return False, None, None, 0
-        inl = torch.nonzero(d_flags[best], as_tuple=False).flatten()          # pixel order = the solver's order
+        launch(best_model, _lib.ptr(d_flags), 0)             # the inlier set of the best hypothesis
+        inl = torch.nonzero(d_flags, as_tuple=False).flatten()                # pixel order = the solver's order
         obj_in = frame.d_pts.index_select(0, inl).cpu().numpy()
         pix = inl.cpu().numpy()
     rvec, tvec = refit(obj_in, _pixels(pix, W), K, best_model, flags)

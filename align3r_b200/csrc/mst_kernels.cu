@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(256) k_pnp_inliers(const float* __restrict__ p
         const float err = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
         in = (double)err <= h.thr2;
     }
-    if (p < P) flags[p] = in ? 1 : 0;
+    if (flags && p < P) flags[p] = in ? 1 : 0;
     const int n = __syncthreads_count(in);
     if (threadIdx.x == 0 && n) atomicAdd(count, n);
 }
@@ -255,8 +255,8 @@ __global__ void __launch_bounds__(256) k_similarity_points(const float4* __restr
 }
 
 // the sampled points of one hypothesis: row idx[k] of the solver's list = pixel sel[idx[k]] -> (x, y, z, pixel)
-struct Idx8 { int32_t v[8]; };
-__global__ void k_pnp_gather(const float* __restrict__ pts, const int64_t* __restrict__ sel, const Idx8 idx, int n,
+struct Idx64 { int32_t v[64]; };
+__global__ void k_pnp_gather(const float* __restrict__ pts, const int64_t* __restrict__ sel, const Idx64 idx, int n,
                              float* __restrict__ out) {
     const int k = threadIdx.x;
     if (k >= n) return;
@@ -361,7 +361,7 @@ int a3r_init_depth(const float* predw, int64_t pix_stride, const int32_t* src, c
 int a3r_pnp_inliers(const float* pts, const uint8_t* mask, int32_t W, int64_t P, const double* hyp, uint8_t* flags,
                     int32_t* count, void* stream) {
     if (P <= 0) return A3R_OK;
-    if (!pts || !mask || !hyp || !flags || !count || W <= 0) return a3r_fail(A3R_E_ARG, "a3r_pnp_inliers: NULL pointer or W <= 0");
+    if (!pts || !mask || !hyp || !count || W <= 0) return a3r_fail(A3R_E_ARG, "a3r_pnp_inliers: NULL pointer or W <= 0");
     cudaStream_t st = (cudaStream_t)stream;
     PnpHyp h;
     for (int k = 0; k < 9; ++k) h.R[k] = hyp[k];
@@ -386,10 +386,10 @@ int a3r_similarity_points(const float* plane, int64_t P, const float* sim, float
 
 int a3r_pnp_gather(const float* pts, const int64_t* sel, const int32_t* idx, int32_t n, float* out, void* stream) {
     if (n <= 0) return A3R_OK;
-    if (!pts || !sel || !idx || !out || n > 8) return a3r_fail(A3R_E_ARG, "a3r_pnp_gather: NULL pointer or more than 8 rows");
-    Idx8 v;
-    for (int k = 0; k < 8; ++k) v.v[k] = k < n ? idx[k] : 0;
-    k_pnp_gather<<<1, 32, 0, (cudaStream_t)stream>>>(pts, sel, v, n, out);
+    if (!pts || !sel || !idx || !out || n > 64) return a3r_fail(A3R_E_ARG, "a3r_pnp_gather: NULL pointer or more than 64 rows");
+    Idx64 v;
+    for (int k = 0; k < 64; ++k) v.v[k] = k < n ? idx[k] : 0;
+    k_pnp_gather<<<1, 64, 0, (cudaStream_t)stream>>>(pts, sel, v, n, out);
     A3R_CUDA(cudaGetLastError());
     return A3R_OK;
 }

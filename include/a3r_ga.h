@@ -361,7 +361,7 @@ int a3r_init_depth(const float *predw, int64_t pix_stride, const int32_t *src, c
  * PnPRansacCallback::computeError re-projects every point for every hypothesis on the host).  pts [P][3] fp32 world points of
  * a frame (pixel p = v * W + u is observed at (u, v)), mask [P] bytes (the points handed to the solver), hyp = 17 HOST doubles:
  * world-to-camera R (9, row-major), t (3), fx, fy, cx, cy, squared re-projection threshold.  Writes flags [P] (1 = masked-in
- * inlier) and *count (device int32).  Operation by operation OpenCV's arithmetic (fp64 without FMA contraction, projection
+ * inlier; NULL: the count only) and *count (device int32).  Operation by operation OpenCV's arithmetic (fp64 without FMA contraction, projection
  * rounded to fp32, fp32 squared error, fp64 comparison): the inlier sets are cv::solvePnPRansac's. */
 int a3r_pnp_inliers(const float *pts, const uint8_t *mask, int32_t W, int64_t P, const double *hyp, uint8_t *flags,
                     int32_t *count, void *stream);
@@ -370,8 +370,8 @@ int a3r_pnp_inliers(const float *pts, const uint8_t *mask, int32_t W, int64_t P,
  * every operation rounded on its own in numpy's order (the similarity of the spanning tree, reference init_im_poses.py:272-279
  * applies it before fast_pnp).  sim = 12 HOST floats: A (9, row-major), t (3). */
 int a3r_similarity_points(const float *plane, int64_t P, const float *sim, float *out, void *stream);
-/* The n <= 8 sampled points of one RANSAC hypothesis: row idx[k] (HOST int32) of the solver's point list, whose k-th entry is
- * pixel sel[k] (device int64, ascending), -> out [n][4] = x, y, z, pixel. */
+/* The n <= 64 sampled points of a batch of RANSAC hypotheses: row idx[k] (HOST int32) of the solver's point list, whose k-th
+ * entry is pixel sel[k] (device int64, ascending), -> out [n][4] = x, y, z, pixel. */
 int a3r_pnp_gather(const float *pts, const int64_t *sel, const int32_t *idx, int32_t n, float *out, void *stream);
 
 #ifdef __cplusplus

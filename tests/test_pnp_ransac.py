@@ -53,6 +53,24 @@ def restated(pts3d, msk, K, iterations, reproj, flags):
     return True, rvec, tvec, np.searchsorted(sel, pix)           # indices in the solver's list, as cv2 returns them
 
 
+def restated_batched(pts3d, msk, K, iterations, reproj, flags, batch):
+    """The batched form of the loop (what run_on_frame drives on the device), with the numpy inlier test."""
+    H, W, _ = pts3d.shape
+    frame = pr.HostFrame(pts3d, msk, "cpu")
+    mflat = np.asarray(msk).reshape(-1)
+    count, keep = numpy_inlier_test(frame.flat, mflat, W, K, reproj)
+
+    def count_batch(models):
+        return [count(rvec, tvec)[0] for rvec, tvec in models]
+    model = pr.ransac_loop_batched(frame.rows_batched, K, frame.count, count_batch, iterations, batch=batch)
+    if model is None:
+        return False, None, None, None
+    n, token = count(*model)
+    pix = np.flatnonzero(keep[token])
+    rvec, tvec = pr.refit(frame.flat[pix], pr._pixels(pix, W), K, model, flags)
+    return True, rvec, tvec, np.searchsorted(frame.sel, pix)
+
+
 def scene(H, W, noise, outliers, seed):
     r = np.random.default_rng(seed)
     u, v = np.meshgrid(np.arange(W), np.arange(H))
@@ -83,6 +101,12 @@ def test_restated_loop_equals_opencv(seed):
     if ok:
         assert np.array_equal(inl.ravel(), inl2)
         assert np.array_equal(rvec, rvec2) and np.array_equal(tvec, tvec2)
+    for batch in (1, 4, 8):          # hypotheses tested several at a time, OpenCV's decisions replayed on the counts
+        ok3, rvec3, tvec3, inl3 = restated_batched(X, msk, K, iterations, 5, cv2.SOLVEPNP_SQPNP, batch)
+        assert bool(ok) == bool(ok3)
+        if ok:
+            assert np.array_equal(inl.ravel(), inl3), batch
+            assert np.array_equal(rvec, rvec3) and np.array_equal(tvec, tvec3), batch
 
 
 def test_generator_and_loop_shortening():
