@@ -16,7 +16,8 @@ Step 1's re-projection of every point for every hypothesis is the time (~8 ms ea
 ``cv::RNG`` and of ``getSubset``), the loop control and the loop shortening are restated in Python, the five-point EPnP
 solves and the final refit ARE OpenCV's (``cv2.solvePnP``), and the per-hypothesis inlier test runs on the device
 (``a3r_pnp_inliers``: OpenCV's arithmetic operation by operation - fp64 without FMA contraction, fp32 projection, fp32
-squared error).  The inlier sets, and with them the refit, are identical to ``cv2.solvePnPRansac``'s: checked against it
+squared error).  The hypotheses are tested a batch at a time (``ransac_loop_batched``): OpenCV's samples come from a generator
+no result feeds back into, so the next subsets are known ahead and OpenCV's decisions can be replayed on the batch's counts.  The inlier sets, and with them the refit, are identical to ``cv2.solvePnPRansac``'s: checked against it
 on the CPU (``tests/test_pnp_ransac.py``: the same loop with the inlier test in numpy), on the GPU
 (``tests/test_gpu_parity.py::test_device_ransac_pnp_equals_opencv``) and ONCE PER PROCESS on the first real solve
 (``_self_check``): on any difference the process falls back to ``cv2.solvePnPRansac`` for good and says so.
